@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py — pairs/sec of the BF-Hamming + GMS hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--impl reference]
+
+Workload (N=1): BASELINE.json configs[1] — synthetic 640x480 pairs, 10k keypoints / 256-bit descriptors
+per image, GMS defaults — as a batch of P DISTINCT pairs per step (P*800 KB of inputs > the 126 MB L2, so no
+L2 flush is needed between steps).  N>1: N*P distinct pairs; rank 0 generates the descriptor/keypoint set,
+ONE NCCL broadcast shares it, each rank matches its own contiguous shard of the pair list (no data-path
+collective; weak scaling); timing = max over ranks.
+
+`value`   : pairs/s with the image set already resident in HBM (device pointers adopted by the C ABI).
+`e2e`     : pairs/s through the C ABI with HOST (pinned) buffers: H2D of descriptors+keypoints and D2H of
+            matches, masks and counts inside the timed region, every step.
+`roofline`: the dominant kernel (Hamming), timed with CUDA events on the library's stream.
+`cpu_baseline` / --impl reference: the reference's CPU path (OpenCV BFMatcher via cv2 when importable, else
+            the C oracle port, all host threads; GMS = single-threaded oracle port, as OpenCV's GMS is) on a
+            bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W_IMG, H_IMG, N_KP = 640, 480, 10_000
+WORKLOAD = "cfg2: synthetic 640x480 pairs, 10k kpts x 256-bit desc per image, BF-Hamming + GMS defaults"
+
+
+# ----------------------------------------------------------------------------------------------------
+def gen_pairs_torch(n_pairs, seed, device):
+    """P distinct config-2-shaped pairs generated on the device (same distribution as synth.make_pair:
+    50% inliers = warped copies with ~8% bit flips and 1 px noise, 1% duplicate train rows)."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    P, n = n_pairs, N_KP
+    wh = torch.tensor([W_IMG, H_IMG], device=device, dtype=torch.float32)
+    hi = torch.tensor([np.nextafter(np.float32(W_IMG), np.float32(0)), np.nextafter(np.float32(H_IMG), np.float32(0))],
+                      device=device)
+    desc = torch.randint(0, 256, (P, 2, n, 32), device=device, dtype=torch.uint8, generator=g)
+    kp = torch.rand((P, 2, n, 2), device=device, generator=g) * wh
+    n_in = n // 2
+    src = torch.rand((P, n), device=device, generator=g).argsort(1)[:, :n_in]
+    slots = torch.rand((P, n), device=device, generator=g).argsort(1)[:, :n_in]
+    pidx = torch.arange(P, device=device)[:, None]
+    p = kp[pidx, 0, src] + wh * 0.03 + torch.randn((P, n_in, 2), device=device, generator=g)
+    ok = ((p >= 0) & (p < wh - 1)).all(-1)
+    weights = (2 ** torch.arange(7, -1, -1, device=device, dtype=torch.int32))
+    flips = (torch.rand((P, n_in, 32, 8), device=device, generator=g) < 0.08).to(torch.int32)
+    flips = (flips * weights).sum(-1).to(torch.uint8)
+    d_in = desc[pidx, 0, src] ^ flips
+    kp2 = kp[:, 1].clone()
+    d2 = desc[:, 1].clone()
+    cur_k = kp2[pidx, slots]
+    cur_d = d2[pidx, slots]
+    kp2[pidx, slots] = torch.where(ok[..., None], p, cur_k)
+    d2[pidx, slots] = torch.where(ok[..., None], d_in, cur_d)
+    n_dup = n // 100
+    a = torch.randint(0, n, (P, n_dup), device=device, generator=g)
+    b = torch.randint(0, n, (P, n_dup), device=device, generator=g)
+    d2[pidx, a] = d2[pidx, b]
+    kp[:, 1] = kp2
+    desc[:, 1] = d2
+    kp = torch.minimum(kp.clamp_(min=0), hi)
+    return desc.reshape(P * 2 * n, 32).contiguous(), kp.reshape(P * 2 * n, 2).contiguous()
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_pairs(desc, kp, n_pairs_sample, threads):
+    """The reference's CPU path on `n_pairs_sample` pairs of the workload.  Returns (seconds, description)."""
+    import oracle
+
+    oracle.build()
+    oracle.set_num_threads(threads)
+    try:
+        import cv2
+
+        cv2.setNumThreads(threads)
+        bf = cv2.BFMatcher(cv2.NORM_HAMMING, False)
+    except Exception:
+        cv2, bf = None, None
+    q = np.arange(N_KP, dtype=np.int32)
+    t_cv, t_or, t_gms = 0.0, 0.0, 0.0
+    for p in range(n_pairs_sample):
+        d1 = desc[(2 * p) * N_KP:(2 * p + 1) * N_KP]
+        d2 = desc[(2 * p + 1) * N_KP:(2 * p + 2) * N_KP]
+        k1 = kp[(2 * p) * N_KP:(2 * p + 1) * N_KP]
+        k2 = kp[(2 * p + 1) * N_KP:(2 * p + 2) * N_KP]
+        t0 = time.perf_counter()
+        idx, _ = oracle.bf_hamming(d1, d2)
+        t_or += time.perf_counter() - t0
+        if bf is not None:
+            t0 = time.perf_counter()
+            m = bf.match(d1, d2)
+            t_cv += time.perf_counter() - t0
+            assert m[17].trainIdx == idx[17]
+        t0 = time.perf_counter()
+        oracle.gms((W_IMG, H_IMG), (W_IMG, H_IMG), k1, k2, q, idx)
+        t_gms += time.perf_counter() - t0
+    if bf is not None and t_cv < t_or:
+        t_bf, which = t_cv, "cv2.BFMatcher(NORM_HAMMING) %s" % cv2.__version__
+    else:
+        t_bf, which = t_or, "C oracle port (pthreads, popcnt)"
+    desc_s = ("%d pairs of the workload; BF = %s on %d threads (%.1f ms/pair; other BF impl: %.1f ms/pair), "
+              "GMS = C oracle port, 1 thread (%.2f ms/pair)" %
+              (n_pairs_sample, which, threads, 1e3 * t_bf / n_pairs_sample,
+               1e3 * (t_or if which.startswith("cv2") else t_cv) / n_pairs_sample, 1e3 * t_gms / n_pairs_sample))
+    return t_bf + t_gms, desc_s
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path, all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    from sfm_gms_b200 import synth
+
+    threads = os.cpu_count() or 1
+    sample = args.ref_pairs
+    s = synth.make_pair_batch(sample, W_IMG, H_IMG, N_KP, seed0=2)
+    for _ in range(args.warmup):
+        cpu_reference_pairs(s["desc"], s["kp"], 1, threads)
+    t_total, desc_s = 0.0, ""
+    for _ in range(args.steps):
+        t, desc_s = cpu_reference_pairs(s["desc"], s["kp"], sample, threads)
+        t_total += t
+    pairs_s = sample * args.steps / t_total
+    line = {"impl": "reference", "metric": "image pairs/sec (ORB-10k, BF-Hamming+GMS)", "value": pairs_s,
+            "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_step": sample, "note": "CPU path; rank 0 only"},
+            "cpu_baseline": {"value": pairs_s, "unit": "pairs/s", "cores": threads, "kind": "port",
+                             "sample": "each step = " + desc_s},
+            "e2e": {"value": pairs_s, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--pairs", type=int, default=256, help="pairs per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-pairs", type=int, default=8, help="pairs per step of the CPU reference arm")
+    ap.add_argument("--cpu-pairs", type=int, default=16, help="pairs in the cpu_baseline sample")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "tc"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import sfm_gms_b200 as sg
+    from sfm_gms_b200 import api
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    P = args.pairs
+    total_pairs = P * world
+    n_rows = total_pairs * 2 * N_KP
+
+    # ---- the shared descriptor/keypoint set: generated on rank 0, ONE NCCL broadcast ------------------
+    if rank == 0:
+        desc_all, kp_all = gen_pairs_torch(total_pairs, 2, dev)
+    else:
+        desc_all = torch.empty((n_rows, 32), dtype=torch.uint8, device=dev)
+        kp_all = torch.empty((n_rows, 2), dtype=torch.float32, device=dev)
+    bcast_ms = 0.0
+    if world > 1:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dist.broadcast(desc_all, 0)
+        dist.broadcast(kp_all, 0)
+        torch.cuda.synchronize()
+        bcast_ms = 1e3 * (time.perf_counter() - t0)
+    offsets = np.arange(2 * total_pairs + 1, dtype=np.int64) * N_KP
+    sizes = np.tile(np.array([[W_IMG, H_IMG]], np.int32), (2 * total_pairs, 1))
+    # shard: rank r owns pairs [r*P, (r+1)*P) of the global list (pair p = images 2p, 2p+1)
+    my_pairs = (np.arange(rank * P, (rank + 1) * P, dtype=np.int32)[:, None] * 2 + np.array([[0, 1]], np.int32))
+    my_pairs = np.ascontiguousarray(my_pairs.astype(np.int32))
+
+    ctx = sg.Context(local_rank)
+    if args.kernel != "auto":
+        ctx.set_option(api.OPT_HAMMING_KERNEL, api.HAMMING_POPC if args.kernel == "popc" else api.HAMMING_TC)
+    ctx.set_option(api.OPT_TIMING, 1)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    # device-resident outputs for the `value` arm
+    tot_m = P * N_KP
+    o_ninl = torch.zeros(P, dtype=torch.int32, device=dev)
+    o_bh = torch.zeros(P, dtype=torch.int32, device=dev)
+    o_ml = torch.zeros(P, dtype=torch.int32, device=dev)
+    o_ti = torch.zeros(tot_m, dtype=torch.int32, device=dev)
+    o_di = torch.zeros(tot_m, dtype=torch.int32, device=dev)
+    o_mk = torch.zeros(tot_m, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def step_resident():
+        ctx.match_pairs_raw(my_pairs, 0, 0, 6.0, api.SFMGMS_DEVICE, o_ninl.data_ptr(), o_bh.data_ptr(), o_ml.data_ptr(),
+                            o_ti.data_ptr(), o_di.data_ptr(), o_mk.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- value: inputs resident in HBM -----------------------------------------------------------------
+    ctx.set_images_raw(offsets, desc_all.data_ptr(), kp_all.data_ptr(), sizes, api.SFMGMS_DEVICE,
+                       keepalive=(desc_all, kp_all))
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.kernel_launches
+    ham_ms, gms_ms, ham_launches = [], [], 0
+
+    def step_resident_timed():
+        nonlocal ham_launches
+        step_resident()
+        a, b, c = ctx.last_timing()
+        ham_ms.append(a)
+        gms_ms.append(b)
+        ham_launches += c
+
+    ms_total = timed(step_resident_timed, args.steps)
+    launches = ctx.kernel_launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = total_pairs * args.steps / (ms_total * 1e-3)
+    n_inl_dev = o_ninl.cpu().numpy().copy()
+
+    # ---- e2e: host (pinned) buffers through the C ABI, H2D + D2H inside the timed region ---------------
+    lo, hi = rank * P * 2 * N_KP, (rank + 1) * P * 2 * N_KP
+    h_desc = desc_all[lo:hi].cpu().pin_memory()
+    h_kp = kp_all[lo:hi].cpu().pin_memory()
+    loc_off = np.arange(2 * P + 1, dtype=np.int64) * N_KP
+    loc_sizes = sizes[: 2 * P]
+    loc_pairs = np.ascontiguousarray(np.arange(2 * P, dtype=np.int32).reshape(-1, 2))
+    h_ninl = torch.zeros(P, dtype=torch.int32).pin_memory()
+    h_bh = torch.zeros(P, dtype=torch.int32).pin_memory()
+    h_ml = torch.zeros(P, dtype=torch.int32).pin_memory()
+    h_ti = torch.zeros(tot_m, dtype=torch.int32).pin_memory()
+    h_di = torch.zeros(tot_m, dtype=torch.int32).pin_memory()
+    h_mk = torch.zeros(tot_m, dtype=torch.uint8).pin_memory()
+    h2d = h_desc.numel() + h_kp.numel() * 4
+    d2h = 3 * P * 4 + tot_m * 9
+
+    def step_e2e():
+        ctx.set_images_raw(loc_off, h_desc.data_ptr(), h_kp.data_ptr(), loc_sizes, api.SFMGMS_HOST)
+        ctx.match_pairs_raw(loc_pairs, 0, 0, 6.0, api.SFMGMS_HOST, h_ninl.data_ptr(), h_bh.data_ptr(), h_ml.data_ptr(),
+                            h_ti.data_ptr(), h_di.data_ptr(), h_mk.data_ptr())
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    ms_e2e_dev = timed(step_e2e, args.steps)
+    wall_e2e = time.perf_counter() - t0
+    e2e_value = total_pairs * args.steps / (ms_e2e_dev * 1e-3)
+    assert np.array_equal(h_ninl.numpy(), n_inl_dev), "e2e and resident arms disagree"
+
+    # ---- gather per-rank inlier totals on the host (no data-path collective; just the report) ---------
+    inl_total = torch.tensor([int(n_inl_dev.sum())], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(inl_total)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        kind = "tc" if (args.kernel == "tc" or (args.kernel == "auto" and _tc_built())) else "popc"
+        ham_avg_ms = float(np.mean(ham_ms)) / max(1, ham_launches / max(1, len(ham_ms)))
+        dists = float(P) * N_KP * N_KP           # distance evaluations per launch (one launch per step)
+        per_launch_s = float(np.mean(ham_ms)) * 1e-3
+        sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+        if kind == "popc":
+            # INT/popc pipe: 8 POPC.b32 per distance; POPC issues 16 lanes/clk/SM
+            achieved = 8 * dists / per_launch_s / 1e9
+            peak = 16 * 148 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e9
+            roof = {"bound": "int_popc", "kernel": "hamming_popc_kernel", "achieved": achieved, "peak": peak,
+                    "unit": "Gpopc/s", "frac": achieved / peak,
+                    "peak_source": "nominal 16 POPC lanes/clk/SM x 148 SMs x sm_max_mhz (no measured INT peak in "
+                                   "MEASURED_PEAKS.json)",
+                    "traffic": None, "algorithmic_units_per_launch": dists, "avg_launch_ms": per_launch_s * 1e3}
+        else:
+            ops = 2.0 * 256 * dists               # int8 MACs*2 on the unpacked +-1 operands
+            achieved = ops / per_launch_s / 1e12
+            peak = 2.0 * peaks.get("bf16_tflops_sustained", 1413.3)
+            roof = {"bound": "tensor", "kernel": "hamming_tc_kernel", "achieved": achieved, "peak": peak,
+                    "unit": "TOP/s", "frac": achieved / peak,
+                    "peak_source": "2 x measured sustained bf16 (int8 dense = 2x bf16 rate on sm_100a), "
+                                   "MEASURED_PEAKS.json",
+                    "traffic": None, "algorithmic_units_per_launch": dists, "avg_launch_ms": per_launch_s * 1e3}
+        line = {"metric": "image pairs/sec (ORB-10k, BF-Hamming+GMS)", "value": value, "unit": "pairs/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+                "us_per_pair": 1e3 * ms_total / args.steps / total_pairs * world, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (f32/f64 cell+threshold decisions)",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": P, "hamming_kernel": kind,
+                           "l2": "inputs per step (%.0f MB/GPU) exceed the 126 MB L2; no flush" % (P * 0.8192),
+                           "parallelism": "pair-sharded x%d, one NCCL broadcast of the shared set (%.1f ms, untimed)"
+                                          % (world, bcast_ms)},
+                "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e_dev / args.steps,
+                        "wall_ms_per_step": 1e3 * wall_e2e / args.steps},
+                "gpu_launches": int(launches), "roofline": roof,
+                "stage_ms_per_step": {"hamming": float(np.mean(ham_ms)), "gms": float(np.mean(gms_ms))},
+                "clocks": clocks, "inliers_total": int(inl_total.item())}
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            n_s = min(args.cpu_pairs, P)
+            hd, hk = h_desc.numpy(), h_kp.numpy()
+            t, desc_s = cpu_reference_pairs(hd, hk, n_s, threads)
+            line["cpu_baseline"] = {"value": n_s / t, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                    "sample": desc_s}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _tc_built():
+    import ctypes
+
+    from sfm_gms_b200 import api
+    try:
+        c = api.Context(int(os.environ.get("LOCAL_RANK", "0")))
+        try:
+            c.set_option(api.OPT_HAMMING_KERNEL, api.HAMMING_TC)
+            ok = True
+        except api.SfmGmsError:
+            ok = False
+        c.close()
+        return ok
+    except Exception:
+        return False
+
+
+if __name__ == "__main__":
+    main()

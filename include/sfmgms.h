@@ -1,0 +1,135 @@
+/*
+ * sfmgms.h — C ABI of the B200-native BF-Hamming + GMS matching stage.
+ *
+ * Drop-in boundary for the two calls the reference makes back to back
+ *     matcherBF->match(desc1, desc2, matches);                         FeatureMatchUtil.cpp:68
+ *     cv::xfeatures2d::matchGMS(size1, size2, kp1, kp2, matches, out,  FeatureMatchUtil.cpp:69
+ *                               withRotation, withScale[, thresholdFactor]);
+ * (also DisparityUtil.cpp:143+149 and :296+299; bruteForceMatch at FeatureMatchUtil.cpp:20-31 for the
+ * cross-check variant).  The reference itself has no FFI: both callees are OpenCV C++ methods
+ * (SURVEY.md §8b).  Every entry point below names the reference interface it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types; never throws; returns SFMGMS_OK (0) or an
+ *    SFMGMS_ERR_* code, with a human-readable message available from sfmgms_last_error().
+ *  - the caller owns every buffer it passes in (as with OpenCV's const& inputs / cleared outputs);
+ *    the context owns all device memory it allocates.
+ *  - one context per host thread / per GPU; calls on a context are synchronous on return.
+ *  - descriptors are 256-bit ORB descriptors: CV_8U rows of desc_bytes == 32, C-contiguous.
+ *  - keypoints are read as two consecutive floats (pt.x, pt.y) every `stride_bytes`
+ *    (8 for packed xy, 28 for an array of cv::KeyPoint); matches as int32 queryIdx/trainIdx every
+ *    `stride_bytes` (4 for plain arrays, 16 for an array of cv::DMatch).
+ *  - there is no CPU fallback: without a CUDA device sfmgms_create fails.
+ */
+#ifndef SFMGMS_H_
+#define SFMGMS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFMGMS_OK 0
+#define SFMGMS_ERR_ARG 1        /* null/negative/inconsistent argument, desc_bytes != 32 */
+#define SFMGMS_ERR_TRAIN_ROWS 2 /* train rows >= 2^18: OpenCV's CV_Assert(rows < IMGIDX_ONE) in BFMatcher */
+#define SFMGMS_ERR_DOMAIN 3     /* a matched keypoint lies outside [0,w)x[0,h): undefined behaviour in OpenCV GMS */
+#define SFMGMS_ERR_INDEX 4      /* queryIdx/trainIdx out of range: undefined behaviour in OpenCV GMS */
+#define SFMGMS_ERR_CUDA 5       /* CUDA runtime error (message in sfmgms_last_error) */
+#define SFMGMS_ERR_STATE 6      /* call order violated (e.g. match_pairs before set_images) */
+
+#define SFMGMS_MAX_TRAIN_ROWS (1 << 18)
+
+/* where a buffer lives */
+#define SFMGMS_HOST 0
+#define SFMGMS_DEVICE 1
+
+/* Hamming kernel selection (sfmgms_set_option key SFMGMS_OPT_HAMMING_KERNEL) */
+#define SFMGMS_OPT_HAMMING_KERNEL 1
+#define SFMGMS_HAMMING_AUTO 0
+#define SFMGMS_HAMMING_POPC 1   /* XOR/popc CUDA-core kernel */
+#define SFMGMS_HAMMING_TC 2     /* tcgen05 int8 tensor-core kernel (unpacked +-1 bits, TMEM accumulators) */
+#define SFMGMS_OPT_GMS_CHUNK_BYTES 2 /* scratch budget per GMS chunk (bytes), default 64 MiB */
+#define SFMGMS_OPT_TIMING 3          /* 1: record CUDA events around the Hamming and GMS stages of each batch */
+
+typedef struct sfmgms_ctx sfmgms_ctx;
+
+/* ---- life cycle ------------------------------------------------------------------------------ */
+int sfmgms_create(sfmgms_ctx** out, int device);
+void sfmgms_destroy(sfmgms_ctx* ctx);
+const char* sfmgms_last_error(const sfmgms_ctx* ctx); /* ctx may be NULL: message of the failed create */
+int sfmgms_version(void);
+int sfmgms_set_option(sfmgms_ctx* ctx, int key, int64_t value);
+/* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
+int64_t sfmgms_kernel_launches(const sfmgms_ctx* ctx);
+/* With SFMGMS_OPT_TIMING on: device milliseconds (CUDA events on the context stream) of the last batch:
+ * out_ms[0] = Hamming kernel(s), out_ms[1] = GMS kernels, out_ms[2] = number of Hamming kernel launches. */
+int sfmgms_last_timing(sfmgms_ctx* ctx, double* out_ms /*3*/);
+/* the CUDA stream (cudaStream_t) the context launches on, for event timing by the caller */
+void* sfmgms_stream(sfmgms_ctx* ctx);
+
+/* ---- stage 1: replaces cv::BFMatcher(NORM_HAMMING, crossCheck=false)::match -------------------
+ * (FeatureMatchUtil.cpp:66-68).  For every query row i: train_idx[i] = lowest j minimising
+ * popcount(q_i ^ t_j), dist[i] = that popcount; matches are in query order (queryIdx = i, imgIdx = 0).
+ * *n_matches = nq, or 0 when nt == 0 (OpenCV returns an empty vector).  nt >= 2^18 -> SFMGMS_ERR_TRAIN_ROWS. */
+int sfmgms_bf_hamming(sfmgms_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt,
+                      int desc_bytes, int32_t* train_idx, int32_t* dist, int* n_matches);
+
+/* Cross-check variant: cv::BFMatcher(NORM_HAMMING, crossCheck=true)::match (bruteForceMatch,
+ * FeatureMatchUtil.cpp:22-23).  keep[i] = 1 iff query i is also the nearest query of its own nearest
+ * train row (lowest-index tie-breaks on both sides); OpenCV emits exactly the kept (i, train_idx[i]). */
+int sfmgms_bf_hamming_crosscheck(sfmgms_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt,
+                                 int desc_bytes, int32_t* train_idx, int32_t* dist, uint8_t* keep);
+
+/* ---- stage 2: replaces cv::xfeatures2d::matchGMS ----------------------------------------------
+ * (FeatureMatchUtil.cpp:69; DisparityUtil.cpp:149,299).  mask[i] (0/1) for each of the n_matches input
+ * matches; *mask_len = n_matches, or 0 if rotation/scale search was requested and every hypothesis had
+ * zero inliers (the reference then leaves its vector<bool> untouched = empty); *n_inliers = the count.
+ * best_hyp (may be NULL): scaleIdx*8 + (rotationType-1) of the winning hypothesis, -1 if none.
+ * NOTE argument order: with_rotation BEFORE with_scale, as in OpenCV's matchGMS. */
+int sfmgms_gms(sfmgms_ctx* ctx, int w1, int h1, int w2, int h2, const void* kp1, int n1, int kp1_stride_bytes,
+               const void* kp2, int n2, int kp2_stride_bytes, const int32_t* query_idx,
+               const int32_t* train_idx, int idx_stride_bytes, int n_matches, int with_rotation,
+               int with_scale, double threshold_factor, uint8_t* mask, int* mask_len, int* n_inliers,
+               int* best_hyp);
+
+/* ---- fused stage 1+2 for one pair (the whole FeatureMatchUtil.cpp:66-69 block) -----------------
+ * Matches never leave the device between the stages.  Outputs as above; any of train_idx/dist/mask may
+ * be NULL.  n_matches = n1 (0 when n2 == 0). */
+int sfmgms_match_pair(sfmgms_ctx* ctx, const uint8_t* desc1, int n1, const uint8_t* desc2, int n2,
+                      int desc_bytes, const void* kp1, int kp1_stride_bytes, const void* kp2,
+                      int kp2_stride_bytes, int w1, int h1, int w2, int h2, int with_rotation, int with_scale,
+                      double threshold_factor, int32_t* train_idx, int32_t* dist, uint8_t* mask, int* mask_len,
+                      int* n_inliers, int* best_hyp);
+
+/* ---- multi-pair (all-pairs / sliding-window SfM matching over an image set) --------------------
+ * sfmgms_set_images: register n_images images.  kp_offsets[n_images+1] (host array) gives each
+ * image's first keypoint row in desc (rows of 32 bytes) and kp_xy (rows of 2 floats); sizes_wh is a HOST
+ * array [n_images*2] (width, height).  location == SFMGMS_HOST: desc/kp_xy are host buffers, copied to
+ * the device (pinned staging, async H2D).  location == SFMGMS_DEVICE: desc/kp_xy are device pointers on the
+ * context's device (e.g. the target of an NCCL broadcast) and are adopted without a copy; they must stay
+ * alive until the next set_images/destroy. */
+int sfmgms_set_images(sfmgms_ctx* ctx, int n_images, const int64_t* kp_offsets, const uint8_t* desc,
+                      const float* kp_xy, const int32_t* sizes_wh, int location);
+
+/* sfmgms_match_pairs: for each pair p = (pairs[2p], pairs[2p+1]) = (query image, train image) run
+ * BFMatcher::match + matchGMS.  Per-match outputs are concatenated in pair order; pair p's rows start at
+ * match_offsets[p] (= sum of n1 over earlier pairs; sfmgms_match_offsets computes them).
+ * out_location selects host or device pointers for ALL outputs; each output may be NULL.
+ *   n_inliers[n_pairs], best_hyp[n_pairs], mask_len[n_pairs]  (int32)
+ *   train_idx[total], dist[total] (int32), mask[total] (uint8, all-zero for a pair whose mask_len is 0) */
+int sfmgms_match_pairs(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int with_rotation, int with_scale,
+                       double threshold_factor, int out_location, int32_t* n_inliers, int32_t* best_hyp,
+                       int32_t* mask_len, int32_t* train_idx, int32_t* dist, uint8_t* mask);
+int sfmgms_match_offsets(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int64_t* match_offsets /*n_pairs+1*/);
+
+/* ----  inlier coordinate compaction: replaces the gather loop SfMUtil.cpp:25-35 ------
+ * After sfmgms_match_pairs, emit for pair `pair_index` of the LAST batch the inlier coordinates
+ * pts1[k] = kp1[queryIdx].pt, pts2[k] = kp2[trainIdx].pt in match order (k < n_inliers), ready for
+ * findEssentialMat (SfMUtil.cpp:39).  pts1/pts2: host float arrays of capacity*2; *n_out = n_inliers. */
+int sfmgms_inlier_points(sfmgms_ctx* ctx, int pair_index, float* pts1, float* pts2, int capacity, int* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFMGMS_H_ */

@@ -1,0 +1,112 @@
+"""ctypes loader for the CPU oracle (oracle/sfmgms_oracle.c).
+
+TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs; never from sfm_gms_b200/ (the product path).
+Reference behaviour restated: FeatureMatchUtil.cpp:66-69 (BFMatcher::match + matchGMS); see the
+C file's header for the pinning status.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libsfmgms_oracle.so")
+    src = os.path.join(_HERE, "sfmgms_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libsfmgms_oracle.so")
+        if not os.path.exists(so):
+            build()
+        L = ctypes.CDLL(so)
+        u8p = ctypes.POINTER(ctypes.c_uint8)
+        i32p = ctypes.POINTER(ctypes.c_int32)
+        f32p = ctypes.POINTER(ctypes.c_float)
+        ip = ctypes.POINTER(ctypes.c_int)
+        L.oracle_bf_hamming.argtypes = [u8p, ctypes.c_int, u8p, ctypes.c_int, ctypes.c_int, i32p, i32p, ip]
+        L.oracle_bf_hamming.restype = ctypes.c_int
+        L.oracle_bf_hamming_crosscheck.argtypes = [u8p, ctypes.c_int, u8p, ctypes.c_int, ctypes.c_int, i32p, i32p, u8p]
+        L.oracle_bf_hamming_crosscheck.restype = ctypes.c_int
+        L.oracle_gms.argtypes = [ctypes.c_int] * 4 + [f32p, ctypes.c_int, ctypes.c_int, f32p, ctypes.c_int,
+                                                      ctypes.c_int, i32p, i32p, ctypes.c_int, ctypes.c_int,
+                                                      ctypes.c_int, ctypes.c_int, ctypes.c_double, u8p, ip, ip,
+                                                      ip, ip]
+        L.oracle_gms.restype = ctypes.c_int
+        L.oracle_set_num_threads.argtypes = [ctypes.c_int]
+        L.oracle_num_threads.restype = ctypes.c_int
+        _LIB = L
+    return _LIB
+
+
+def _p(a, t):
+    return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+def set_num_threads(n):
+    lib().oracle_set_num_threads(int(n))
+
+
+def bf_hamming(q, t):
+    """-> (train_idx int32[nq], dist int32[nq]); both empty if t is empty (cv2 returns no matches)."""
+    q = np.ascontiguousarray(q, dtype=np.uint8)
+    t = np.ascontiguousarray(t, dtype=np.uint8)
+    nq, nt = q.shape[0], t.shape[0]
+    db = q.shape[1] if q.ndim == 2 else t.shape[1]
+    idx = np.empty(nq, np.int32)
+    dist = np.empty(nq, np.int32)
+    n = ctypes.c_int(0)
+    rc = lib().oracle_bf_hamming(_p(q, ctypes.c_uint8), nq, _p(t, ctypes.c_uint8), nt, db,
+                                 _p(idx, ctypes.c_int32), _p(dist, ctypes.c_int32), ctypes.byref(n))
+    if rc:
+        raise ValueError("oracle_bf_hamming rc=%d" % rc)
+    return idx[: n.value], dist[: n.value]
+
+
+def bf_hamming_crosscheck(q, t):
+    q = np.ascontiguousarray(q, dtype=np.uint8)
+    t = np.ascontiguousarray(t, dtype=np.uint8)
+    nq, nt = q.shape[0], t.shape[0]
+    idx = np.empty(nq, np.int32)
+    dist = np.empty(nq, np.int32)
+    keep = np.zeros(nq, np.uint8)
+    rc = lib().oracle_bf_hamming_crosscheck(_p(q, ctypes.c_uint8), nq, _p(t, ctypes.c_uint8), nt, q.shape[1],
+                                            _p(idx, ctypes.c_int32), _p(dist, ctypes.c_int32),
+                                            _p(keep, ctypes.c_uint8))
+    if rc:
+        raise ValueError("oracle_bf_hamming_crosscheck rc=%d" % rc)
+    return idx, dist, keep.astype(bool)
+
+
+def gms(size1, size2, kp1_xy, kp2_xy, query_idx, train_idx, with_rotation=False, with_scale=False,
+        threshold_factor=6.0):
+    """matchGMS semantics.  size = (width, height).  Returns dict(mask, n_inliers, hyp_counts, best_hyp).
+
+    mask has length n_matches, or 0 when rotation/scale search found nothing (reference quirk).
+    """
+    kp1 = np.ascontiguousarray(kp1_xy, dtype=np.float32).reshape(-1, 2)
+    kp2 = np.ascontiguousarray(kp2_xy, dtype=np.float32).reshape(-1, 2)
+    qi = np.ascontiguousarray(query_idx, dtype=np.int32)
+    ti = np.ascontiguousarray(train_idx, dtype=np.int32)
+    n = qi.shape[0]
+    mask = np.zeros(max(n, 1), np.uint8)
+    mlen, ninl, bh = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(-1)
+    hyp = np.full(40, -1, np.int32)
+    rc = lib().oracle_gms(int(size1[0]), int(size1[1]), int(size2[0]), int(size2[1]),
+                          _p(kp1, ctypes.c_float), kp1.shape[0], 2, _p(kp2, ctypes.c_float), kp2.shape[0], 2,
+                          _p(qi, ctypes.c_int32), _p(ti, ctypes.c_int32), 1, n, int(bool(with_rotation)),
+                          int(bool(with_scale)), float(threshold_factor), _p(mask, ctypes.c_uint8),
+                          ctypes.byref(mlen), ctypes.byref(ninl), _p(hyp, ctypes.c_int), ctypes.byref(bh))
+    if rc:
+        raise ValueError("oracle_gms rc=%d" % rc)
+    return dict(mask=mask[: mlen.value].astype(bool), n_inliers=ninl.value, hyp_counts=hyp, best_hyp=bh.value)

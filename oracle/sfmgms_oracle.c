@@ -1,0 +1,340 @@
+/*
+ * sfmgms_oracle.c — CPU restatement of the BF-Hamming + GMS matching path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load this library.  The product
+ * path (sfm_gms_b200/, include/sfmgms.h) never links, imports or falls back to it.
+ *
+ * What it restates (all reference paths are relative to /root/reference):
+ *   stage 1  cv::BFMatcher(NORM_HAMMING, crossCheck=false)::match
+ *            call site SfM-GMS/SfM-GMS/FeatureMatchUtil.cpp:66-68 (also :22-23, :40-41).
+ *            The arithmetic lives in OpenCV features2d 4.5.x (third party, binary-only in the
+ *            reference: SfM-GMS/lib/opencv_world45{1,2}.lib).  Semantics pinned against the
+ *            executable cv2 4.13 BFMatcher in tests/test_oracle.py and tests/golden/.
+ *   stage 2  cv::xfeatures2d::matchGMS  (OpenCV-contrib xfeatures2d 4.5.2, modules/xfeatures2d/src/gms.cpp)
+ *            call sites FeatureMatchUtil.cpp:69 (true,true), DisparityUtil.cpp:149,299 (defaults).
+ *            Third-party, binary-only in the reference (SfM-GMS/bin/opencv_xfeatures2d452.dll);
+ *            the algorithm below follows the disassembly-verified specification in
+ *            /root/repo/SURVEY.md Appendix A (virtual addresses quoted per function).
+ *
+ * PARITY PINNING: stage 1 is pinned by an executable reference (cv2).  Stage 2 has NO
+ * executable reference and the reference ships NO tests or golden vectors for it: it is pinned
+ * by (a) the constants extracted from the DLL, (b) the survey's independent numpy-restatement
+ * anchors on the reference's own images and (c) hand-derivable
+ * micro-cases.  => GMS parity is "unpinned by reference tests" in the sense of the task brief.
+ *
+ * Build: see oracle/Makefile (-O2 -ffp-contract=off: every f32/f64 op is separately rounded,
+ * exactly like the divss/mulss/addsd/divsd/sqrtsd/mulsd sequence in the DLL).
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define GRID_L 20 /* left grid 20x20: DLL @VA 0x180046ac6 */
+
+/* ROT[8][9], 1-based, DLL .rdata 0x18012f520. */
+static const int ROT[8][9] = {
+    {1, 2, 3, 4, 5, 6, 7, 8, 9}, {4, 1, 2, 7, 5, 3, 8, 9, 6}, {7, 4, 1, 8, 5, 2, 9, 6, 3},
+    {8, 7, 4, 9, 5, 1, 6, 3, 2}, {9, 8, 7, 6, 5, 4, 3, 2, 1}, {6, 9, 8, 3, 5, 7, 2, 1, 4},
+    {3, 6, 9, 2, 5, 8, 1, 4, 7}, {2, 3, 6, 1, 5, 9, 4, 7, 8}};
+
+/* cvFloor / cvRound as OpenCV defines them (SURVEY Appendix A "Helpers"). */
+static inline int cv_floor_f(float v) { int i = (int)v; return i - (i > v); }
+static inline int cv_floor_d(double v) { int i = (int)v; return i - (i > v); }
+static inline int cv_round_d(double v) { return (int)lrint(v); } /* cvtsd2si: half-to-even */
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 1: brute-force Hamming NN.  SURVEY §8(a1) / Appendix B.
+ * strict '<' scan in increasing train index => lowest trainIdx on ties.
+ * Returns 0, or -1 on bad arguments (nt >= 2^18 mirrors OpenCV's IMGIDX_ONE assert).
+ * nt == 0 => no matches are produced (caller sees n_matches = 0); outputs untouched.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const uint8_t *q, *t;
+    int nt, desc_bytes, i0, i1;
+    int32_t *train_idx, *dist;
+} bf_job_t;
+
+static void* bf_worker(void* arg) {
+    const bf_job_t* jb = (const bf_job_t*)arg;
+    const int desc_bytes = jb->desc_bytes;
+    const int words = desc_bytes / 8, tail = desc_bytes % 8;
+    for (int i = jb->i0; i < jb->i1; ++i) {
+        const uint8_t* a = jb->q + (size_t)i * desc_bytes;
+        int best = 0x7fffffff, bestj = -1;
+        for (int j = 0; j < jb->nt; ++j) {
+            const uint8_t* b = jb->t + (size_t)j * desc_bytes;
+            int d = 0;
+            for (int w = 0; w < words; ++w) {
+                uint64_t x, y;
+                memcpy(&x, a + 8 * w, 8);
+                memcpy(&y, b + 8 * w, 8);
+                d += __builtin_popcountll(x ^ y);
+            }
+            for (int k = 0; k < tail; ++k)
+                d += __builtin_popcount((unsigned)(a[8 * words + k] ^ b[8 * words + k]));
+            if (d < best) { best = d; bestj = j; } /* strict '<': lowest trainIdx on ties */
+        }
+        jb->train_idx[i] = bestj;
+        jb->dist[i] = best;
+    }
+    return NULL;
+}
+
+static int g_threads = 1;
+/* Threads used by oracle_bf_hamming (OpenCV's batchDistance is parallel_for_ over query rows;
+ * GMS is single-threaded in OpenCV and stays so here). */
+void oracle_set_num_threads(int n) { g_threads = n < 1 ? 1 : (n > 256 ? 256 : n); }
+int oracle_num_threads(void) { return g_threads; }
+
+int oracle_bf_hamming(const uint8_t* q, int nq, const uint8_t* t, int nt, int desc_bytes,
+                      int32_t* train_idx, int32_t* dist, int* n_matches) {
+    if (nq < 0 || nt < 0 || desc_bytes <= 0 || nt >= (1 << 18)) return -1;
+    if (nt == 0) { if (n_matches) *n_matches = 0; return 0; }
+    int nth = g_threads;
+    if (nth > nq) nth = nq > 0 ? nq : 1;
+    bf_job_t jobs[256];
+    pthread_t th[256];
+    for (int k = 0; k < nth; ++k) {
+        bf_job_t jb = {q, t, nt, desc_bytes, (int)((long)nq * k / nth),
+                       (int)((long)nq * (k + 1) / nth), train_idx, dist};
+        jobs[k] = jb;
+    }
+    for (int k = 1; k < nth; ++k) pthread_create(&th[k], NULL, bf_worker, &jobs[k]);
+    bf_worker(&jobs[0]);
+    for (int k = 1; k < nth; ++k) pthread_join(th[k], NULL);
+    if (n_matches) *n_matches = nq;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 2: GMS.  One struct mirrors the GMSMatcher object (DLL ctor @VA 0x180046900).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int n;                 /* mNumberMatches */
+    const float* p1;       /* normalised points image 1 (x,y) */
+    const float* p2;       /* normalised points image 2 */
+    const int32_t* mq;     /* match.first  (queryIdx) */
+    const int32_t* mt;     /* match.second (trainIdx) */
+    int wr, hr, gr;        /* right grid (setScale) */
+    int32_t* hist;         /* GL x GR motion statistics */
+    int32_t* cnt;          /* GL points per left cell */
+    int32_t* cp;           /* GL cell pairs */
+    int32_t* pl;           /* per match: pair.first  */
+    int32_t* pr;           /* per match: pair.second */
+    uint8_t* mask;         /* per match inlier mask of the current run */
+    int32_t nbl[GRID_L * GRID_L][9];
+    int32_t* nbr;          /* GR x 9 */
+    double factor;
+} gms_t;
+
+/* neighbors(W,H): DLL @VA 0x180048030. */
+static void build_nb9(int32_t* nb, int w, int h) {
+    for (int idx = 0; idx < w * h; ++idx) {
+        int x = idx % w, y = idx / w;
+        for (int k = 0; k < 9; ++k) nb[idx * 9 + k] = -1;
+        for (int yi = -1; yi <= 1; ++yi)
+            for (int xi = -1; xi <= 1; ++xi) {
+                int xx = x + xi, yy = y + yi;
+                if (xx < 0 || xx >= w || yy < 0 || yy >= h) continue;
+                nb[idx * 9 + (yi + 1) * 3 + (xi + 1)] = xx + yy * w;
+            }
+    }
+}
+
+/* SCALE table, DLL .data 0x1802c5008; [2],[3] are sqrt() results at static init. */
+static double scale_ratio(int s) {
+    switch (s) {
+        case 0: return 1.0;
+        case 1: return 0.5;
+        case 2: return 1.0 / sqrt(2.0);
+        case 3: return sqrt(2.0);
+        default: return 2.0;
+    }
+}
+
+/* setScale: DLL @VA 0x180048c10.  => (wr,gr) = (20,400)(10,100)(14,196)(28,784)(40,1600). */
+static void set_scale(gms_t* g, int s) {
+    g->wr = cv_round_d((double)GRID_L * scale_ratio(s));
+    g->hr = cv_round_d((double)GRID_L * scale_ratio(s));
+    g->gr = g->wr * g->hr;
+    build_nb9(g->nbr, g->wr, g->hr);
+}
+
+/* getGridIndexLeft: DLL @VA 0x180047bc0.  f32 multiply, f64 add of 0.5 on the shifted axis. */
+static int left_idx(const float* p, int type) {
+    float fx = (float)GRID_L * p[0];
+    float fy = (float)GRID_L * p[1];
+    int x = (type == 2 || type == 4) ? cv_floor_d((double)fx + 0.5) : cv_floor_f(fx);
+    int y = (type == 3 || type == 4) ? cv_floor_d((double)fy + 0.5) : cv_floor_f(fy);
+    if (x >= GRID_L || y >= GRID_L) return -1;
+    return x + y * GRID_L;
+}
+
+/* getGridIndexRight: DLL @VA 0x180047d60 (no bounds check in the reference; the supported
+ * domain 0<=x<w, 0<=y<h keeps it inside [0,gr), validated by oracle_gms before any run). */
+static int right_idx(const gms_t* g, const float* p) {
+    return cv_floor_f((float)g->wr * p[0]) + cv_floor_f((float)g->hr * p[1]) * g->wr;
+}
+
+/* verifyCellPairs: DLL @VA 0x180048d10. */
+static void verify(gms_t* g, int rot) {
+    const int* rp = ROT[rot - 1];
+    const int GL = GRID_L * GRID_L;
+    for (int i = 0; i < GL; ++i) {
+        const int32_t* row = g->hist + (size_t)i * g->gr;
+        long sum = 0;
+        for (int j = 0; j < g->gr; ++j) sum += row[j]; /* cv::sum(row) @VA 0x180048da0 */
+        if (sum == 0) { g->cp[i] = -1; continue; }
+        int maxv = 0;
+        for (int j = 0; j < g->gr; ++j)
+            if (row[j] > maxv) { g->cp[i] = j; maxv = row[j]; }
+        int score = 0, num = 0;
+        double thresh = 0.0;
+        for (int k = 0; k < 9; ++k) {
+            int ll = g->nbl[i][k];
+            int rr = g->nbr[g->cp[i] * 9 + rp[k] - 1];
+            if (ll == -1 || rr == -1) continue;
+            score += g->hist[(size_t)ll * g->gr + rr];
+            thresh += (double)g->cnt[ll];
+            num++;
+        }
+        thresh = g->factor * sqrt(thresh / (double)num); /* divsd, sqrtsd, mulsd */
+        if ((double)score < thresh) g->cp[i] = -2;
+    }
+}
+
+/* run: DLL @VA 0x180048630 (assignMatchPairs inlined @VA 0x1800489e0). Returns popcount(mask). */
+static int run(gms_t* g, int rot) {
+    const int GL = GRID_L * GRID_L;
+    memset(g->mask, 0, (size_t)g->n);
+    for (int i = 0; i < g->n; ++i) { g->pl[i] = 0; g->pr[i] = 0; }
+    for (int type = 1; type <= 4; ++type) {
+        memset(g->hist, 0, sizeof(int32_t) * (size_t)GL * g->gr);
+        for (int i = 0; i < GL; ++i) { g->cp[i] = -1; g->cnt[i] = 0; }
+        for (int i = 0; i < g->n; ++i) {
+            int l = g->pl[i] = left_idx(g->p1 + 2 * (size_t)g->mq[i], type);
+            int r;
+            if (type == 1) r = g->pr[i] = right_idx(g, g->p2 + 2 * (size_t)g->mt[i]);
+            else r = g->pr[i];
+            if (l < 0 || r < 0) continue;
+            g->hist[(size_t)l * g->gr + r]++;
+            g->cnt[l]++;
+        }
+        verify(g, rot);
+        for (int i = 0; i < g->n; ++i)
+            if (g->pl[i] >= 0 && g->cp[g->pl[i]] == g->pr[i]) g->mask[i] = 1;
+    }
+    int c = 0;
+    for (int i = 0; i < g->n; ++i) c += g->mask[i];
+    return c;
+}
+
+/*
+ * matchGMS / GMSMatcher::getInlierMask (DLL @VA 0x180048280 / 0x180047dc0).
+ *
+ * kp*_xy: keypoint pixel coordinates, interleaved x,y (stride in floats given by kp_stride,
+ *         2 for packed; 7 for an array of cv::KeyPoint).
+ * mask:   n_matches bytes (0/1).  *mask_len is n_matches, or 0 when rotation/scale search was
+ *         requested and every hypothesis scored 0 (the reference leaves the vector untouched).
+ * hyp_counts (optional, 40 ints): inlier count per hypothesis in scale-major order, -1 = not run.
+ * best_hyp (optional): scale*8 + (rot-1) of the winning hypothesis (-1 if none).
+ * Returns 0; -2 if a referenced keypoint is outside [0,w)x[0,h) (UB in the reference);
+ * -3 if a match index is out of range (UB in the reference); -1 on bad arguments.
+ */
+int oracle_gms(int w1, int h1, int w2, int h2, const float* kp1_xy, int n1, int kp1_stride,
+               const float* kp2_xy, int n2, int kp2_stride, const int32_t* query_idx,
+               const int32_t* train_idx, int idx_stride, int n_matches, int with_rotation,
+               int with_scale, double threshold_factor, uint8_t* mask, int* mask_len,
+               int* n_inliers, int* hyp_counts, int* best_hyp) {
+    if (n1 < 0 || n2 < 0 || n_matches < 0 || w1 <= 0 || h1 <= 0 || w2 <= 0 || h2 <= 0) return -1;
+    const int GL = GRID_L * GRID_L;
+    int rc = 0;
+    gms_t g;
+    memset(&g, 0, sizeof g);
+    float* p1 = (float*)malloc(sizeof(float) * 2 * (size_t)(n1 ? n1 : 1));
+    float* p2 = (float*)malloc(sizeof(float) * 2 * (size_t)(n2 ? n2 : 1));
+    int32_t* mq = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n_matches ? n_matches : 1));
+    int32_t* mt = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n_matches ? n_matches : 1));
+    /* normalizePoints: DLL @VA 0x180048420 — f32 divss by (float)size. */
+    for (int i = 0; i < n1; ++i) {
+        p1[2 * i] = kp1_xy[(size_t)i * kp1_stride] / (float)w1;
+        p1[2 * i + 1] = kp1_xy[(size_t)i * kp1_stride + 1] / (float)h1;
+    }
+    for (int i = 0; i < n2; ++i) {
+        p2[2 * i] = kp2_xy[(size_t)i * kp2_stride] / (float)w2;
+        p2[2 * i + 1] = kp2_xy[(size_t)i * kp2_stride + 1] / (float)h2;
+    }
+    for (int i = 0; i < n_matches; ++i) {
+        mq[i] = query_idx[(size_t)i * idx_stride];
+        mt[i] = train_idx[(size_t)i * idx_stride];
+        if (mq[i] < 0 || mq[i] >= n1 || mt[i] < 0 || mt[i] >= n2) { rc = -3; goto done; }
+        const float* a = kp1_xy + (size_t)mq[i] * kp1_stride;
+        const float* b = kp2_xy + (size_t)mt[i] * kp2_stride;
+        if (!(a[0] >= 0.f && a[0] < (float)w1 && a[1] >= 0.f && a[1] < (float)h1) ||
+            !(b[0] >= 0.f && b[0] < (float)w2 && b[1] >= 0.f && b[1] < (float)h2)) {
+            rc = -2;
+            goto done;
+        }
+    }
+    g.n = n_matches; g.p1 = p1; g.p2 = p2; g.mq = mq; g.mt = mt; g.factor = threshold_factor;
+    g.hist = (int32_t*)malloc(sizeof(int32_t) * (size_t)GL * 1600);
+    g.cnt = (int32_t*)malloc(sizeof(int32_t) * GL);
+    g.cp = (int32_t*)malloc(sizeof(int32_t) * GL);
+    g.pl = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n_matches ? n_matches : 1));
+    g.pr = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n_matches ? n_matches : 1));
+    g.mask = (uint8_t*)malloc((size_t)(n_matches ? n_matches : 1));
+    g.nbr = (int32_t*)malloc(sizeof(int32_t) * 1600 * 9);
+    build_nb9(&g.nbl[0][0], GRID_L, GRID_L);
+
+    if (hyp_counts) for (int k = 0; k < 40; ++k) hyp_counts[k] = -1;
+    int best = 0, bh = -1, len = 0;
+    if (!with_rotation && !with_scale) {
+        set_scale(&g, 0);
+        best = run(&g, 1);
+        if (n_matches) memcpy(mask, g.mask, (size_t)n_matches);
+        len = n_matches;
+        bh = 0;
+        if (hyp_counts) hyp_counts[0] = best;
+    } else {
+        for (int s = 0; s < (with_scale ? 5 : 1); ++s) {
+            set_scale(&g, s);
+            for (int r = 1; r <= (with_rotation ? 8 : 1); ++r) {
+                int c = run(&g, r);
+                if (hyp_counts) hyp_counts[s * 8 + r - 1] = c;
+                if (c > best) { /* strict >, first wins */
+                    memcpy(mask, g.mask, (size_t)n_matches);
+                    best = c; len = n_matches; bh = s * 8 + r - 1;
+                }
+            }
+        }
+    }
+    if (mask_len) *mask_len = len;
+    if (n_inliers) *n_inliers = best;
+    if (best_hyp) *best_hyp = bh;
+    free(g.hist); free(g.cnt); free(g.cp); free(g.pl); free(g.pr); free(g.mask); free(g.nbr);
+done:
+    free(p1); free(p2); free(mq); free(mt);
+    return rc;
+}
+
+/* (f2) cross-check helper for the "next" row: mutual nearest neighbours, as
+ * BFMatcher(NORM_HAMMING, crossCheck=true) does (FeatureMatchUtil.cpp:22 uses crossCheck=true
+ * with NORM_L2): keep (i, j*) iff i is also the NN of j* when the roles are swapped. */
+int oracle_bf_hamming_crosscheck(const uint8_t* q, int nq, const uint8_t* t, int nt,
+                                 int desc_bytes, int32_t* train_idx, int32_t* dist,
+                                 uint8_t* keep) {
+    if (nq >= (1 << 18)) return -1;
+    int n = 0;
+    int rc = oracle_bf_hamming(q, nq, t, nt, desc_bytes, train_idx, dist, &n);
+    if (rc) return rc;
+    if (nt == 0 || nq == 0) return 0;
+    int32_t* back = (int32_t*)malloc(sizeof(int32_t) * (size_t)nt);
+    int32_t* bd = (int32_t*)malloc(sizeof(int32_t) * (size_t)nt);
+    rc = oracle_bf_hamming(t, nt, q, nq, desc_bytes, back, bd, &n);
+    for (int i = 0; i < nq; ++i) keep[i] = (back[train_idx[i]] == i);
+    free(back); free(bd);
+    return rc;
+}

@@ -1,0 +1,368 @@
+"""Host-side mirror of the reference's matching interface, over the C ABI (include/sfmgms.h).
+
+Mirrors, with the same names / argument meaning / error behaviour:
+  * ``cv::BFMatcher(NORM_HAMMING[, crossCheck])::match(query, train)``   FeatureMatchUtil.cpp:22-23, 66-68
+  * ``cv::xfeatures2d::matchGMS(size1, size2, kp1, kp2, matches1to2, withRotation, withScale,
+    thresholdFactor)``                                                    FeatureMatchUtil.cpp:69
+  * upstream ``gms_matcher(vkp1, size1, vkp2, size2, vDMatches).GetInlierMask(vbInliers, WithScale,
+    WithRotation)`` (scale BEFORE rotation — SURVEY fact 4).
+Everything here is plumbing (ctypes, numpy views); all arithmetic runs in libsfmgms.so on the GPU.
+"""
+import ctypes
+import os
+import threading
+from collections import namedtuple
+
+import numpy as np
+
+NORM_HAMMING = 6  # cv::NORM_HAMMING
+
+SFMGMS_HOST, SFMGMS_DEVICE = 0, 1
+OPT_HAMMING_KERNEL, OPT_GMS_CHUNK_BYTES, OPT_TIMING = 1, 2, 3
+HAMMING_AUTO, HAMMING_POPC, HAMMING_TC = 0, 1, 2
+
+_ERR_NAMES = {1: "ERR_ARG", 2: "ERR_TRAIN_ROWS", 3: "ERR_DOMAIN", 4: "ERR_INDEX", 5: "ERR_CUDA", 6: "ERR_STATE"}
+
+DMatch = namedtuple("DMatch", ["queryIdx", "trainIdx", "imgIdx", "distance"])
+
+
+class SfmGmsError(RuntimeError):
+    """Raised where OpenCV would throw cv::Exception (and for CUDA failures)."""
+
+    def __init__(self, code, msg):
+        super().__init__("sfmgms %s (%d): %s" % (_ERR_NAMES.get(code, "ERR"), code, msg))
+        self.code = code
+
+
+_LIB = None
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsfmgms.so")
+
+
+def load_library():
+    """Load libsfmgms.so.  Fails loudly: there is no fallback implementation."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError("%s is missing: build it with `python -m sfm_gms_b200.build` (nvcc, sm_100a). "
+                          "There is no CPU fallback." % _LIB_PATH)
+    L = ctypes.CDLL(_LIB_PATH)
+    c_int, c_void_p, c_double, c_i64 = ctypes.c_int, ctypes.c_void_p, ctypes.c_double, ctypes.c_int64
+    P = ctypes.POINTER
+    L.sfmgms_create.argtypes = [P(c_void_p), c_int]
+    L.sfmgms_destroy.argtypes = [c_void_p]
+    L.sfmgms_destroy.restype = None
+    L.sfmgms_last_error.argtypes = [c_void_p]
+    L.sfmgms_last_error.restype = ctypes.c_char_p
+    L.sfmgms_version.restype = c_int
+    L.sfmgms_set_option.argtypes = [c_void_p, c_int, c_i64]
+    L.sfmgms_kernel_launches.argtypes = [c_void_p]
+    L.sfmgms_kernel_launches.restype = c_i64
+    L.sfmgms_last_timing.argtypes = [c_void_p, c_void_p]
+    L.sfmgms_stream.argtypes = [c_void_p]
+    L.sfmgms_stream.restype = c_void_p
+    L.sfmgms_bf_hamming.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, P(c_int)]
+    L.sfmgms_bf_hamming_crosscheck.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p,
+                                               c_void_p, c_void_p]
+    L.sfmgms_gms.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
+                             c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p, P(c_int),
+                             P(c_int), P(c_int)]
+    L.sfmgms_match_pair.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,
+                                    c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_void_p, c_void_p,
+                                    c_void_p, P(c_int), P(c_int), P(c_int)]
+    L.sfmgms_set_images.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int]
+    L.sfmgms_match_offsets.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
+    L.sfmgms_match_pairs.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p]
+    L.sfmgms_inlier_points.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, P(c_int)]
+    _LIB = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def _kp_xy(kps):
+    """cv2.KeyPoint sequence or (N,2) array -> C-contiguous float32 (N,2)."""
+    if isinstance(kps, np.ndarray):
+        a = np.ascontiguousarray(kps, dtype=np.float32)
+        return a.reshape(-1, 2)
+    if len(kps) == 0:
+        return np.zeros((0, 2), np.float32)
+    return np.array([k.pt for k in kps], dtype=np.float32).reshape(-1, 2)
+
+
+def _match_idx(matches):
+    """Sequence of DMatch-like objects, or (queryIdx, trainIdx) arrays -> two int32 arrays."""
+    if isinstance(matches, tuple) and len(matches) == 2 and isinstance(matches[0], np.ndarray):
+        return (np.ascontiguousarray(matches[0], dtype=np.int32), np.ascontiguousarray(matches[1], dtype=np.int32))
+    n = len(matches)
+    q = np.fromiter((m.queryIdx for m in matches), dtype=np.int32, count=n)
+    t = np.fromiter((m.trainIdx for m in matches), dtype=np.int32, count=n)
+    return q, t
+
+
+def _size(sz):
+    """cv::Size convention: (width, height)."""
+    return int(sz[0]), int(sz[1])
+
+
+class Context:
+    """One per host thread / per GPU (SURVEY §8b threading)."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self._lib.sfmgms_create(ctypes.byref(h), int(device))
+        if rc:
+            raise SfmGmsError(rc, self._lib.sfmgms_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+        self._keep = None  # keeps adopted device tensors alive
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sfmgms_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise SfmGmsError(rc, self._lib.sfmgms_last_error(self._h).decode())
+
+    # -- options / introspection -------------------------------------------------------------------
+    def set_option(self, key, value):
+        self._check(self._lib.sfmgms_set_option(self._h, int(key), int(value)))
+
+    @property
+    def kernel_launches(self):
+        return int(self._lib.sfmgms_kernel_launches(self._h))
+
+    def last_timing(self):
+        """(hamming_ms, gms_ms, hamming_launches) of the last batch; needs set_option(OPT_TIMING, 1)."""
+        out = np.zeros(3, np.float64)
+        self._check(self._lib.sfmgms_last_timing(self._h, _ptr(out)))
+        return float(out[0]), float(out[1]), int(out[2])
+
+    @property
+    def stream(self):
+        return int(self._lib.sfmgms_stream(self._h) or 0)
+
+    # -- stage 1 ------------------------------------------------------------------------------------
+    def bf_hamming(self, query, train):
+        """-> (train_idx int32[n], dist int32[n]); n = len(query), or 0 if train is empty."""
+        q, t = self._desc(query), self._desc(train)
+        idx = np.empty(q.shape[0], np.int32)
+        dist = np.empty(q.shape[0], np.int32)
+        n = ctypes.c_int(0)
+        self._check(self._lib.sfmgms_bf_hamming(self._h, _ptr(q), q.shape[0], _ptr(t), t.shape[0], 32, _ptr(idx),
+                                                _ptr(dist), ctypes.byref(n)))
+        return idx[: n.value], dist[: n.value]
+
+    def bf_hamming_crosscheck(self, query, train):
+        q, t = self._desc(query), self._desc(train)
+        idx = np.full(q.shape[0], -1, np.int32)
+        dist = np.full(q.shape[0], -1, np.int32)
+        keep = np.zeros(q.shape[0], np.uint8)
+        self._check(self._lib.sfmgms_bf_hamming_crosscheck(self._h, _ptr(q), q.shape[0], _ptr(t), t.shape[0], 32,
+                                                           _ptr(idx), _ptr(dist), _ptr(keep)))
+        return idx, dist, keep.astype(bool)
+
+    @staticmethod
+    def _desc(d):
+        d = np.ascontiguousarray(d)
+        if d.dtype != np.uint8:
+            raise SfmGmsError(1, "descriptors must be CV_8U (uint8), got %s" % d.dtype)  # OpenCV asserts type
+        if d.ndim != 2 and d.size == 0:
+            d = d.reshape(0, 32)
+        if d.ndim != 2 or d.shape[1] != 32:
+            raise SfmGmsError(1, "descriptors must be N x 32 bytes (256-bit), got %s" % (d.shape,))
+        return d
+
+    # -- stage 2 ------------------------------------------------------------------------------------
+    def gms(self, size1, size2, kp1, kp2, query_idx, train_idx, with_rotation=False, with_scale=False,
+            threshold_factor=6.0):
+        """-> dict(mask bool[mask_len], n_inliers, best_hyp).  OpenCV argument order (rotation, scale)."""
+        w1, h1 = _size(size1)
+        w2, h2 = _size(size2)
+        k1, k2 = _kp_xy(kp1), _kp_xy(kp2)
+        qi = np.ascontiguousarray(query_idx, dtype=np.int32)
+        ti = np.ascontiguousarray(train_idx, dtype=np.int32)
+        n = qi.shape[0]
+        mask = np.zeros(max(n, 1), np.uint8)
+        ml, ni, bh = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(-1)
+        self._check(self._lib.sfmgms_gms(self._h, w1, h1, w2, h2, _ptr(k1), k1.shape[0], 8, _ptr(k2), k2.shape[0], 8,
+                                         _ptr(qi), _ptr(ti), 4, n, int(bool(with_rotation)), int(bool(with_scale)),
+                                         float(threshold_factor), _ptr(mask), ctypes.byref(ml), ctypes.byref(ni),
+                                         ctypes.byref(bh)))
+        return dict(mask=mask[: ml.value].astype(bool), n_inliers=ni.value, best_hyp=bh.value)
+
+    # -- fused pair ---------------------------------------------------------------------------------
+    def match_pair(self, desc1, desc2, kp1, kp2, size1, size2, with_rotation=False, with_scale=False,
+                   threshold_factor=6.0):
+        d1, d2 = self._desc(desc1), self._desc(desc2)
+        k1, k2 = _kp_xy(kp1), _kp_xy(kp2)
+        if k1.shape[0] != d1.shape[0] or k2.shape[0] != d2.shape[0]:
+            raise SfmGmsError(1, "keypoint / descriptor row counts differ")
+        w1, h1 = _size(size1)
+        w2, h2 = _size(size2)
+        n1 = d1.shape[0]
+        nm = n1 if d2.shape[0] else 0
+        idx = np.empty(max(n1, 1), np.int32)
+        dist = np.empty(max(n1, 1), np.int32)
+        mask = np.zeros(max(n1, 1), np.uint8)
+        ml, ni, bh = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(-1)
+        self._check(self._lib.sfmgms_match_pair(self._h, _ptr(d1), n1, _ptr(d2), d2.shape[0], 32, _ptr(k1), 8,
+                                                _ptr(k2), 8, w1, h1, w2, h2, int(bool(with_rotation)),
+                                                int(bool(with_scale)), float(threshold_factor), _ptr(idx),
+                                                _ptr(dist), _ptr(mask), ctypes.byref(ml), ctypes.byref(ni),
+                                                ctypes.byref(bh)))
+        return dict(train_idx=idx[:nm], dist=dist[:nm], mask=mask[: ml.value].astype(bool), n_inliers=ni.value,
+                    best_hyp=bh.value)
+
+    # -- multi-pair ---------------------------------------------------------------------------------
+    def set_images(self, kp_offsets, desc, kp_xy, sizes_wh):
+        """Register an image set from HOST numpy arrays (copied to the device)."""
+        off = np.ascontiguousarray(kp_offsets, dtype=np.int64)
+        d = self._desc(desc)
+        k = np.ascontiguousarray(kp_xy, dtype=np.float32).reshape(-1, 2)
+        s = np.ascontiguousarray(sizes_wh, dtype=np.int32).reshape(-1, 2)
+        n_images = off.shape[0] - 1
+        if s.shape[0] != n_images or d.shape[0] != off[-1] or k.shape[0] != off[-1]:
+            raise SfmGmsError(1, "image-set array shapes are inconsistent")
+        self._check(self._lib.sfmgms_set_images(self._h, n_images, _ptr(off), _ptr(d), _ptr(k), _ptr(s), SFMGMS_HOST))
+        self._offsets = off
+        self._keep = None
+
+    def set_images_device(self, kp_offsets, desc_ptr, kp_ptr, sizes_wh, keepalive=None):
+        """Adopt device buffers (e.g. torch tensors that received an NCCL broadcast) without a copy."""
+        off = np.ascontiguousarray(kp_offsets, dtype=np.int64)
+        s = np.ascontiguousarray(sizes_wh, dtype=np.int32).reshape(-1, 2)
+        self._check(self._lib.sfmgms_set_images(self._h, off.shape[0] - 1, _ptr(off), ctypes.c_void_p(int(desc_ptr)),
+                                                ctypes.c_void_p(int(kp_ptr)), _ptr(s), SFMGMS_DEVICE))
+        self._offsets = off
+        self._keep = keepalive
+
+    def match_offsets(self, pairs):
+        pr = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        out = np.zeros(pr.shape[0] + 1, np.int64)
+        self._check(self._lib.sfmgms_match_offsets(self._h, _ptr(pr), pr.shape[0], _ptr(out)))
+        return out
+
+    def match_pairs(self, pairs, with_rotation=False, with_scale=False, threshold_factor=6.0, want_matches=True,
+                    want_mask=True):
+        """Host outputs.  -> dict(n_inliers, best_hyp, mask_len, offsets[, train_idx, dist][, mask])."""
+        pr = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        n = pr.shape[0]
+        off = self.match_offsets(pr)
+        total = int(off[-1])
+        ninl = np.zeros(n, np.int32)
+        bh = np.zeros(n, np.int32)
+        ml = np.zeros(n, np.int32)
+        ti = np.empty(total, np.int32) if want_matches else None
+        di = np.empty(total, np.int32) if want_matches else None
+        mk = np.zeros(total, np.uint8) if want_mask else None
+        self._check(self._lib.sfmgms_match_pairs(self._h, _ptr(pr), n, int(bool(with_rotation)), int(bool(with_scale)),
+                                                 float(threshold_factor), SFMGMS_HOST, _ptr(ninl), _ptr(bh), _ptr(ml),
+                                                 _ptr(ti), _ptr(di), _ptr(mk)))
+        out = dict(n_inliers=ninl, best_hyp=bh, mask_len=ml, offsets=off)
+        if want_matches:
+            out["train_idx"], out["dist"] = ti, di
+        if want_mask:
+            out["mask"] = mk
+        return out
+
+    def match_pairs_raw(self, pairs_np, with_rotation, with_scale, threshold_factor, out_location, n_inliers=0,
+                        best_hyp=0, mask_len=0, train_idx=0, dist=0, mask=0):
+        """Raw-pointer form (ints are addresses; 0 = NULL) for callers that manage their own buffers
+        (bench.py: pinned host tensors or device tensors)."""
+        p = lambda v: ctypes.c_void_p(int(v)) if v else None  # noqa: E731
+        self._check(self._lib.sfmgms_match_pairs(self._h, _ptr(pairs_np), pairs_np.shape[0], int(with_rotation),
+                                                 int(with_scale), float(threshold_factor), int(out_location),
+                                                 p(n_inliers), p(best_hyp), p(mask_len), p(train_idx), p(dist),
+                                                 p(mask)))
+
+    def set_images_raw(self, kp_offsets, desc_ptr, kp_ptr, sizes_wh, location, keepalive=None):
+        off = np.ascontiguousarray(kp_offsets, dtype=np.int64)
+        s = np.ascontiguousarray(sizes_wh, dtype=np.int32).reshape(-1, 2)
+        self._check(self._lib.sfmgms_set_images(self._h, off.shape[0] - 1, _ptr(off), ctypes.c_void_p(int(desc_ptr)),
+                                                ctypes.c_void_p(int(kp_ptr)), _ptr(s), int(location)))
+        self._offsets = off
+        self._keep = keepalive
+
+    def inlier_points(self, pair_index, capacity):
+        p1 = np.empty((max(capacity, 1), 2), np.float32)
+        p2 = np.empty((max(capacity, 1), 2), np.float32)
+        n = ctypes.c_int(0)
+        self._check(self._lib.sfmgms_inlier_points(self._h, int(pair_index), _ptr(p1), _ptr(p2), int(capacity),
+                                                   ctypes.byref(n)))
+        m = min(n.value, capacity)
+        return p1[:m], p2[:m], n.value
+
+
+_default = threading.local()
+
+
+def default_context(device=0):
+    ctxs = getattr(_default, "ctxs", None)
+    if ctxs is None:
+        ctxs = _default.ctxs = {}
+    if device not in ctxs:
+        ctxs[device] = Context(device)
+    return ctxs[device]
+
+
+class BFMatcher:
+    """cv::BFMatcher look-alike for NORM_HAMMING (FeatureMatchUtil.cpp:22, 66)."""
+
+    def __init__(self, normType=NORM_HAMMING, crossCheck=False, ctx=None):
+        if normType != NORM_HAMMING:
+            raise SfmGmsError(1, "only NORM_HAMMING is implemented (north-star scope); got normType=%r" % (normType,))
+        self.crossCheck = bool(crossCheck)
+        self._ctx = ctx
+
+    @staticmethod
+    def create(normType=NORM_HAMMING, crossCheck=False):
+        return BFMatcher(normType, crossCheck)
+
+    def match(self, queryDescriptors, trainDescriptors):
+        """-> list[DMatch] exactly as cv2 returns it (query order; cross-check drops non-mutual rows)."""
+        ctx = self._ctx or default_context()
+        if self.crossCheck:
+            idx, dist, keep = ctx.bf_hamming_crosscheck(queryDescriptors, trainDescriptors)
+            return [DMatch(int(i), int(idx[i]), 0, float(dist[i])) for i in np.nonzero(keep)[0]]
+        idx, dist = ctx.bf_hamming(queryDescriptors, trainDescriptors)
+        return [DMatch(i, int(idx[i]), 0, float(dist[i])) for i in range(len(idx))]
+
+
+def matchGMS(size1, size2, keypoints1, keypoints2, matches1to2, withRotation=False, withScale=False,
+             thresholdFactor=6.0, ctx=None):
+    """cv::xfeatures2d::matchGMS: returns the sub-list of matches1to2 kept by GMS, input order preserved."""
+    ctx = ctx or default_context()
+    q, t = _match_idx(matches1to2)
+    r = ctx.gms(size1, size2, keypoints1, keypoints2, q, t, withRotation, withScale, thresholdFactor)
+    keep = np.nonzero(r["mask"])[0]
+    if isinstance(matches1to2, tuple):
+        return q[keep], t[keep]
+    return [matches1to2[i] for i in keep]
+
+
+class gms_matcher:
+    """Upstream header-only API: gms_matcher(vkp1, size1, vkp2, size2, vDMatches).GetInlierMask(...)."""
+
+    def __init__(self, vkp1, size1, vkp2, size2, vDMatches, ctx=None):
+        self._args = (size1, size2, _kp_xy(vkp1), _kp_xy(vkp2)) + _match_idx(vDMatches)
+        self._ctx = ctx
+
+    def GetInlierMask(self, WithScale=False, WithRotation=False):
+        """-> (num_inliers, vbInliers).  NOTE upstream order: scale first, rotation second; threshold 6."""
+        ctx = self._ctx or default_context()
+        s1, s2, k1, k2, q, t = self._args
+        r = ctx.gms(s1, s2, k1, k2, q, t, with_rotation=WithRotation, with_scale=WithScale, threshold_factor=6.0)
+        return r["n_inliers"], r["mask"]

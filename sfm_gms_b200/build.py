@@ -1,0 +1,62 @@
+"""Builds sfm_gms_b200/libsfmgms.so (CUDA kernels + C ABI) in-tree with nvcc for sm_100a.
+
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SOURCES = ["capi.cu", "hamming_popc.cu", "hamming_tc.cu", "gms.cu"]
+HEADERS = ["common.cuh", "hamming_tc.cuh", os.path.join("..", "..", "include", "sfmgms.h")]
+LIB = os.path.join(HERE, "libsfmgms.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "--fmad=false",            # GMS decisions must round each FP op separately
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
+    "-Xptxas", "-v",
+]
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not _stale():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    bdir = os.path.join(HERE, "build")
+    os.makedirs(bdir, exist_ok=True)
+    procs = []
+    for s in SOURCES:
+        o = os.path.join(bdir, s.replace(".cu", ".o"))
+        objs.append(o)
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", o]
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for s, p in procs:
+        out, _ = p.communicate()
+        log.append("== %s ==\n%s" % (s, out))
+        if p.returncode != 0:
+            sys.stderr.write("\n".join(log))
+            raise RuntimeError("nvcc failed on %s" % s)
+    with open(os.path.join(bdir, "ptxas.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

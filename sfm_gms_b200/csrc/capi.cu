@@ -1,0 +1,700 @@
+// capi.cu — the C ABI (include/sfmgms.h) over the CUDA kernels: context, buffers, batching.
+// No CPU fallback exists anywhere in this file: every entry point either runs the sm_100a kernels or
+// returns an error code.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/sfmgms.h"
+#include "common.cuh"
+#include "hamming_tc.cuh"
+
+using namespace sfmgms;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct HostBuf {  // pinned staging
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+char g_create_error[512] = "";
+
+}  // namespace
+
+struct sfmgms_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    char err[512] = "";
+    int64_t launches = 0;
+    int hamming_kernel = SFMGMS_HAMMING_AUTO;
+    size_t gms_chunk_bytes = 64ull << 20;
+    int timing = 0;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    double last_ms[3] = {0, 0, 0};
+
+    // generic device buffers
+    DevBuf d_pairs, d_results, d_key, d_mask, d_hist, d_msc, d_q, d_t, d_kp1, d_kp2, d_mq, d_mt, d_out_i32, d_pts;
+    DevBuf d_set_desc, d_set_kp;
+    HostBuf h_stage, h_pairs_pinned, h_results;
+    TcState tc;   // tensor-core Hamming operand cache (hamming_tc.cu)
+
+    // image set
+    int n_images = 0;
+    std::vector<int64_t> offsets;
+    std::vector<int32_t> sizes;
+    const uint8_t* set_desc = nullptr;   // device
+    const float* set_kp = nullptr;       // device
+    uint64_t set_version = 0;
+
+    // last batch (for sfmgms_inlier_points)
+    std::vector<PairDesc> last_pairs;
+    std::vector<PairResult> last_results;
+};
+
+namespace {
+
+int fail(sfmgms_ctx* c, int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    if (c) vsnprintf(c->err, sizeof c->err, fmt, ap);
+    else vsnprintf(g_create_error, sizeof g_create_error, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(ctx, SFMGMS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+__global__ void decode_keys_kernel(const uint32_t* __restrict__ key, long long n, int32_t* __restrict__ train_idx,
+                                   int32_t* __restrict__ dist) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += step) {
+        const uint32_t k = key[i];
+        const bool none = (k == kKeyInit);
+        if (train_idx) train_idx[i] = none ? -1 : (int32_t)(k & kTrainIdxMask);
+        if (dist) dist[i] = none ? -1 : (int32_t)(k >> kTrainIdxBits);
+    }
+}
+
+// cross-check: for each train row j the nearest query (lowest query index on ties) is rkey[j];
+// keep[i] = (rkey[train(i)] & mask) == i
+__global__ void crosscheck_kernel(const uint32_t* __restrict__ key, const uint32_t* __restrict__ rkey, int nq,
+                                  uint8_t* __restrict__ keep) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const uint32_t k = key[i];
+    keep[i] = (k != kKeyInit) && ((rkey[k & kTrainIdxMask] & kTrainIdxMask) == (uint32_t)i);
+}
+
+// (§8f-1) ordered compaction of inlier coordinates for one pair: single CTA, chunked scan
+__global__ void __launch_bounds__(1024) inlier_points_kernel(PairDesc pd, float2* __restrict__ pts1,
+                                                              float2* __restrict__ pts2, int capacity,
+                                                              int* __restrict__ n_out) {
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < pd.n_matches; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int m = (i < pd.n_matches) ? (pd.mask[i] != 0) : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, m);
+        const int within = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int k = 0; k < 32; ++k) { int v = wsum[k]; if (k < warp) woff += v; tot += v; }
+        const int pos = carry + woff + within;
+        if (m && pos < capacity) {
+            const int qi = pd.mq ? pd.mq[i] : i;
+            const int ti = pd.mt ? pd.mt[i] : (int)(pd.key[i] & kTrainIdxMask);
+            pts1[pos] = reinterpret_cast<const float2*>(pd.kp1)[qi];
+            pts2[pos] = reinterpret_cast<const float2*>(pd.kp2)[ti];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_out = carry;
+}
+
+int choose_hamming(const sfmgms_ctx* c) {
+    if (c->hamming_kernel == SFMGMS_HAMMING_AUTO) return tc_available() ? SFMGMS_HAMMING_TC : SFMGMS_HAMMING_POPC;
+    return c->hamming_kernel;
+}
+
+// Uploads the pair table, runs Hamming (optional) + GMS (optional), downloads the per-pair results.
+// hp[].key / hp[].mask must already point into device memory; keys must be initialised to kKeyInit.
+int run_batch(sfmgms_ctx* ctx, std::vector<PairDesc>& hp, bool do_hamming, bool do_gms, int with_rotation,
+              int with_scale, double factor) {
+    const int n = (int)hp.size();
+    ctx->last_results.assign(n, PairResult{0, -1, 0, 0});
+    if (n == 0) return SFMGMS_OK;
+    cudaStream_t st = ctx->stream;
+    CU(ctx->d_pairs.ensure(sizeof(PairDesc) * n));
+    CU(ctx->h_pairs_pinned.ensure(sizeof(PairDesc) * n));
+    memcpy(ctx->h_pairs_pinned.p, hp.data(), sizeof(PairDesc) * n);
+    CU(cudaMemcpyAsync(ctx->d_pairs.p, ctx->h_pairs_pinned.p, sizeof(PairDesc) * n, cudaMemcpyHostToDevice, st));
+    const PairDesc* dp = static_cast<const PairDesc*>(ctx->d_pairs.p);
+    int ham_launches = 0;
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[0], st));
+    if (do_hamming) {
+        const int kind = choose_hamming(ctx);
+        for (int c0 = 0; c0 < n; c0 += 32768) {
+            const int cn = (n - c0 < 32768) ? n - c0 : 32768;
+            int l;
+            if (kind == SFMGMS_HAMMING_TC) {
+                l = launch_hamming_tc(ctx->tc, dp + c0, hp.data() + c0, cn, ctx->sm_count, st);
+                if (l < 0) return fail(ctx, SFMGMS_ERR_CUDA, "tensor-core Hamming launch failed: %s", tc_last_error());
+            } else {
+                l = launch_hamming_popc(dp + c0, hp.data() + c0, cn, ctx->sm_count, st);
+            }
+            ctx->launches += l;
+            ham_launches += l;
+        }
+        CU(cudaGetLastError());
+    }
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[1], st));
+    if (do_gms) {
+        CU(ctx->d_results.ensure(sizeof(PairResult) * n));
+        CU(cudaMemsetAsync(ctx->d_results.p, 0, sizeof(PairResult) * n, st));
+        const int n_scales = with_scale ? kNumScales : 1;
+        const size_t per_pair = gms_scratch_bytes_per_pair(n_scales);
+        size_t budget = ctx->gms_chunk_bytes;
+        if (budget < per_pair) budget = per_pair;
+        if (budget > per_pair * (size_t)n) budget = per_pair * (size_t)n;
+        CU(ctx->d_hist.ensure(budget));
+        long long total_m = 0;
+        for (auto& p : hp) total_m += p.n_matches;
+        CU(ctx->d_msc.ensure(gms_match_scratch_bytes(total_m, n_scales)));
+        int l = launch_gms(dp, hp.data(), n, with_rotation, with_scale, factor,
+                           static_cast<PairResult*>(ctx->d_results.p), ctx->d_hist.p, budget, ctx->d_msc.p, st);
+        if (l < 0) return fail(ctx, SFMGMS_ERR_CUDA, "GMS scratch too small");
+        ctx->launches += l;
+        CU(cudaGetLastError());
+        CU(ctx->h_results.ensure(sizeof(PairResult) * n));
+        CU(cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, sizeof(PairResult) * n, cudaMemcpyDeviceToHost, st));
+        if (ctx->timing) CU(cudaEventRecord(ctx->ev[2], st));
+        CU(cudaStreamSynchronize(st));
+        memcpy(ctx->last_results.data(), ctx->h_results.p, sizeof(PairResult) * n);
+        for (int p = 0; p < n; ++p) {
+            const int s = ctx->last_results[p].status;
+            if (s == 4) return fail(ctx, SFMGMS_ERR_INDEX, "pair %d: queryIdx/trainIdx out of range", p);
+            if (s == 3) return fail(ctx, SFMGMS_ERR_DOMAIN, "pair %d: matched keypoint outside [0,w)x[0,h)", p);
+        }
+    } else if (ctx->timing) {
+        CU(cudaEventRecord(ctx->ev[2], st));
+        CU(cudaStreamSynchronize(st));
+    }
+    if (ctx->timing) {
+        float a = 0.f, b = 0.f;
+        CU(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
+        CU(cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]));
+        ctx->last_ms[0] = a; ctx->last_ms[1] = b; ctx->last_ms[2] = ham_launches;
+    }
+    return SFMGMS_OK;
+}
+
+// gather (x,y) float pairs at a byte stride into a packed device buffer via pinned staging
+int upload_xy(sfmgms_ctx* ctx, const void* src, int n, int stride_bytes, DevBuf& dst, size_t stage_off) {
+    CU(dst.ensure((size_t)(n > 0 ? n : 1) * 8));
+    if (n <= 0) return SFMGMS_OK;
+    if (stride_bytes == 8) {
+        CU(cudaMemcpyAsync(dst.p, src, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        return SFMGMS_OK;
+    }
+    float* stg = reinterpret_cast<float*>(static_cast<char*>(ctx->h_stage.p) + stage_off);
+    const char* s = static_cast<const char*>(src);
+    for (int i = 0; i < n; ++i) memcpy(stg + 2 * (size_t)i, s + (size_t)i * stride_bytes, 8);
+    CU(cudaMemcpyAsync(dst.p, stg, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    return SFMGMS_OK;
+}
+
+int upload_idx(sfmgms_ctx* ctx, const int32_t* src, int n, int stride_bytes, DevBuf& dst, size_t stage_off) {
+    CU(dst.ensure((size_t)(n > 0 ? n : 1) * 4));
+    if (n <= 0) return SFMGMS_OK;
+    if (stride_bytes == 4) {
+        CU(cudaMemcpyAsync(dst.p, src, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        return SFMGMS_OK;
+    }
+    int32_t* stg = reinterpret_cast<int32_t*>(static_cast<char*>(ctx->h_stage.p) + stage_off);
+    const char* s = reinterpret_cast<const char*>(src);
+    for (int i = 0; i < n; ++i) memcpy(stg + i, s + (size_t)i * stride_bytes, 4);
+    CU(cudaMemcpyAsync(dst.p, stg, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return SFMGMS_OK;
+}
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace
+
+#define GUARD_BEGIN                  \
+    if (!ctx) return SFMGMS_ERR_ARG; \
+    DeviceGuard guard__(ctx->device); \
+    try {
+#define GUARD_END                                                        \
+    }                                                                    \
+    catch (const std::bad_alloc&) {                                      \
+        return fail(ctx, SFMGMS_ERR_ARG, "host allocation failed");      \
+    }                                                                    \
+    catch (...) {                                                        \
+        return fail(ctx, SFMGMS_ERR_ARG, "unexpected C++ exception");    \
+    }
+
+extern "C" {
+
+int sfmgms_version(void) { return 100; }
+
+int sfmgms_create(sfmgms_ctx** out, int device) {
+    if (!out) return fail(nullptr, SFMGMS_ERR_ARG, "out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return fail(nullptr, SFMGMS_ERR_CUDA, "no CUDA device (%s); this library has no CPU fallback",
+                    cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, SFMGMS_ERR_ARG, "device %d out of range [0,%d)", device, count);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, SFMGMS_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, SFMGMS_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    sfmgms_ctx* c = new (std::nothrow) sfmgms_ctx();
+    if (!c) return fail(nullptr, SFMGMS_ERR_ARG, "host allocation failed");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    DeviceGuard g(device);
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(nullptr, SFMGMS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return SFMGMS_OK;
+}
+
+void sfmgms_destroy(sfmgms_ctx* ctx) {
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->d_pairs, &ctx->d_results, &ctx->d_key, &ctx->d_mask, &ctx->d_hist, &ctx->d_msc, &ctx->d_q,
+                      &ctx->d_t, &ctx->d_kp1, &ctx->d_kp2, &ctx->d_mq, &ctx->d_mt, &ctx->d_out_i32, &ctx->d_pts,
+                      &ctx->d_set_desc, &ctx->d_set_kp};
+    for (DevBuf* b : bufs) b->release();
+    tc_release(ctx->tc);
+    ctx->h_stage.release(); ctx->h_pairs_pinned.release(); ctx->h_results.release();
+    for (int k = 0; k < 3; ++k) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* sfmgms_last_error(const sfmgms_ctx* ctx) { return ctx ? ctx->err : g_create_error; }
+
+int sfmgms_set_option(sfmgms_ctx* ctx, int key, int64_t value) {
+    if (!ctx) return SFMGMS_ERR_ARG;
+    if (key == SFMGMS_OPT_HAMMING_KERNEL) {
+        if (value < 0 || value > 2) return fail(ctx, SFMGMS_ERR_ARG, "bad hamming kernel %lld", (long long)value);
+        if (value == SFMGMS_HAMMING_TC && !tc_available())
+            return fail(ctx, SFMGMS_ERR_ARG, "tensor-core Hamming kernel not available in this build");
+        ctx->hamming_kernel = (int)value;
+        return SFMGMS_OK;
+    }
+    if (key == SFMGMS_OPT_GMS_CHUNK_BYTES) {
+        if (value < (1 << 20)) return fail(ctx, SFMGMS_ERR_ARG, "chunk budget too small");
+        ctx->gms_chunk_bytes = (size_t)value;
+        return SFMGMS_OK;
+    }
+    if (key == SFMGMS_OPT_TIMING) {
+        DeviceGuard g(ctx->device);
+        if (value && !ctx->ev[0])
+            for (int k = 0; k < 3; ++k)
+                if (cudaEventCreate(&ctx->ev[k]) != cudaSuccess) return fail(ctx, SFMGMS_ERR_CUDA, "cudaEventCreate failed");
+        ctx->timing = value ? 1 : 0;
+        return SFMGMS_OK;
+    }
+    return fail(ctx, SFMGMS_ERR_ARG, "unknown option %d", key);
+}
+
+int sfmgms_last_timing(sfmgms_ctx* ctx, double* out_ms) {
+    if (!ctx || !out_ms) return SFMGMS_ERR_ARG;
+    if (!ctx->timing) return fail(ctx, SFMGMS_ERR_STATE, "SFMGMS_OPT_TIMING is off");
+    for (int k = 0; k < 3; ++k) out_ms[k] = ctx->last_ms[k];
+    return SFMGMS_OK;
+}
+
+int64_t sfmgms_kernel_launches(const sfmgms_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* sfmgms_stream(sfmgms_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// ---------------------------------------------------------------------------------------------------
+static int bf_common(sfmgms_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt, int desc_bytes) {
+    if (nq < 0 || nt < 0) return fail(ctx, SFMGMS_ERR_ARG, "negative row count");
+    if (desc_bytes != kDescBytes) return fail(ctx, SFMGMS_ERR_ARG, "desc_bytes must be 32 (256-bit descriptors), got %d", desc_bytes);
+    if ((nq > 0 && !query) || (nt > 0 && !train)) return fail(ctx, SFMGMS_ERR_ARG, "null descriptor pointer");
+    if (nt >= SFMGMS_MAX_TRAIN_ROWS)
+        return fail(ctx, SFMGMS_ERR_TRAIN_ROWS, "train rows %d >= 2^18 (OpenCV BFMatcher: rows < IMGIDX_ONE)", nt);
+    return SFMGMS_OK;
+}
+
+int sfmgms_bf_hamming(sfmgms_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt, int desc_bytes,
+                      int32_t* train_idx, int32_t* dist, int* n_matches) {
+    GUARD_BEGIN
+    int rc = bf_common(ctx, query, nq, train, nt, desc_bytes);
+    if (rc) return rc;
+    if (n_matches) *n_matches = (nt == 0) ? 0 : nq;
+    if (nt == 0 || nq == 0) return SFMGMS_OK;
+    cudaStream_t st = ctx->stream;
+    CU(ctx->d_q.ensure((size_t)nq * 32)); CU(ctx->d_t.ensure((size_t)nt * 32));
+    CU(ctx->d_key.ensure((size_t)nq * 4)); CU(ctx->d_out_i32.ensure((size_t)nq * 8));
+    CU(cudaMemcpyAsync(ctx->d_q.p, query, (size_t)nq * 32, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_t.p, train, (size_t)nt * 32, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(ctx->d_key.p, 0xFF, (size_t)nq * 4, st));
+    std::vector<PairDesc> hp(1);
+    PairDesc& p = hp[0];
+    memset(&p, 0, sizeof p);
+    p.desc1 = (const uint8_t*)ctx->d_q.p; p.desc2 = (const uint8_t*)ctx->d_t.p;
+    p.key = (uint32_t*)ctx->d_key.p; p.n1 = nq; p.n2 = nt; p.n_matches = nq;
+    rc = run_batch(ctx, hp, true, false, 0, 0, 0.0);
+    if (rc) return rc;
+    int32_t* o = (int32_t*)ctx->d_out_i32.p;
+    decode_keys_kernel<<<(nq + 255) / 256, 256, 0, st>>>(p.key, nq, o, o + nq);
+    ctx->launches++;
+    if (train_idx) CU(cudaMemcpyAsync(train_idx, o, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    if (dist) CU(cudaMemcpyAsync(dist, o + nq, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SFMGMS_OK;
+    GUARD_END
+}
+
+int sfmgms_bf_hamming_crosscheck(sfmgms_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt,
+                                 int desc_bytes, int32_t* train_idx, int32_t* dist, uint8_t* keep) {
+    GUARD_BEGIN
+    int rc = bf_common(ctx, query, nq, train, nt, desc_bytes);
+    if (rc) return rc;
+    if (nq >= SFMGMS_MAX_TRAIN_ROWS) return fail(ctx, SFMGMS_ERR_TRAIN_ROWS, "query rows %d >= 2^18", nq);
+    if (nt == 0 || nq == 0) return SFMGMS_OK;
+    cudaStream_t st = ctx->stream;
+    CU(ctx->d_q.ensure((size_t)nq * 32)); CU(ctx->d_t.ensure((size_t)nt * 32));
+    CU(ctx->d_key.ensure((size_t)(nq + nt) * 4)); CU(ctx->d_out_i32.ensure((size_t)nq * 8)); CU(ctx->d_mask.ensure(nq));
+    CU(cudaMemcpyAsync(ctx->d_q.p, query, (size_t)nq * 32, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_t.p, train, (size_t)nt * 32, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(ctx->d_key.p, 0xFF, (size_t)(nq + nt) * 4, st));
+    std::vector<PairDesc> hp(2);
+    memset(hp.data(), 0, sizeof(PairDesc) * 2);
+    hp[0].desc1 = (const uint8_t*)ctx->d_q.p; hp[0].desc2 = (const uint8_t*)ctx->d_t.p;
+    hp[0].key = (uint32_t*)ctx->d_key.p; hp[0].n1 = nq; hp[0].n2 = nt; hp[0].n_matches = nq;
+    hp[1].desc1 = hp[0].desc2; hp[1].desc2 = hp[0].desc1;      // roles swapped: one extra "pair"
+    hp[1].key = hp[0].key + nq; hp[1].n1 = nt; hp[1].n2 = nq; hp[1].n_matches = nt; hp[1].match_base = nq;
+    rc = run_batch(ctx, hp, true, false, 0, 0, 0.0);
+    if (rc) return rc;
+    int32_t* o = (int32_t*)ctx->d_out_i32.p;
+    decode_keys_kernel<<<(nq + 255) / 256, 256, 0, st>>>(hp[0].key, nq, o, o + nq);
+    crosscheck_kernel<<<(nq + 255) / 256, 256, 0, st>>>(hp[0].key, hp[1].key, nq, (uint8_t*)ctx->d_mask.p);
+    ctx->launches += 2;
+    if (train_idx) CU(cudaMemcpyAsync(train_idx, o, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    if (dist) CU(cudaMemcpyAsync(dist, o + nq, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    if (keep) CU(cudaMemcpyAsync(keep, ctx->d_mask.p, (size_t)nq, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SFMGMS_OK;
+    GUARD_END
+}
+
+static int gms_args(sfmgms_ctx* ctx, int w1, int h1, int w2, int h2, int n1, int n2, int s1, int s2) {
+    if (w1 <= 0 || h1 <= 0 || w2 <= 0 || h2 <= 0) return fail(ctx, SFMGMS_ERR_ARG, "image sizes must be positive");
+    if (n1 < 0 || n2 < 0) return fail(ctx, SFMGMS_ERR_ARG, "negative keypoint count");
+    if (s1 < 8 || s2 < 8) return fail(ctx, SFMGMS_ERR_ARG, "keypoint stride must be >= 8 bytes");
+    return SFMGMS_OK;
+}
+
+int sfmgms_gms(sfmgms_ctx* ctx, int w1, int h1, int w2, int h2, const void* kp1, int n1, int kp1_stride_bytes,
+               const void* kp2, int n2, int kp2_stride_bytes, const int32_t* query_idx, const int32_t* train_idx,
+               int idx_stride_bytes, int n_matches, int with_rotation, int with_scale, double threshold_factor,
+               uint8_t* mask, int* mask_len, int* n_inliers, int* best_hyp) {
+    GUARD_BEGIN
+    int rc = gms_args(ctx, w1, h1, w2, h2, n1, n2, kp1_stride_bytes, kp2_stride_bytes);
+    if (rc) return rc;
+    if (n_matches < 0 || idx_stride_bytes < 4) return fail(ctx, SFMGMS_ERR_ARG, "bad match count/stride");
+    if ((n1 > 0 && !kp1) || (n2 > 0 && !kp2) || (n_matches > 0 && (!query_idx || !train_idx)))
+        return fail(ctx, SFMGMS_ERR_ARG, "null input pointer");
+    cudaStream_t st = ctx->stream;
+    const size_t o1 = 0, o2 = align256((size_t)n1 * 8), o3 = o2 + align256((size_t)n2 * 8),
+                 o4 = o3 + align256((size_t)n_matches * 4);
+    CU(ctx->h_stage.ensure(o4 + align256((size_t)n_matches * 4)));
+    if ((rc = upload_xy(ctx, kp1, n1, kp1_stride_bytes, ctx->d_kp1, o1))) return rc;
+    if ((rc = upload_xy(ctx, kp2, n2, kp2_stride_bytes, ctx->d_kp2, o2))) return rc;
+    if ((rc = upload_idx(ctx, query_idx, n_matches, idx_stride_bytes, ctx->d_mq, o3))) return rc;
+    if ((rc = upload_idx(ctx, train_idx, n_matches, idx_stride_bytes, ctx->d_mt, o4))) return rc;
+    CU(ctx->d_mask.ensure((size_t)(n_matches > 0 ? n_matches : 1)));
+    std::vector<PairDesc> hp(1);
+    PairDesc& p = hp[0];
+    memset(&p, 0, sizeof p);
+    p.kp1 = (const float*)ctx->d_kp1.p; p.kp2 = (const float*)ctx->d_kp2.p;
+    p.mq = (const int32_t*)ctx->d_mq.p; p.mt = (const int32_t*)ctx->d_mt.p;
+    p.mask = (uint8_t*)ctx->d_mask.p;
+    p.n1 = n1; p.n2 = n2; p.n_matches = n_matches; p.w1 = w1; p.h1 = h1; p.w2 = w2; p.h2 = h2;
+    rc = run_batch(ctx, hp, false, true, with_rotation, with_scale, threshold_factor);
+    ctx->last_pairs = hp;
+    if (rc) return rc;
+    const PairResult& r = ctx->last_results[0];
+    if (mask && r.mask_len > 0) {
+        CU(cudaMemcpyAsync(mask, p.mask, (size_t)r.mask_len, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    if (mask_len) *mask_len = r.mask_len;
+    if (n_inliers) *n_inliers = r.n_inliers;
+    if (best_hyp) *best_hyp = r.best_hyp;
+    return SFMGMS_OK;
+    GUARD_END
+}
+
+int sfmgms_match_pair(sfmgms_ctx* ctx, const uint8_t* desc1, int n1, const uint8_t* desc2, int n2, int desc_bytes,
+                      const void* kp1, int kp1_stride_bytes, const void* kp2, int kp2_stride_bytes, int w1, int h1,
+                      int w2, int h2, int with_rotation, int with_scale, double threshold_factor, int32_t* train_idx,
+                      int32_t* dist, uint8_t* mask, int* mask_len, int* n_inliers, int* best_hyp) {
+    GUARD_BEGIN
+    int rc = bf_common(ctx, desc1, n1, desc2, n2, desc_bytes);
+    if (rc) return rc;
+    if ((rc = gms_args(ctx, w1, h1, w2, h2, n1, n2, kp1_stride_bytes, kp2_stride_bytes))) return rc;
+    if ((n1 > 0 && !kp1) || (n2 > 0 && !kp2)) return fail(ctx, SFMGMS_ERR_ARG, "null keypoint pointer");
+    cudaStream_t st = ctx->stream;
+    const int nm = (n2 == 0) ? 0 : n1;
+    const size_t o2 = align256((size_t)n1 * 8);
+    CU(ctx->h_stage.ensure(o2 + align256((size_t)n2 * 8)));
+    CU(ctx->d_q.ensure((size_t)(n1 + 1) * 32)); CU(ctx->d_t.ensure((size_t)(n2 + 1) * 32));
+    CU(ctx->d_key.ensure((size_t)(n1 + 1) * 4)); CU(ctx->d_out_i32.ensure((size_t)(n1 + 1) * 8));
+    CU(ctx->d_mask.ensure((size_t)n1 + 1));
+    if (n1) CU(cudaMemcpyAsync(ctx->d_q.p, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, st));
+    if (n2) CU(cudaMemcpyAsync(ctx->d_t.p, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, st));
+    if ((rc = upload_xy(ctx, kp1, n1, kp1_stride_bytes, ctx->d_kp1, 0))) return rc;
+    if ((rc = upload_xy(ctx, kp2, n2, kp2_stride_bytes, ctx->d_kp2, o2))) return rc;
+    CU(cudaMemsetAsync(ctx->d_key.p, 0xFF, (size_t)(n1 + 1) * 4, st));
+    std::vector<PairDesc> hp(1);
+    PairDesc& p = hp[0];
+    memset(&p, 0, sizeof p);
+    p.desc1 = (const uint8_t*)ctx->d_q.p; p.desc2 = (const uint8_t*)ctx->d_t.p;
+    p.kp1 = (const float*)ctx->d_kp1.p; p.kp2 = (const float*)ctx->d_kp2.p;
+    p.key = (uint32_t*)ctx->d_key.p; p.mask = (uint8_t*)ctx->d_mask.p;
+    p.n1 = n1; p.n2 = n2; p.n_matches = nm; p.w1 = w1; p.h1 = h1; p.w2 = w2; p.h2 = h2;
+    rc = run_batch(ctx, hp, nm > 0, true, with_rotation, with_scale, threshold_factor);
+    ctx->last_pairs = hp;
+    if (rc) return rc;
+    const PairResult& r = ctx->last_results[0];
+    if (nm > 0 && (train_idx || dist)) {
+        int32_t* o = (int32_t*)ctx->d_out_i32.p;
+        decode_keys_kernel<<<(nm + 255) / 256, 256, 0, st>>>(p.key, nm, o, o + nm);
+        ctx->launches++;
+        if (train_idx) CU(cudaMemcpyAsync(train_idx, o, (size_t)nm * 4, cudaMemcpyDeviceToHost, st));
+        if (dist) CU(cudaMemcpyAsync(dist, o + nm, (size_t)nm * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (mask && r.mask_len > 0) CU(cudaMemcpyAsync(mask, p.mask, (size_t)r.mask_len, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (mask_len) *mask_len = r.mask_len;
+    if (n_inliers) *n_inliers = r.n_inliers;
+    if (best_hyp) *best_hyp = r.best_hyp;
+    return SFMGMS_OK;
+    GUARD_END
+}
+
+// ---------------------------------------------------------------------------------------------------
+int sfmgms_set_images(sfmgms_ctx* ctx, int n_images, const int64_t* kp_offsets, const uint8_t* desc,
+                      const float* kp_xy, const int32_t* sizes_wh, int location) {
+    GUARD_BEGIN
+    if (n_images < 0 || !kp_offsets || !sizes_wh) return fail(ctx, SFMGMS_ERR_ARG, "bad image-set arguments");
+    if (kp_offsets[0] != 0) return fail(ctx, SFMGMS_ERR_ARG, "kp_offsets[0] must be 0");
+    for (int i = 0; i < n_images; ++i) {
+        const int64_t n = kp_offsets[i + 1] - kp_offsets[i];
+        if (n < 0) return fail(ctx, SFMGMS_ERR_ARG, "kp_offsets not monotone at image %d", i);
+        if (n >= SFMGMS_MAX_TRAIN_ROWS) return fail(ctx, SFMGMS_ERR_TRAIN_ROWS, "image %d has %lld rows >= 2^18", i, (long long)n);
+        if (sizes_wh[2 * i] <= 0 || sizes_wh[2 * i + 1] <= 0) return fail(ctx, SFMGMS_ERR_ARG, "image %d has a non-positive size", i);
+    }
+    const int64_t total = kp_offsets[n_images];
+    if (total > 0 && (!desc || !kp_xy)) return fail(ctx, SFMGMS_ERR_ARG, "null descriptor/keypoint pointer");
+    if (location == SFMGMS_HOST) {
+        CU(ctx->d_set_desc.ensure((size_t)total * 32 + 32)); CU(ctx->d_set_kp.ensure((size_t)total * 8 + 8));
+        if (total) {
+            CU(cudaMemcpyAsync(ctx->d_set_desc.p, desc, (size_t)total * 32, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->d_set_kp.p, kp_xy, (size_t)total * 8, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        ctx->set_desc = (const uint8_t*)ctx->d_set_desc.p; ctx->set_kp = (const float*)ctx->d_set_kp.p;
+    } else if (location == SFMGMS_DEVICE) {
+        if (((uintptr_t)desc & 15) || ((uintptr_t)kp_xy & 7)) return fail(ctx, SFMGMS_ERR_ARG, "device buffers must be 16-byte (desc) / 8-byte (kp) aligned");
+        ctx->set_desc = desc; ctx->set_kp = kp_xy;
+    } else {
+        return fail(ctx, SFMGMS_ERR_ARG, "bad location %d", location);
+    }
+    ctx->n_images = n_images;
+    ctx->offsets.assign(kp_offsets, kp_offsets + n_images + 1);
+    ctx->sizes.assign(sizes_wh, sizes_wh + 2 * (size_t)n_images);
+    ctx->set_version++;
+    tc_invalidate(ctx->tc);
+    return SFMGMS_OK;
+    GUARD_END
+}
+
+int sfmgms_match_offsets(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int64_t* match_offsets) {
+    GUARD_BEGIN
+    if (n_pairs < 0 || (n_pairs > 0 && !pairs) || !match_offsets) return fail(ctx, SFMGMS_ERR_ARG, "bad arguments");
+    int64_t o = 0;
+    for (int p = 0; p < n_pairs; ++p) {
+        const int a = pairs[2 * p];
+        if (a < 0 || a >= ctx->n_images || pairs[2 * p + 1] < 0 || pairs[2 * p + 1] >= ctx->n_images)
+            return fail(ctx, SFMGMS_ERR_ARG, "pair %d references an image outside the set", p);
+        match_offsets[p] = o;
+        o += ctx->offsets[a + 1] - ctx->offsets[a];
+    }
+    match_offsets[n_pairs] = o;
+    return SFMGMS_OK;
+    GUARD_END
+}
+
+int sfmgms_match_pairs(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int with_rotation, int with_scale,
+                       double threshold_factor, int out_location, int32_t* n_inliers, int32_t* best_hyp,
+                       int32_t* mask_len, int32_t* train_idx, int32_t* dist, uint8_t* mask) {
+    GUARD_BEGIN
+    if (n_pairs < 0 || (n_pairs > 0 && !pairs)) return fail(ctx, SFMGMS_ERR_ARG, "bad pair list");
+    if (out_location != SFMGMS_HOST && out_location != SFMGMS_DEVICE) return fail(ctx, SFMGMS_ERR_ARG, "bad out_location");
+    if (n_pairs > 0 && ctx->n_images == 0) return fail(ctx, SFMGMS_ERR_STATE, "sfmgms_set_images has not been called");
+    cudaStream_t st = ctx->stream;
+    std::vector<PairDesc> hp((size_t)n_pairs);
+    int64_t total = 0;
+    for (int p = 0; p < n_pairs; ++p) {
+        const int a = pairs[2 * p], b = pairs[2 * p + 1];
+        if (a < 0 || a >= ctx->n_images || b < 0 || b >= ctx->n_images)
+            return fail(ctx, SFMGMS_ERR_ARG, "pair %d references an image outside the set", p);
+        PairDesc& d = hp[p];
+        memset(&d, 0, sizeof d);
+        d.n1 = (int)(ctx->offsets[a + 1] - ctx->offsets[a]);
+        d.n2 = (int)(ctx->offsets[b + 1] - ctx->offsets[b]);
+        d.desc1 = ctx->set_desc + ctx->offsets[a] * 32; d.desc2 = ctx->set_desc + ctx->offsets[b] * 32;
+        d.kp1 = ctx->set_kp + ctx->offsets[a] * 2; d.kp2 = ctx->set_kp + ctx->offsets[b] * 2;
+        d.w1 = ctx->sizes[2 * a]; d.h1 = ctx->sizes[2 * a + 1]; d.w2 = ctx->sizes[2 * b]; d.h2 = ctx->sizes[2 * b + 1];
+        d.n_matches = d.n2 == 0 ? 0 : d.n1;
+        d.match_base = total;
+        total += d.n1;
+    }
+    CU(ctx->d_key.ensure((size_t)total * 4 + 4));
+    const bool dev_out = (out_location == SFMGMS_DEVICE);
+    uint8_t* dmask = (dev_out && mask) ? mask : nullptr;
+    if (!dmask) { CU(ctx->d_mask.ensure((size_t)total + 1)); dmask = (uint8_t*)ctx->d_mask.p; }
+    for (int p = 0; p < n_pairs; ++p) {
+        hp[p].key = (uint32_t*)ctx->d_key.p + hp[p].match_base;
+        hp[p].mask = dmask + hp[p].match_base;
+    }
+    if (total) {
+        CU(cudaMemsetAsync(ctx->d_key.p, 0xFF, (size_t)total * 4, st));
+        CU(cudaMemsetAsync(dmask, 0, (size_t)total, st));
+    }
+    for (int p = 0; p < n_pairs; ++p) hp[p].pair_index = p, hp[p].img1 = pairs[2 * p], hp[p].img2 = pairs[2 * p + 1];
+    int rc = run_batch(ctx, hp, true, true, with_rotation, with_scale, threshold_factor);
+    ctx->last_pairs = hp;
+    if (rc) return rc;
+    // per-pair results
+    if (n_inliers || best_hyp || mask_len) {
+        std::vector<int32_t> tmp((size_t)n_pairs * 3);
+        for (int p = 0; p < n_pairs; ++p) {
+            tmp[p] = ctx->last_results[p].n_inliers;
+            tmp[n_pairs + p] = ctx->last_results[p].best_hyp;
+            tmp[2 * (size_t)n_pairs + p] = ctx->last_results[p].mask_len;
+        }
+        int32_t* outs[3] = {n_inliers, best_hyp, mask_len};
+        for (int k = 0; k < 3; ++k) {
+            if (!outs[k] || n_pairs == 0) continue;
+            if (dev_out) CU(cudaMemcpy(outs[k], tmp.data() + (size_t)k * n_pairs, (size_t)n_pairs * 4, cudaMemcpyHostToDevice));
+            else memcpy(outs[k], tmp.data() + (size_t)k * n_pairs, (size_t)n_pairs * 4);
+        }
+    }
+    if (total && (train_idx || dist)) {
+        int32_t *dti = nullptr, *ddi = nullptr;
+        if (dev_out) { dti = train_idx; ddi = dist; }
+        else {
+            CU(ctx->d_out_i32.ensure((size_t)total * 8));
+            dti = (int32_t*)ctx->d_out_i32.p; ddi = dti + total;
+            if (!train_idx) dti = nullptr;
+            if (!dist) ddi = nullptr;
+        }
+        decode_keys_kernel<<<(unsigned)((total + 255) / 256 > 8192 ? 8192 : (total + 255) / 256), 256, 0, st>>>(
+            (const uint32_t*)ctx->d_key.p, total, dti, ddi);
+        ctx->launches++;
+        if (!dev_out) {
+            if (train_idx) CU(cudaMemcpyAsync(train_idx, dti, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+            if (dist) CU(cudaMemcpyAsync(dist, ddi, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    if (total && mask && !dev_out) CU(cudaMemcpyAsync(mask, dmask, (size_t)total, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SFMGMS_OK;
+    GUARD_END
+}
+
+int sfmgms_inlier_points(sfmgms_ctx* ctx, int pair_index, float* pts1, float* pts2, int capacity, int* n_out) {
+    GUARD_BEGIN
+    if (pair_index < 0 || pair_index >= (int)ctx->last_pairs.size()) return fail(ctx, SFMGMS_ERR_STATE, "no such pair in the last batch");
+    if (capacity < 0 || !n_out || (capacity > 0 && (!pts1 || !pts2))) return fail(ctx, SFMGMS_ERR_ARG, "bad arguments");
+    const PairDesc& pd = ctx->last_pairs[pair_index];
+    const PairResult& r = ctx->last_results[pair_index];
+    if (r.mask_len == 0 || pd.n_matches == 0) { *n_out = 0; return SFMGMS_OK; }
+    cudaStream_t st = ctx->stream;
+    CU(ctx->d_pts.ensure((size_t)capacity * 16 + 16));
+    float2* d1 = (float2*)ctx->d_pts.p;
+    float2* d2 = d1 + capacity;
+    int* dn = (int*)(d2 + capacity);
+    inlier_points_kernel<<<1, 1024, 0, st>>>(pd, d1, d2, capacity, dn);
+    ctx->launches++;
+    int n = 0;
+    CU(cudaMemcpyAsync(&n, dn, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const int m = n < capacity ? n : capacity;
+    if (m > 0) {
+        CU(cudaMemcpy(pts1, d1, (size_t)m * 8, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(pts2, d2, (size_t)m * 8, cudaMemcpyDeviceToHost));
+    }
+    *n_out = n;
+    return SFMGMS_OK;
+    GUARD_END
+}
+
+}  // extern "C"

@@ -1,0 +1,66 @@
+// common.cuh — shared device/host definitions for the BF-Hamming + GMS path (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sfmgms {
+
+constexpr int kDescBytes = 32;          // 256-bit ORB descriptor
+constexpr int kDescWords = 8;           // as uint32
+constexpr int kTrainIdxBits = 18;       // OpenCV: train rows < IMGIDX_ONE = 2^18
+constexpr uint32_t kTrainIdxMask = (1u << kTrainIdxBits) - 1u;
+constexpr uint32_t kKeyInit = 0xFFFFFFFFu;  // > any (dist<<18 | idx) with dist <= 256
+
+constexpr int kGridL = 20;              // left grid 20x20 (DLL @VA 0x180046ac6)
+constexpr int kCellsL = kGridL * kGridL;
+constexpr int kNumScales = 5;
+constexpr int kNumRot = 8;
+constexpr int kMaxHyp = kNumScales * kNumRot;
+constexpr uint16_t kNoCell = 0xFFFFu;
+
+// right grid width per scale index: cvRound(20 * {1, .5, 1/sqrt2, sqrt2, 2}) (setScale, DLL @VA 0x180048c10)
+__host__ __device__ inline int right_grid_w(int s) {
+    return s == 0 ? 20 : s == 1 ? 10 : s == 2 ? 14 : s == 3 ? 28 : 40;
+}
+
+// One image pair of a batch, as the kernels see it (device pointers).
+struct PairDesc {
+    const uint8_t* desc1;   // n1 x 32 (may be null for a GMS-only call)
+    const uint8_t* desc2;   // n2 x 32
+    const float* kp1;       // n1 x 2 pixel coordinates
+    const float* kp2;       // n2 x 2
+    const int32_t* mq;      // n_matches queryIdx, or null => queryIdx = i (BFMatcher::match order)
+    const int32_t* mt;      // n_matches trainIdx, or null => taken from key[i] & kTrainIdxMask
+    uint32_t* key;          // n1 packed (dist << 18 | trainIdx) written by the Hamming kernels
+    uint8_t* mask;          // n_matches inlier mask (output)
+    int n1, n2, n_matches;
+    int w1, h1, w2, h2;
+    long long match_base;   // offset of this pair's rows in the batch-concatenated per-match arrays
+    int img1, img2;         // image-set indices (-1 for ad-hoc single-pair calls)
+    int pair_index;
+};
+
+// Per-batch GMS result (one per pair).
+struct PairResult {
+    int n_inliers;
+    int best_hyp;   // scale*8 + rot-1, -1 if none
+    int mask_len;   // n_matches or 0
+    int status;     // 0 ok, SFMGMS_ERR_DOMAIN, SFMGMS_ERR_INDEX
+};
+
+// launchers (each returns the number of kernel launches it issued; errors via cudaGetLastError)
+int launch_hamming_popc(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, int sm_count,
+                        cudaStream_t st);
+
+struct GmsScratch {
+    // per pair in chunk, sized by gms_scratch_bytes()
+    void* base;
+    size_t bytes;
+};
+size_t gms_scratch_bytes_per_pair(int n_scales);
+size_t gms_match_scratch_bytes(long long n_matches_total, int n_scales);
+int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, int with_rotation, int with_scale,
+               double factor, PairResult* d_results, void* d_hist_scratch, size_t hist_scratch_bytes,
+               void* d_match_scratch, cudaStream_t st);
+
+}  // namespace sfmgms

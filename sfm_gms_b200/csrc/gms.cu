@@ -1,0 +1,330 @@
+// gms.cu — Grid-based Motion Statistics inlier voting (general path: dense histograms in global/L2).
+//
+// Replaces cv::xfeatures2d::matchGMS (reference call sites FeatureMatchUtil.cpp:69, DisparityUtil.cpp:149,299;
+// algorithm = OpenCV-contrib 4.5.2 GMSMatcher, restated from SURVEY.md Appendix A).  Rows of SURVEY §8(a):
+//   a4 normalizePoints + a5 getGridIndexLeft/Right + a7 assignMatchPairs  -> gms_assign_kernel
+//   a8 verifyCellPairs (argmax, 3x3 support, f64 threshold)               -> gms_verify_kernel
+//   a9 run (mark + count) / a10 getInlierMask (best hypothesis)          -> gms_count / gms_select / gms_mask
+//
+// Work sharing the reference does not do: the 4 left indices of a match do not depend on scale/rotation,
+// the right index only on scale, rotation only on verify => 20 histograms serve all 40 hypotheses
+// (the reference rebuilds 160).
+//
+// Floating point: the three decisions that hinge on FP are evaluated with explicitly rounded intrinsics
+// (__fdiv_rn, __fmul_rn, __dadd_rn, __ddiv_rn, __dsqrt_rn, __dmul_rn): no FMA contraction, no fast math —
+// bit-identical to the divss/mulss/addsd/divsd/sqrtsd/mulsd sequence of the reference binary.
+// Integer histogram atomics are order-independent => results are deterministic.
+//
+// Roofline: HBM/L2 bandwidth.  Algorithmic bytes per pair (SURVEY §8d figure ii):
+//   sum over used (scale,shift) of [4*400*G_r zero + 4*400*G_r scan + 12*N RMW] + 8*N*H mark + N.
+#include "common.cuh"
+
+namespace sfmgms {
+
+namespace {
+
+// ROT[8][9], 1-based (DLL .rdata 0x18012f520)
+__constant__ int8_t c_rot[kNumRot][9] = {
+    {1, 2, 3, 4, 5, 6, 7, 8, 9}, {4, 1, 2, 7, 5, 3, 8, 9, 6}, {7, 4, 1, 8, 5, 2, 9, 6, 3},
+    {8, 7, 4, 9, 5, 1, 6, 3, 2}, {9, 8, 7, 6, 5, 4, 3, 2, 1}, {6, 9, 8, 3, 5, 7, 2, 1, 4},
+    {3, 6, 9, 2, 5, 8, 1, 4, 7}, {2, 3, 6, 1, 5, 9, 4, 7, 8}};
+
+// cvFloor: i = trunc(v); i - (i > v)   (SURVEY Appendix A helpers)
+__device__ __forceinline__ int cv_floor_f(float v) { int i = (int)v; return i - ((float)i > v); }
+__device__ __forceinline__ int cv_floor_d(double v) { int i = (int)v; return i - ((double)i > v); }
+
+// neighbors(W,H) slot k of cell idx, -1 outside (DLL @VA 0x180048030) — computed, not tabulated
+__device__ __forceinline__ int nb9(int idx, int k, int w, int h) {
+    int x = idx % w + (k % 3) - 1;
+    int y = idx / w + (k / 3) - 1;
+    return (x < 0 || x >= w || y < 0 || y >= h) ? -1 : x + y * w;
+}
+
+// ---- per-pair scratch layout (int32 units unless noted) ---------------------------------------------
+struct Layout {
+    int n_scales, n_rot;
+    size_t cnt_off;       // [4][400] int32
+    size_t counts_off;    // [40] int32
+    size_t hist_off[kNumScales];  // [4][400][G_r] int32
+    size_t cp_off;        // [n_scales][n_rot][4][400] int16 (stored in int32 units, rounded up)
+    size_t zero_words;    // words [0, zero_words) must be zero before assign (cnt, counts, hists)
+    size_t total_words;
+};
+
+__host__ __device__ inline Layout make_layout(int n_scales, int n_rot) {
+    Layout L;
+    L.n_scales = n_scales; L.n_rot = n_rot;
+    size_t o = 0;
+    L.cnt_off = o; o += 4 * kCellsL;
+    L.counts_off = o; o += 64;
+    for (int s = 0; s < kNumScales; ++s) {
+        L.hist_off[s] = o;
+        if (s < n_scales) { int w = right_grid_w(s); o += (size_t)4 * kCellsL * w * w; }
+    }
+    L.zero_words = o;
+    L.cp_off = o; o += ((size_t)n_scales * n_rot * 4 * kCellsL + 1) / 2;
+    L.total_words = (o + 31) & ~(size_t)31;
+    return L;
+}
+
+// ---- a4 + a5 + a7: normalise, cell indices for all shifts/scales, histogram RMW ----------------------
+__global__ void __launch_bounds__(256) gms_assign_kernel(const PairDesc* __restrict__ pairs, PairResult* results,
+                                                         int32_t* scratch, Layout L, uint16_t* lidx,
+                                                         uint16_t* ridx, long long chunk_match_base,
+                                                         long long chunk_matches) {
+    const PairDesc pd = pairs[blockIdx.z];
+    int32_t* sp = scratch + (size_t)blockIdx.z * L.total_words;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pd.n_matches; i += gridDim.x * blockDim.x) {
+        const long long mi = pd.match_base - chunk_match_base + i;
+        int qi = pd.mq ? pd.mq[i] : i;
+        int ti = pd.mt ? pd.mt[i] : (int)(pd.key[i] & kTrainIdxMask);
+        bool ok = true;
+        if (qi < 0 || qi >= pd.n1 || ti < 0 || ti >= pd.n2) { atomicMax(&results[blockIdx.z].status, 4); ok = false; }
+        float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
+        if (ok) {
+            float2 a = reinterpret_cast<const float2*>(pd.kp1)[qi];
+            float2 b = reinterpret_cast<const float2*>(pd.kp2)[ti];
+            x1 = a.x; y1 = a.y; x2 = b.x; y2 = b.y;
+            // supported domain 0 <= x < w, 0 <= y < h (outside is UB in the reference; NaN fails too)
+            if (!(x1 >= 0.f && x1 < (float)pd.w1 && y1 >= 0.f && y1 < (float)pd.h1 && x2 >= 0.f &&
+                  x2 < (float)pd.w2 && y2 >= 0.f && y2 < (float)pd.h2)) {
+                atomicMax(&results[blockIdx.z].status, 3);
+                ok = false;
+            }
+        }
+        if (!ok) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) lidx[(size_t)t * chunk_matches + mi] = kNoCell;
+            for (int s = 0; s < L.n_scales; ++s) ridx[(size_t)s * chunk_matches + mi] = kNoCell;
+            continue;
+        }
+        // normalizePoints (f32 divide), DLL @VA 0x180048420
+        const float nx1 = __fdiv_rn(x1, (float)pd.w1), ny1 = __fdiv_rn(y1, (float)pd.h1);
+        const float nx2 = __fdiv_rn(x2, (float)pd.w2), ny2 = __fdiv_rn(y2, (float)pd.h2);
+        // getGridIndexLeft, DLL @VA 0x180047bc0: f32 multiply, f64 +0.5 on the shifted axis only
+        const float fx = __fmul_rn((float)kGridL, nx1), fy = __fmul_rn((float)kGridL, ny1);
+        const int xa = cv_floor_f(fx), ya = cv_floor_f(fy);
+        const int xb = cv_floor_d(__dadd_rn((double)fx, 0.5)), yb = cv_floor_d(__dadd_rn((double)fy, 0.5));
+        int l[4];
+        l[0] = (xa >= kGridL || ya >= kGridL) ? -1 : xa + ya * kGridL;
+        l[1] = (xb >= kGridL || ya >= kGridL) ? -1 : xb + ya * kGridL;
+        l[2] = (xa >= kGridL || yb >= kGridL) ? -1 : xa + yb * kGridL;
+        l[3] = (xb >= kGridL || yb >= kGridL) ? -1 : xb + yb * kGridL;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            lidx[(size_t)t * chunk_matches + mi] = l[t] < 0 ? kNoCell : (uint16_t)l[t];
+            if (l[t] >= 0) atomicAdd(&sp[L.cnt_off + t * kCellsL + l[t]], 1);
+        }
+        for (int s = 0; s < L.n_scales; ++s) {
+            // getGridIndexRight, DLL @VA 0x180047d60
+            const int w = right_grid_w(s);
+            const int rx = cv_floor_f(__fmul_rn((float)w, nx2)), ry = cv_floor_f(__fmul_rn((float)w, ny2));
+            const int r = rx + ry * w;   // in [0, w*w) for in-domain points
+            ridx[(size_t)s * chunk_matches + mi] = (uint16_t)r;
+            int32_t* h = sp + L.hist_off[s];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (l[t] >= 0) atomicAdd(&h[((size_t)t * kCellsL + l[t]) * (w * w) + r], 1);
+        }
+    }
+}
+
+// ---- a8: verifyCellPairs, one warp per (pair, scale, shift, left cell) ------------------------------
+__global__ void __launch_bounds__(256) gms_verify_kernel(int32_t* scratch, Layout L, double factor,
+                                                         int n_pairs) {
+    const int warps_per_pair = L.n_scales * 4 * kCellsL;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gw >= (long long)warps_per_pair * n_pairs) return;
+    const int lane = threadIdx.x & 31;
+    const int p = (int)(gw / warps_per_pair);
+    int rem = (int)(gw % warps_per_pair);
+    const int s = rem / (4 * kCellsL); rem %= 4 * kCellsL;
+    const int t = rem / kCellsL;
+    const int cell = rem % kCellsL;
+    int32_t* sp = scratch + (size_t)p * L.total_words;
+    const int w = right_grid_w(s), gr = w * w;
+    const int32_t* hist = sp + L.hist_off[s] + (size_t)t * kCellsL * gr;
+    const int32_t* cnt = sp + L.cnt_off + t * kCellsL;
+    int16_t* cpv = reinterpret_cast<int16_t*>(sp + L.cp_off);
+
+    const int ccount = cnt[cell];
+    int cp = -1;
+    if (ccount > 0) {
+        // argmax with strict '>' from maxv = 0 => lowest j among the maxima, count > 0
+        const int32_t* row = hist + (size_t)cell * gr;
+        uint32_t bestk = 0;
+        for (int j = lane; j < gr; j += 32) {
+            uint32_t c = (uint32_t)row[j];
+            uint32_t k = (c << 11) | (uint32_t)(2047 - j);
+            bestk = (c > 0 && k > bestk) ? k : bestk;
+        }
+        bestk = __reduce_max_sync(0xffffffffu, bestk);
+        cp = 2047 - (int)(bestk & 2047u);
+    }
+    for (int r = 0; r < L.n_rot; ++r) {
+        int out = cp;
+        if (cp >= 0) {
+            int v = 0, c = 0;
+            bool valid = false;
+            if (lane < 9) {
+                const int ll = nb9(cell, lane, kGridL, kGridL);
+                const int rr = nb9(cp, c_rot[r][lane] - 1, w, w);
+                valid = (ll != -1 && rr != -1);
+                if (valid) { v = hist[(size_t)ll * gr + rr]; c = cnt[ll]; }
+            }
+            const int score = __reduce_add_sync(0xffffffffu, v);
+            const int tsum = __reduce_add_sync(0xffffffffu, c);       // exact: integers
+            const int num = __popc(__ballot_sync(0xffffffffu, valid));
+            // thresh = factor * sqrt(T / n): divsd, sqrtsd, mulsd — three separately rounded f64 ops
+            const double thresh = __dmul_rn(factor, __dsqrt_rn(__ddiv_rn((double)tsum, (double)num)));
+            if ((double)score < thresh) out = -2;
+        }
+        if (lane == 0) cpv[(((size_t)s * L.n_rot + r) * 4 + t) * kCellsL + cell] = (int16_t)out;
+    }
+}
+
+__device__ __forceinline__ bool is_inlier(const int16_t* cpv_h, const uint16_t* lidx, uint16_t r,
+                                          long long chunk_matches, long long mi) {
+    bool inl = false;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const uint16_t l = lidx[(size_t)t * chunk_matches + mi];
+        if (l != kNoCell) inl |= (cpv_h[t * kCellsL + l] == (int16_t)r);
+    }
+    return inl;
+}
+
+// ---- a9: mark + count, for every hypothesis (blockIdx.y).  With write_mask (no-flag call) also the mask.
+__global__ void __launch_bounds__(256) gms_count_kernel(const PairDesc* __restrict__ pairs, int32_t* scratch,
+                                                        Layout L, const uint16_t* __restrict__ lidx,
+                                                        const uint16_t* __restrict__ ridx,
+                                                        long long chunk_match_base, long long chunk_matches,
+                                                        int write_mask) {
+    const PairDesc pd = pairs[blockIdx.z];
+    int32_t* sp = scratch + (size_t)blockIdx.z * L.total_words;
+    const int hyp = blockIdx.y;                    // s * n_rot + r
+    const int s = hyp / L.n_rot;
+    const int16_t* cpv_h = reinterpret_cast<const int16_t*>(sp + L.cp_off) + (size_t)hyp * 4 * kCellsL;
+    int local = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pd.n_matches; i += gridDim.x * blockDim.x) {
+        const long long mi = pd.match_base - chunk_match_base + i;
+        const uint16_t r = ridx[(size_t)s * chunk_matches + mi];
+        const bool inl = (r != kNoCell) && is_inlier(cpv_h, lidx, r, chunk_matches, mi);
+        local += inl;
+        if (write_mask) pd.mask[i] = inl;
+    }
+    local = __reduce_add_sync(0xffffffffu, local);
+    __shared__ int wsum[8];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += wsum[k];
+        if (tot) atomicAdd(&sp[L.counts_off + hyp], tot);
+    }
+}
+
+// ---- a10: getInlierMask — best hypothesis, scale-major / rotation-minor, strict '>' (first wins) -----
+__global__ void gms_select_kernel(const PairDesc* __restrict__ pairs, PairResult* results,
+                                  const int32_t* scratch, Layout L, int n_pairs, int flags_on) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const int32_t* counts = scratch + (size_t)p * L.total_words + L.counts_off;
+    PairResult r = results[p];
+    if (!flags_on) {
+        r.n_inliers = counts[0]; r.best_hyp = 0; r.mask_len = pairs[p].n_matches;
+    } else {
+        int best = 0, bh = -1;
+        for (int s = 0; s < L.n_scales; ++s)
+            for (int k = 0; k < L.n_rot; ++k) {
+                int c = counts[s * L.n_rot + k];
+                if (c > best) { best = c; bh = s * kNumRot + k; }
+            }
+        r.n_inliers = best; r.best_hyp = bh; r.mask_len = bh < 0 ? 0 : pairs[p].n_matches;
+    }
+    results[p] = r;
+}
+
+// ---- mask of the winning hypothesis (flag calls only) ----------------------------------------------
+__global__ void __launch_bounds__(256) gms_mask_kernel(const PairDesc* __restrict__ pairs,
+                                                       const PairResult* __restrict__ results,
+                                                       const int32_t* scratch, Layout L,
+                                                       const uint16_t* __restrict__ lidx,
+                                                       const uint16_t* __restrict__ ridx,
+                                                       long long chunk_match_base, long long chunk_matches) {
+    const PairDesc pd = pairs[blockIdx.z];
+    const int bh = results[blockIdx.z].best_hyp;
+    const int32_t* sp = scratch + (size_t)blockIdx.z * L.total_words;
+    const int s = bh < 0 ? 0 : bh / kNumRot, r8 = bh < 0 ? 0 : bh % kNumRot;
+    const int hyp = s * L.n_rot + r8;
+    const int16_t* cpv_h = reinterpret_cast<const int16_t*>(sp + L.cp_off) + (size_t)hyp * 4 * kCellsL;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pd.n_matches; i += gridDim.x * blockDim.x) {
+        const long long mi = pd.match_base - chunk_match_base + i;
+        bool inl = false;
+        if (bh >= 0) {
+            const uint16_t r = ridx[(size_t)s * chunk_matches + mi];
+            inl = (r != kNoCell) && is_inlier(cpv_h, lidx, r, chunk_matches, mi);
+        }
+        pd.mask[i] = inl;
+    }
+}
+
+}  // namespace
+
+size_t gms_scratch_bytes_per_pair(int n_scales) { return make_layout(n_scales, kNumRot).total_words * 4; }
+size_t gms_match_scratch_bytes(long long n_matches_total, int n_scales) {
+    return (size_t)n_matches_total * 2 * (4 + n_scales) + 256;
+}
+
+// Runs GMS for n_pairs pairs, in chunks sized so that the dense histograms of a chunk fit the scratch
+// budget (kept L2-resident by the caller's choice of hist_scratch_bytes).
+int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, int with_rotation, int with_scale,
+               double factor, PairResult* d_results, void* d_hist_scratch, size_t hist_scratch_bytes,
+               void* d_match_scratch, cudaStream_t st) {
+    if (n_pairs <= 0) return 0;
+    const int n_scales = with_scale ? kNumScales : 1;
+    const int n_rot = with_rotation ? kNumRot : 1;
+    const int flags_on = (with_rotation || with_scale) ? 1 : 0;
+    const Layout L = make_layout(n_scales, n_rot);
+    const size_t per_pair = L.total_words * 4;
+    int chunk_cap = (int)(hist_scratch_bytes / per_pair);
+    if (chunk_cap < 1) return -1;
+    if (chunk_cap > 32768) chunk_cap = 32768;
+    int launches = 0;
+    int32_t* scratch = static_cast<int32_t*>(d_hist_scratch);
+    for (int c0 = 0; c0 < n_pairs; c0 += chunk_cap) {
+        const int cn = (n_pairs - c0 < chunk_cap) ? n_pairs - c0 : chunk_cap;
+        long long cm = 0;
+        int max_m = 0;
+        for (int p = c0; p < c0 + cn; ++p) { cm += h_pairs[p].n_matches; if (h_pairs[p].n_matches > max_m) max_m = h_pairs[p].n_matches; }
+        const long long cbase = h_pairs[c0].match_base;
+        // per-match cell indices for this chunk: lidx[4][cm], ridx[n_scales][cm] (uint16)
+        uint16_t* lidx = static_cast<uint16_t*>(d_match_scratch);
+        uint16_t* ridx = lidx + (size_t)4 * cm;
+        // zero cnt/counts/hist of every pair in the chunk (cp is fully rewritten by verify)
+        cudaMemsetAsync(scratch, 0, (size_t)cn * per_pair, st);
+        const int bx = max_m > 0 ? (max_m + 255) / 256 : 1;
+        if (max_m > 0) {
+            gms_assign_kernel<<<dim3(bx, 1, cn), 256, 0, st>>>(d_pairs + c0, d_results + c0, scratch, L, lidx, ridx,
+                                                             cbase, cm);
+            ++launches;
+        }
+        const long long warps = (long long)cn * n_scales * 4 * kCellsL;
+        gms_verify_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(scratch, L, factor, cn);
+        ++launches;
+        if (max_m > 0) {
+            gms_count_kernel<<<dim3(bx, n_scales * n_rot, cn), 256, 0, st>>>(d_pairs + c0, scratch, L, lidx, ridx, cbase,
+                                                                         cm, flags_on ? 0 : 1);
+            ++launches;
+        }
+        gms_select_kernel<<<(cn + 127) / 128, 128, 0, st>>>(d_pairs + c0, d_results + c0, scratch, L, cn, flags_on);
+        ++launches;
+        if (flags_on && max_m > 0) {
+            gms_mask_kernel<<<dim3(bx, 1, cn), 256, 0, st>>>(d_pairs + c0, d_results + c0, scratch, L, lidx, ridx, cbase, cm);
+            ++launches;
+        }
+    }
+    return launches;
+}
+
+}  // namespace sfmgms

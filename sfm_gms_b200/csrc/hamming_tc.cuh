@@ -1,0 +1,25 @@
+// hamming_tc.cuh — interface of the tcgen05 (int8 tensor-core) Hamming kernel, see hamming_tc.cu.
+#pragma once
+#include "common.cuh"
+
+namespace sfmgms {
+
+struct TcState {
+    void* d_ops = nullptr;      // unpacked +-1 int8 operands of the registered image set / ad-hoc pair
+    size_t ops_cap = 0;
+    void* d_work = nullptr;     // work-unit table
+    size_t work_cap = 0;
+    void* h_work = nullptr;     // pinned
+    size_t h_work_cap = 0;
+    bool set_valid = false;     // operands of the current image set are unpacked
+};
+
+bool tc_available();
+const char* tc_last_error();
+void tc_invalidate(TcState& s);
+void tc_release(TcState& s);
+// returns the number of kernel launches, or -1 on error
+int launch_hamming_tc(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, int sm_count,
+                      cudaStream_t st);
+
+}  // namespace sfmgms

@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""Generate the committed golden fixtures under tests/golden/ (run in the BUILD container only).
+
+Sources of truth, per field:
+  desc*/kp*/size*      cv2 4.13 ORB (nfeatures, fastThreshold=0) on the reference's own images
+                       /root/reference/SfM-GMS/SourceImages/* (BASELINE.json configs[0]).
+  bf_train/bf_dist     cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=False).match  -- the EXECUTABLE
+                       reference for stage 1 (FeatureMatchUtil.cpp:66-68 call shape).
+  xc_*                 cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match (FeatureMatchUtil.cpp:22).
+  anchor_*             SURVEY.md Appendix C per-hypothesis inlier counts (survey's independent numpy
+                       restatement of the DLL disassembly) -- typed in from SURVEY.md, NOT computed here.
+  gms_mask_*           the C oracle's masks (regression pin of the oracle itself; no executable
+                       reference exists for stage 2 -- see oracle/sfmgms_oracle.c header).
+/root/reference is not available on the GPU box; tests only read the .npz files written here.
+"""
+import os
+import sys
+
+import cv2
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import oracle  # noqa: E402
+
+R = "/root/reference/SfM-GMS/SourceImages/"
+
+ANCHORS = {
+    "pikabun12": dict(default=3704, best=4090, best_hyp=8, counts=[
+        3704, 2995, 2379, 2196, 2258, 2255, 2506, 3091, 4090, 3704, 3181, 3140, 3213, 3144, 3401, 3882,
+        4056, 3451, 3053, 2868, 2847, 2844, 3159, 3729, 3567, 2666, 1991, 1756, 1786, 1718, 2070, 2864,
+        2697, 1727, 928, 921, 928, 967, 983, 1922]),
+    "disparityLR": dict(default=6504, best=6740, best_hyp=8, counts=[
+        6504, 5926, 5002, 4922, 4928, 4921, 4980, 6145, 6740, 6605, 6105, 6008, 5935, 6143, 6145, 6585,
+        6525, 6337, 5474, 5336, 5357, 5389, 5698, 6304, 5907, 5038, 3471, 3275, 3275, 3210, 3569, 4951,
+        4753, 3523, 1878, 1806, 1763, 1768, 1805, 3417]),
+}
+
+
+def orb_pair(a, b, nfeat, rot180=False):
+    i1, i2 = cv2.imread(R + a), cv2.imread(R + b)
+    if rot180:  # main.cpp:36 img_rotate(img2, 180)
+        i2 = cv2.rotate(i2, cv2.ROTATE_180)
+    orb = cv2.ORB_create(nfeat)
+    orb.setFastThreshold(0)
+    k1, d1 = orb.detectAndCompute(i1, None)
+    k2, d2 = orb.detectAndCompute(i2, None)
+    p1 = np.array([k.pt for k in k1], np.float32)
+    p2 = np.array([k.pt for k in k2], np.float32)
+    return (i1.shape[1], i1.shape[0]), (i2.shape[1], i2.shape[0]), p1, p2, d1, d2
+
+
+def pack(name, s1, s2, p1, p2, d1, d2, anchors=None):
+    m = cv2.BFMatcher(cv2.NORM_HAMMING, False).match(d1, d2)
+    bt = np.array([x.trainIdx for x in m], np.int32)
+    bd = np.array([int(x.distance) for x in m], np.int32)
+    assert [x.queryIdx for x in m] == list(range(len(m)))
+    xm = cv2.BFMatcher(cv2.NORM_HAMMING, True).match(d1, d2)
+    xq = np.array([x.queryIdx for x in xm], np.int32)
+    xt = np.array([x.trainIdx for x in xm], np.int32)
+    out = dict(size1=np.array(s1, np.int32), size2=np.array(s2, np.int32), kp1=p1, kp2=p2, desc1=d1, desc2=d2,
+               bf_train=bt, bf_dist=bd, xc_query=xq, xc_train=xt)
+    q = np.arange(len(bt), dtype=np.int32)
+    for tag, rot, sc in [("00", 0, 0), ("10", 1, 0), ("01", 0, 1), ("11", 1, 1)]:
+        r = oracle.gms(s1, s2, p1, p2, q, bt, rot, sc)
+        out["gms_mask_" + tag] = np.packbits(r["mask"])
+        out["gms_len_" + tag] = np.int32(len(r["mask"]))
+        out["gms_n_" + tag] = np.int32(r["n_inliers"])
+        out["gms_hyp_" + tag] = r["hyp_counts"]
+        out["gms_best_" + tag] = np.int32(r["best_hyp"])
+    if anchors:
+        out["anchor_counts"] = np.array(anchors["counts"], np.int32)
+        out["anchor_default"] = np.int32(anchors["default"])
+        out["anchor_best"] = np.int32(anchors["best"])
+        out["anchor_best_hyp"] = np.int32(anchors["best_hyp"])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, len(p1), len(p2), "default", int(out["gms_n_00"]), "rs", int(out["gms_n_11"]),
+          "best_hyp", int(out["gms_best_11"]), "xc", len(xq))
+
+
+def tie_case():
+    """cv2-pinned tie-break fixture: duplicates everywhere."""
+    rng = np.random.default_rng(7)
+    base = rng.integers(0, 256, (50, 32), dtype=np.uint8)
+    t = np.concatenate([base, base, base])  # every train row triplicated
+    q = base[rng.integers(0, 50, 64)].copy()
+    q[::3, 5] ^= 0x10
+    m = cv2.BFMatcher(cv2.NORM_HAMMING, False).match(q, t)
+    # low-entropy descriptors: many equal distances
+    q2 = rng.integers(0, 2, (257, 32), dtype=np.uint8) * 255
+    t2 = rng.integers(0, 2, (1031, 32), dtype=np.uint8) * 255
+    m2 = cv2.BFMatcher(cv2.NORM_HAMMING, False).match(q2, t2)
+    np.savez_compressed(os.path.join(HERE, "bf_ties.npz"), q=q, t=t,
+                        train=np.array([x.trainIdx for x in m], np.int32),
+                        dist=np.array([int(x.distance) for x in m], np.int32), q2=q2, t2=t2,
+                        train2=np.array([x.trainIdx for x in m2], np.int32),
+                        dist2=np.array([int(x.distance) for x in m2], np.int32))
+    print("bf_ties", max(x.trainIdx for x in m))
+
+
+if __name__ == "__main__":
+    oracle.build()
+    oracle.set_num_threads(os.cpu_count())
+    pack("pikabun12", *orb_pair("PikaBun1.jpg", "PikaBun2.jpg", 10000), anchors=ANCHORS["pikabun12"])
+    pack("disparityLR", *orb_pair("Disparity_L.jpg", "Disparity_R.jpg", 10000), anchors=ANCHORS["disparityLR"])
+    pack("view01_2k", *orb_pair("view0.png", "view1.png", 2000))
+    pack("bun12_rot180_3k", *orb_pair("Bun1.jpg", "Bun2.jpg", 3000, rot180=True))
+    tie_case()

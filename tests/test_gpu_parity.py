@@ -1,0 +1,341 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI (ctypes), against
+the CPU oracle on the same inputs and against the committed golden fixtures.  Bit-exact: the path is
+integer (indices, distances, masks); the three FP decisions inside GMS are reproduced exactly.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from microcases import MICROCASES, run_microcase
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = ["popc", "tc"]
+
+
+def _select(ctx, kernel):
+    from sfm_gms_b200 import api
+
+    try:
+        ctx.set_option(api.OPT_HAMMING_KERNEL, api.HAMMING_POPC if kernel == "popc" else api.HAMMING_TC)
+    except api.SfmGmsError as e:
+        pytest.skip("kernel %s not available: %s" % (kernel, e))
+
+
+@pytest.fixture(params=KERNELS)
+def kctx(ctx, request):
+    from sfm_gms_b200 import api
+
+    _select(ctx, request.param)
+    yield ctx
+    ctx.set_option(api.OPT_HAMMING_KERNEL, api.HAMMING_AUTO)
+
+
+# ---- stage 1 ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["pikabun12", "disparityLR", "view01_2k", "bun12_rot180_3k"])
+def test_bf_golden_cv2(kctx, name):
+    g = load_golden(name)
+    idx, dist = kctx.bf_hamming(g["desc1"], g["desc2"])
+    assert np.array_equal(idx, g["bf_train"]) and np.array_equal(dist, g["bf_dist"])
+
+
+def test_bf_ties_golden_cv2(kctx):
+    g = load_golden("bf_ties")
+    idx, dist = kctx.bf_hamming(g["q"], g["t"])
+    assert np.array_equal(idx, g["train"]) and np.array_equal(dist, g["dist"])
+    idx, dist = kctx.bf_hamming(g["q2"], g["t2"])
+    assert np.array_equal(idx, g["train2"]) and np.array_equal(dist, g["dist2"])
+
+
+@pytest.mark.parametrize("nq,nt", [(1, 1), (1, 5000), (5000, 1), (31, 33), (127, 129), (128, 128), (129, 255),
+                                   (512, 256), (513, 257), (1000, 999), (4097, 2049), (10000, 10000)])
+def test_bf_ragged_vs_oracle(kctx, oracle_mod, nq, nt):
+    rng = np.random.default_rng(nq * 7919 + nt)
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    if nt > 8:  # plant exact and near duplicates to exercise tie-breaks across tile borders
+        t[nt // 2] = t[1]
+        t[nt - 1] = t[0]
+        q[0] = t[0]
+        q[nq // 2] = t[1]
+    idx, dist = kctx.bf_hamming(q, t)
+    oi, od = oracle_mod.bf_hamming(q, t)
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+
+
+def test_bf_low_entropy_many_ties(kctx, oracle_mod):
+    rng = np.random.default_rng(3)
+    q = (rng.integers(0, 2, (3000, 32), dtype=np.uint8) * 255).astype(np.uint8)
+    t = (rng.integers(0, 2, (2500, 32), dtype=np.uint8) * 255).astype(np.uint8)
+    idx, dist = kctx.bf_hamming(q, t)
+    oi, od = oracle_mod.bf_hamming(q, t)
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+    z = np.zeros((700, 32), np.uint8)
+    f = np.full((900, 32), 255, np.uint8)
+    idx, dist = kctx.bf_hamming(z, f)
+    assert (idx == 0).all() and (dist == 256).all()   # maximum distance, all tied: index 0
+
+
+def test_bf_empty_and_limits(kctx):
+    from sfm_gms_b200 import SfmGmsError
+
+    q = np.zeros((5, 32), np.uint8)
+    idx, dist = kctx.bf_hamming(q, np.zeros((0, 32), np.uint8))
+    assert len(idx) == 0 and len(dist) == 0
+    idx, dist = kctx.bf_hamming(np.zeros((0, 32), np.uint8), q)
+    assert len(idx) == 0
+    with pytest.raises(SfmGmsError) as e:
+        kctx.bf_hamming(q, np.zeros((1 << 18, 32), np.uint8))
+    assert e.value.code == 2
+    with pytest.raises(SfmGmsError):
+        kctx.bf_hamming(np.zeros((5, 16), np.uint8), q)
+
+
+def test_bf_max_train_rows(kctx, oracle_mod):
+    """train rows = 2^18 - 1 (OpenCV's maximum); sampled queries against the oracle."""
+    rng = np.random.default_rng(99)
+    nt = (1 << 18) - 1
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    q = rng.integers(0, 256, (300, 32), dtype=np.uint8)
+    q[7] = t[nt - 1]
+    t[5] = t[nt - 2]
+    q[8] = t[nt - 2]
+    idx, dist = kctx.bf_hamming(q, t)
+    oi, od = oracle_mod.bf_hamming(q, t)
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+    assert idx[7] == nt - 1 and dist[7] == 0 and idx[8] == 5
+
+
+def test_crosscheck_golden_cv2(kctx):
+    for name in ["view01_2k", "bun12_rot180_3k"]:
+        g = load_golden(name)
+        idx, dist, keep = kctx.bf_hamming_crosscheck(g["desc1"], g["desc2"])
+        assert np.array_equal(np.nonzero(keep)[0], g["xc_query"])
+        assert np.array_equal(idx[keep], g["xc_train"])
+
+
+# ---- stage 2 ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["pikabun12", "disparityLR", "view01_2k", "bun12_rot180_3k"])
+def test_gms_golden(ctx, name):
+    g = load_golden(name)
+    q = np.arange(len(g["bf_train"]), dtype=np.int32)
+    for tag, rot, sc in [("00", 0, 0), ("10", 1, 0), ("01", 0, 1), ("11", 1, 1)]:
+        r = ctx.gms(g["size1"], g["size2"], g["kp1"], g["kp2"], q, g["bf_train"], rot, sc)
+        n = int(g["gms_len_" + tag])
+        assert len(r["mask"]) == n and r["n_inliers"] == int(g["gms_n_" + tag]), tag
+        assert np.array_equal(r["mask"], np.unpackbits(g["gms_mask_" + tag])[:n].astype(bool)), tag
+        assert r["best_hyp"] == int(g["gms_best_" + tag]), tag
+    if "anchor_default" in g:
+        r = ctx.gms(g["size1"], g["size2"], g["kp1"], g["kp2"], q, g["bf_train"])
+        assert r["n_inliers"] == int(g["anchor_default"])
+        r = ctx.gms(g["size1"], g["size2"], g["kp1"], g["kp2"], q, g["bf_train"], True, True)
+        assert r["n_inliers"] == int(g["anchor_best"]) and r["best_hyp"] == int(g["anchor_best_hyp"])
+
+
+@pytest.mark.parametrize("case", sorted(MICROCASES))
+def test_gms_microcases(ctx, case):
+    def gms_fn(s1, s2, k1, k2, q, t, rot, sc, factor):
+        return ctx.gms(s1, s2, k1, k2, q, t, rot, sc, factor)
+
+    run_microcase(case, gms_fn)
+
+
+@pytest.mark.parametrize("factor", [0.5, 3.0, 6.0, 6.0000001, 9.75])
+def test_gms_threshold_factor_vs_oracle(ctx, oracle_mod, factor):
+    g = load_golden("view01_2k")
+    q = np.arange(len(g["bf_train"]), dtype=np.int32)
+    for rot, sc in [(0, 0), (1, 1)]:
+        r = ctx.gms(g["size1"], g["size2"], g["kp1"], g["kp2"], q, g["bf_train"], rot, sc, factor)
+        o = oracle_mod.gms(g["size1"], g["size2"], g["kp1"], g["kp2"], q, g["bf_train"], rot, sc, factor)
+        assert np.array_equal(r["mask"], o["mask"]) and r["best_hyp"] == o["best_hyp"]
+
+
+def test_gms_arbitrary_matches_and_strides(ctx, oracle_mod):
+    """matchGMS takes ANY match list (subset, repeated, unordered — e.g. FLANN output, DisparityUtil.cpp:143)
+    and arrays of cv::KeyPoint (28 B) / cv::DMatch (16 B): exercise the strided C-ABI form."""
+    import ctypes
+
+    from sfm_gms_b200 import load_library
+
+    g = load_golden("bun12_rot180_3k")
+    rng = np.random.default_rng(4)
+    n1, n2 = len(g["kp1"]), len(g["kp2"])
+    sel = rng.permutation(n1)[:2000]
+    qi = sel.astype(np.int32)
+    ti = g["bf_train"][sel].astype(np.int32)
+    qi[:50] = qi[50:100]  # repeated query indices are legal input
+    o = oracle_mod.gms(g["size1"], g["size2"], g["kp1"], g["kp2"], qi, ti, True, False)
+    # KeyPoint-like records: 7 floats (pt.x, pt.y, size, angle, response, octave, class_id)
+    kp1 = np.zeros((n1, 7), np.float32); kp1[:, :2] = g["kp1"]; kp1[:, 2:] = 31.0
+    kp2 = np.zeros((n2, 7), np.float32); kp2[:, :2] = g["kp2"]; kp2[:, 2:] = -7.0
+    dm = np.zeros((len(qi), 4), np.int32); dm[:, 0] = qi; dm[:, 1] = ti; dm[:, 2] = 0; dm[:, 3] = 12345
+    lib = load_library()
+    mask = np.zeros(len(qi), np.uint8)
+    ml, ni, bh = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = lib.sfmgms_gms(ctx._h, int(g["size1"][0]), int(g["size1"][1]), int(g["size2"][0]), int(g["size2"][1]),
+                        kp1.ctypes.data, n1, 28, kp2.ctypes.data, n2, 28, dm.ctypes.data, dm.ctypes.data + 4, 16,
+                        len(qi), 1, 0, 6.0, mask.ctypes.data, ctypes.byref(ml), ctypes.byref(ni), ctypes.byref(bh))
+    assert rc == 0
+    assert ml.value == len(o["mask"]) and ni.value == o["n_inliers"] and bh.value == o["best_hyp"]
+    assert np.array_equal(mask[: ml.value].astype(bool), o["mask"])
+
+
+def test_gms_undefined_inputs_are_errors(ctx):
+    from sfm_gms_b200 import SfmGmsError
+
+    kp = np.array([[1.0, 1.0], [639.0, 10.0]], np.float32)
+    with pytest.raises(SfmGmsError) as e:
+        ctx.gms((639, 480), (640, 480), kp, kp, [0, 1], [0, 1])
+    assert e.value.code == 3
+    with pytest.raises(SfmGmsError) as e:
+        ctx.gms((640, 480), (640, 480), kp, kp, [0, 1], [0, 2])
+    assert e.value.code == 4
+    nan = np.array([[np.nan, 1.0], [3.0, 10.0]], np.float32)
+    with pytest.raises(SfmGmsError):
+        ctx.gms((640, 480), (640, 480), nan, kp, [0, 1], [0, 1])
+    r = ctx.gms((640, 480), (640, 480), kp, kp, [], [])
+    assert len(r["mask"]) == 0 and r["n_inliers"] == 0
+
+
+# ---- fused pair, BASELINE.json configs -------------------------------------------------------------
+def _oracle_pair(oracle_mod, d, rot, sc):
+    idx, dist = oracle_mod.bf_hamming(d["desc1"], d["desc2"])
+    q = np.arange(len(idx), dtype=np.int32)
+    r = oracle_mod.gms(d["size1"], d["size2"], d["kp1"], d["kp2"], q, idx, rot, sc)
+    return idx, dist, r
+
+
+def test_config2_synthetic_pair(kctx, oracle_mod):
+    from sfm_gms_b200 import synth
+
+    d = synth.make_config("cfg2_640x480_10k")
+    r = kctx.match_pair(d["desc1"], d["desc2"], d["kp1"], d["kp2"], d["size1"], d["size2"])
+    idx, dist, o = _oracle_pair(oracle_mod, d, False, False)
+    assert np.array_equal(r["train_idx"], idx) and np.array_equal(r["dist"], dist)
+    assert np.array_equal(r["mask"], o["mask"]) and r["n_inliers"] == o["n_inliers"] > 1000
+
+
+def test_config3_synthetic_pair_rot_scale(kctx, oracle_mod):
+    from sfm_gms_b200 import synth
+
+    d = synth.make_config("cfg3_1080p_50k_rs")
+    r = kctx.match_pair(d["desc1"], d["desc2"], d["kp1"], d["kp2"], d["size1"], d["size2"], True, True)
+    idx, dist, o = _oracle_pair(oracle_mod, d, True, True)
+    assert np.array_equal(r["train_idx"], idx) and np.array_equal(r["dist"], dist)
+    assert np.array_equal(r["mask"], o["mask"]) and r["best_hyp"] == o["best_hyp"] and o["best_hyp"] not in (0, -1)
+
+
+def test_config4_synthetic_200k(kctx, oracle_mod):
+    """Full size 200k x 200k.  The oracle BF would take minutes, so: (a) a 1,500-row sample of the queries is
+    checked bit-exactly against the oracle over the FULL train set, (b) the distance of every returned match
+    is recomputed independently (numpy) and must be consistent, (c) GMS on the GPU's full match list is
+    compared bit-exactly with the oracle GMS on the same list (H=1 and H=40)."""
+    from sfm_gms_b200 import synth
+
+    d = synth.make_config("cfg4_4k_200k")
+    n = len(d["desc1"])
+    r = kctx.match_pair(d["desc1"], d["desc2"], d["kp1"], d["kp2"], d["size1"], d["size2"])
+    rng = np.random.default_rng(44)
+    sel = np.sort(rng.permutation(n)[:1500])
+    oi, od = oracle_mod.bf_hamming(d["desc1"][sel], d["desc2"])
+    assert np.array_equal(r["train_idx"][sel], oi) and np.array_equal(r["dist"][sel], od)
+    x = d["desc1"] ^ d["desc2"][r["train_idx"]]
+    assert np.array_equal(np.unpackbits(x, axis=1).sum(1), r["dist"])
+    q = np.arange(n, dtype=np.int32)
+    o = oracle_mod.gms(d["size1"], d["size2"], d["kp1"], d["kp2"], q, r["train_idx"])
+    assert np.array_equal(r["mask"], o["mask"]) and r["n_inliers"] == o["n_inliers"]
+    r40 = kctx.gms(d["size1"], d["size2"], d["kp1"], d["kp2"], q, r["train_idx"], True, True)
+    o40 = oracle_mod.gms(d["size1"], d["size2"], d["kp1"], d["kp2"], q, r["train_idx"], True, True)
+    assert np.array_equal(r40["mask"], o40["mask"]) and r40["best_hyp"] == o40["best_hyp"]
+
+
+# ---- multi-pair ------------------------------------------------------------------------------------
+def _ragged_set(rng, sizes_n):
+    from sfm_gms_b200 import synth
+
+    descs, kps, wh = [], [], []
+    base = synth.make_pair(800, 600, max(sizes_n), 123)
+    for k, n in enumerate(sizes_n):
+        w, h = 800 - 16 * k, 600 + 8 * k
+        idx = rng.permutation(len(base["desc1"]))[:n]
+        descs.append(synth.flip_bits(rng, base["desc1"][idx], 0.04))
+        xy = base["kp1"][idx] * np.array([w / 800.0, h / 600.0], np.float32) + rng.normal(0, 0.7, (n, 2))
+        kps.append(synth._inside(xy, w, h))
+        wh.append((w, h))
+    off = np.concatenate([[0], np.cumsum(sizes_n)]).astype(np.int64)
+    return off, np.concatenate(descs), np.concatenate(kps), np.array(wh, np.int32)
+
+
+@pytest.mark.parametrize("rot,sc", [(0, 0), (1, 1)])
+def test_match_pairs_ragged_vs_oracle(kctx, oracle_mod, rot, sc):
+    from sfm_gms_b200 import api
+
+    rng = np.random.default_rng(77)
+    sizes_n = [3000, 2500, 0, 1777, 4096, 1]
+    off, desc, kp, wh = _ragged_set(rng, sizes_n)
+    kctx.set_images(off, desc, kp, wh)
+    pairs = np.array([(0, 1), (1, 0), (0, 3), (4, 0), (2, 1), (1, 2), (5, 4), (3, 3), (4, 5)], np.int32)
+    kctx.set_option(api.OPT_GMS_CHUNK_BYTES, 8 << 20)  # force several GMS chunks
+    try:
+        out = kctx.match_pairs(pairs, rot, sc)
+    finally:
+        kctx.set_option(api.OPT_GMS_CHUNK_BYTES, 64 << 20)
+    mo = out["offsets"]
+    for p, (a, b) in enumerate(pairs):
+        d1, d2 = desc[off[a]:off[a + 1]], desc[off[b]:off[b + 1]]
+        k1, k2 = kp[off[a]:off[a + 1]], kp[off[b]:off[b + 1]]
+        oi, od = oracle_mod.bf_hamming(d1, d2)
+        sl = slice(mo[p], mo[p + 1])
+        if len(d2) == 0:
+            assert (out["train_idx"][sl] == -1).all() and out["n_inliers"][p] == 0 and out["mask_len"][p] == 0
+            continue
+        assert np.array_equal(out["train_idx"][sl], oi) and np.array_equal(out["dist"][sl], od), p
+        o = oracle_mod.gms(wh[a], wh[b], k1, k2, np.arange(len(oi), dtype=np.int32), oi, rot, sc)
+        assert out["n_inliers"][p] == o["n_inliers"] and out["mask_len"][p] == len(o["mask"]), p
+        assert out["best_hyp"][p] == o["best_hyp"], p
+        m = out["mask"][sl].astype(bool)
+        assert np.array_equal(m[: len(o["mask"])], o["mask"]) and not m[len(o["mask"]):].any(), p
+        # §8f-1: inlier coordinate compaction (SfMUtil.cpp:25-35)
+        p1, p2, n = kctx.inlier_points(p, len(oi) + 1)
+        keep = np.nonzero(o["mask"])[0] if len(o["mask"]) else np.zeros(0, int)
+        assert n == len(keep)
+        assert np.array_equal(p1, k1[keep]) and np.array_equal(p2, k2[oi[keep]])
+
+
+def test_match_pairs_properties_full_batch(kctx):
+    """Size-independent properties on a config-2-sized batch: determinism (two runs identical), symmetry of
+    the distance (dist(i -> j*) equals the recomputed popcount), and n_inliers == popcount(mask)."""
+    from sfm_gms_b200 import synth
+
+    s = synth.make_pair_batch(6)
+    kctx.set_images(s["offsets"], s["desc"], s["kp"], s["sizes"])
+    a = kctx.match_pairs(s["pairs"])
+    b = kctx.match_pairs(s["pairs"])
+    for k in ["train_idx", "dist", "mask", "n_inliers"]:
+        assert np.array_equal(a[k], b[k]), k
+    mo = a["offsets"]
+    for p, (i, j) in enumerate(s["pairs"]):
+        sl = slice(mo[p], mo[p + 1])
+        d1 = s["desc"][s["offsets"][i]:s["offsets"][i + 1]]
+        d2 = s["desc"][s["offsets"][j]:s["offsets"][j + 1]]
+        x = d1 ^ d2[a["train_idx"][sl]]
+        assert np.array_equal(np.unpackbits(x, axis=1).sum(1), a["dist"][sl])
+        assert a["n_inliers"][p] == int(a["mask"][sl].sum()) > 1000
+
+
+# ---- cv2-shaped Python surface -----------------------------------------------------------------------
+def test_cv2_shaped_api(ctx):
+    import sfm_gms_b200 as sg
+
+    g = load_golden("view01_2k")
+    m = sg.BFMatcher(sg.NORM_HAMMING).match(g["desc1"], g["desc2"])
+    assert [x.trainIdx for x in m] == g["bf_train"].tolist() and m[5].queryIdx == 5 and m[5].imgIdx == 0
+    assert [int(x.distance) for x in m] == g["bf_dist"].tolist()
+    out = sg.matchGMS(g["size1"], g["size2"], g["kp1"], g["kp2"], m, withRotation=False, withScale=False)
+    exp = np.unpackbits(g["gms_mask_00"])[: len(m)].astype(bool)
+    assert [x.queryIdx for x in out] == np.nonzero(exp)[0].tolist()
+    # upstream class: scale FIRST, rotation second
+    n, mask = sg.gms_matcher(g["kp1"], g["size1"], g["kp2"], g["size2"], m).GetInlierMask(False, True)
+    assert n == int(g["gms_n_10"]) and np.array_equal(mask, np.unpackbits(g["gms_mask_10"])[: len(m)].astype(bool))
+    xm = sg.BFMatcher(sg.NORM_HAMMING, crossCheck=True).match(g["desc1"], g["desc2"])
+    assert [x.queryIdx for x in xm] == g["xc_query"].tolist() and [x.trainIdx for x in xm] == g["xc_train"].tolist()
