@@ -65,7 +65,7 @@ struct sfmgms_ctx {
     double last_ms[3] = {0, 0, 0};
 
     // generic device buffers
-    DevBuf d_pairs, d_results, d_key, d_mask, d_hist, d_msc, d_q, d_t, d_kp1, d_kp2, d_mq, d_mt, d_out_i32, d_pts;
+    DevBuf d_pairs, d_results, d_key, d_mask, d_hist, d_msc, d_q, d_kp1, d_kp2, d_mq, d_mt, d_out_i32, d_pts;
     DevBuf d_set_desc, d_set_kp;
     HostBuf h_stage, h_pairs_pinned, h_results;
     TcState tc;   // tensor-core Hamming operand cache (hamming_tc.cu)
@@ -181,6 +181,7 @@ int run_batch(sfmgms_ctx* ctx, std::vector<PairDesc>& hp, bool do_hamming, bool 
     CU(cudaMemcpyAsync(ctx->d_pairs.p, ctx->h_pairs_pinned.p, sizeof(PairDesc) * n, cudaMemcpyHostToDevice, st));
     const PairDesc* dp = static_cast<const PairDesc*>(ctx->d_pairs.p);
     int ham_launches = 0;
+    if (hp[0].img1 < 0) tc_invalidate(ctx->tc);   // ad-hoc buffers: contents change between calls
     if (ctx->timing) CU(cudaEventRecord(ctx->ev[0], st));
     if (do_hamming) {
         const int kind = choose_hamming(ctx);
@@ -323,7 +324,7 @@ void sfmgms_destroy(sfmgms_ctx* ctx) {
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_pairs, &ctx->d_results, &ctx->d_key, &ctx->d_mask, &ctx->d_hist, &ctx->d_msc, &ctx->d_q,
-                      &ctx->d_t, &ctx->d_kp1, &ctx->d_kp2, &ctx->d_mq, &ctx->d_mt, &ctx->d_out_i32, &ctx->d_pts,
+                      &ctx->d_kp1, &ctx->d_kp2, &ctx->d_mq, &ctx->d_mt, &ctx->d_out_i32, &ctx->d_pts,
                       &ctx->d_set_desc, &ctx->d_set_kp};
     for (DevBuf* b : bufs) b->release();
     tc_release(ctx->tc);
@@ -347,6 +348,11 @@ int sfmgms_set_option(sfmgms_ctx* ctx, int key, int64_t value) {
     if (key == SFMGMS_OPT_GMS_CHUNK_BYTES) {
         if (value < (1 << 20)) return fail(ctx, SFMGMS_ERR_ARG, "chunk budget too small");
         ctx->gms_chunk_bytes = (size_t)value;
+        return SFMGMS_OK;
+    }
+    if (key == SFMGMS_OPT_TC_OPERAND_CACHE) {
+        ctx->tc.cache_enabled = value != 0;
+        tc_invalidate(ctx->tc);
         return SFMGMS_OK;
     }
     if (key == SFMGMS_OPT_TIMING) {
@@ -388,16 +394,17 @@ int sfmgms_bf_hamming(sfmgms_ctx* ctx, const uint8_t* query, int nq, const uint8
     if (n_matches) *n_matches = (nt == 0) ? 0 : nq;
     if (nt == 0 || nq == 0) return SFMGMS_OK;
     cudaStream_t st = ctx->stream;
-    CU(ctx->d_q.ensure((size_t)nq * 32)); CU(ctx->d_t.ensure((size_t)nt * 32));
+    CU(ctx->d_q.ensure((size_t)(nq + nt) * 32));   // q|t contiguous: one operand array (tensor-core path)
+    uint8_t* d_train = (uint8_t*)ctx->d_q.p + (size_t)nq * 32;
     CU(ctx->d_key.ensure((size_t)nq * 4)); CU(ctx->d_out_i32.ensure((size_t)nq * 8));
     CU(cudaMemcpyAsync(ctx->d_q.p, query, (size_t)nq * 32, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->d_t.p, train, (size_t)nt * 32, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_train, train, (size_t)nt * 32, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(ctx->d_key.p, 0xFF, (size_t)nq * 4, st));
     std::vector<PairDesc> hp(1);
     PairDesc& p = hp[0];
     memset(&p, 0, sizeof p);
-    p.desc1 = (const uint8_t*)ctx->d_q.p; p.desc2 = (const uint8_t*)ctx->d_t.p;
-    p.key = (uint32_t*)ctx->d_key.p; p.n1 = nq; p.n2 = nt; p.n_matches = nq;
+    p.desc1 = (const uint8_t*)ctx->d_q.p; p.desc2 = d_train;
+    p.key = (uint32_t*)ctx->d_key.p; p.n1 = nq; p.n2 = nt; p.n_matches = nq; p.img1 = p.img2 = -1;
     rc = run_batch(ctx, hp, true, false, 0, 0, 0.0);
     if (rc) return rc;
     int32_t* o = (int32_t*)ctx->d_out_i32.p;
@@ -418,17 +425,19 @@ int sfmgms_bf_hamming_crosscheck(sfmgms_ctx* ctx, const uint8_t* query, int nq, 
     if (nq >= SFMGMS_MAX_TRAIN_ROWS) return fail(ctx, SFMGMS_ERR_TRAIN_ROWS, "query rows %d >= 2^18", nq);
     if (nt == 0 || nq == 0) return SFMGMS_OK;
     cudaStream_t st = ctx->stream;
-    CU(ctx->d_q.ensure((size_t)nq * 32)); CU(ctx->d_t.ensure((size_t)nt * 32));
+    CU(ctx->d_q.ensure((size_t)(nq + nt) * 32));
+    uint8_t* d_train = (uint8_t*)ctx->d_q.p + (size_t)nq * 32;
     CU(ctx->d_key.ensure((size_t)(nq + nt) * 4)); CU(ctx->d_out_i32.ensure((size_t)nq * 8)); CU(ctx->d_mask.ensure(nq));
     CU(cudaMemcpyAsync(ctx->d_q.p, query, (size_t)nq * 32, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->d_t.p, train, (size_t)nt * 32, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_train, train, (size_t)nt * 32, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(ctx->d_key.p, 0xFF, (size_t)(nq + nt) * 4, st));
     std::vector<PairDesc> hp(2);
     memset(hp.data(), 0, sizeof(PairDesc) * 2);
-    hp[0].desc1 = (const uint8_t*)ctx->d_q.p; hp[0].desc2 = (const uint8_t*)ctx->d_t.p;
+    hp[0].desc1 = (const uint8_t*)ctx->d_q.p; hp[0].desc2 = d_train;
     hp[0].key = (uint32_t*)ctx->d_key.p; hp[0].n1 = nq; hp[0].n2 = nt; hp[0].n_matches = nq;
     hp[1].desc1 = hp[0].desc2; hp[1].desc2 = hp[0].desc1;      // roles swapped: one extra "pair"
     hp[1].key = hp[0].key + nq; hp[1].n1 = nt; hp[1].n2 = nq; hp[1].n_matches = nt; hp[1].match_base = nq;
+    hp[0].img1 = hp[0].img2 = hp[1].img1 = hp[1].img2 = -1;
     rc = run_batch(ctx, hp, true, false, 0, 0, 0.0);
     if (rc) return rc;
     int32_t* o = (int32_t*)ctx->d_out_i32.p;
@@ -475,7 +484,7 @@ int sfmgms_gms(sfmgms_ctx* ctx, int w1, int h1, int w2, int h2, const void* kp1,
     p.kp1 = (const float*)ctx->d_kp1.p; p.kp2 = (const float*)ctx->d_kp2.p;
     p.mq = (const int32_t*)ctx->d_mq.p; p.mt = (const int32_t*)ctx->d_mt.p;
     p.mask = (uint8_t*)ctx->d_mask.p;
-    p.n1 = n1; p.n2 = n2; p.n_matches = n_matches; p.w1 = w1; p.h1 = h1; p.w2 = w2; p.h2 = h2;
+    p.n1 = n1; p.n2 = n2; p.n_matches = n_matches; p.w1 = w1; p.h1 = h1; p.w2 = w2; p.h2 = h2; p.img1 = p.img2 = -1;
     rc = run_batch(ctx, hp, false, true, with_rotation, with_scale, threshold_factor);
     ctx->last_pairs = hp;
     if (rc) return rc;
@@ -504,21 +513,22 @@ int sfmgms_match_pair(sfmgms_ctx* ctx, const uint8_t* desc1, int n1, const uint8
     const int nm = (n2 == 0) ? 0 : n1;
     const size_t o2 = align256((size_t)n1 * 8);
     CU(ctx->h_stage.ensure(o2 + align256((size_t)n2 * 8)));
-    CU(ctx->d_q.ensure((size_t)(n1 + 1) * 32)); CU(ctx->d_t.ensure((size_t)(n2 + 1) * 32));
+    CU(ctx->d_q.ensure((size_t)(n1 + n2 + 1) * 32));
+    uint8_t* d_train = (uint8_t*)ctx->d_q.p + (size_t)n1 * 32;
     CU(ctx->d_key.ensure((size_t)(n1 + 1) * 4)); CU(ctx->d_out_i32.ensure((size_t)(n1 + 1) * 8));
     CU(ctx->d_mask.ensure((size_t)n1 + 1));
     if (n1) CU(cudaMemcpyAsync(ctx->d_q.p, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, st));
-    if (n2) CU(cudaMemcpyAsync(ctx->d_t.p, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, st));
+    if (n2) CU(cudaMemcpyAsync(d_train, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, st));
     if ((rc = upload_xy(ctx, kp1, n1, kp1_stride_bytes, ctx->d_kp1, 0))) return rc;
     if ((rc = upload_xy(ctx, kp2, n2, kp2_stride_bytes, ctx->d_kp2, o2))) return rc;
     CU(cudaMemsetAsync(ctx->d_key.p, 0xFF, (size_t)(n1 + 1) * 4, st));
     std::vector<PairDesc> hp(1);
     PairDesc& p = hp[0];
     memset(&p, 0, sizeof p);
-    p.desc1 = (const uint8_t*)ctx->d_q.p; p.desc2 = (const uint8_t*)ctx->d_t.p;
+    p.desc1 = (const uint8_t*)ctx->d_q.p; p.desc2 = d_train;
     p.kp1 = (const float*)ctx->d_kp1.p; p.kp2 = (const float*)ctx->d_kp2.p;
     p.key = (uint32_t*)ctx->d_key.p; p.mask = (uint8_t*)ctx->d_mask.p;
-    p.n1 = n1; p.n2 = n2; p.n_matches = nm; p.w1 = w1; p.h1 = h1; p.w2 = w2; p.h2 = h2;
+    p.n1 = n1; p.n2 = n2; p.n_matches = nm; p.w1 = w1; p.h1 = h1; p.w2 = w2; p.h2 = h2; p.img1 = p.img2 = -1;
     rc = run_batch(ctx, hp, nm > 0, true, with_rotation, with_scale, threshold_factor);
     ctx->last_pairs = hp;
     if (rc) return rc;

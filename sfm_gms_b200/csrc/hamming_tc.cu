@@ -1,10 +1,365 @@
-// hamming_tc.cu — placeholder until the tcgen05 kernel lands: reports "not available" so the context
-// selects the popc kernel.  (No CPU path: both kernels are sm_100a CUDA.)
+// hamming_tc.cu — brute-force Hamming nearest neighbour on the 5th-gen tensor cores (tcgen05, sm_100a).
+//
+// Replaces cv::BFMatcher(NORM_HAMMING)::match (reference call site FeatureMatchUtil.cpp:68).
+//
+// Idea: unpack each 256-bit descriptor to 256 int8 values in {-1,+1}.  Then for query a and train b
+//     <a,b> = 256 - 2*hamming(a,b)      (exact in the s32 accumulator)
+// so the nearest neighbour is the arg-MAX of an int8 GEMM row, lowest column on ties.  The GEMM runs as
+// tcgen05.mma.kind::i8 (M=128, N=128, K=32 per instruction) with the accumulators in TMEM; the epilogue
+// never materialises the N1 x N2 distance matrix: it reduces each accumulator row to (max, first argmax)
+// straight out of TMEM and merges across CTAs with one atomicMin on the packed key (dist<<18 | trainIdx),
+// which is order-independent => deterministic and bit-identical to OpenCV's strict-'<' scan.
+//
+// Kernel structure (persistent, warp-specialised, 1 CTA/SM, 384 threads):
+//   warp 0   TMA producer: A (query) sub-tiles once per work unit, B (train) tiles through a 4-stage ring;
+//            both via cp.async.bulk.tensor.2d (128B swizzle) from the unpacked operand array
+//   warp 1   MMA issuer: one elected lane issues tcgen05.mma, tcgen05.commit signals mbarriers
+//   warp 2   TMEM allocator (all 512 columns = 4 accumulator slots of 128x128 s32)
+//   warp 3   idle
+//   warps 4-11  epilogue: tcgen05.ld 32 lanes x 32 columns at a time; a chunk max (cheap) guards the
+//            rare "new row maximum" path that extracts the first column attaining it
+// Work unit = (pair, 256 query rows, contiguous range of 128-row train tiles); B traffic per CTA is
+// 32 KB per 2 x 8 MMAs (~1024 clk) = ~32 B/clk/SM, inside the L2 budget (B300_MICROARCH: ~6.3 KB/clk chip).
+//
+// Roofline: tensor pipe.  Algorithmic work = 2*256 int8 OPs per distance.
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstring>
+
 #include "hamming_tc.cuh"
 
 namespace sfmgms {
-bool tc_available() { return false; }
-const char* tc_last_error() { return "tensor-core Hamming kernel not built"; }
+
+namespace {
+
+constexpr int BM = 128;            // UMMA M: query rows per A sub-tile (TMEM lanes)
+constexpr int MSUB = 2;            // A sub-tiles per work unit
+constexpr int BN = 128;            // UMMA N: train rows per B tile (TMEM columns)
+constexpr int KBYTES = 256;        // unpacked descriptor: 256 x int8
+constexpr int KCH = 128;           // bytes per 128B-swizzle chunk
+constexpr int NKCH = KBYTES / KCH; // 2
+constexpr int UMMA_K = 32;         // K per tcgen05.mma for 8-bit operands
+constexpr int STAGES = 4;          // B ring
+constexpr int ACC_SLOTS = 4;       // TMEM: 4 x 128 columns
+constexpr int TILE_BYTES = BM * KCH;             // 16 KB: one [128 rows x 128 B] swizzled chunk
+constexpr int A_BYTES = MSUB * NKCH * TILE_BYTES;  // 64 KB
+constexpr int B_STAGE_BYTES = NKCH * TILE_BYTES;   // 32 KB
+constexpr int SMEM_DATA = A_BYTES + STAGES * B_STAGE_BYTES;  // 192 KB
+constexpr int SMEM_BYTES = SMEM_DATA + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kThreads = 384;
+constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarps = 8;
+
+struct alignas(16) WorkUnit {
+    uint32_t a_row0;     // first operand row (global, in the unpacked array) of this unit's queries
+    uint32_t b_row0;     // operand row of the train image's row 0
+    int32_t n_rows;      // valid query rows in this unit (<= 256)
+    int32_t t_begin;     // first train row (multiple of BN)
+    int32_t t_end;       // one past the last train row of this unit (<= n2)
+    int32_t pad;
+    uint32_t* key;       // &key[first query row of the unit]
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 columns of 32-bit accumulators -> 32 registers per thread (thread = TMEM lane)
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, int (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile [rows x 128 B], rows contiguous (8-row groups 1024 B apart).
+// Descriptor fields (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type=SWIZZLE_128B(2) [61,64).
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;                    // LBO (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;          // SBO: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor (InstrDescriptor): c_format=S32(2)@4, a_format=INT8(1)@7, b_format=INT8(1)@10,
+// a_major=K(0)@15, b_major=K(0)@16, n_dim=N>>3 @17, m_dim=M>>4 @24.
+constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// ---- operand unpack: 256 bits -> 256 x int8 in {-1,+1} -------------------------------------------------
+// thread = one 32-bit word of a descriptor -> 32 output bytes (2 x 128-bit stores); bit b of byte k -> K index 8k+b
+__global__ void __launch_bounds__(256) unpack_pm1_kernel(const uint32_t* __restrict__ desc, long long n_words,
+                                                         uint4* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (; i < n_words; i += step) {
+        const uint32_t w = __ldg(desc + i);
+        uint32_t o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t nib = (w >> (4 * k)) & 0xFu;
+            const uint32_t m = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+            o[k] = ~(m * 0xFFu) | m;       // byte = 0x01 where bit set, 0xFF (-1) where clear
+        }
+        out[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
+        out[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+// ---- the tcgen05 kernel -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+hamming_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkUnit* __restrict__ units, int n_units) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 128B swizzle needs 1024 B alignment
+    const uint32_t a_smem = smem_base;
+    const uint32_t b_smem = smem_base + A_BYTES;
+    const uint32_t bar_base = smem_base + SMEM_DATA;
+    // barriers (8 B each)
+    const uint32_t full_bar = bar_base;                       // [STAGES]  TMA -> MMA
+    const uint32_t empty_bar = bar_base + 8 * STAGES;          // [STAGES]  MMA -> TMA
+    const uint32_t a_full_bar = bar_base + 16 * STAGES;        // TMA -> MMA (A tile of the unit)
+    const uint32_t a_empty_bar = a_full_bar + 8;               // MMA -> TMA
+    const uint32_t tfull_bar = a_full_bar + 16;                // [ACC_SLOTS] MMA -> epilogue
+    const uint32_t tempty_bar = tfull_bar + 8 * ACC_SLOTS;     // [ACC_SLOTS] epilogue -> MMA
+    const uint32_t tmem_ptr_smem = tempty_bar + 8 * ACC_SLOTS; // 4 B: TMEM base address
+    volatile uint32_t* tmem_ptr_generic =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_smem - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+        mbar_init(a_full_bar, 1);
+        mbar_init(a_empty_bar, 1);
+        for (int s = 0; s < ACC_SLOTS; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, kEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_smem), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_generic;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+            uint32_t stage = 0, phase = 0, a_phase = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const WorkUnit wu = units[u];
+                const int nsub = (wu.n_rows + BM - 1) / BM;
+                mbar_wait(a_empty_bar, a_phase ^ 1);              // previous unit's MMAs are done with A
+                mbar_expect_tx(a_full_bar, (uint32_t)(nsub * NKCH * TILE_BYTES));
+                for (int s = 0; s < nsub; ++s)
+                    for (int kc = 0; kc < NKCH; ++kc)
+                        tma_load_2d(a_smem + (s * NKCH + kc) * TILE_BYTES, &tmap, kc * KCH,
+                                    (int)(wu.a_row0 + s * BM), a_full_bar);
+                a_phase ^= 1;
+                for (int t = wu.t_begin; t < wu.t_end; t += BN) {
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    mbar_expect_tx(full_bar + 8 * stage, (uint32_t)B_STAGE_BYTES);
+                    for (int kc = 0; kc < NKCH; ++kc)
+                        tma_load_2d(b_smem + stage * B_STAGE_BYTES + kc * TILE_BYTES, &tmap, kc * KCH,
+                                    (int)(wu.b_row0 + t), full_bar + 8 * stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, a_phase = 0, slot = 0, slot_phase = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const WorkUnit wu = units[u];
+                const int nsub = (wu.n_rows + BM - 1) / BM;
+                mbar_wait(a_full_bar, a_phase);
+                a_phase ^= 1;
+                for (int t = wu.t_begin; t < wu.t_end; t += BN) {
+                    mbar_wait(full_bar + 8 * stage, phase);
+                    tc_fence_after();
+                    for (int s = 0; s < nsub; ++s) {
+                        mbar_wait(tempty_bar + 8 * slot, slot_phase ^ 1);   // epilogue drained this accumulator
+                        tc_fence_after();
+                        const uint32_t d = tmem_base + slot * BN;
+#pragma unroll
+                        for (int kc = 0; kc < NKCH; ++kc) {
+#pragma unroll
+                            for (int ks = 0; ks < KCH / UMMA_K; ++ks) {
+                                const uint64_t ad = make_sdesc(a_smem + (s * NKCH + kc) * TILE_BYTES + ks * UMMA_K);
+                                const uint64_t bd = make_sdesc(b_smem + stage * B_STAGE_BYTES + kc * TILE_BYTES + ks * UMMA_K);
+                                tc_mma_i8(d, ad, bd, kIdesc, (kc | ks) ? 1u : 0u);
+                            }
+                        }
+                        tc_commit(tfull_bar + 8 * slot);                   // accumulator ready for the epilogue
+                        if (++slot == ACC_SLOTS) { slot = 0; slot_phase ^= 1; }
+                    }
+                    tc_commit(empty_bar + 8 * stage);                      // B stage reusable once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(a_empty_bar);                                     // A reusable
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ================= epilogue: row-wise (max, first argmax) straight from TMEM =================
+        const int e = warp - kEpiWarp0;
+        const int quad = warp & 3;              // TMEM lane quadrant this warp may access
+        const int half = e >> 2;                // which 64 of the 128 accumulator columns
+        uint32_t slot = 0, slot_phase = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const WorkUnit wu = units[u];
+            const int nsub = (wu.n_rows + BM - 1) / BM;
+            int best_val[MSUB], best_idx[MSUB];
+#pragma unroll
+            for (int s = 0; s < MSUB; ++s) { best_val[s] = -0x7fffffff; best_idx[s] = 0; }
+            for (int t = wu.t_begin; t < wu.t_end; t += BN) {
+                const int valid = wu.t_end - t;       // columns >= valid are outside the train image
+#pragma unroll
+                for (int s = 0; s < MSUB; ++s) {
+                    if (s < nsub) {
+                        mbar_wait(tfull_bar + 8 * slot, slot_phase);
+                        tc_fence_after();
+                        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * BN + half * 64;
+                        int v0[32], v1[32];
+                        tc_ld32(taddr, v0);
+                        tc_ld32(taddr + 32, v1);
+                        tc_wait_ld();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty_bar + 8 * slot);   // values are in registers now
+                        if (++slot == ACC_SLOTS) { slot = 0; slot_phase ^= 1; }
+                        const int c0 = half * 64;
+                        if (c0 + 64 > valid) {                               // tail tile: mask outside columns
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (c0 + j >= valid) v0[j] = -0x7fffffff;
+                                if (c0 + 32 + j >= valid) v1[j] = -0x7fffffff;
+                            }
+                        }
+                        int m0 = v0[0], m1 = v1[0];
+#pragma unroll
+                        for (int j = 1; j < 32; ++j) { m0 = max(m0, v0[j]); m1 = max(m1, v1[j]); }
+                        if (m0 > best_val[s]) {          // rare after the first tiles: strict '>' keeps the earliest
+                            int idx = 31;
+#pragma unroll
+                            for (int j = 30; j >= 0; --j) idx = (v0[j] == m0) ? j : idx;
+                            best_val[s] = m0; best_idx[s] = t + c0 + idx;
+                        }
+                        if (m1 > best_val[s]) {
+                            int idx = 31;
+#pragma unroll
+                            for (int j = 30; j >= 0; --j) idx = (v1[j] == m1) ? j : idx;
+                            best_val[s] = m1; best_idx[s] = t + c0 + 32 + idx;
+                        }
+                    }
+                }
+            }
+            // merge: two column halves (and other train-range splits) meet in global memory
+#pragma unroll
+            for (int s = 0; s < MSUB; ++s) {
+                const int row = s * BM + quad * 32 + lane;
+                if (s < nsub && row < wu.n_rows && best_val[s] > -0x7fffffff) {
+                    const uint32_t dist = (uint32_t)(KBYTES - best_val[s]) >> 1;   // <a,b> = 256 - 2*hamming
+                    atomicMin(wu.key + row, (dist << kTrainIdxBits) | (uint32_t)best_idx[s]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+char g_tc_err[256] = "";
+EncodeTiledFn g_encode = nullptr;
+
+bool load_encode() {
+    if (g_encode) return true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+        return false;
+    }
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return true;
+}
+
+bool ensure_dev(void*& p, size_t& cap, size_t bytes) {
+    if (bytes <= cap) return true;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    const size_t want = bytes + bytes / 8 + 4096;
+    if (cudaMalloc(&p, want) != cudaSuccess) { snprintf(g_tc_err, sizeof g_tc_err, "cudaMalloc(%zu) failed", want); return false; }
+    cap = want;
+    return true;
+}
+
+}  // namespace
+
+bool tc_available() { return true; }
+const char* tc_last_error() { return g_tc_err; }
 void tc_invalidate(TcState& s) { s.set_valid = false; }
 void tc_release(TcState& s) {
     if (s.d_ops) cudaFree(s.d_ops);
@@ -12,5 +367,127 @@ void tc_release(TcState& s) {
     if (s.h_work) cudaFreeHost(s.h_work);
     s = TcState();
 }
-int launch_hamming_tc(TcState&, const PairDesc*, const PairDesc*, int, int, cudaStream_t) { return -1; }
+
+// Unpacks descriptor rows [0, n_rows) at `desc` (device, 32 B each) into s.d_ops (256 B each).
+int tc_unpack(TcState& s, const uint8_t* desc, long long n_rows, cudaStream_t st) {
+    if (!ensure_dev(s.d_ops, s.ops_cap, (size_t)(n_rows + BM) * KBYTES)) return -1;
+    if (n_rows == 0) return 0;
+    const long long n_words = n_rows * kDescWords;
+    long long blocks = (n_words + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    unpack_pm1_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(desc), n_words,
+                                                        static_cast<uint4*>(s.d_ops));
+    s.ops_rows = n_rows;
+    return 1;
+}
+
+// Precondition (as for the popc kernel): keys initialised to kKeyInit.  The operands of all pairs must lie
+// in ONE contiguous descriptor array starting at `desc_base` (the image set, or the ad-hoc q|t buffers):
+// row index of a pair's descriptors = (ptr - desc_base) / 32.
+int launch_hamming_tc(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, int sm_count,
+                      cudaStream_t st) {
+    (void)d_pairs;
+    if (n_pairs <= 0) return 0;
+    if (!load_encode()) return -1;
+    int launches = 0;
+    // operand array = span of descriptor rows referenced by this batch
+    const uint8_t* lo = nullptr;
+    const uint8_t* hi = nullptr;
+    for (int p = 0; p < n_pairs; ++p) {
+        const PairDesc& pd = h_pairs[p];
+        if (pd.n1 <= 0 || pd.n2 <= 0) continue;
+        const uint8_t* ends[2][2] = {{pd.desc1, pd.desc1 + (size_t)pd.n1 * 32}, {pd.desc2, pd.desc2 + (size_t)pd.n2 * 32}};
+        for (auto& e : ends) {
+            if (!lo || e[0] < lo) lo = e[0];
+            if (!hi || e[1] > hi) hi = e[1];
+        }
+    }
+    if (!lo) return 0;
+    const long long n_rows = (hi - lo) / 32;
+    long long ref_rows = 0;
+    for (int p = 0; p < n_pairs; ++p) ref_rows += (long long)h_pairs[p].n1 + h_pairs[p].n2;
+    if (n_rows > 64 * ref_rows + 4096) {   // the span must be one descriptor array, not two unrelated allocations
+        snprintf(g_tc_err, sizeof g_tc_err, "descriptor operands are not in one contiguous array");
+        return -1;
+    }
+    if (n_rows >= (1ll << 31)) { snprintf(g_tc_err, sizeof g_tc_err, "operand span too large"); return -1; }
+    if (!(s.set_valid && s.ops_src == lo && s.ops_rows == n_rows)) {
+        const int l = tc_unpack(s, lo, n_rows, st);
+        if (l < 0) return -1;
+        launches += l;
+        s.ops_src = lo;
+        s.set_valid = s.cache_enabled;
+    }
+    // tensor map over the unpacked array: dim0 = K bytes (256), dim1 = rows; box 128 B x 128 rows, 128B swizzle
+    CUtensorMap tmap;
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)KBYTES, (cuuint64_t)(n_rows + BM)};
+        const cuuint64_t gstride[1] = {(cuuint64_t)KBYTES};
+        const cuuint32_t box[2] = {(cuuint32_t)KCH, (cuuint32_t)BM};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = g_encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, s.d_ops, gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }
+    }
+    // work units: (pair, 256-query block, train-tile range).  Small batches split the train range so every SM works.
+    long long qblocks = 0;
+    int max_tiles = 1;
+    for (int p = 0; p < n_pairs; ++p) {
+        if (h_pairs[p].n1 <= 0 || h_pairs[p].n2 <= 0) continue;
+        qblocks += (h_pairs[p].n1 + BM * MSUB - 1) / (BM * MSUB);
+        const int tiles = (h_pairs[p].n2 + BN - 1) / BN;
+        if (tiles > max_tiles) max_tiles = tiles;
+    }
+    int tsplit = 1;
+    if (qblocks < 2LL * sm_count) {
+        long long t = (2LL * sm_count + qblocks - 1) / qblocks;
+        if (t > max_tiles) t = max_tiles;
+        tsplit = (int)(t < 1 ? 1 : t);
+    }
+    const size_t max_units = (size_t)qblocks * tsplit;
+    const size_t wbytes = max_units * sizeof(WorkUnit);
+    if (wbytes > s.h_work_cap) {
+        if (s.h_work) cudaFreeHost(s.h_work);
+        s.h_work = nullptr; s.h_work_cap = 0;
+        if (cudaMallocHost(&s.h_work, wbytes + wbytes / 4 + 4096) != cudaSuccess) { snprintf(g_tc_err, sizeof g_tc_err, "cudaMallocHost failed"); return -1; }
+        s.h_work_cap = wbytes + wbytes / 4 + 4096;
+    }
+    if (!ensure_dev(s.d_work, s.work_cap, wbytes)) return -1;
+    WorkUnit* wu = static_cast<WorkUnit*>(s.h_work);
+    size_t n_units = 0;
+    for (int p = 0; p < n_pairs; ++p) {
+        const PairDesc& pd = h_pairs[p];
+        if (pd.n1 <= 0 || pd.n2 <= 0) continue;
+        const uint32_t arow = (uint32_t)((pd.desc1 - lo) / 32), brow = (uint32_t)((pd.desc2 - lo) / 32);
+        const int tiles = (pd.n2 + BN - 1) / BN;
+        const int tper = (tiles + tsplit - 1) / tsplit;
+        for (int q0 = 0; q0 < pd.n1; q0 += BM * MSUB) {
+            for (int ts = 0; ts * tper < tiles; ++ts) {
+                WorkUnit& w = wu[n_units++];
+                w.a_row0 = arow + q0;
+                w.b_row0 = brow;
+                w.n_rows = (pd.n1 - q0 < BM * MSUB) ? pd.n1 - q0 : BM * MSUB;
+                w.t_begin = ts * tper * BN;
+                const int te = (ts + 1) * tper * BN;
+                w.t_end = te < pd.n2 ? te : pd.n2;
+                w.pad = 0;
+                w.key = pd.key + q0;
+            }
+        }
+    }
+    if (n_units == 0) return launches;
+    if (cudaMemcpyAsync(s.d_work, wu, n_units * sizeof(WorkUnit), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        snprintf(g_tc_err, sizeof g_tc_err, "work table upload failed");
+        return -1;
+    }
+    if (cudaFuncSetAttribute(hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+        snprintf(g_tc_err, sizeof g_tc_err, "cudaFuncSetAttribute(smem=%d) failed", SMEM_BYTES);
+        return -1;
+    }
+    const int grid = (int)(n_units < (size_t)sm_count ? n_units : (size_t)sm_count);
+    hamming_tc_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(tmap, static_cast<const WorkUnit*>(s.d_work), (int)n_units);
+    return launches + 1;
+}
+
 }  // namespace sfmgms

@@ -11,7 +11,10 @@ struct TcState {
     size_t work_cap = 0;
     void* h_work = nullptr;     // pinned
     size_t h_work_cap = 0;
-    bool set_valid = false;     // operands of the current image set are unpacked
+    bool set_valid = false;     // d_ops holds the unpacked form of [ops_src, ops_src + 32*ops_rows)
+    bool cache_enabled = true;  // keep the unpacked operands across calls until tc_invalidate()
+    const uint8_t* ops_src = nullptr;
+    long long ops_rows = 0;
 };
 
 bool tc_available();
