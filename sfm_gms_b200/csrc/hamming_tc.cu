@@ -11,7 +11,8 @@
 // which is order-independent => deterministic and bit-identical to OpenCV's strict-'<' scan.
 //
 // Kernel structure (persistent, warp-specialised, 1 CTA/SM, 384 threads):
-//   warp 0   TMA producer: A (query) sub-tiles once per work unit, B (train) tiles through a 4-stage ring;
+//   warp 0   TMA producer: A (query) sub-tiles once per work unit (double-buffered), B (train) tiles through a
+//            3-stage ring;
 //            both via cp.async.bulk.tensor.2d (128B swizzle) from the unpacked operand array
 //   warp 1   MMA issuer: one elected lane issues tcgen05.mma, tcgen05.commit signals mbarriers
 //   warp 2   TMEM allocator (all 512 columns = 4 accumulator slots of 128x128 s32)
@@ -25,6 +26,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "hamming_tc.cuh"
@@ -40,12 +42,14 @@ constexpr int KBYTES = 256;        // unpacked descriptor: 256 x int8
 constexpr int KCH = 128;           // bytes per 128B-swizzle chunk
 constexpr int NKCH = KBYTES / KCH; // 2
 constexpr int UMMA_K = 32;         // K per tcgen05.mma for 8-bit operands
-constexpr int STAGES = 4;          // B ring
+constexpr int STAGES = 3;          // B ring
+constexpr int A_BUFS = 2;          // A double buffer: the next unit's queries land while this unit computes
 constexpr int ACC_SLOTS = 4;       // TMEM: 4 x 128 columns
 constexpr int TILE_BYTES = BM * KCH;             // 16 KB: one [128 rows x 128 B] swizzled chunk
-constexpr int A_BYTES = MSUB * NKCH * TILE_BYTES;  // 64 KB
+constexpr int A_BUF_BYTES = MSUB * NKCH * TILE_BYTES;  // 64 KB
+constexpr int A_BYTES = A_BUFS * A_BUF_BYTES;      // 128 KB
 constexpr int B_STAGE_BYTES = NKCH * TILE_BYTES;   // 32 KB
-constexpr int SMEM_DATA = A_BYTES + STAGES * B_STAGE_BYTES;  // 192 KB
+constexpr int SMEM_DATA = A_BYTES + STAGES * B_STAGE_BYTES;  // 224 KB
 constexpr int SMEM_BYTES = SMEM_DATA + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kThreads = 384;
 constexpr int kEpiWarp0 = 4;
@@ -94,14 +98,20 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
+// Shared-memory matrix descriptors are passed as (lo, hi) halves: hi is one constant for every operand
+// tile of this kernel, lo = (address >> 4) | LBO field, so stepping K or switching stage is a 32-bit add.
+template <int kAccumulate>
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                          uint32_t idesc) {
     asm volatile(
         "{\n\t"
+        ".reg .b64 da, db;\n\t"
         ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n\t"
+        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "n"(kAccumulate) : "memory");
 }
 // 32 lanes x 32 columns of 32-bit accumulators -> 32 registers per thread (thread = TMEM lane)
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, int (&v)[32]) {
@@ -120,14 +130,11 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 // K-major, 128B-swizzled operand tile [rows x 128 B], rows contiguous (8-row groups 1024 B apart).
 // Descriptor fields (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout_type=SWIZZLE_128B(2) [61,64).
-__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;                    // LBO (ignored for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;          // SBO: 8 rows x 128 B
-    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
-    return d;
+constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4)      // SBO: 8 rows x 128 B
+                             | (1u << 14)               // descriptor version (Blackwell)
+                             | (2u << 29);              // SWIZZLE_128B
+__device__ __forceinline__ uint32_t sdesc_lo(uint32_t smem_addr) {
+    return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);  // start address | LBO (ignored for swizzled K-major)
 }
 // Instruction descriptor (InstrDescriptor): c_format=S32(2)@4, a_format=INT8(1)@7, b_format=INT8(1)@10,
 // a_major=K(0)@15, b_major=K(0)@16, n_dim=N>>3 @17, m_dim=M>>4 @24.
@@ -154,6 +161,7 @@ __global__ void __launch_bounds__(256) unpack_pm1_kernel(const uint32_t* __restr
 }
 
 // ---- the tcgen05 kernel -------------------------------------------------------------------------------
+template <int dbg>   // dbg != 0: timing experiments only (results invalid); production is dbg = 0
 __global__ void __launch_bounds__(kThreads, 1)
 hamming_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkUnit* __restrict__ units, int n_units) {
     extern __shared__ uint8_t smem_raw[];
@@ -163,10 +171,10 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkUnit* __re
     const uint32_t bar_base = smem_base + SMEM_DATA;
     // barriers (8 B each)
     const uint32_t full_bar = bar_base;                       // [STAGES]  TMA -> MMA
-    const uint32_t empty_bar = bar_base + 8 * STAGES;          // [STAGES]  MMA -> TMA
-    const uint32_t a_full_bar = bar_base + 16 * STAGES;        // TMA -> MMA (A tile of the unit)
-    const uint32_t a_empty_bar = a_full_bar + 8;               // MMA -> TMA
-    const uint32_t tfull_bar = a_full_bar + 16;                // [ACC_SLOTS] MMA -> epilogue
+    const uint32_t empty_bar = full_bar + 8 * STAGES;          // [STAGES]  MMA -> TMA
+    const uint32_t a_full_bar = empty_bar + 8 * STAGES;        // [A_BUFS]  TMA -> MMA (query tile of a unit)
+    const uint32_t a_empty_bar = a_full_bar + 8 * A_BUFS;      // [A_BUFS]  MMA -> TMA
+    const uint32_t tfull_bar = a_empty_bar + 8 * A_BUFS;       // [ACC_SLOTS] MMA -> epilogue
     const uint32_t tempty_bar = tfull_bar + 8 * ACC_SLOTS;     // [ACC_SLOTS] epilogue -> MMA
     const uint32_t tmem_ptr_smem = tempty_bar + 8 * ACC_SLOTS; // 4 B: TMEM base address
     volatile uint32_t* tmem_ptr_generic =
@@ -177,8 +185,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkUnit* __re
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-        mbar_init(a_full_bar, 1);
-        mbar_init(a_empty_bar, 1);
+        for (int s = 0; s < A_BUFS; ++s) { mbar_init(a_full_bar + 8 * s, 1); mbar_init(a_empty_bar + 8 * s, 1); }
         for (int s = 0; s < ACC_SLOTS; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -196,17 +203,17 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkUnit* __re
         // ================= TMA producer =================
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-            uint32_t stage = 0, phase = 0, a_phase = 0;
+            uint32_t stage = 0, phase = 0, abuf = 0, a_phase = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const WorkUnit wu = units[u];
                 const int nsub = (wu.n_rows + BM - 1) / BM;
-                mbar_wait(a_empty_bar, a_phase ^ 1);              // previous unit's MMAs are done with A
-                mbar_expect_tx(a_full_bar, (uint32_t)(nsub * NKCH * TILE_BYTES));
+                mbar_wait(a_empty_bar + 8 * abuf, a_phase ^ 1);   // the unit two back is done with this A buffer
+                mbar_expect_tx(a_full_bar + 8 * abuf, (uint32_t)(nsub * NKCH * TILE_BYTES));
                 for (int s = 0; s < nsub; ++s)
                     for (int kc = 0; kc < NKCH; ++kc)
-                        tma_load_2d(a_smem + (s * NKCH + kc) * TILE_BYTES, &tmap, kc * KCH,
-                                    (int)(wu.a_row0 + s * BM), a_full_bar);
-                a_phase ^= 1;
+                        tma_load_2d(a_smem + abuf * A_BUF_BYTES + (s * NKCH + kc) * TILE_BYTES, &tmap, kc * KCH,
+                                    (int)(wu.a_row0 + s * BM), a_full_bar + 8 * abuf);
+                if (++abuf == A_BUFS) { abuf = 0; a_phase ^= 1; }
                 for (int t = wu.t_begin; t < wu.t_end; t += BN) {
                     mbar_wait(empty_bar + 8 * stage, phase ^ 1);
                     mbar_expect_tx(full_bar + 8 * stage, (uint32_t)B_STAGE_BYTES);
@@ -220,35 +227,39 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkUnit* __re
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0, a_phase = 0, slot = 0, slot_phase = 0;
+            uint32_t stage = 0, phase = 0, abuf = 0, a_phase = 0, slot = 0, slot_phase = 0;
+            const uint32_t a_lo0 = sdesc_lo(a_smem), b_lo0 = sdesc_lo(b_smem);
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const WorkUnit wu = units[u];
                 const int nsub = (wu.n_rows + BM - 1) / BM;
-                mbar_wait(a_full_bar, a_phase);
-                a_phase ^= 1;
-                for (int t = wu.t_begin; t < wu.t_end; t += BN) {
+                const int ntiles = (wu.t_end - wu.t_begin + BN - 1) / BN;
+                mbar_wait(a_full_bar + 8 * abuf, a_phase);
+                const uint32_t a_lo_buf = a_lo0 + abuf * (A_BUF_BYTES >> 4);
+                for (int ti = 0; ti < ntiles; ++ti) {
                     mbar_wait(full_bar + 8 * stage, phase);
-                    tc_fence_after();
+                    const uint32_t b_lo = b_lo0 + stage * (B_STAGE_BYTES >> 4);
                     for (int s = 0; s < nsub; ++s) {
                         mbar_wait(tempty_bar + 8 * slot, slot_phase ^ 1);   // epilogue drained this accumulator
                         tc_fence_after();
                         const uint32_t d = tmem_base + slot * BN;
-#pragma unroll
-                        for (int kc = 0; kc < NKCH; ++kc) {
-#pragma unroll
-                            for (int ks = 0; ks < KCH / UMMA_K; ++ks) {
-                                const uint64_t ad = make_sdesc(a_smem + (s * NKCH + kc) * TILE_BYTES + ks * UMMA_K);
-                                const uint64_t bd = make_sdesc(b_smem + stage * B_STAGE_BYTES + kc * TILE_BYTES + ks * UMMA_K);
-                                tc_mma_i8(d, ad, bd, kIdesc, (kc | ks) ? 1u : 0u);
-                            }
-                        }
+                        const uint32_t a_lo = a_lo_buf + s * ((NKCH * TILE_BYTES) >> 4);
+                        // K = 256 = 2 swizzle chunks x 4 steps of 32 (one 128x128x32 int8 MMA each)
+                        tc_mma_i8<0>(d, a_lo + 0, b_lo + 0, kDescHi, kIdesc);
+                        tc_mma_i8<1>(d, a_lo + 2, b_lo + 2, kDescHi, kIdesc);
+                        tc_mma_i8<1>(d, a_lo + 4, b_lo + 4, kDescHi, kIdesc);
+                        tc_mma_i8<1>(d, a_lo + 6, b_lo + 6, kDescHi, kIdesc);
+                        tc_mma_i8<1>(d, a_lo + (TILE_BYTES >> 4) + 0, b_lo + (TILE_BYTES >> 4) + 0, kDescHi, kIdesc);
+                        tc_mma_i8<1>(d, a_lo + (TILE_BYTES >> 4) + 2, b_lo + (TILE_BYTES >> 4) + 2, kDescHi, kIdesc);
+                        tc_mma_i8<1>(d, a_lo + (TILE_BYTES >> 4) + 4, b_lo + (TILE_BYTES >> 4) + 4, kDescHi, kIdesc);
+                        tc_mma_i8<1>(d, a_lo + (TILE_BYTES >> 4) + 6, b_lo + (TILE_BYTES >> 4) + 6, kDescHi, kIdesc);
                         tc_commit(tfull_bar + 8 * slot);                   // accumulator ready for the epilogue
                         if (++slot == ACC_SLOTS) { slot = 0; slot_phase ^= 1; }
                     }
                     tc_commit(empty_bar + 8 * stage);                      // B stage reusable once these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(a_empty_bar);                                     // A reusable
+                tc_commit(a_empty_bar + 8 * abuf);                          // A buffer reusable
+                if (++abuf == A_BUFS) { abuf = 0; a_phase ^= 1; }
             }
         }
     } else if (warp >= kEpiWarp0) {
@@ -272,14 +283,20 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkUnit* __re
                         tc_fence_after();
                         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * BN + half * 64;
                         int v0[32], v1[32];
-                        tc_ld32(taddr, v0);
-                        tc_ld32(taddr + 32, v1);
-                        tc_wait_ld();
+                        if (dbg == 2) {       // DEBUG (timing experiments only): no TMEM read
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) { v0[j] = j; v1[j] = j; }
+                        } else {
+                            tc_ld32(taddr, v0);
+                            tc_ld32(taddr + 32, v1);
+                            tc_wait_ld();
+                        }
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty_bar + 8 * slot);   // values are in registers now
                         if (++slot == ACC_SLOTS) { slot = 0; slot_phase ^= 1; }
                         const int c0 = half * 64;
+                        if (dbg == 1) { best_val[s] = max(best_val[s], v0[0] + v1[31]); continue; }  // DEBUG: no ALU
                         if (c0 + 64 > valid) {                               // tail tile: mask outside columns
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
@@ -481,12 +498,14 @@ int launch_hamming_tc(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pai
         snprintf(g_tc_err, sizeof g_tc_err, "work table upload failed");
         return -1;
     }
-    if (cudaFuncSetAttribute(hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+    static const int dbg = getenv("SFMGMS_TC_DEBUG") ? atoi(getenv("SFMGMS_TC_DEBUG")) : 0;   // timing experiments only
+    auto kern = dbg == 1 ? hamming_tc_kernel<1> : dbg == 2 ? hamming_tc_kernel<2> : hamming_tc_kernel<0>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
         snprintf(g_tc_err, sizeof g_tc_err, "cudaFuncSetAttribute(smem=%d) failed", SMEM_BYTES);
         return -1;
     }
     const int grid = (int)(n_units < (size_t)sm_count ? n_units : (size_t)sm_count);
-    hamming_tc_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(tmap, static_cast<const WorkUnit*>(s.d_work), (int)n_units);
+    kern<<<grid, kThreads, SMEM_BYTES, st>>>(tmap, static_cast<const WorkUnit*>(s.d_work), (int)n_units);
     return launches + 1;
 }
 
