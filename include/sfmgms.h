@@ -125,6 +125,18 @@ int sfmgms_match_pairs(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int w
                        int32_t* mask_len, int32_t* train_idx, int32_t* dist, uint8_t* mask);
 int sfmgms_match_offsets(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int64_t* match_offsets /*n_pairs+1*/);
 
+/* sfmgms_match_image_set: sfmgms_set_images(SFMGMS_HOST) + sfmgms_match_pairs(SFMGMS_HOST outputs) in ONE
+ * synchronous call that pipelines internally: the image set goes to the device in chunks on a copy stream while
+ * earlier pairs already compute, and finished pairs' results return on a third stream.  Pairs are processed in
+ * list order; a pair starts as soon as both of its images have arrived, so order the list by image index for the
+ * best overlap (consecutive / sliding-window pairs do this naturally).  All pointers are HOST pointers (pinned
+ * memory gives true overlap; pageable memory still works).  Outputs as for sfmgms_match_pairs.  On return the
+ * image set stays registered (as after sfmgms_set_images). */
+int sfmgms_match_image_set(sfmgms_ctx* ctx, int n_images, const int64_t* kp_offsets, const uint8_t* desc,
+                           const float* kp_xy, const int32_t* sizes_wh, const int32_t* pairs, int n_pairs,
+                           int with_rotation, int with_scale, double threshold_factor, int32_t* n_inliers,
+                           int32_t* best_hyp, int32_t* mask_len, int32_t* train_idx, int32_t* dist, uint8_t* mask);
+
 /* ----  inlier coordinate compaction: replaces the gather loop SfMUtil.cpp:25-35 ------
  * After sfmgms_match_pairs, emit for pair `pair_index` of the LAST batch the inlier coordinates
  * pts1[k] = kp1[queryIdx].pt, pts2[k] = kp2[trainIdx].pt in match order (k < n_inliers), ready for

@@ -35,7 +35,8 @@ class SfmGmsError(RuntimeError):
 
 
 _LIB = None
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsfmgms.so")
+# SFMGMS_LIB: developer override to load an experimental build of the same library (kernel tuning only)
+_LIB_PATH = os.environ.get("SFMGMS_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsfmgms.so")
 
 
 def load_library():
@@ -74,6 +75,8 @@ def load_library():
     L.sfmgms_match_offsets.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
     L.sfmgms_match_pairs.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p]
+    L.sfmgms_match_image_set.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                         c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.sfmgms_inlier_points.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, P(c_int)]
     _LIB = L
     return L
@@ -295,6 +298,45 @@ class Context:
                                                 ctypes.c_void_p(int(kp_ptr)), _ptr(s), int(location)))
         self._offsets = off
         self._keep = keepalive
+
+    def match_image_set(self, kp_offsets, desc, kp_xy, sizes_wh, pairs, with_rotation=False, with_scale=False,
+                        threshold_factor=6.0):
+        """set_images + match_pairs in one internally pipelined call (H2D / compute / D2H overlap)."""
+        off = np.ascontiguousarray(kp_offsets, dtype=np.int64)
+        d = self._desc(desc)
+        k = np.ascontiguousarray(kp_xy, dtype=np.float32).reshape(-1, 2)
+        s = np.ascontiguousarray(sizes_wh, dtype=np.int32).reshape(-1, 2)
+        pr = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        n = pr.shape[0]
+        if s.shape[0] != off.shape[0] - 1 or d.shape[0] != off[-1] or k.shape[0] != off[-1]:
+            raise SfmGmsError(1, "image-set array shapes are inconsistent")
+        if n and (pr.min() < 0 or pr.max() >= s.shape[0]):
+            raise SfmGmsError(1, "a pair references an image outside the set")
+        mo = np.zeros(n + 1, np.int64)
+        np.cumsum((off[1:] - off[:-1])[pr[:, 0]], out=mo[1:])
+        total = int(mo[-1])
+        out = dict(n_inliers=np.zeros(n, np.int32), best_hyp=np.zeros(n, np.int32), mask_len=np.zeros(n, np.int32),
+                   offsets=mo, train_idx=np.empty(total, np.int32), dist=np.empty(total, np.int32),
+                   mask=np.zeros(total, np.uint8))
+        self._check(self._lib.sfmgms_match_image_set(self._h, s.shape[0], _ptr(off), _ptr(d), _ptr(k), _ptr(s), _ptr(pr), n,
+                                                     int(bool(with_rotation)), int(bool(with_scale)),
+                                                     float(threshold_factor), _ptr(out["n_inliers"]),
+                                                     _ptr(out["best_hyp"]), _ptr(out["mask_len"]), _ptr(out["train_idx"]),
+                                                     _ptr(out["dist"]), _ptr(out["mask"])))
+        self._offsets = off
+        return out
+
+    def match_image_set_raw(self, kp_offsets, desc_ptr, kp_ptr, sizes_wh, pairs_np, with_rotation, with_scale,
+                            threshold_factor, n_inliers=0, best_hyp=0, mask_len=0, train_idx=0, dist=0, mask=0):
+        """Raw-pointer form (host addresses; 0 = NULL) for callers with their own pinned buffers (bench.py)."""
+        p = lambda v: ctypes.c_void_p(int(v)) if v else None  # noqa: E731
+        off = np.ascontiguousarray(kp_offsets, dtype=np.int64)
+        s = np.ascontiguousarray(sizes_wh, dtype=np.int32).reshape(-1, 2)
+        self._check(self._lib.sfmgms_match_image_set(self._h, off.shape[0] - 1, _ptr(off), p(desc_ptr), p(kp_ptr), _ptr(s),
+                                                     _ptr(pairs_np), pairs_np.shape[0], int(with_rotation),
+                                                     int(with_scale), float(threshold_factor), p(n_inliers), p(best_hyp),
+                                                     p(mask_len), p(train_idx), p(dist), p(mask)))
+        self._offsets = off
 
     def inlier_points(self, pair_index, capacity):
         p1 = np.empty((max(capacity, 1), 2), np.float32)

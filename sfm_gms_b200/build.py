@@ -29,18 +29,30 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: build an experimental variant (e.g. defines=["-DSFMGMS_TC_MSUB=3"], out="libsfmgms_msub3.so")."""
+    global LIB
+    if out:
+        LIB_SAVE = LIB
+        try:
+            LIB = os.path.join(HERE, out)
+            return _build(True, verbose, list(defines), os.path.join(HERE, "build_" + out.replace(".so", "")))
+        finally:
+            LIB = LIB_SAVE
     if not force and not _stale():
         return LIB
+    return _build(force, verbose, [], os.path.join(HERE, "build"))
+
+
+def _build(force, verbose, defines, bdir):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
-    bdir = os.path.join(HERE, "build")
     os.makedirs(bdir, exist_ok=True)
     procs = []
     for s in SOURCES:
         o = os.path.join(bdir, s.replace(".cu", ".o"))
         objs.append(o)
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + defines + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for s, p in procs:
@@ -59,4 +71,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

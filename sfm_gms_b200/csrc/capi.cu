@@ -5,6 +5,8 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <ctime>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -61,6 +63,9 @@ struct sfmgms_ctx {
     int hamming_kernel = SFMGMS_HAMMING_AUTO;
     size_t gms_chunk_bytes = 64ull << 20;
     int timing = 0;
+    bool timing_mid_pending = false;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // pipelined host<->device copies (match_image_set)
+    std::vector<cudaEvent_t> events;                           // pool of timing-disabled events
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     double last_ms[3] = {0, 0, 0};
 
@@ -167,70 +172,99 @@ int choose_hamming(const sfmgms_ctx* c) {
     return c->hamming_kernel;
 }
 
-// Uploads the pair table, runs Hamming (optional) + GMS (optional), downloads the per-pair results.
-// hp[].key / hp[].mask must already point into device memory; keys must be initialised to kKeyInit.
-int run_batch(sfmgms_ctx* ctx, std::vector<PairDesc>& hp, bool do_hamming, bool do_gms, int with_rotation,
-              int with_scale, double factor) {
-    const int n = (int)hp.size();
-    ctx->last_results.assign(n, PairResult{0, -1, 0, 0});
+// Copies the pair table of a whole batch to the device (async on the context stream).
+int upload_pairs(sfmgms_ctx* ctx, const std::vector<PairDesc>& hp) {
+    const size_t n = hp.size();
     if (n == 0) return SFMGMS_OK;
-    cudaStream_t st = ctx->stream;
     CU(ctx->d_pairs.ensure(sizeof(PairDesc) * n));
     CU(ctx->h_pairs_pinned.ensure(sizeof(PairDesc) * n));
+    CU(ctx->d_results.ensure(sizeof(PairResult) * n));
     memcpy(ctx->h_pairs_pinned.p, hp.data(), sizeof(PairDesc) * n);
-    CU(cudaMemcpyAsync(ctx->d_pairs.p, ctx->h_pairs_pinned.p, sizeof(PairDesc) * n, cudaMemcpyHostToDevice, st));
-    const PairDesc* dp = static_cast<const PairDesc*>(ctx->d_pairs.p);
-    int ham_launches = 0;
-    if (hp[0].img1 < 0) tc_invalidate(ctx->tc);   // ad-hoc buffers: contents change between calls
-    if (ctx->timing) CU(cudaEventRecord(ctx->ev[0], st));
+    CU(cudaMemcpyAsync(ctx->d_pairs.p, ctx->h_pairs_pinned.p, sizeof(PairDesc) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_results.p, 0, sizeof(PairResult) * n, ctx->stream));
+    return SFMGMS_OK;
+}
+
+// Enqueues Hamming (optional) + GMS (optional) for pairs [r0, r0+rn) of an uploaded batch.  Asynchronous: nothing
+// here waits for the device.  Scratch reuse across ranges is ordered by the stream.
+int enqueue_range(sfmgms_ctx* ctx, const std::vector<PairDesc>& hp, int r0, int rn, bool do_hamming, bool do_gms,
+                  int with_rotation, int with_scale, double factor, int* ham_launches) {
+    if (rn <= 0) return SFMGMS_OK;
+    cudaStream_t st = ctx->stream;
+    const PairDesc* dp = static_cast<const PairDesc*>(ctx->d_pairs.p) + r0;
+    const PairDesc* hpp = hp.data() + r0;
+    if (hpp[0].img1 < 0) tc_invalidate(ctx->tc);   // ad-hoc buffers: contents change between calls
     if (do_hamming) {
         const int kind = choose_hamming(ctx);
-        for (int c0 = 0; c0 < n; c0 += 32768) {
-            const int cn = (n - c0 < 32768) ? n - c0 : 32768;
+        for (int c0 = 0; c0 < rn; c0 += 32768) {
+            const int cn = (rn - c0 < 32768) ? rn - c0 : 32768;
             int l;
             if (kind == SFMGMS_HAMMING_TC) {
-                l = launch_hamming_tc(ctx->tc, dp + c0, hp.data() + c0, cn, ctx->sm_count, st);
+                l = launch_hamming_tc(ctx->tc, dp + c0, hpp + c0, cn, ctx->sm_count, st);
                 if (l < 0) return fail(ctx, SFMGMS_ERR_CUDA, "tensor-core Hamming launch failed: %s", tc_last_error());
             } else {
-                l = launch_hamming_popc(dp + c0, hp.data() + c0, cn, ctx->sm_count, st);
+                l = launch_hamming_popc(dp + c0, hpp + c0, cn, ctx->sm_count, st);
             }
             ctx->launches += l;
-            ham_launches += l;
+            if (ham_launches) *ham_launches += l;
         }
         CU(cudaGetLastError());
     }
-    if (ctx->timing) CU(cudaEventRecord(ctx->ev[1], st));
+    if (ctx->timing && ctx->timing_mid_pending) { CU(cudaEventRecord(ctx->ev[1], st)); ctx->timing_mid_pending = false; }
     if (do_gms) {
-        CU(ctx->d_results.ensure(sizeof(PairResult) * n));
-        CU(cudaMemsetAsync(ctx->d_results.p, 0, sizeof(PairResult) * n, st));
         const int n_scales = with_scale ? kNumScales : 1;
         const size_t per_pair = gms_scratch_bytes_per_pair(n_scales);
         size_t budget = ctx->gms_chunk_bytes;
         if (budget < per_pair) budget = per_pair;
-        if (budget > per_pair * (size_t)n) budget = per_pair * (size_t)n;
+        if (budget > per_pair * (size_t)rn) budget = per_pair * (size_t)rn;
         CU(ctx->d_hist.ensure(budget));
-        long long total_m = 0;
-        for (auto& p : hp) total_m += p.n_matches;
-        CU(ctx->d_msc.ensure(gms_match_scratch_bytes(total_m, n_scales)));
-        int l = launch_gms(dp, hp.data(), n, with_rotation, with_scale, factor,
-                           static_cast<PairResult*>(ctx->d_results.p), ctx->d_hist.p, budget, ctx->d_msc.p, st);
+        CU(ctx->d_msc.ensure(gms_match_scratch_bytes(gms_match_rows(hpp, rn), n_scales)));
+        int l = launch_gms(dp, hpp, rn, with_rotation, with_scale, factor,
+                           static_cast<PairResult*>(ctx->d_results.p) + r0, ctx->d_hist.p, budget, ctx->d_msc.p, st);
         if (l < 0) return fail(ctx, SFMGMS_ERR_CUDA, "GMS scratch too small");
         ctx->launches += l;
         CU(cudaGetLastError());
+    }
+    return SFMGMS_OK;
+}
+
+// Waits for the batch, downloads the per-pair results and turns device-side status flags into error codes.
+int finish_batch(sfmgms_ctx* ctx, int n, bool do_gms) {
+    cudaStream_t st = ctx->stream;
+    ctx->last_results.assign(n, PairResult{0, -1, 0, 0});
+    if (do_gms && n > 0) {
         CU(ctx->h_results.ensure(sizeof(PairResult) * n));
         CU(cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, sizeof(PairResult) * n, cudaMemcpyDeviceToHost, st));
-        if (ctx->timing) CU(cudaEventRecord(ctx->ev[2], st));
-        CU(cudaStreamSynchronize(st));
+    }
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[2], st));
+    CU(cudaStreamSynchronize(st));
+    tc_reset_arena(ctx->tc);
+    if (do_gms && n > 0) {
         memcpy(ctx->last_results.data(), ctx->h_results.p, sizeof(PairResult) * n);
         for (int p = 0; p < n; ++p) {
             const int s = ctx->last_results[p].status;
             if (s == 4) return fail(ctx, SFMGMS_ERR_INDEX, "pair %d: queryIdx/trainIdx out of range", p);
             if (s == 3) return fail(ctx, SFMGMS_ERR_DOMAIN, "pair %d: matched keypoint outside [0,w)x[0,h)", p);
         }
-    } else if (ctx->timing) {
-        CU(cudaEventRecord(ctx->ev[2], st));
-        CU(cudaStreamSynchronize(st));
     }
+    return SFMGMS_OK;
+}
+
+// One synchronous batch: upload table, Hamming + GMS over all pairs, results back.
+// hp[].key / hp[].mask must already point into device memory; keys must be initialised to kKeyInit.
+int run_batch(sfmgms_ctx* ctx, std::vector<PairDesc>& hp, bool do_hamming, bool do_gms, int with_rotation,
+              int with_scale, double factor) {
+    const int n = (int)hp.size();
+    ctx->last_results.assign(n, PairResult{0, -1, 0, 0});
+    if (n == 0) return SFMGMS_OK;
+    int rc = upload_pairs(ctx, hp);
+    if (rc) return rc;
+    int ham_launches = 0;
+    if (ctx->timing) { CU(cudaEventRecord(ctx->ev[0], ctx->stream)); ctx->timing_mid_pending = true; }
+    rc = enqueue_range(ctx, hp, 0, n, do_hamming, do_gms, with_rotation, with_scale, factor, &ham_launches);
+    if (rc) { cudaStreamSynchronize(ctx->stream); tc_reset_arena(ctx->tc); return rc; }
+    rc = finish_batch(ctx, n, do_gms);
+    if (rc) return rc;
     if (ctx->timing) {
         float a = 0.f, b = 0.f;
         CU(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
@@ -330,6 +364,9 @@ void sfmgms_destroy(sfmgms_ctx* ctx) {
     tc_release(ctx->tc);
     ctx->h_stage.release(); ctx->h_pairs_pinned.release(); ctx->h_results.release();
     for (int k = 0; k < 3; ++k) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -601,15 +638,9 @@ int sfmgms_match_offsets(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int
     GUARD_END
 }
 
-int sfmgms_match_pairs(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int with_rotation, int with_scale,
-                       double threshold_factor, int out_location, int32_t* n_inliers, int32_t* best_hyp,
-                       int32_t* mask_len, int32_t* train_idx, int32_t* dist, uint8_t* mask) {
-    GUARD_BEGIN
-    if (n_pairs < 0 || (n_pairs > 0 && !pairs)) return fail(ctx, SFMGMS_ERR_ARG, "bad pair list");
-    if (out_location != SFMGMS_HOST && out_location != SFMGMS_DEVICE) return fail(ctx, SFMGMS_ERR_ARG, "bad out_location");
-    if (n_pairs > 0 && ctx->n_images == 0) return fail(ctx, SFMGMS_ERR_STATE, "sfmgms_set_images has not been called");
-    cudaStream_t st = ctx->stream;
-    std::vector<PairDesc> hp((size_t)n_pairs);
+// Builds the PairDesc table of a pair list over the registered image set (device pointers, match offsets).
+static int build_pair_table(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, std::vector<PairDesc>& hp, int64_t* total_out) {
+    hp.assign((size_t)n_pairs, PairDesc());
     int64_t total = 0;
     for (int p = 0; p < n_pairs; ++p) {
         const int a = pairs[2 * p], b = pairs[2 * p + 1];
@@ -624,8 +655,25 @@ int sfmgms_match_pairs(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int w
         d.w1 = ctx->sizes[2 * a]; d.h1 = ctx->sizes[2 * a + 1]; d.w2 = ctx->sizes[2 * b]; d.h2 = ctx->sizes[2 * b + 1];
         d.n_matches = d.n2 == 0 ? 0 : d.n1;
         d.match_base = total;
+        d.pair_index = p; d.img1 = a; d.img2 = b;
         total += d.n1;
     }
+    *total_out = total;
+    return SFMGMS_OK;
+}
+
+int sfmgms_match_pairs(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int with_rotation, int with_scale,
+                       double threshold_factor, int out_location, int32_t* n_inliers, int32_t* best_hyp,
+                       int32_t* mask_len, int32_t* train_idx, int32_t* dist, uint8_t* mask) {
+    GUARD_BEGIN
+    if (n_pairs < 0 || (n_pairs > 0 && !pairs)) return fail(ctx, SFMGMS_ERR_ARG, "bad pair list");
+    if (out_location != SFMGMS_HOST && out_location != SFMGMS_DEVICE) return fail(ctx, SFMGMS_ERR_ARG, "bad out_location");
+    if (n_pairs > 0 && ctx->n_images == 0) return fail(ctx, SFMGMS_ERR_STATE, "sfmgms_set_images has not been called");
+    cudaStream_t st = ctx->stream;
+    std::vector<PairDesc> hp;
+    int64_t total = 0;
+    int rc = build_pair_table(ctx, pairs, n_pairs, hp, &total);
+    if (rc) return rc;
     CU(ctx->d_key.ensure((size_t)total * 4 + 4));
     const bool dev_out = (out_location == SFMGMS_DEVICE);
     uint8_t* dmask = (dev_out && mask) ? mask : nullptr;
@@ -638,8 +686,7 @@ int sfmgms_match_pairs(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int w
         CU(cudaMemsetAsync(ctx->d_key.p, 0xFF, (size_t)total * 4, st));
         CU(cudaMemsetAsync(dmask, 0, (size_t)total, st));
     }
-    for (int p = 0; p < n_pairs; ++p) hp[p].pair_index = p, hp[p].img1 = pairs[2 * p], hp[p].img2 = pairs[2 * p + 1];
-    int rc = run_batch(ctx, hp, true, true, with_rotation, with_scale, threshold_factor);
+    rc = run_batch(ctx, hp, true, true, with_rotation, with_scale, threshold_factor);
     ctx->last_pairs = hp;
     if (rc) return rc;
     // per-pair results
@@ -676,6 +723,189 @@ int sfmgms_match_pairs(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int w
     }
     if (total && mask && !dev_out) CU(cudaMemcpyAsync(mask, dmask, (size_t)total, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return SFMGMS_OK;
+    GUARD_END
+}
+
+static int get_event(sfmgms_ctx* ctx, size_t k, cudaEvent_t* out) {
+    while (ctx->events.size() <= k) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->events.push_back(e);
+    }
+    *out = ctx->events[k];
+    return SFMGMS_OK;
+}
+
+int sfmgms_match_image_set(sfmgms_ctx* ctx, int n_images, const int64_t* kp_offsets, const uint8_t* desc,
+                           const float* kp_xy, const int32_t* sizes_wh, const int32_t* pairs, int n_pairs,
+                           int with_rotation, int with_scale, double threshold_factor, int32_t* n_inliers,
+                           int32_t* best_hyp, int32_t* mask_len, int32_t* train_idx, int32_t* dist, uint8_t* mask) {
+    GUARD_BEGIN
+    if (n_images < 0 || !kp_offsets || !sizes_wh) return fail(ctx, SFMGMS_ERR_ARG, "bad image-set arguments");
+    if (n_pairs < 0 || (n_pairs > 0 && !pairs)) return fail(ctx, SFMGMS_ERR_ARG, "bad pair list");
+    if (kp_offsets[0] != 0) return fail(ctx, SFMGMS_ERR_ARG, "kp_offsets[0] must be 0");
+    for (int i = 0; i < n_images; ++i) {
+        const int64_t n = kp_offsets[i + 1] - kp_offsets[i];
+        if (n < 0) return fail(ctx, SFMGMS_ERR_ARG, "kp_offsets not monotone at image %d", i);
+        if (n >= SFMGMS_MAX_TRAIN_ROWS) return fail(ctx, SFMGMS_ERR_TRAIN_ROWS, "image %d has %lld rows >= 2^18", i, (long long)n);
+        if (sizes_wh[2 * i] <= 0 || sizes_wh[2 * i + 1] <= 0) return fail(ctx, SFMGMS_ERR_ARG, "image %d has a non-positive size", i);
+    }
+    const int64_t total_rows = kp_offsets[n_images];
+    if (total_rows > 0 && (!desc || !kp_xy)) return fail(ctx, SFMGMS_ERR_ARG, "null descriptor/keypoint pointer");
+    cudaStream_t st = ctx->stream;
+    if (!ctx->h2d_stream) CU(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    if (!ctx->d2h_stream) CU(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    CU(cudaStreamSynchronize(st));   // nothing of an earlier call may still read the buffers re-used below
+    CU(ctx->d_set_desc.ensure((size_t)total_rows * 32 + 32));
+    CU(ctx->d_set_kp.ensure((size_t)total_rows * 8 + 8));
+    ctx->set_desc = (const uint8_t*)ctx->d_set_desc.p; ctx->set_kp = (const float*)ctx->d_set_kp.p;
+    ctx->n_images = n_images;
+    ctx->offsets.assign(kp_offsets, kp_offsets + n_images + 1);
+    ctx->sizes.assign(sizes_wh, sizes_wh + 2 * (size_t)n_images);
+    ctx->set_version++;
+    tc_invalidate(ctx->tc);
+
+    static const bool trace = getenv("SFMGMS_TRACE") != nullptr;   // developer aid: print the stream timeline
+    auto now_ms = []() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t_enter = now_ms();
+    double t_h2d0 = 0, t_enq = 0, t_fin = 0;
+    std::vector<cudaEvent_t> tr_h2d, tr_cmp;
+    std::vector<std::pair<cudaEvent_t, const char*>> tr_marks;
+    auto mark = [&](const char* label) { if (trace) { cudaEvent_t t; cudaEventCreate(&t); cudaEventRecord(t, st); tr_marks.push_back({t, label}); } };
+    cudaEvent_t tr0 = nullptr;
+    if (trace) { cudaEventCreate(&tr0); cudaEventRecord(tr0, ctx->h2d_stream); t_h2d0 = now_ms(); }
+    // ---- image chunks (H2D on the copy stream, one event per chunk).  Chunks are ENQUEUED lazily, a little
+    // ahead of the pairs that need them: the copy engine serves H2D requests of all streams in FIFO order, so the
+    // small table uploads of a sub-batch (pair table, work units) must not queue behind the whole image set. ----
+    const size_t kChunkBytes = 12u << 20;
+    const int kLookahead = 2;
+    std::vector<int> chunk_of_image((size_t)n_images, 0);
+    std::vector<int> chunk_first;   // first image of each chunk; chunk c = images [chunk_first[c], chunk_first[c+1])
+    {
+        int i0 = 0;
+        while (i0 < n_images) {
+            int i1 = i0;
+            size_t bytes = 0;
+            while (i1 < n_images && (bytes == 0 || bytes + (size_t)(kp_offsets[i1 + 1] - kp_offsets[i1]) * 40 <= kChunkBytes)) {
+                bytes += (size_t)(kp_offsets[i1 + 1] - kp_offsets[i1]) * 40;
+                chunk_of_image[i1] = (int)chunk_first.size();
+                ++i1;
+            }
+            chunk_first.push_back(i0);
+            i0 = i1;
+        }
+        chunk_first.push_back(n_images);
+    }
+    const int n_chunks = (int)chunk_first.size() - 1;
+    for (int c = 0; c < n_chunks; ++c) { cudaEvent_t e; int rc0 = get_event(ctx, (size_t)c, &e); if (rc0) return rc0; }
+    int next_chunk = 0;
+    auto issue_chunks_upto = [&](int c_last) -> int {
+        for (; next_chunk <= c_last && next_chunk < n_chunks; ++next_chunk) {
+            const int64_t r0 = kp_offsets[chunk_first[next_chunk]], r1 = kp_offsets[chunk_first[next_chunk + 1]];
+            if (r1 > r0) {
+                CU(cudaMemcpyAsync((uint8_t*)ctx->d_set_desc.p + r0 * 32, desc + r0 * 32, (size_t)(r1 - r0) * 32, cudaMemcpyHostToDevice, ctx->h2d_stream));
+                CU(cudaMemcpyAsync((float*)ctx->d_set_kp.p + r0 * 2, kp_xy + r0 * 2, (size_t)(r1 - r0) * 8, cudaMemcpyHostToDevice, ctx->h2d_stream));
+            }
+            CU(cudaEventRecord(ctx->events[(size_t)next_chunk], ctx->h2d_stream));
+            if (trace) { cudaEvent_t t; cudaEventCreate(&t); cudaEventRecord(t, ctx->h2d_stream); tr_h2d.push_back(t); }
+        }
+        return SFMGMS_OK;
+    };
+    // ---- pair table ----
+    std::vector<PairDesc> hp;
+    int64_t total = 0;
+    int rc = build_pair_table(ctx, pairs, n_pairs, hp, &total);
+    if (rc) { cudaStreamSynchronize(ctx->h2d_stream); return rc; }
+    CU(ctx->d_key.ensure((size_t)total * 4 + 4));
+    CU(ctx->d_mask.ensure((size_t)total + 1));
+    CU(ctx->d_out_i32.ensure((size_t)total * 8 + 8));
+    uint8_t* dmask = (uint8_t*)ctx->d_mask.p;
+    int32_t* dti = (int32_t*)ctx->d_out_i32.p;
+    int32_t* ddi = dti + total;
+    for (int p = 0; p < n_pairs; ++p) {
+        hp[p].key = (uint32_t*)ctx->d_key.p + hp[p].match_base;
+        hp[p].mask = dmask + hp[p].match_base;
+    }
+    if (total) {
+        CU(cudaMemsetAsync(ctx->d_key.p, 0xFF, (size_t)total * 4, st));
+        CU(cudaMemsetAsync(dmask, 0, (size_t)total, st));
+    }
+    mark("memsets-queued");
+    rc = upload_pairs(ctx, hp);
+    if (rc) { cudaStreamSynchronize(ctx->h2d_stream); return rc; }
+    mark("pairs-uploaded");
+    if (ctx->timing) { CU(cudaEventRecord(ctx->ev[0], st)); CU(cudaEventRecord(ctx->ev[1], st)); ctx->timing_mid_pending = false; }
+    // ---- sub-batches in list order: wait for the chunk(s) they need, compute, hand results to the D2H stream ----
+    int n_ranges = n_pairs >= 64 ? 8 : (n_pairs >= 8 ? 4 : 1);
+    const int per = (n_pairs + n_ranges - 1) / (n_ranges > 0 ? n_ranges : 1);
+    int ham_launches = 0;
+    size_t ev_k = (size_t)n_chunks;
+    for (int r0 = 0; r0 < n_pairs; r0 += per) {
+        const int rn = (n_pairs - r0 < per) ? n_pairs - r0 : per;
+        int need = 0;
+        for (int p = r0; p < r0 + rn; ++p) {
+            const int c = chunk_of_image[hp[p].img1] > chunk_of_image[hp[p].img2] ? chunk_of_image[hp[p].img1] : chunk_of_image[hp[p].img2];
+            if (c > need) need = c;
+        }
+        if (trace) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); fprintf(stderr, "[sfmgms trace] host t=%.3f ms: range at pair %d needs chunk %d\n", ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6, r0, need); }
+        if ((rc = issue_chunks_upto(need + kLookahead))) return rc;
+        mark("before-wait");
+        CU(cudaStreamWaitEvent(st, ctx->events[(size_t)need], 0));
+        mark("after-wait");
+        rc = enqueue_range(ctx, hp, r0, rn, true, true, with_rotation, with_scale, threshold_factor, &ham_launches);
+        if (rc) { cudaStreamSynchronize(ctx->h2d_stream); cudaStreamSynchronize(st); tc_reset_arena(ctx->tc); return rc; }
+        const int64_t m0 = hp[r0].match_base;
+        const int64_t m1 = (r0 + rn < n_pairs) ? hp[r0 + rn].match_base : total;
+        if (m1 > m0) {
+            if (train_idx || dist) {
+                decode_keys_kernel<<<(unsigned)(((m1 - m0) + 255) / 256 > 4096 ? 4096 : ((m1 - m0) + 255) / 256), 256, 0, st>>>(
+                    (const uint32_t*)ctx->d_key.p + m0, m1 - m0, train_idx ? dti + m0 : nullptr, dist ? ddi + m0 : nullptr);
+                ctx->launches++;
+            }
+            cudaEvent_t e;
+            rc = get_event(ctx, ev_k++, &e);
+            if (rc) return rc;
+            CU(cudaEventRecord(e, st));
+            if (trace) { cudaEvent_t t; cudaEventCreate(&t); cudaEventRecord(t, st); tr_cmp.push_back(t); }
+            CU(cudaStreamWaitEvent(ctx->d2h_stream, e, 0));
+            if (train_idx) CU(cudaMemcpyAsync(train_idx + m0, dti + m0, (size_t)(m1 - m0) * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+            if (dist) CU(cudaMemcpyAsync(dist + m0, ddi + m0, (size_t)(m1 - m0) * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+            if (mask) CU(cudaMemcpyAsync(mask + m0, dmask + m0, (size_t)(m1 - m0), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        }
+    }
+    {
+        const int rc2 = issue_chunks_upto(n_chunks - 1);   // images no pair referenced still belong to the registered set
+        if (rc2) return rc2;
+    }
+    t_enq = now_ms();
+    rc = finish_batch(ctx, n_pairs, true);
+    t_fin = now_ms();
+    CU(cudaStreamSynchronize(ctx->h2d_stream));
+    CU(cudaStreamSynchronize(ctx->d2h_stream));
+    ctx->last_pairs = hp;
+    if (trace) {
+        cudaEvent_t tend; cudaEventCreate(&tend); cudaEventRecord(tend, ctx->d2h_stream); cudaEventSynchronize(tend);
+        float ms;
+        fprintf(stderr, "[sfmgms trace] h2d chunks done at ms:");
+        for (cudaEvent_t t : tr_h2d) { cudaEventElapsedTime(&ms, tr0, t); fprintf(stderr, " %.2f", ms); cudaEventDestroy(t); }
+        fprintf(stderr, "\n[sfmgms trace] marks:");
+        for (auto& m : tr_marks) { cudaEventElapsedTime(&ms, tr0, m.first); fprintf(stderr, " %s=%.2f", m.second, ms); cudaEventDestroy(m.first); }
+        fprintf(stderr, "\n[sfmgms trace] compute ranges done at ms:");
+        for (cudaEvent_t t : tr_cmp) { cudaEventElapsedTime(&ms, tr0, t); fprintf(stderr, " %.2f", ms); cudaEventDestroy(t); }
+        cudaEventElapsedTime(&ms, tr0, tend);
+        fprintf(stderr, "\n[sfmgms trace] d2h done at ms: %.2f\n", ms);
+        fprintf(stderr, "[sfmgms trace] host: enter->first h2d %.2f ms, ->all enqueued %.2f, ->finish_batch done %.2f, ->now %.2f\n",
+                t_h2d0 - t_enter, t_enq - t_enter, t_fin - t_enter, now_ms() - t_enter);
+        cudaEventDestroy(tend); cudaEventDestroy(tr0);
+    }
+    if (rc) return rc;
+    if (ctx->timing) { ctx->last_ms[0] = 0; ctx->last_ms[1] = 0; ctx->last_ms[2] = ham_launches; }
+    for (int p = 0; p < n_pairs; ++p) {
+        if (n_inliers) n_inliers[p] = ctx->last_results[p].n_inliers;
+        if (best_hyp) best_hyp[p] = ctx->last_results[p].best_hyp;
+        if (mask_len) mask_len[p] = ctx->last_results[p].mask_len;
+    }
     return SFMGMS_OK;
     GUARD_END
 }

@@ -58,6 +58,7 @@ struct GmsScratch {
     size_t bytes;
 };
 size_t gms_scratch_bytes_per_pair(int n_scales);
+long long gms_match_rows(const PairDesc* h_pairs, int n);   // rows of the per-match arrays spanned by n pairs
 size_t gms_match_scratch_bytes(long long n_matches_total, int n_scales);
 int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, int with_rotation, int with_scale,
                double factor, PairResult* d_results, void* d_hist_scratch, size_t hist_scratch_bytes,

@@ -271,6 +271,12 @@ __global__ void __launch_bounds__(256) gms_mask_kernel(const PairDesc* __restric
 
 }  // namespace
 
+long long gms_match_rows(const PairDesc* h_pairs, int n) {
+    if (n <= 0) return 0;
+    const PairDesc& last = h_pairs[n - 1];
+    const long long rows_last = last.mq ? last.n_matches : (last.n1 > last.n_matches ? last.n1 : last.n_matches);
+    return last.match_base + rows_last - h_pairs[0].match_base;
+}
 size_t gms_scratch_bytes_per_pair(int n_scales) { return make_layout(n_scales, kNumRot).total_words * 4; }
 size_t gms_match_scratch_bytes(long long n_matches_total, int n_scales) {
     return (size_t)n_matches_total * 2 * (4 + n_scales) + 256;
@@ -294,10 +300,12 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
     int32_t* scratch = static_cast<int32_t*>(d_hist_scratch);
     for (int c0 = 0; c0 < n_pairs; c0 += chunk_cap) {
         const int cn = (n_pairs - c0 < chunk_cap) ? n_pairs - c0 : chunk_cap;
-        long long cm = 0;
         int max_m = 0;
-        for (int p = c0; p < c0 + cn; ++p) { cm += h_pairs[p].n_matches; if (h_pairs[p].n_matches > max_m) max_m = h_pairs[p].n_matches; }
+        for (int p = c0; p < c0 + cn; ++p) if (h_pairs[p].n_matches > max_m) max_m = h_pairs[p].n_matches;
+        // rows of the per-match arrays spanned by this chunk: match_base advances by a pair's ROW count (n1 for
+        // fused pairs, even when an empty train image leaves it with 0 matches), not by n_matches
         const long long cbase = h_pairs[c0].match_base;
+        const long long cm = gms_match_rows(h_pairs + c0, cn);
         // per-match cell indices for this chunk: lidx[4][cm], ridx[n_scales][cm] (uint16)
         uint16_t* lidx = static_cast<uint16_t*>(d_match_scratch);
         uint16_t* ridx = lidx + (size_t)4 * cm;

@@ -11,6 +11,7 @@ struct TcState {
     size_t work_cap = 0;
     void* h_work = nullptr;     // pinned
     size_t h_work_cap = 0;
+    size_t work_used = 0;       // arena cursor (bytes) into h_work/d_work; reset by tc_reset_arena() after a sync
     bool set_valid = false;     // d_ops holds the unpacked form of [ops_src, ops_src + 32*ops_rows)
     bool cache_enabled = true;  // keep the unpacked operands across calls until tc_invalidate()
     const uint8_t* ops_src = nullptr;
@@ -21,6 +22,9 @@ bool tc_available();
 const char* tc_last_error();
 void tc_invalidate(TcState& s);
 void tc_release(TcState& s);
+// The work-unit tables of all launches since the last stream synchronisation live side by side in a pinned
+// arena (the CPU must not overwrite a table whose H2D copy is still queued).  Call after synchronising.
+void tc_reset_arena(TcState& s);
 // returns the number of kernel launches, or -1 on error
 int launch_hamming_tc(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, int sm_count,
                       cudaStream_t st);

@@ -266,8 +266,9 @@ def _ragged_set(rng, sizes_n):
     return off, np.concatenate(descs), np.concatenate(kps), np.array(wh, np.int32)
 
 
+@pytest.mark.parametrize("chunk_mb", [8, 64])
 @pytest.mark.parametrize("rot,sc", [(0, 0), (1, 1)])
-def test_match_pairs_ragged_vs_oracle(kctx, oracle_mod, rot, sc):
+def test_match_pairs_ragged_vs_oracle(kctx, oracle_mod, rot, sc, chunk_mb):
     from sfm_gms_b200 import api
 
     rng = np.random.default_rng(77)
@@ -275,7 +276,8 @@ def test_match_pairs_ragged_vs_oracle(kctx, oracle_mod, rot, sc):
     off, desc, kp, wh = _ragged_set(rng, sizes_n)
     kctx.set_images(off, desc, kp, wh)
     pairs = np.array([(0, 1), (1, 0), (0, 3), (4, 0), (2, 1), (1, 2), (5, 4), (3, 3), (4, 5)], np.int32)
-    kctx.set_option(api.OPT_GMS_CHUNK_BYTES, 8 << 20)  # force several GMS chunks
+    kctx.set_option(api.OPT_GMS_CHUNK_BYTES, chunk_mb << 20)  # 8 MB: several GMS chunks; 64 MB: one chunk that
+    # contains pairs with an empty train image (rows without matches) in its middle
     try:
         out = kctx.match_pairs(pairs, rot, sc)
     finally:
@@ -300,6 +302,24 @@ def test_match_pairs_ragged_vs_oracle(kctx, oracle_mod, rot, sc):
         keep = np.nonzero(o["mask"])[0] if len(o["mask"]) else np.zeros(0, int)
         assert n == len(keep)
         assert np.array_equal(p1, k1[keep]) and np.array_equal(p2, k2[oi[keep]])
+
+
+@pytest.mark.parametrize("rot,sc", [(0, 0), (1, 0)])
+def test_match_image_set_pipelined_equals_match_pairs(kctx, rot, sc):
+    """The internally pipelined one-call form (chunked H2D / compute / D2H overlap) must return exactly what
+    set_images + match_pairs returns, for in-order, out-of-order and repeated pairs over a ragged set."""
+    rng = np.random.default_rng(78)
+    sizes_n = [2100, 1900, 0, 1777, 2500, 1, 3000, 2048, 2047]
+    off, desc, kp, wh = _ragged_set(rng, sizes_n)
+    pairs = np.array([(0, 1), (1, 3), (3, 4), (4, 6), (6, 7), (7, 8), (8, 0), (2, 1), (1, 2), (5, 4), (0, 1), (7, 6),
+                      (6, 4), (3, 3), (4, 8), (8, 7), (0, 8), (1, 0)], np.int32)
+    kctx.set_images(off, desc, kp, wh)
+    a = kctx.match_pairs(pairs, rot, sc)
+    b = kctx.match_image_set(off, desc, kp, wh, pairs, rot, sc)
+    for k in ["n_inliers", "best_hyp", "mask_len", "offsets", "train_idx", "dist", "mask"]:
+        assert np.array_equal(a[k], b[k]), k
+    c = kctx.match_pairs(pairs, rot, sc)   # the set stays registered after the pipelined call
+    assert np.array_equal(a["mask"], c["mask"]) and np.array_equal(a["train_idx"], c["train_idx"])
 
 
 def test_match_pairs_properties_full_batch(kctx):
