@@ -226,27 +226,32 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     P = args.pairs
     total_pairs = P * world
-    n_rows = total_pairs * 2 * N_KP
 
-    # ---- the shared descriptor/keypoint set: generated on rank 0, ONE NCCL broadcast ------------------
-    if rank == 0:
-        desc_all, kp_all = gen_pairs_torch(total_pairs, 2, dev)
-    else:
-        desc_all = torch.empty((n_rows, 32), dtype=torch.uint8, device=dev)
-        kp_all = torch.empty((n_rows, 2), dtype=torch.float32, device=dev)
+    # ---- the shared descriptor/keypoint set: generated on rank 0, ONE NCCL broadcast per array --------
+    from sfm_gms_b200 import dist as sd
+
     bcast_ms = 0.0
     if world > 1:
+        iset = None
+        if rank == 0:
+            d0, k0 = gen_pairs_torch(total_pairs, 2, dev)
+            iset = dict(offsets=np.arange(2 * total_pairs + 1, dtype=np.int64) * N_KP,
+                        sizes=np.tile(np.array([[W_IMG, H_IMG]], np.int32), (2 * total_pairs, 1)), desc=d0, kp=k0)
         torch.cuda.synchronize()
+        dist.barrier()
         t0 = time.perf_counter()
-        dist.broadcast(desc_all, 0)
-        dist.broadcast(kp_all, 0)
+        got = sd.broadcast_image_set(iset, 0, dev)
         torch.cuda.synchronize()
         bcast_ms = 1e3 * (time.perf_counter() - t0)
+        desc_all, kp_all = got["desc"], got["kp"]
+    else:
+        desc_all, kp_all = gen_pairs_torch(total_pairs, 2, dev)
     offsets = np.arange(2 * total_pairs + 1, dtype=np.int64) * N_KP
     sizes = np.tile(np.array([[W_IMG, H_IMG]], np.int32), (2 * total_pairs, 1))
-    # shard: rank r owns pairs [r*P, (r+1)*P) of the global list (pair p = images 2p, 2p+1)
-    my_pairs = (np.arange(rank * P, (rank + 1) * P, dtype=np.int32)[:, None] * 2 + np.array([[0, 1]], np.int32))
-    my_pairs = np.ascontiguousarray(my_pairs.astype(np.int32))
+    # shard: rank r owns the contiguous block [r*P, (r+1)*P) of the global pair list (pair p = images 2p, 2p+1)
+    all_pairs = np.arange(2 * total_pairs, dtype=np.int32).reshape(-1, 2)
+    my_idx, my_pairs = sd.shard_pairs(all_pairs, rank, world, "contiguous")
+    assert len(my_idx) == P and my_idx[0] == rank * P
 
     ctx = sg.Context(local_rank)
     if args.kernel != "auto":

@@ -1,0 +1,226 @@
+// sfmgms.hpp — header-only C++ mirror of the reference's matching interface over the C ABI (include/sfmgms.h).
+//
+// The reference calls, back to back (SfM-GMS/SfM-GMS/FeatureMatchUtil.cpp:66-69):
+//     Ptr<BFMatcher> matcherBF = BFMatcher::create();  matcherBF->match(desc1, desc2, matches);
+//     cv::xfeatures2d::matchGMS(img1.size(), img2.size(), kpts1, kpts2, matches, matchesGMS, true, true);
+// This header offers the same names, argument order and error behaviour on layout-compatible PODs
+// (OpenCV's C++ headers are not needed):
+//     sfmgms::cv::BFMatcher(sfmgms::cv::NORM_HAMMING[, crossCheck]).match(desc1, n1, desc2, n2, matches)
+//     sfmgms::cv::xfeatures2d::matchGMS(size1, size2, kp1, kp2, matches1to2, matchesGMS,
+//                                       withRotation=false, withScale=false, thresholdFactor=6.0)
+//     sfmgms::gms_matcher(vkp1, size1, vkp2, size2, vDMatches).GetInlierMask(vbInliers, WithScale, WithRotation)
+// and, with -DSFMGMS_WITH_OPENCV (OpenCV headers present), overloads on the real cv:: types so that
+// FeatureMatchUtil.cpp only has to switch the two call lines.
+//
+// NOTE the two upstream conventions: matchGMS(..., withRotation, withScale, ...) versus
+// GetInlierMask(mask, WithScale, WithRotation).  Both are reproduced as they are; nothing is transposed.
+// Errors: where OpenCV throws cv::Exception (CV_Assert) this throws sfmgms::Error (std::runtime_error).
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/sfmgms.h"
+
+namespace sfmgms {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error("sfmgms error " + std::to_string(c) + ": " + m), code(c) {}
+};
+
+// One context per host thread / per GPU (SURVEY §8b threading).
+class Context {
+   public:
+    explicit Context(int device = 0) {
+        if (int rc = sfmgms_create(&ctx_, device)) throw Error(rc, sfmgms_last_error(nullptr));
+    }
+    ~Context() { sfmgms_destroy(ctx_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    sfmgms_ctx* get() const { return ctx_; }
+    void check(int rc) const {
+        if (rc) throw Error(rc, sfmgms_last_error(ctx_));
+    }
+    static Context& thread_default() {
+        static thread_local Context c(0);
+        return c;
+    }
+
+   private:
+    sfmgms_ctx* ctx_ = nullptr;
+};
+
+namespace cv {
+
+enum { NORM_HAMMING = 6 };
+
+// Layout-compatible with cv::Point2f / cv::Size / cv::KeyPoint (28 B) / cv::DMatch (16 B); strides verified
+// against the reference binary (0x1c and 0x10).
+struct Point2f { float x, y; };
+struct Size {
+    int width, height;
+    Size(int w = 0, int h = 0) : width(w), height(h) {}
+};
+struct KeyPoint {
+    Point2f pt;
+    float size, angle, response;
+    int octave, class_id;
+};
+struct DMatch {
+    int queryIdx, trainIdx, imgIdx;
+    float distance;
+    bool operator<(const DMatch& m) const { return distance < m.distance; }
+};
+static_assert(sizeof(KeyPoint) == 28, "cv::KeyPoint layout");
+static_assert(sizeof(DMatch) == 16, "cv::DMatch layout");
+
+// cv::BFMatcher(NORM_HAMMING[, crossCheck]) — descriptors are CV_8U rows of 32 bytes.
+class BFMatcher {
+   public:
+    explicit BFMatcher(int normType = NORM_HAMMING, bool crossCheck = false, Context* ctx = nullptr)
+        : cross_(crossCheck), ctx_(ctx) {
+        if (normType != NORM_HAMMING) throw Error(SFMGMS_ERR_ARG, "only NORM_HAMMING is implemented");
+    }
+    // matches.clear(); then one DMatch per query row in query order (cross-check: only the mutual ones)
+    void match(const uint8_t* query, int nq, const uint8_t* train, int nt, std::vector<DMatch>& matches,
+               int desc_bytes = 32) const {
+        Context& c = ctx_ ? *ctx_ : Context::thread_default();
+        matches.clear();
+        std::vector<int32_t> idx((size_t)(nq > 0 ? nq : 0)), dist(idx.size());
+        if (cross_) {
+            std::vector<uint8_t> keep(idx.size());
+            c.check(sfmgms_bf_hamming_crosscheck(c.get(), query, nq, train, nt, desc_bytes, idx.data(), dist.data(), keep.data()));
+            if (nt == 0) return;
+            for (int i = 0; i < nq; ++i)
+                if (keep[i]) matches.push_back(DMatch{i, idx[i], 0, (float)dist[i]});
+            return;
+        }
+        int n = 0;
+        c.check(sfmgms_bf_hamming(c.get(), query, nq, train, nt, desc_bytes, idx.data(), dist.data(), &n));
+        matches.reserve((size_t)n);
+        for (int i = 0; i < n; ++i) matches.push_back(DMatch{i, idx[i], 0, (float)dist[i]});
+    }
+
+   private:
+    bool cross_;
+    Context* ctx_;
+};
+
+namespace xfeatures2d {
+
+// cv::xfeatures2d::matchGMS — exact OpenCV parameter order (…, withRotation, withScale, thresholdFactor).
+inline void matchGMS(const Size& size1, const Size& size2, const std::vector<KeyPoint>& keypoints1,
+                     const std::vector<KeyPoint>& keypoints2, const std::vector<DMatch>& matches1to2,
+                     std::vector<DMatch>& matchesGMS, bool withRotation = false, bool withScale = false,
+                     double thresholdFactor = 6.0, Context* ctx = nullptr) {
+    Context& c = ctx ? *ctx : Context::thread_default();
+    std::vector<uint8_t> mask(matches1to2.size() + 1);
+    int mask_len = 0, n_inliers = 0;
+    c.check(sfmgms_gms(c.get(), size1.width, size1.height, size2.width, size2.height,
+                       keypoints1.empty() ? nullptr : &keypoints1[0].pt.x, (int)keypoints1.size(), (int)sizeof(KeyPoint),
+                       keypoints2.empty() ? nullptr : &keypoints2[0].pt.x, (int)keypoints2.size(), (int)sizeof(KeyPoint),
+                       matches1to2.empty() ? nullptr : &matches1to2[0].queryIdx,
+                       matches1to2.empty() ? nullptr : &matches1to2[0].trainIdx, (int)sizeof(DMatch),
+                       (int)matches1to2.size(), withRotation ? 1 : 0, withScale ? 1 : 0, thresholdFactor, mask.data(),
+                       &mask_len, &n_inliers, nullptr));
+    matchesGMS.clear();                                   // as the reference does (DLL @VA 0x18004831e)
+    for (int i = 0; i < mask_len; ++i)
+        if (mask[i]) matchesGMS.push_back(matches1to2[i]);  // input order preserved
+}
+
+}  // namespace xfeatures2d
+}  // namespace cv
+
+// Upstream header-only API (JiaWang-Bian gms_matcher.h), of which OpenCV's GMSMatcher is the port.
+class gms_matcher {
+   public:
+    gms_matcher(const std::vector<cv::KeyPoint>& vkp1, const cv::Size size1, const std::vector<cv::KeyPoint>& vkp2,
+                const cv::Size size2, const std::vector<cv::DMatch>& vDMatches, Context* ctx = nullptr)
+        : kp1_(vkp1), kp2_(vkp2), m_(vDMatches), s1_(size1), s2_(size2), ctx_(ctx) {}
+
+    // returns the number of inliers; vbInliers gets one flag per input match.
+    // Upstream order: WithScale FIRST, WithRotation second; threshold factor fixed at 6.
+    int GetInlierMask(std::vector<bool>& vbInliers, bool WithScale = false, bool WithRotation = false) {
+        Context& c = ctx_ ? *ctx_ : Context::thread_default();
+        std::vector<uint8_t> mask(m_.size() + 1);
+        int mask_len = 0, n_inliers = 0;
+        c.check(sfmgms_gms(c.get(), s1_.width, s1_.height, s2_.width, s2_.height, kp1_.empty() ? nullptr : &kp1_[0].pt.x,
+                           (int)kp1_.size(), (int)sizeof(cv::KeyPoint), kp2_.empty() ? nullptr : &kp2_[0].pt.x,
+                           (int)kp2_.size(), (int)sizeof(cv::KeyPoint), m_.empty() ? nullptr : &m_[0].queryIdx,
+                           m_.empty() ? nullptr : &m_[0].trainIdx, (int)sizeof(cv::DMatch), (int)m_.size(),
+                           WithRotation ? 1 : 0, WithScale ? 1 : 0, 6.0, mask.data(), &mask_len, &n_inliers, nullptr));
+        if (mask_len > 0 || (!WithScale && !WithRotation)) {   // best == 0 with a search on: vector left untouched
+            vbInliers.assign((size_t)mask_len, false);
+            for (int i = 0; i < mask_len; ++i) vbInliers[i] = mask[i] != 0;
+        }
+        return n_inliers;
+    }
+
+   private:
+    const std::vector<cv::KeyPoint>& kp1_;
+    const std::vector<cv::KeyPoint>& kp2_;
+    const std::vector<cv::DMatch>& m_;
+    cv::Size s1_, s2_;
+    Context* ctx_;
+};
+
+// The whole FeatureMatchUtil.cpp:66-69 block in one call: matches never leave the device between stages.
+inline void matchBFHammingGMS(const uint8_t* desc1, const uint8_t* desc2, const std::vector<cv::KeyPoint>& kpts1,
+                              const std::vector<cv::KeyPoint>& kpts2, const cv::Size& size1, const cv::Size& size2,
+                              std::vector<cv::DMatch>& matches, std::vector<cv::DMatch>& matchesGMS,
+                              bool withRotation = false, bool withScale = false, double thresholdFactor = 6.0,
+                              Context* ctx = nullptr) {
+    Context& c = ctx ? *ctx : Context::thread_default();
+    const int n1 = (int)kpts1.size(), n2 = (int)kpts2.size();
+    std::vector<int32_t> idx((size_t)n1 + 1), dist((size_t)n1 + 1);
+    std::vector<uint8_t> mask((size_t)n1 + 1);
+    int mask_len = 0, n_inl = 0;
+    c.check(sfmgms_match_pair(c.get(), desc1, n1, desc2, n2, 32, n1 ? &kpts1[0].pt.x : nullptr, (int)sizeof(cv::KeyPoint),
+                              n2 ? &kpts2[0].pt.x : nullptr, (int)sizeof(cv::KeyPoint), size1.width, size1.height,
+                              size2.width, size2.height, withRotation ? 1 : 0, withScale ? 1 : 0, thresholdFactor,
+                              idx.data(), dist.data(), mask.data(), &mask_len, &n_inl, nullptr));
+    matches.clear();
+    matchesGMS.clear();
+    const int nm = n2 == 0 ? 0 : n1;
+    for (int i = 0; i < nm; ++i) matches.push_back(cv::DMatch{i, idx[i], 0, (float)dist[i]});
+    for (int i = 0; i < mask_len; ++i)
+        if (mask[i]) matchesGMS.push_back(matches[i]);
+}
+
+}  // namespace sfmgms
+
+#ifdef SFMGMS_WITH_OPENCV
+// Adaptor on the real OpenCV types: cv::KeyPoint / cv::DMatch are layout-identical to the PODs above.
+#include <opencv2/core.hpp>
+#include <opencv2/features2d.hpp>
+namespace sfmgms {
+inline void match(const ::cv::Mat& desc1, const ::cv::Mat& desc2, std::vector<::cv::DMatch>& matches) {
+    CV_Assert(desc1.type() == CV_8U && desc2.type() == CV_8U && desc1.cols == 32 && desc2.cols == 32 &&
+              desc1.isContinuous() && desc2.isContinuous());
+    std::vector<cv::DMatch> m;
+    cv::BFMatcher().match(desc1.ptr<uint8_t>(), desc1.rows, desc2.ptr<uint8_t>(), desc2.rows, m);
+    matches.resize(m.size());
+    if (!m.empty()) std::memcpy((void*)matches.data(), m.data(), m.size() * sizeof(cv::DMatch));
+}
+inline void matchGMS(const ::cv::Size& size1, const ::cv::Size& size2, const std::vector<::cv::KeyPoint>& kp1,
+                     const std::vector<::cv::KeyPoint>& kp2, const std::vector<::cv::DMatch>& matches1to2,
+                     std::vector<::cv::DMatch>& matchesGMS, bool withRotation = false, bool withScale = false,
+                     double thresholdFactor = 6.0) {
+    static_assert(sizeof(::cv::KeyPoint) == sizeof(cv::KeyPoint) && sizeof(::cv::DMatch) == sizeof(cv::DMatch), "layout");
+    Context& c = Context::thread_default();
+    std::vector<uint8_t> mask(matches1to2.size() + 1);
+    int mask_len = 0, n_inl = 0;
+    c.check(sfmgms_gms(c.get(), size1.width, size1.height, size2.width, size2.height, kp1.empty() ? nullptr : &kp1[0].pt.x,
+                       (int)kp1.size(), (int)sizeof(::cv::KeyPoint), kp2.empty() ? nullptr : &kp2[0].pt.x, (int)kp2.size(),
+                       (int)sizeof(::cv::KeyPoint), matches1to2.empty() ? nullptr : &matches1to2[0].queryIdx,
+                       matches1to2.empty() ? nullptr : &matches1to2[0].trainIdx, (int)sizeof(::cv::DMatch),
+                       (int)matches1to2.size(), withRotation, withScale, thresholdFactor, mask.data(), &mask_len, &n_inl,
+                       nullptr));
+    matchesGMS.clear();
+    for (int i = 0; i < mask_len; ++i)
+        if (mask[i]) matchesGMS.push_back(matches1to2[i]);
+}
+}  // namespace sfmgms
+#endif

@@ -359,3 +359,40 @@ def test_cv2_shaped_api(ctx):
     assert n == int(g["gms_n_10"]) and np.array_equal(mask, np.unpackbits(g["gms_mask_10"])[: len(m)].astype(bool))
     xm = sg.BFMatcher(sg.NORM_HAMMING, crossCheck=True).match(g["desc1"], g["desc2"])
     assert [x.queryIdx for x in xm] == g["xc_query"].tolist() and [x.trainIdx for x in xm] == g["xc_train"].tolist()
+
+
+# ---- the C++ shim (sfmgms.hpp): BFMatcher::match + matchGMS exactly as FeatureMatchUtil.cpp:66-69 calls them ----
+@pytest.mark.parametrize("rot,sc,tag", [(0, 0, "00"), (1, 1, "11")])
+def test_cxx_shim_demo_matches_golden(tmp_path, rot, sc, tag):
+    import os
+    import subprocess
+
+    from conftest import ROOT
+
+    exe = os.path.join(ROOT, "sfm_gms_b200", "cxx", "demo_match")
+    assert os.path.exists(exe), "build it with __graft_entry__.build()"
+    g = load_golden("bun12_rot180_3k")
+    n1, n2 = len(g["kp1"]), len(g["kp2"])
+    pair = tmp_path / "pair.bin"
+    with open(pair, "wb") as f:
+        np.array([g["size1"][0], g["size1"][1], g["size2"][0], g["size2"][1], n1, n2], np.int32).tofile(f)
+        g["kp1"].astype(np.float32).tofile(f)
+        g["kp2"].astype(np.float32).tofile(f)
+        g["desc1"].tofile(f)
+        g["desc2"].tofile(f)
+    out = tmp_path / "out.bin"
+    subprocess.check_call([exe, str(pair), str(rot), str(sc), str(out)], timeout=120)
+    raw = np.fromfile(out, np.uint8)
+    n = int(raw[:4].view(np.int32)[0])
+    o = 4
+    ti = raw[o:o + 4 * n].view(np.int32); o += 4 * n
+    di = raw[o:o + 4 * n].view(np.int32); o += 4 * n
+    ng = int(raw[o:o + 4].view(np.int32)[0]); o += 4
+    gq = raw[o:o + 4 * ng].view(np.int32); o += 4 * ng
+    nc = int(raw[o:o + 4].view(np.int32)[0]); o += 4
+    mk = raw[o:o + n].astype(bool); o += n
+    nf = int(raw[o:o + 4].view(np.int32)[0])
+    assert n == n1 and np.array_equal(ti, g["bf_train"]) and np.array_equal(di, g["bf_dist"])
+    exp = np.unpackbits(g["gms_mask_" + tag])[:n].astype(bool)
+    assert ng == int(g["gms_n_" + tag]) and np.array_equal(gq, np.nonzero(exp)[0])
+    assert nc == ng and np.array_equal(mk, exp) and nf == ng
