@@ -49,6 +49,7 @@ extern "C" {
 #define SFMGMS_HAMMING_AUTO 0
 #define SFMGMS_HAMMING_POPC 1   /* XOR/popc CUDA-core kernel */
 #define SFMGMS_HAMMING_TC 2     /* tcgen05 int8 tensor-core kernel (unpacked +-1 bits, TMEM accumulators) */
+#define SFMGMS_HAMMING_FP4 3    /* tcgen05 block-scaled FP4 (kind::mxf4) kernel: +-1 as E2M1, unit scales */
 #define SFMGMS_OPT_GMS_CHUNK_BYTES 2 /* scratch budget per GMS chunk (bytes), default 64 MiB */
 #define SFMGMS_OPT_TC_OPERAND_CACHE 4 /* 1 (default): keep the unpacked +-1 operands of the image set across
                                          sfmgms_match_pairs calls; 0: unpack again on every call */

@@ -17,7 +17,7 @@ for nq, nt in shapes:
     t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
     q[0] = t[nt - 1]; t[nt // 2] = t[0]
     oi, od = oracle.bf_hamming(q, t)
-    for name, k in [("popc", api.HAMMING_POPC), ("tc", api.HAMMING_TC)]:
+    for name, k in [("popc", api.HAMMING_POPC), ("tc", api.HAMMING_TC), ("fp4", api.HAMMING_FP4)]:
         ctx.set_option(api.OPT_HAMMING_KERNEL, k)
         ctx.set_option(api.OPT_TIMING, 1)
         for rep in range(3):

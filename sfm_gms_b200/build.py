@@ -8,8 +8,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["capi.cu", "hamming_popc.cu", "hamming_tc.cu", "gms.cu"]
-HEADERS = ["common.cuh", "hamming_tc.cuh", os.path.join("..", "..", "include", "sfmgms.h")]
+SOURCES = ["capi.cu", "hamming_popc.cu", "hamming_tc.cu", "hamming_fp4.cu", "gms.cu"]
+HEADERS = ["common.cuh", "hamming_tc.cuh", "tc_ptx.cuh", os.path.join("..", "..", "include", "sfmgms.h")]
 LIB = os.path.join(HERE, "libsfmgms.so")
 
 NVCC_FLAGS = [

@@ -202,6 +202,9 @@ int enqueue_range(sfmgms_ctx* ctx, const std::vector<PairDesc>& hp, int r0, int 
             if (kind == SFMGMS_HAMMING_TC) {
                 l = launch_hamming_tc(ctx->tc, dp + c0, hpp + c0, cn, ctx->sm_count, st);
                 if (l < 0) return fail(ctx, SFMGMS_ERR_CUDA, "tensor-core Hamming launch failed: %s", tc_last_error());
+            } else if (kind == SFMGMS_HAMMING_FP4) {
+                l = launch_hamming_fp4(ctx->tc, dp + c0, hpp + c0, cn, ctx->sm_count, st);
+                if (l < 0) return fail(ctx, SFMGMS_ERR_CUDA, "fp4 tensor-core Hamming launch failed: %s", fp4_last_error());
             } else {
                 l = launch_hamming_popc(dp + c0, hpp + c0, cn, ctx->sm_count, st);
             }
@@ -376,7 +379,7 @@ const char* sfmgms_last_error(const sfmgms_ctx* ctx) { return ctx ? ctx->err : g
 int sfmgms_set_option(sfmgms_ctx* ctx, int key, int64_t value) {
     if (!ctx) return SFMGMS_ERR_ARG;
     if (key == SFMGMS_OPT_HAMMING_KERNEL) {
-        if (value < 0 || value > 2) return fail(ctx, SFMGMS_ERR_ARG, "bad hamming kernel %lld", (long long)value);
+        if (value < 0 || value > 3) return fail(ctx, SFMGMS_ERR_ARG, "bad hamming kernel %lld", (long long)value);
         if (value == SFMGMS_HAMMING_TC && !tc_available())
             return fail(ctx, SFMGMS_ERR_ARG, "tensor-core Hamming kernel not available in this build");
         ctx->hamming_kernel = (int)value;

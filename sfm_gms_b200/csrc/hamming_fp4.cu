@@ -1,0 +1,463 @@
+// hamming_fp4.cu — brute-force Hamming nearest neighbour as a block-scaled FP4 GEMM (tcgen05 kind::mxf4).
+//
+// Same idea as hamming_tc.cu (replaces cv::BFMatcher(NORM_HAMMING)::match, FeatureMatchUtil.cpp:68): a descriptor
+// bit becomes +1 / -1, <a,b> = 256 - 2*hamming(a,b), the nearest train row is the row arg-max.  Here the +-1
+// values are E2M1 (4-bit) numbers, two per byte, with all UE8M0 block scales = 2^0: the products and the fp32
+// accumulation are exact (|sum| <= 256), the operand rows shrink to 128 bytes (one 128B-swizzle row = the whole
+// K), and the tensor pipe runs the mxf4 rate (K = 64 per instruction, 4 instructions per 128x128 accumulator).
+// Block scales: every scale byte this kernel could ever address is 0x7F, so the scale-factor layout in TMEM does
+// not matter: 32 TMEM columns are filled with 0x7F7F7F7F once per CTA.
+//
+// Kernel structure (persistent, warp-specialised, 1 CTA/SM, 384 threads): warp 0 TMA producer (query sub-tiles
+// double-buffered per work unit, train tiles through a ring), warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4-11 epilogue (tcgen05.ld -> row max / first arg-max -> atomicMin(dist<<18|trainIdx)).
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "hamming_tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace sfmgms {
+
+namespace {
+
+using namespace tcptx;
+
+constexpr int BM = 128;            // UMMA M
+#ifndef SFMGMS_FP4_MSUB
+#define SFMGMS_FP4_MSUB 4
+#endif
+constexpr int MSUB = SFMGMS_FP4_MSUB;  // query sub-tiles per work unit
+constexpr int BN = 240;            // UMMA N: 2 accumulator slots x 240 columns + 32 scale columns = 512 TMEM columns
+constexpr int ROWB = 128;          // bytes per unpacked row: 256 x e2m1
+constexpr int UMMA_KB = 32;        // bytes of K per mxf4 MMA (64 elements)
+constexpr int NKSTEP = ROWB / UMMA_KB;   // 4
+constexpr int A_BUFS = 2;
+constexpr int TILE_BYTES = BM * ROWB;    // 16 KB: one query sub-tile
+constexpr int BTILE_BYTES = BN * ROWB;   // 30 KB: one train tile (multiple of 1024: stays swizzle-aligned)
+constexpr int A_BUF_BYTES = MSUB * TILE_BYTES;
+constexpr int STAGES = (222 * 1024 - A_BUFS * A_BUF_BYTES) / BTILE_BYTES;   // 3 (MSUB=4) / 5 (MSUB=2)
+constexpr int SMEM_DATA = A_BUFS * A_BUF_BYTES + STAGES * BTILE_BYTES;
+constexpr int SMEM_BYTES = SMEM_DATA + 1024 + 256;
+constexpr int ACC_SLOTS = 2;
+constexpr int SF_COL = ACC_SLOTS * BN;   // TMEM columns [480, 512): block scales (all 1.0)
+constexpr int SF_COLS = 32;
+constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarps = 12;           // 3 per TMEM lane quadrant, 80 accumulator columns each
+constexpr int kEpiCols = BN / 3;        // 80 = one x64 + one x16 tcgen05.ld
+constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);   // 640
+static_assert(STAGES >= 3, "B ring too shallow");
+static_assert(BTILE_BYTES % 1024 == 0 && kEpiCols == 80 && SF_COL + SF_COLS <= 512, "layout");
+
+// Epilogue index packing: key_j = <a,b_j> + (127 - j)/128 for column j < 80 of a warp's part.  One FADD per
+// element (FMA pipe; the addend is a constant-bank operand), then a plain max tree (ALU pipe): the maximum key
+// carries the maximum dot product (its integer part) AND the lowest column attaining it (its fraction).
+// |dot| <= 256 and the fraction has 7 bits: every key is exact in fp32.
+__constant__ float c_colkey[80] = {127.f / 128.f, 126.f / 128.f, 125.f / 128.f, 124.f / 128.f, 123.f / 128.f, 122.f / 128.f, 121.f / 128.f, 120.f / 128.f, 119.f / 128.f, 118.f / 128.f, 117.f / 128.f, 116.f / 128.f, 115.f / 128.f, 114.f / 128.f, 113.f / 128.f, 112.f / 128.f, 111.f / 128.f, 110.f / 128.f, 109.f / 128.f, 108.f / 128.f, 107.f / 128.f, 106.f / 128.f, 105.f / 128.f, 104.f / 128.f, 103.f / 128.f, 102.f / 128.f, 101.f / 128.f, 100.f / 128.f, 99.f / 128.f, 98.f / 128.f, 97.f / 128.f, 96.f / 128.f, 95.f / 128.f, 94.f / 128.f, 93.f / 128.f, 92.f / 128.f, 91.f / 128.f, 90.f / 128.f, 89.f / 128.f, 88.f / 128.f, 87.f / 128.f, 86.f / 128.f, 85.f / 128.f, 84.f / 128.f, 83.f / 128.f, 82.f / 128.f, 81.f / 128.f, 80.f / 128.f, 79.f / 128.f, 78.f / 128.f, 77.f / 128.f, 76.f / 128.f, 75.f / 128.f, 74.f / 128.f, 73.f / 128.f, 72.f / 128.f, 71.f / 128.f, 70.f / 128.f, 69.f / 128.f, 68.f / 128.f, 67.f / 128.f, 66.f / 128.f, 65.f / 128.f, 64.f / 128.f, 63.f / 128.f, 62.f / 128.f, 61.f / 128.f, 60.f / 128.f, 59.f / 128.f, 58.f / 128.f, 57.f / 128.f, 56.f / 128.f, 55.f / 128.f, 54.f / 128.f, 53.f / 128.f, 52.f / 128.f, 51.f / 128.f, 50.f / 128.f, 49.f / 128.f, 48.f / 128.f};
+
+struct alignas(16) WorkUnit {
+    uint32_t a_row0, b_row0;   // operand rows (in the unpacked array) of the unit's first query / the train image's row 0
+    int32_t n_rows, t_begin, t_end, pad;
+    uint32_t* key;
+};
+
+constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t sdesc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+// InstrDescriptorBlockScaled: a_format=E2M1(1)@7, b_format=E2M1(1)@10, K-major both, n_dim=N>>3 @17,
+// scale_format=UE8M0(1)@23, m_dim=M>>4 @24, a_sf_id=b_sf_id=0, k_size=0 (K64 dense)
+constexpr uint32_t kIdesc = (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | (1u << 23) | ((uint32_t)(BM >> 4) << 24);
+
+template <int kAccumulate>
+__device__ __forceinline__ void tc_mma_mxf4(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                            uint32_t idesc, uint32_t sfa, uint32_t sfb) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b64 da, db;\n\t"
+        ".reg .pred p;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %7, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], da, db, %4, [%5], [%6], p;\n\t"
+        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(sfa), "r"(sfb), "n"(kAccumulate) : "memory");
+}
+
+// 32 descriptor bits -> 32 e2m1 values (+1.0 = 0x2, -1.0 = 0xA), element k in nibble k (low nibble first)
+__device__ __forceinline__ uint4 fp4_from_word(uint32_t w) {
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t b = (w >> (8 * q)) & 0xFFu;       // 8 bits -> 8 nibbles
+        // spread bit i to bit 4*i+3 (the e2m1 sign) : set bit = +1 => sign 0; clear bit = -1 => sign 1
+        uint32_t s = (b | (b << 12)) & 0x000F000Fu;       // nibbles: bits 0-3 at [0,4), bits 4-7 at [16,20)
+        s = (s | (s << 6)) & 0x03030303u;                 // pairs of bits per byte
+        s = (s | (s << 3)) & 0x11111111u;                 // one bit per nibble (at nibble bit 0)
+        o[q] = 0x22222222u | ((~s & 0x11111111u) << 3);   // 0x2 magnitude (1.0) | sign where the bit is clear
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void __launch_bounds__(256) unpack_fp4_kernel(const uint32_t* __restrict__ desc, long long n_words,
+                                                         uint4* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (; i < n_words; i += step) out[i] = fp4_from_word(__ldg(desc + i));
+}
+
+__global__ void __launch_bounds__(256) pull_table_kernel(const uint4* __restrict__ host_src, uint4* __restrict__ dst, int n16) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = host_src[i];
+}
+
+template <int dbg>   // dbg != 0: timing experiments only (results invalid); production is dbg = 0
+__global__ void __launch_bounds__(kThreads, 1)
+hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmapB,
+                   const WorkUnit* __restrict__ units, int n_units) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_smem = smem_base;
+    const uint32_t b_smem = smem_base + A_BUFS * A_BUF_BYTES;
+    const uint32_t bar_base = smem_base + SMEM_DATA;
+    const uint32_t full_bar = bar_base;
+    const uint32_t empty_bar = full_bar + 8 * STAGES;
+    const uint32_t a_full_bar = empty_bar + 8 * STAGES;
+    const uint32_t a_empty_bar = a_full_bar + 8 * A_BUFS;
+    const uint32_t tfull_bar = a_empty_bar + 8 * A_BUFS;
+    const uint32_t tempty_bar = tfull_bar + 8 * ACC_SLOTS;
+    const uint32_t tmem_ptr_smem = tempty_bar + 8 * ACC_SLOTS;
+    volatile uint32_t* tmem_ptr_generic =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_smem - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+        for (int s = 0; s < A_BUFS; ++s) { mbar_init(a_full_bar + 8 * s, 1); mbar_init(a_empty_bar + 8 * s, 1); }
+        for (int s = 0; s < ACC_SLOTS; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, kEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_smem), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_generic;
+    // block scales: 0x7F = 2^0 everywhere (warps 4-7 cover the four lane quadrants)
+    if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
+        uint32_t ones[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) ones[k] = 0x7F7F7F7Fu;
+        const uint32_t t = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + SF_COL;
+        tc_st16(t, ones);
+        tc_st16(t + 16, ones);
+        tc_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
+            uint32_t stage = 0, phase = 0, abuf = 0, a_phase = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const WorkUnit wu = units[u];
+                const int nsub = (wu.n_rows + BM - 1) / BM;
+                mbar_wait(a_empty_bar + 8 * abuf, a_phase ^ 1);
+                mbar_expect_tx(a_full_bar + 8 * abuf, (uint32_t)(nsub * TILE_BYTES));
+                for (int s = 0; s < nsub; ++s)
+                    tma_load_2d(a_smem + abuf * A_BUF_BYTES + s * TILE_BYTES, &tmap, 0, (int)(wu.a_row0 + s * BM),
+                                a_full_bar + 8 * abuf);
+                if (++abuf == A_BUFS) { abuf = 0; a_phase ^= 1; }
+                for (int t = wu.t_begin; t < wu.t_end; t += BN) {
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    mbar_expect_tx(full_bar + 8 * stage, (uint32_t)BTILE_BYTES);
+                    tma_load_2d(b_smem + stage * BTILE_BYTES, &tmapB, 0, (int)(wu.b_row0 + t), full_bar + 8 * stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, abuf = 0, a_phase = 0, slot = 0, slot_phase = 0;
+            const uint32_t a_lo0 = sdesc_lo(a_smem), b_lo0 = sdesc_lo(b_smem);
+            const uint32_t sf = tmem_base + SF_COL;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const WorkUnit wu = units[u];
+                const int nsub = (wu.n_rows + BM - 1) / BM;
+                const int ntiles = (wu.t_end - wu.t_begin + BN - 1) / BN;
+                mbar_wait(a_full_bar + 8 * abuf, a_phase);
+                const uint32_t a_lo_buf = a_lo0 + abuf * (A_BUF_BYTES >> 4);
+                for (int ti = 0; ti < ntiles; ++ti) {
+                    mbar_wait(full_bar + 8 * stage, phase);
+                    const uint32_t b_lo = b_lo0 + stage * (BTILE_BYTES >> 4);
+                    for (int s = 0; s < nsub; ++s) {
+                        mbar_wait(tempty_bar + 8 * slot, slot_phase ^ 1);
+                        tc_fence_after();
+                        const uint32_t d = tmem_base + slot * BN;
+                        const uint32_t a_lo = a_lo_buf + s * (TILE_BYTES >> 4);
+                        if (dbg != 3) {   // DEBUG 3: no tensor work
+                        tc_mma_mxf4<0>(d, a_lo + 0, b_lo + 0, kDescHi, kIdesc, sf, sf);
+                        tc_mma_mxf4<1>(d, a_lo + 2, b_lo + 2, kDescHi, kIdesc, sf, sf);
+                        tc_mma_mxf4<1>(d, a_lo + 4, b_lo + 4, kDescHi, kIdesc, sf, sf);
+                        tc_mma_mxf4<1>(d, a_lo + 6, b_lo + 6, kDescHi, kIdesc, sf, sf);
+                        }
+                        tc_commit(tfull_bar + 8 * slot);
+                        if (++slot == ACC_SLOTS) { slot = 0; slot_phase ^= 1; }
+                    }
+                    tc_commit(empty_bar + 8 * stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(a_empty_bar + 8 * abuf);
+                if (++abuf == A_BUFS) { abuf = 0; a_phase ^= 1; }
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ================= epilogue: 12 warps; warp = (lane quadrant, 80-column part) of every accumulator ==========
+        const int quad = warp & 3;                        // TMEM lanes [32*quad, 32*quad+32)
+        const int c0 = ((warp - kEpiWarp0) >> 2) * kEpiCols; // accumulator columns [c0, c0+80)
+        uint32_t slot = 0, slot_phase = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const WorkUnit wu = units[u];
+            const int nsub = (wu.n_rows + BM - 1) / BM;
+            float best_val[MSUB];
+            int best_dot[MSUB], best_idx[MSUB];
+#pragma unroll
+            for (int s = 0; s < MSUB; ++s) { best_val[s] = -1.0e30f; best_dot[s] = -100000; best_idx[s] = dbg ? 0 : -1; }
+            for (int t = wu.t_begin; t < wu.t_end; t += BN) {
+                const int valid = wu.t_end - t;
+#pragma unroll
+                for (int s = 0; s < MSUB; ++s) {
+                    if (s < nsub) {
+                        mbar_wait(tfull_bar + 8 * slot, slot_phase);
+                        tc_fence_after();
+                        int ra[64], rb[16];
+                        if (dbg == 4) {    // DEBUG 4: no TMEM read, no ALU
+#pragma unroll
+                            for (int j = 0; j < 64; ++j) ra[j] = 0;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) rb[j] = 0;
+                        } else {
+                            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * BN + c0;
+                            tc_ld64(taddr, ra);
+                            tc_ld16(taddr + 64, rb);
+                            tc_wait_ld();
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty_bar + 8 * slot);   // values are in registers now
+                        if (++slot == ACC_SLOTS) { slot = 0; slot_phase ^= 1; }
+                        if (dbg == 4) continue;
+                        float v[kEpiCols];
+#pragma unroll
+                        for (int j = 0; j < 64; ++j) v[j] = __int_as_float(ra[j]) + c_colkey[j];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[64 + j] = __int_as_float(rb[j]) + c_colkey[64 + j];
+                        if (dbg == 1) { best_val[s] = fmaxf(best_val[s], v[0] + v[79]); continue; }   // DEBUG 1: no ALU
+                        if (c0 + kEpiCols > valid) {                         // tail tile: mask columns outside the image
+#pragma unroll
+                            for (int j = 0; j < kEpiCols; ++j)
+                                if (c0 + j >= valid) v[j] = -1.0e30f;
+                        }
+                        float m = v[0];
+#pragma unroll
+                        for (int j = 1; j < kEpiCols; ++j) m = fmaxf(m, v[j]);
+                        // m = dot + (127 - j*)/128: strict '>' on the integer part keeps the earliest tile / part
+                        const float fl = floorf(m);
+                        const int dot = (int)fl;
+                        if (m > -1.0e29f && dot > best_dot[s]) {
+                            best_dot[s] = dot;
+                            best_idx[s] = t + c0 + 127 - (int)((m - fl) * 128.0f);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < MSUB; ++s) {
+                const int row = s * BM + quad * 32 + lane;
+                if (s < nsub && row < wu.n_rows && best_idx[s] >= 0) {
+                    const uint32_t dist = dbg ? 7u + (best_val[s] > 0.f) : (uint32_t)(256 - best_dot[s]) >> 1;   // <a,b> = 256 - 2*hamming
+                    atomicMin(wu.key + row, (dist << kTrainIdxBits) | (uint32_t)best_idx[s]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+char g_err[256] = "";
+EncodeTiledFn g_encode = nullptr;
+
+bool load_encode() {
+    if (g_encode) return true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+        return false;
+    }
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return true;
+}
+
+bool ensure_dev(void*& p, size_t& cap, size_t bytes) {
+    if (bytes <= cap) return true;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    const size_t want = bytes + bytes / 8 + 4096;
+    if (cudaMalloc(&p, want) != cudaSuccess) { snprintf(g_err, sizeof g_err, "cudaMalloc(%zu) failed", want); return false; }
+    cap = want;
+    return true;
+}
+
+}  // namespace
+
+const char* fp4_last_error() { return g_err; }
+
+int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, int sm_count,
+                       cudaStream_t st) {
+    (void)d_pairs;
+    if (n_pairs <= 0) return 0;
+    if (!load_encode()) return -1;
+    int launches = 0;
+    const uint8_t* lo = nullptr;
+    const uint8_t* hi = nullptr;
+    long long ref_rows = 0;
+    for (int p = 0; p < n_pairs; ++p) {
+        const PairDesc& pd = h_pairs[p];
+        ref_rows += (long long)pd.n1 + pd.n2;
+        if (pd.n1 <= 0 || pd.n2 <= 0) continue;
+        const uint8_t* ends[2][2] = {{pd.desc1, pd.desc1 + (size_t)pd.n1 * 32}, {pd.desc2, pd.desc2 + (size_t)pd.n2 * 32}};
+        for (auto& e : ends) {
+            if (!lo || e[0] < lo) lo = e[0];
+            if (!hi || e[1] > hi) hi = e[1];
+        }
+    }
+    if (!lo) return 0;
+    const long long n_rows = (hi - lo) / 32;
+    if (n_rows >= (1ll << 31) || n_rows > 64 * ref_rows + 4096) {
+        snprintf(g_err, sizeof g_err, "descriptor operands are not in one contiguous array");
+        return -1;
+    }
+    if (!(s.set_valid && s.ops_src == lo && s.ops_rows == n_rows && s.ops_row_bytes == ROWB)) {
+        if (!ensure_dev(s.d_ops, s.ops_cap, (size_t)(n_rows + 256) * ROWB)) return -1;
+        const long long n_words = n_rows * kDescWords;
+        long long blocks = (n_words + 255) / 256;
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        unpack_fp4_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(lo), n_words,
+                                                            static_cast<uint4*>(s.d_ops));
+        ++launches;
+        s.ops_src = lo; s.ops_rows = n_rows; s.ops_row_bytes = ROWB;
+        s.set_valid = s.cache_enabled;
+    }
+    CUtensorMap tmap;
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)ROWB, (cuuint64_t)(n_rows + 256)};
+        const cuuint64_t gstride[1] = {(cuuint64_t)ROWB};
+        const cuuint32_t box[2] = {(cuuint32_t)ROWB, (cuuint32_t)BM};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = g_encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, s.d_ops, gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }
+    }
+    CUtensorMap tmapB;
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)ROWB, (cuuint64_t)(n_rows + 256)};
+        const cuuint64_t gstride[1] = {(cuuint64_t)ROWB};
+        const cuuint32_t box[2] = {(cuuint32_t)ROWB, (cuuint32_t)BN};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = g_encode(&tmapB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, s.d_ops, gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled(B) failed (%d)", (int)r); return -1; }
+    }
+    long long qblocks = 0;
+    int max_tiles = 1;
+    for (int p = 0; p < n_pairs; ++p) {
+        if (h_pairs[p].n1 <= 0 || h_pairs[p].n2 <= 0) continue;
+        qblocks += (h_pairs[p].n1 + BM * MSUB - 1) / (BM * MSUB);
+        const int tiles = (h_pairs[p].n2 + BN - 1) / BN;
+        if (tiles > max_tiles) max_tiles = tiles;
+    }
+    int tsplit = 1;
+    if (qblocks < 2LL * sm_count) {
+        long long t = (2LL * sm_count + qblocks - 1) / qblocks;
+        if (t > max_tiles) t = max_tiles;
+        tsplit = (int)(t < 1 ? 1 : t);
+    }
+    const size_t max_units = (size_t)qblocks * tsplit;
+    const size_t wbytes = (max_units * sizeof(WorkUnit) + 255) & ~(size_t)255;
+    if (s.work_used + wbytes > s.h_work_cap || s.work_used + wbytes > s.work_cap) {
+        if (cudaStreamSynchronize(st) != cudaSuccess) { snprintf(g_err, sizeof g_err, "stream sync failed"); return -1; }
+        s.work_used = 0;
+        if (16 * wbytes > s.h_work_cap) {
+            if (s.h_work) cudaFreeHost(s.h_work);
+            s.h_work = nullptr; s.h_work_cap = 0;
+            const size_t want = 16 * wbytes + (8u << 20);
+            if (cudaMallocHost(&s.h_work, want) != cudaSuccess) { snprintf(g_err, sizeof g_err, "cudaMallocHost failed"); return -1; }
+            s.h_work_cap = want;
+        }
+        if (!ensure_dev(s.d_work, s.work_cap, s.h_work_cap)) return -1;
+    }
+    WorkUnit* wu = reinterpret_cast<WorkUnit*>(static_cast<char*>(s.h_work) + s.work_used);
+    WorkUnit* d_wu = reinterpret_cast<WorkUnit*>(static_cast<char*>(s.d_work) + s.work_used);
+    size_t n_units = 0;
+    for (int p = 0; p < n_pairs; ++p) {
+        const PairDesc& pd = h_pairs[p];
+        if (pd.n1 <= 0 || pd.n2 <= 0) continue;
+        const uint32_t arow = (uint32_t)((pd.desc1 - lo) / 32), brow = (uint32_t)((pd.desc2 - lo) / 32);
+        const int tiles = (pd.n2 + BN - 1) / BN;
+        const int tper = (tiles + tsplit - 1) / tsplit;
+        for (int q0 = 0; q0 < pd.n1; q0 += BM * MSUB) {
+            for (int ts = 0; ts * tper < tiles; ++ts) {
+                WorkUnit& w = wu[n_units++];
+                w.a_row0 = arow + q0;
+                w.b_row0 = brow;
+                w.n_rows = (pd.n1 - q0 < BM * MSUB) ? pd.n1 - q0 : BM * MSUB;
+                w.t_begin = ts * tper * BN;
+                const int te = (ts + 1) * tper * BN;
+                w.t_end = te < pd.n2 ? te : pd.n2;
+                w.pad = 0;
+                w.key = pd.key + q0;
+            }
+        }
+    }
+    if (n_units == 0) return launches;
+    {
+        const int n16 = (int)(n_units * sizeof(WorkUnit) / 16);
+        int blocks = (n16 + 255) / 256;
+        if (blocks > 64) blocks = 64;
+        pull_table_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(wu), reinterpret_cast<uint4*>(d_wu), n16);
+        ++launches;
+    }
+    static const int dbg = getenv("SFMGMS_TC_DEBUG") ? atoi(getenv("SFMGMS_TC_DEBUG")) : 0;   // timing experiments only
+    auto kern = dbg == 1 ? hamming_fp4_kernel<1> : dbg == 3 ? hamming_fp4_kernel<3> : dbg == 4 ? hamming_fp4_kernel<4>
+                                                                                                   : hamming_fp4_kernel<0>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+        snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute(smem=%d) failed", SMEM_BYTES);
+        return -1;
+    }
+    const int grid = (int)(n_units < (size_t)sm_count ? n_units : (size_t)sm_count);
+    kern<<<grid, kThreads, SMEM_BYTES, st>>>(tmap, tmapB, d_wu, (int)n_units);
+    s.work_used += wbytes;
+    return launches + 1;
+}
+
+}  // namespace sfmgms

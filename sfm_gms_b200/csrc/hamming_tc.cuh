@@ -16,6 +16,7 @@ struct TcState {
     bool cache_enabled = true;  // keep the unpacked operands across calls until tc_invalidate()
     const uint8_t* ops_src = nullptr;
     long long ops_rows = 0;
+    int ops_row_bytes = 0;      // 256 (int8 kernel) or 128 (fp4 kernel)
 };
 
 bool tc_available();
@@ -28,5 +29,10 @@ void tc_reset_arena(TcState& s);
 // returns the number of kernel launches, or -1 on error
 int launch_hamming_tc(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, int sm_count,
                       cudaStream_t st);
+
+// FP4 (tcgen05 kind::mxf4 block-scaled) variant, hamming_fp4.cu — same contract as launch_hamming_tc
+const char* fp4_last_error();
+int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, int sm_count,
+                       cudaStream_t st);
 
 }  // namespace sfmgms
