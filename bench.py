@@ -201,7 +201,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-pairs", type=int, default=8, help="pairs per step of the CPU reference arm")
     ap.add_argument("--cpu-pairs", type=int, default=16, help="pairs in the cpu_baseline sample")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "tc"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "tc", "fp4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -255,7 +255,7 @@ def main():
 
     ctx = sg.Context(local_rank)
     if args.kernel != "auto":
-        ctx.set_option(api.OPT_HAMMING_KERNEL, api.HAMMING_POPC if args.kernel == "popc" else api.HAMMING_TC)
+        ctx.set_option(api.OPT_HAMMING_KERNEL, {"popc": api.HAMMING_POPC, "tc": api.HAMMING_TC, "fp4": api.HAMMING_FP4}[args.kernel])
     ctx.set_option(api.OPT_TIMING, 1)
     ctx.set_option(api.OPT_TC_OPERAND_CACHE, 0)   # re-derive the +-1 operands from the packed descriptors every step
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
@@ -360,7 +360,7 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        kind = "tc" if (args.kernel == "tc" or (args.kernel == "auto" and _tc_built())) else "popc"
+        kind = "fp4" if args.kernel == "auto" else args.kernel
         ham_avg_ms = float(np.mean(ham_ms)) / max(1, ham_launches / max(1, len(ham_ms)))
         dists = float(P) * N_KP * N_KP           # distance evaluations per launch (one launch per step)
         per_launch_s = float(np.mean(ham_ms)) * 1e-3
@@ -375,13 +375,14 @@ def main():
                                    "MEASURED_PEAKS.json)",
                     "traffic": None, "algorithmic_units_per_launch": dists, "avg_launch_ms": per_launch_s * 1e3}
         else:
-            ops = 2.0 * 256 * dists               # int8 MACs*2 on the unpacked +-1 operands
+            ops = 2.0 * 256 * dists               # 2 x MACs on the unpacked +-1 operands
             achieved = ops / per_launch_s / 1e12
-            peak = 2.0 * peaks.get("bf16_tflops_sustained", 1413.3)
-            roof = {"bound": "tensor", "kernel": "hamming_tc_kernel", "achieved": achieved, "peak": peak,
+            mult = 4.0 if kind == "fp4" else 2.0  # dense fp4 (kind::mxf4) = 4x, int8 = 2x the bf16 rate on sm_100a
+            peak = mult * peaks.get("bf16_tflops_sustained", 1413.3)
+            roof = {"bound": "tensor", "kernel": "hamming_%s_kernel" % kind, "achieved": achieved, "peak": peak,
                     "unit": "TOP/s", "frac": achieved / peak,
-                    "peak_source": "2 x measured sustained bf16 (int8 dense = 2x bf16 rate on sm_100a), "
-                                   "MEASURED_PEAKS.json",
+                    "peak_source": "%gx measured sustained bf16 TFLOP/s (MEASURED_PEAKS.json); %s dense rate = %gx bf16 on "
+                                   "sm_100a" % (mult, "mxf4" if kind == "fp4" else "int8", mult),
                     "traffic": None, "algorithmic_units_per_launch": dists, "avg_launch_ms": per_launch_s * 1e3}
         line = {"metric": "image pairs/sec (ORB-10k, BF-Hamming+GMS)", "value": value, "unit": "pairs/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(1024) inlier_points_kernel(PairDesc pd, float2
 }
 
 int choose_hamming(const sfmgms_ctx* c) {
-    if (c->hamming_kernel == SFMGMS_HAMMING_AUTO) return tc_available() ? SFMGMS_HAMMING_TC : SFMGMS_HAMMING_POPC;
+    if (c->hamming_kernel == SFMGMS_HAMMING_AUTO) return SFMGMS_HAMMING_FP4;   // fastest measured (profiles/r1_notes.md)
     return c->hamming_kernel;
 }
 

@@ -45,18 +45,21 @@ constexpr int SMEM_BYTES = SMEM_DATA + 1024 + 256;
 constexpr int ACC_SLOTS = 2;
 constexpr int SF_COL = ACC_SLOTS * BN;   // TMEM columns [480, 512): block scales (all 1.0)
 constexpr int SF_COLS = 32;
-constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarp0 = 0;            // epilogue warps first: the scheduler favours HIGH warp ids, which must be the
 constexpr int kEpiWarps = 12;           // 3 per TMEM lane quadrant, 80 accumulator columns each
 constexpr int kEpiCols = BN / 3;        // 80 = one x64 + one x16 tcgen05.ld
-constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);   // 640
+constexpr int kProdWarp = kEpiWarps;     // latency-critical single-lane roles (TMA producer, MMA issuer)
+constexpr int kMmaWarp = kEpiWarps + 1;
+constexpr int kAllocWarp = kEpiWarps + 2;
+constexpr int kThreads = 32 * (kEpiWarps + 4);   // 512
 static_assert(STAGES >= 3, "B ring too shallow");
 static_assert(BTILE_BYTES % 1024 == 0 && kEpiCols == 80 && SF_COL + SF_COLS <= 512, "layout");
 
 // Epilogue index packing: key_j = <a,b_j> + (127 - j)/128 for column j < 80 of a warp's part.  One FADD per
-// element (FMA pipe; the addend is a constant-bank operand), then a plain max tree (ALU pipe): the maximum key
+// element (FMA pipe; the addend is an immediate), then a plain max tree (ALU pipe): the maximum key
 // carries the maximum dot product (its integer part) AND the lowest column attaining it (its fraction).
 // |dot| <= 256 and the fraction has 7 bits: every key is exact in fp32.
-__constant__ float c_colkey[80] = {127.f / 128.f, 126.f / 128.f, 125.f / 128.f, 124.f / 128.f, 123.f / 128.f, 122.f / 128.f, 121.f / 128.f, 120.f / 128.f, 119.f / 128.f, 118.f / 128.f, 117.f / 128.f, 116.f / 128.f, 115.f / 128.f, 114.f / 128.f, 113.f / 128.f, 112.f / 128.f, 111.f / 128.f, 110.f / 128.f, 109.f / 128.f, 108.f / 128.f, 107.f / 128.f, 106.f / 128.f, 105.f / 128.f, 104.f / 128.f, 103.f / 128.f, 102.f / 128.f, 101.f / 128.f, 100.f / 128.f, 99.f / 128.f, 98.f / 128.f, 97.f / 128.f, 96.f / 128.f, 95.f / 128.f, 94.f / 128.f, 93.f / 128.f, 92.f / 128.f, 91.f / 128.f, 90.f / 128.f, 89.f / 128.f, 88.f / 128.f, 87.f / 128.f, 86.f / 128.f, 85.f / 128.f, 84.f / 128.f, 83.f / 128.f, 82.f / 128.f, 81.f / 128.f, 80.f / 128.f, 79.f / 128.f, 78.f / 128.f, 77.f / 128.f, 76.f / 128.f, 75.f / 128.f, 74.f / 128.f, 73.f / 128.f, 72.f / 128.f, 71.f / 128.f, 70.f / 128.f, 69.f / 128.f, 68.f / 128.f, 67.f / 128.f, 66.f / 128.f, 65.f / 128.f, 64.f / 128.f, 63.f / 128.f, 62.f / 128.f, 61.f / 128.f, 60.f / 128.f, 59.f / 128.f, 58.f / 128.f, 57.f / 128.f, 56.f / 128.f, 55.f / 128.f, 54.f / 128.f, 53.f / 128.f, 52.f / 128.f, 51.f / 128.f, 50.f / 128.f, 49.f / 128.f, 48.f / 128.f};
+// (the addend is written as a compile-time literal so that it becomes an FADD immediate)
 
 struct alignas(16) WorkUnit {
     uint32_t a_row0, b_row0;   // operand rows (in the unpacked array) of the unit's first query / the train image's row 0
@@ -139,7 +142,7 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 2) {
+    if (warp == kAllocWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_smem), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
@@ -161,7 +164,7 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     __syncthreads();
     tc_fence_after();
 
-    if (warp == 0) {
+    if (warp == kProdWarp) {
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
@@ -183,7 +186,7 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, abuf = 0, a_phase = 0, slot = 0, slot_phase = 0;
             const uint32_t a_lo0 = sdesc_lo(a_smem), b_lo0 = sdesc_lo(b_smem);
@@ -218,7 +221,7 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 if (++abuf == A_BUFS) { abuf = 0; a_phase ^= 1; }
             }
         }
-    } else if (warp >= kEpiWarp0) {
+    } else if (warp < kEpiWarps) {
         // ================= epilogue: 12 warps; warp = (lane quadrant, 80-column part) of every accumulator ==========
         const int quad = warp & 3;                        // TMEM lanes [32*quad, 32*quad+32)
         const int c0 = ((warp - kEpiWarp0) >> 2) * kEpiCols; // accumulator columns [c0, c0+80)
@@ -256,9 +259,9 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         if (dbg == 4) continue;
                         float v[kEpiCols];
 #pragma unroll
-                        for (int j = 0; j < 64; ++j) v[j] = __int_as_float(ra[j]) + c_colkey[j];
+                        for (int j = 0; j < 64; ++j) v[j] = __int_as_float(ra[j]) + (float)(127 - j) * 0.0078125f;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[64 + j] = __int_as_float(rb[j]) + c_colkey[64 + j];
+                        for (int j = 0; j < 16; ++j) v[64 + j] = __int_as_float(rb[j]) + (float)(63 - j) * 0.0078125f;
                         if (dbg == 1) { best_val[s] = fmaxf(best_val[s], v[0] + v[79]); continue; }   // DEBUG 1: no ALU
                         if (c0 + kEpiCols > valid) {                         // tail tile: mask columns outside the image
 #pragma unroll
@@ -291,7 +294,7 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == kAllocWarp) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
     }

@@ -10,14 +10,14 @@ from microcases import MICROCASES, run_microcase
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = ["popc", "tc"]
+KERNELS = ["popc", "tc", "fp4"]
 
 
 def _select(ctx, kernel):
     from sfm_gms_b200 import api
 
     try:
-        ctx.set_option(api.OPT_HAMMING_KERNEL, api.HAMMING_POPC if kernel == "popc" else api.HAMMING_TC)
+        ctx.set_option(api.OPT_HAMMING_KERNEL, {"popc": api.HAMMING_POPC, "tc": api.HAMMING_TC, "fp4": api.HAMMING_FP4}[kernel])
     except api.SfmGmsError as e:
         pytest.skip("kernel %s not available: %s" % (kernel, e))
 
