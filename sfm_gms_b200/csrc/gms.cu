@@ -17,6 +17,8 @@
 //
 // Roofline: HBM/L2 bandwidth.  Algorithmic bytes per pair (SURVEY §8d figure ii):
 //   sum over used (scale,shift) of [4*400*G_r zero + 4*400*G_r scan + 12*N RMW] + 8*N*H mark + N.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace sfmgms {
@@ -51,15 +53,17 @@ struct Layout {
     size_t total_words;
 };
 
-__host__ __device__ inline Layout make_layout(int n_scales, int n_rot) {
+// dense = true: histograms live in global memory (general path); dense = false: they live in shared memory
+// (gms_vote_smem_kernel) and the per-pair scratch shrinks to the hypothesis counters and the cell-pair table.
+__host__ __device__ inline Layout make_layout(int n_scales, int n_rot, bool dense = true) {
     Layout L;
     L.n_scales = n_scales; L.n_rot = n_rot;
     size_t o = 0;
-    L.cnt_off = o; o += 4 * kCellsL;
+    L.cnt_off = o; o += dense ? 4 * kCellsL : 0;
     L.counts_off = o; o += 64;
     for (int s = 0; s < kNumScales; ++s) {
         L.hist_off[s] = o;
-        if (s < n_scales) { int w = right_grid_w(s); o += (size_t)4 * kCellsL * w * w; }
+        if (dense && s < n_scales) { int w = right_grid_w(s); o += (size_t)4 * kCellsL * w * w; }
     }
     L.zero_words = o;
     L.cp_off = o; o += ((size_t)n_scales * n_rot * 4 * kCellsL + 1) / 2;
@@ -68,6 +72,7 @@ __host__ __device__ inline Layout make_layout(int n_scales, int n_rot) {
 }
 
 // ---- a4 + a5 + a7: normalise, cell indices for all shifts/scales, histogram RMW ----------------------
+template <bool kHist>   // kHist = false: only the per-match cell indices (the histograms are built in shared memory later)
 __global__ void __launch_bounds__(256) gms_assign_kernel(const PairDesc* __restrict__ pairs, PairResult* results,
                                                          int32_t* scratch, Layout L, uint16_t* lidx,
                                                          uint16_t* ridx, long long chunk_match_base,
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(256) gms_assign_kernel(const PairDesc* __restr
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             lidx[(size_t)t * chunk_matches + mi] = l[t] < 0 ? kNoCell : (uint16_t)l[t];
-            if (l[t] >= 0) atomicAdd(&sp[L.cnt_off + t * kCellsL + l[t]], 1);
+            if (kHist && l[t] >= 0) atomicAdd(&sp[L.cnt_off + t * kCellsL + l[t]], 1);
         }
         for (int s = 0; s < L.n_scales; ++s) {
             // getGridIndexRight, DLL @VA 0x180047d60
@@ -121,10 +126,12 @@ __global__ void __launch_bounds__(256) gms_assign_kernel(const PairDesc* __restr
             const int rx = cv_floor_f(__fmul_rn((float)w, nx2)), ry = cv_floor_f(__fmul_rn((float)w, ny2));
             const int r = rx + ry * w;   // in [0, w*w) for in-domain points
             ridx[(size_t)s * chunk_matches + mi] = (uint16_t)r;
-            int32_t* h = sp + L.hist_off[s];
+            if (kHist) {
+                int32_t* h = sp + L.hist_off[s];
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
-                if (l[t] >= 0) atomicAdd(&h[((size_t)t * kCellsL + l[t]) * (w * w) + r], 1);
+                for (int t = 0; t < 4; ++t)
+                    if (l[t] >= 0) atomicAdd(&h[((size_t)t * kCellsL + l[t]) * (w * w) + r], 1);
+            }
         }
     }
 }
@@ -180,6 +187,79 @@ __global__ void __launch_bounds__(256) gms_verify_kernel(int32_t* scratch, Layou
             if ((double)score < thresh) out = -2;
         }
         if (lane == 0) cpv[(((size_t)s * L.n_rot + r) * 4 + t) * kCellsL + cell] = (int16_t)out;
+    }
+}
+
+// ---- a7 + a8 in shared memory: histogram of one (pair, scale, shift) for a BAND of left-grid rows (+1 halo row
+// on each side, which the 3x3 support needs), built with shared-memory atomics on 16-bit counters (two per word;
+// valid while a pair has < 65536 matches, the launcher checks), then per-cell argmax and verification exactly as
+// gms_verify_kernel.  Nothing but the 400-entry cell-pair table goes back to global memory.
+__global__ void __launch_bounds__(256) gms_vote_smem_kernel(const PairDesc* __restrict__ pairs, int32_t* scratch, Layout L,
+                                                            double factor, const uint16_t* __restrict__ lidx,
+                                                            const uint16_t* __restrict__ ridx, long long chunk_match_base,
+                                                            long long chunk_matches, int s, int band_rows) {
+    extern __shared__ uint32_t sm_u32[];
+    const PairDesc pd = pairs[blockIdx.z];
+    const int t = blockIdx.y;
+    const int w = right_grid_w(s), gr = w * w;
+    const int y0 = blockIdx.x * band_rows, y1 = min(kGridL, y0 + band_rows);
+    const int ys0 = max(0, y0 - 1), ys1 = min(kGridL, y1 + 1);
+    const int cells_sm = (ys1 - ys0) * kGridL;                 // left cells held in shared memory
+    const int hist_words = cells_sm * gr / 2;                   // gr is even for every scale
+    uint32_t* h32 = sm_u32;
+    int* cnt = reinterpret_cast<int*>(sm_u32 + hist_words);
+    for (int i = threadIdx.x; i < hist_words + cells_sm; i += blockDim.x) sm_u32[i] = 0u;
+    __syncthreads();
+    const uint16_t* lt = lidx + (size_t)t * chunk_matches + (pd.match_base - chunk_match_base);
+    const uint16_t* rs = ridx + (size_t)s * chunk_matches + (pd.match_base - chunk_match_base);
+    const int lo = ys0 * kGridL, hi = ys1 * kGridL;
+    for (int i = threadIdx.x; i < pd.n_matches; i += blockDim.x) {
+        const int l = lt[i];
+        if (l >= lo && l < hi) {                                // kNoCell (0xFFFF) fails this test too
+            const int idx = (l - lo) * gr + rs[i];
+            atomicAdd(&cnt[l - lo], 1);
+            atomicAdd(&h32[idx >> 1], 1u << ((idx & 1) * 16));
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    int16_t* cpv = reinterpret_cast<int16_t*>(scratch + (size_t)blockIdx.z * L.total_words + L.cp_off);
+    const uint16_t* h16 = reinterpret_cast<const uint16_t*>(h32);
+    for (int cell = y0 * kGridL + warp; cell < y1 * kGridL; cell += nwarps) {
+        const int local = cell - lo;
+        int cp = -1;
+        if (cnt[local] > 0) {
+            const uint32_t* row = h32 + (size_t)local * (gr / 2);
+            uint32_t bestk = 0;
+            for (int wd = lane; wd < gr / 2; wd += 32) {
+                const uint32_t u = row[wd];
+                const uint32_t c0 = u & 0xFFFFu, c1 = u >> 16;
+                const uint32_t k0 = (c0 << 11) | (uint32_t)(2047 - 2 * wd), k1 = (c1 << 11) | (uint32_t)(2046 - 2 * wd);
+                bestk = (c0 > 0 && k0 > bestk) ? k0 : bestk;
+                bestk = (c1 > 0 && k1 > bestk) ? k1 : bestk;
+            }
+            bestk = __reduce_max_sync(0xffffffffu, bestk);
+            cp = 2047 - (int)(bestk & 2047u);
+        }
+        for (int r = 0; r < L.n_rot; ++r) {
+            int out = cp;
+            if (cp >= 0) {
+                int v = 0, c = 0;
+                bool valid = false;
+                if (lane < 9) {
+                    const int ll = nb9(cell, lane, kGridL, kGridL);
+                    const int rr = nb9(cp, c_rot[r][lane] - 1, w, w);
+                    valid = (ll != -1 && rr != -1);
+                    if (valid) { v = h16[(size_t)(ll - lo) * gr + rr]; c = cnt[ll - lo]; }
+                }
+                const int score = __reduce_add_sync(0xffffffffu, v);
+                const int tsum = __reduce_add_sync(0xffffffffu, c);
+                const int num = __popc(__ballot_sync(0xffffffffu, valid));
+                const double thresh = __dmul_rn(factor, __dsqrt_rn(__ddiv_rn((double)tsum, (double)num)));
+                if ((double)score < thresh) out = -2;
+            }
+            if (lane == 0) cpv[(((size_t)s * L.n_rot + r) * 4 + t) * kCellsL + cell] = (int16_t)out;
+        }
     }
 }
 
@@ -277,13 +357,22 @@ long long gms_match_rows(const PairDesc* h_pairs, int n) {
     const long long rows_last = last.mq ? last.n_matches : (last.n1 > last.n_matches ? last.n1 : last.n_matches);
     return last.match_base + rows_last - h_pairs[0].match_base;
 }
-size_t gms_scratch_bytes_per_pair(int n_scales) { return make_layout(n_scales, kNumRot).total_words * 4; }
+size_t gms_scratch_bytes_per_pair(int n_scales) { return make_layout(n_scales, kNumRot, true).total_words * 4; }
 size_t gms_match_scratch_bytes(long long n_matches_total, int n_scales) {
     return (size_t)n_matches_total * 2 * (4 + n_scales) + 256;
 }
 
-// Runs GMS for n_pairs pairs, in chunks sized so that the dense histograms of a chunk fit the scratch
-// budget (kept L2-resident by the caller's choice of hist_scratch_bytes).
+// Left-grid rows per shared-memory band for scale s: (rows + 2 halo) * 20 cells * (G_r u16 + one int) must fit.
+static int smem_band_rows(int s) { return s == 0 ? 5 : s == 1 ? 20 : s == 2 ? 10 : s == 3 ? 4 : 1; }
+static size_t smem_band_bytes(int s) {
+    const int w = right_grid_w(s), gr = w * w, b = smem_band_rows(s);
+    const int rows = b >= kGridL ? kGridL : b + 2;
+    return (size_t)rows * kGridL * ((size_t)gr * 2 + 4);
+}
+
+// Runs GMS for n_pairs pairs.  Default: histograms in shared memory (one launch per scale for the whole batch).
+// Fallback (a pair with >= 65536 matches, or SFMGMS_GMS_DENSE=1): dense histograms in global memory, in chunks
+// sized so that a chunk's histograms fit the scratch budget (kept L2-resident by the caller's choice).
 int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, int with_rotation, int with_scale,
                double factor, PairResult* d_results, void* d_hist_scratch, size_t hist_scratch_bytes,
                void* d_match_scratch, cudaStream_t st) {
@@ -291,13 +380,20 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
     const int n_scales = with_scale ? kNumScales : 1;
     const int n_rot = with_rotation ? kNumRot : 1;
     const int flags_on = (with_rotation || with_scale) ? 1 : 0;
-    const Layout L = make_layout(n_scales, n_rot);
+    int max_all = 0;
+    for (int p = 0; p < n_pairs; ++p) if (h_pairs[p].n_matches > max_all) max_all = h_pairs[p].n_matches;
+    static const bool force_dense = getenv("SFMGMS_GMS_DENSE") != nullptr;
+    const bool dense = force_dense || max_all >= 65536;
+    const Layout L = make_layout(n_scales, n_rot, dense);
     const size_t per_pair = L.total_words * 4;
     int chunk_cap = (int)(hist_scratch_bytes / per_pair);
     if (chunk_cap < 1) return -1;
     if (chunk_cap > 32768) chunk_cap = 32768;
     int launches = 0;
     int32_t* scratch = static_cast<int32_t*>(d_hist_scratch);
+    if (!dense) {
+        if (cudaFuncSetAttribute(gms_vote_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
+    }
     for (int c0 = 0; c0 < n_pairs; c0 += chunk_cap) {
         const int cn = (n_pairs - c0 < chunk_cap) ? n_pairs - c0 : chunk_cap;
         int max_m = 0;
@@ -312,14 +408,29 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
         // zero cnt/counts/hist of every pair in the chunk (cp is fully rewritten by verify)
         cudaMemsetAsync(scratch, 0, (size_t)cn * per_pair, st);
         const int bx = max_m > 0 ? (max_m + 255) / 256 : 1;
-        if (max_m > 0) {
-            gms_assign_kernel<<<dim3(bx, 1, cn), 256, 0, st>>>(d_pairs + c0, d_results + c0, scratch, L, lidx, ridx,
-                                                             cbase, cm);
+        if (dense) {
+            if (max_m > 0) {
+                gms_assign_kernel<true><<<dim3(bx, 1, cn), 256, 0, st>>>(d_pairs + c0, d_results + c0, scratch, L, lidx, ridx,
+                                                                       cbase, cm);
+                ++launches;
+            }
+            const long long warps = (long long)cn * n_scales * 4 * kCellsL;
+            gms_verify_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(scratch, L, factor, cn);
             ++launches;
+        } else {
+            if (max_m > 0) {
+                gms_assign_kernel<false><<<dim3(bx, 1, cn), 256, 0, st>>>(d_pairs + c0, d_results + c0, scratch, L, lidx, ridx,
+                                                                        cbase, cm);
+                ++launches;
+            }
+            for (int s = 0; s < n_scales; ++s) {
+                const int b = smem_band_rows(s);
+                const int bands = (kGridL + b - 1) / b;
+                gms_vote_smem_kernel<<<dim3(bands, 4, cn), 256, smem_band_bytes(s), st>>>(d_pairs + c0, scratch, L, factor, lidx,
+                                                                                        ridx, cbase, cm, s, b);
+                ++launches;
+            }
         }
-        const long long warps = (long long)cn * n_scales * 4 * kCellsL;
-        gms_verify_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(scratch, L, factor, cn);
-        ++launches;
         if (max_m > 0) {
             gms_count_kernel<<<dim3(bx, n_scales * n_rot, cn), 256, 0, st>>>(d_pairs + c0, scratch, L, lidx, ridx, cbase,
                                                                          cm, flags_on ? 0 : 1);
