@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256) gms_verify_kernel(int32_t* scratch, Layou
 // on each side, which the 3x3 support needs), built with shared-memory atomics on 16-bit counters (two per word;
 // valid while a pair has < 65536 matches, the launcher checks), then per-cell argmax and verification exactly as
 // gms_verify_kernel.  Nothing but the 400-entry cell-pair table goes back to global memory.
-__global__ void __launch_bounds__(256) gms_vote_smem_kernel(const PairDesc* __restrict__ pairs, int32_t* scratch, Layout L,
+__global__ void __launch_bounds__(512) gms_vote_smem_kernel(const PairDesc* __restrict__ pairs, int32_t* scratch, Layout L,
                                                             double factor, const uint16_t* __restrict__ lidx,
                                                             const uint16_t* __restrict__ ridx, long long chunk_match_base,
                                                             long long chunk_matches, int s, int band_rows) {
@@ -208,17 +208,30 @@ __global__ void __launch_bounds__(256) gms_vote_smem_kernel(const PairDesc* __re
     const int hist_words = cells_sm * gr / 2;                   // gr is even for every scale
     uint32_t* h32 = sm_u32;
     int* cnt = reinterpret_cast<int*>(sm_u32 + hist_words);
-    for (int i = threadIdx.x; i < hist_words + cells_sm; i += blockDim.x) sm_u32[i] = 0u;
+    {
+        uint4* z = reinterpret_cast<uint4*>(sm_u32);                   // (hist_words + cells_sm) is a multiple of 4
+        for (int i = threadIdx.x; i < (hist_words + cells_sm) / 4; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     __syncthreads();
     const uint16_t* lt = lidx + (size_t)t * chunk_matches + (pd.match_base - chunk_match_base);
     const uint16_t* rs = ridx + (size_t)s * chunk_matches + (pd.match_base - chunk_match_base);
     const int lo = ys0 * kGridL, hi = ys1 * kGridL;
-    for (int i = threadIdx.x; i < pd.n_matches; i += blockDim.x) {
-        const int l = lt[i];
-        if (l >= lo && l < hi) {                                // kNoCell (0xFFFF) fails this test too
-            const int idx = (l - lo) * gr + rs[i];
-            atomicAdd(&cnt[l - lo], 1);
-            atomicAdd(&h32[idx >> 1], 1u << ((idx & 1) * 16));
+    // 4 independent loads in flight per thread: this loop is latency-bound, not bandwidth-bound
+    for (int i0 = threadIdx.x; i0 < pd.n_matches; i0 += 4 * blockDim.x) {
+        int l[4], r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = i0 + k * blockDim.x;
+            l[k] = i < pd.n_matches ? (int)__ldg(lt + i) : 0xFFFF;
+            r[k] = i < pd.n_matches ? (int)__ldg(rs + i) : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (l[k] >= lo && l[k] < hi) {                      // kNoCell (0xFFFF) fails this test too
+                const int idx = (l[k] - lo) * gr + r[k];
+                atomicAdd(&cnt[l[k] - lo], 1);
+                atomicAdd(&h32[idx >> 1], 1u << ((idx & 1) * 16));
+            }
         }
     }
     __syncthreads();
@@ -426,7 +439,7 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
             for (int s = 0; s < n_scales; ++s) {
                 const int b = smem_band_rows(s);
                 const int bands = (kGridL + b - 1) / b;
-                gms_vote_smem_kernel<<<dim3(bands, 4, cn), 256, smem_band_bytes(s), st>>>(d_pairs + c0, scratch, L, factor, lidx,
+                gms_vote_smem_kernel<<<dim3(bands, 4, cn), 512, smem_band_bytes(s), st>>>(d_pairs + c0, scratch, L, factor, lidx,
                                                                                         ridx, cbase, cm, s, b);
                 ++launches;
             }
