@@ -20,7 +20,6 @@ collective; weak scaling); timing = max over ranks.
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -75,49 +74,50 @@ def gen_pairs_torch(n_pairs, seed, device):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md clocks line), sampled every
+    10 ms through NVML (the same counters nvidia-smi prints; nvidia-smi's own 100 ms minimum period is too coarse for
+    a timed region of tens of milliseconds)."""
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.idx, self.samples, self.stop_flag, self.t = gpu_index, [], False, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.t = threading.Thread(target=self._run, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.t = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                                     nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 9:
-                for k, nm in enumerate(names):
-                    if r[5 + k].lower().startswith("active"):
-                        reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.t is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self.stop_flag = True
+        self.t.join(timeout=1)
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(k for k, bit in names.items() if any(s[2] & bit for s in self.samples))
+        sm = [s[0] for s in self.samples]
+        pw = [s[1] for s in self.samples]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.max_sm), "reasons": reasons,
+                "power_w_median": float(np.median(pw)) if pw else None, "samples": len(sm)}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -195,7 +195,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pairs", type=int, default=256, help="pairs per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -384,6 +384,14 @@ def main():
                     "peak_source": "%gx measured sustained bf16 TFLOP/s (MEASURED_PEAKS.json); %s dense rate = %gx bf16 on "
                                    "sm_100a" % (mult, "mxf4" if kind == "fp4" else "int8", mult),
                     "traffic": None, "algorithmic_units_per_launch": dists, "avg_launch_ms": per_launch_s * 1e3}
+        try:   # DRAM bytes of the dominant kernel from the committed ncu --set full capture (same command, P pairs/launch)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if tr.get("kernel") == roof["kernel"]:
+                roof["traffic"] = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * P / tr["pairs_per_launch"]
+                roof["traffic_source"] = "profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
+                roof["algorithmic_bytes_per_launch"] = P * (2 * N_KP * (128 if kind == "fp4" else 256) + 4 * N_KP)
+        except Exception:
+            pass
         line = {"metric": "image pairs/sec (ORB-10k, BF-Hamming+GMS)", "value": value, "unit": "pairs/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
                 "us_per_pair": 1e3 * ms_total / args.steps / total_pairs * world, "higher_is_better": True,

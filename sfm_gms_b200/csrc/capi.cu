@@ -196,8 +196,9 @@ int enqueue_range(sfmgms_ctx* ctx, const std::vector<PairDesc>& hp, int r0, int 
     if (hpp[0].img1 < 0) tc_invalidate(ctx->tc);   // ad-hoc buffers: contents change between calls
     if (do_hamming) {
         const int kind = choose_hamming(ctx);
-        for (int c0 = 0; c0 < rn; c0 += 32768) {
-            const int cn = (rn - c0 < 32768) ? rn - c0 : 32768;
+        const int kMaxPerLaunch = (kind == SFMGMS_HAMMING_FP4) ? 768 : 32768;   // fp4: launch map is a kernel parameter
+        for (int c0 = 0; c0 < rn; c0 += kMaxPerLaunch) {
+            const int cn = (rn - c0 < kMaxPerLaunch) ? rn - c0 : kMaxPerLaunch;
             int l;
             if (kind == SFMGMS_HAMMING_TC) {
                 l = launch_hamming_tc(ctx->tc, dp + c0, hpp + c0, cn, ctx->sm_count, st);

@@ -61,11 +61,55 @@ static_assert(BTILE_BYTES % 1024 == 0 && kEpiCols == 80 && SF_COL + SF_COLS <= 5
 // |dot| <= 256 and the fraction has 7 bits: every key is exact in fp32.
 // (the addend is written as a compile-time literal so that it becomes an FADD immediate)
 
-struct alignas(16) WorkUnit {
+struct WorkUnit {
     uint32_t a_row0, b_row0;   // operand rows (in the unpacked array) of the unit's first query / the train image's row 0
-    int32_t n_rows, t_begin, t_end, pad;
+    int32_t n_rows, t_begin, t_end;
     uint32_t* key;
 };
+
+// Work decomposition travels as a kernel PARAMETER (no table upload: the copy engine may be busy with a queued
+// image-set transfer, and a PCIe read from the SMs would contend with it): prefix[p] = first unit of pair p.
+// unit = (pair, block of MSUB*128 query rows, one of `tsplit` contiguous ranges of train tiles).
+constexpr int kMaxPairsPerLaunch = 768;
+struct LaunchMap {
+    const uint8_t* lo;         // first descriptor row of the operand span (row index = (ptr - lo) / 32)
+    int n_pairs, tsplit, n_units, pad;
+    int prefix[kMaxPairsPerLaunch + 1];
+};
+
+__host__ __device__ inline int units_of_pair(int n1, int n2, int tsplit, int* nts_out) {
+    if (n1 <= 0 || n2 <= 0) { if (nts_out) *nts_out = 0; return 0; }
+    const int tiles = (n2 + BN - 1) / BN;
+    const int tper = (tiles + tsplit - 1) / tsplit;
+    const int nts = (tiles + tper - 1) / tper;
+    if (nts_out) *nts_out = nts;
+    return ((n1 + BM * MSUB - 1) / (BM * MSUB)) * nts;
+}
+
+__device__ __forceinline__ WorkUnit make_unit(const LaunchMap& lm, const PairDesc* __restrict__ pairs, int u) {
+    int lo = 0, hi = lm.n_pairs;                 // largest p with prefix[p] <= u
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (lm.prefix[mid] <= u) lo = mid; else hi = mid;
+    }
+    const PairDesc* pd = pairs + lo;
+    const int n1 = pd->n1, n2 = pd->n2;
+    int nts;
+    units_of_pair(n1, n2, lm.tsplit, &nts);
+    const int local = u - lm.prefix[lo];
+    const int qb = local / nts, ts = local - qb * nts;
+    const int tiles = (n2 + BN - 1) / BN;
+    const int tper = (tiles + lm.tsplit - 1) / lm.tsplit;
+    const int q0 = qb * (BM * MSUB);
+    WorkUnit w;
+    w.a_row0 = (uint32_t)((pd->desc1 - lm.lo) >> 5) + q0;
+    w.b_row0 = (uint32_t)((pd->desc2 - lm.lo) >> 5);
+    w.n_rows = min(n1 - q0, BM * MSUB);
+    w.t_begin = ts * tper * BN;
+    w.t_end = min((ts + 1) * tper * BN, n2);
+    w.key = pd->key + q0;
+    return w;
+}
 
 constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
 __device__ __forceinline__ uint32_t sdesc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
@@ -109,14 +153,11 @@ __global__ void __launch_bounds__(256) unpack_fp4_kernel(const uint32_t* __restr
     for (; i < n_words; i += step) out[i] = fp4_from_word(__ldg(desc + i));
 }
 
-__global__ void __launch_bounds__(256) pull_table_kernel(const uint4* __restrict__ host_src, uint4* __restrict__ dst, int n16) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = host_src[i];
-}
-
 template <int dbg>   // dbg != 0: timing experiments only (results invalid); production is dbg = 0
 __global__ void __launch_bounds__(kThreads, 1)
 hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmapB,
-                   const WorkUnit* __restrict__ units, int n_units) {
+                   const __grid_constant__ LaunchMap lm, const PairDesc* __restrict__ pairs) {
+    const int n_units = lm.n_units;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_smem = smem_base;
@@ -170,7 +211,7 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
             uint32_t stage = 0, phase = 0, abuf = 0, a_phase = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const WorkUnit wu = units[u];
+                const WorkUnit wu = make_unit(lm, pairs, u);
                 const int nsub = (wu.n_rows + BM - 1) / BM;
                 mbar_wait(a_empty_bar + 8 * abuf, a_phase ^ 1);
                 mbar_expect_tx(a_full_bar + 8 * abuf, (uint32_t)(nsub * TILE_BYTES));
@@ -192,7 +233,7 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             const uint32_t a_lo0 = sdesc_lo(a_smem), b_lo0 = sdesc_lo(b_smem);
             const uint32_t sf = tmem_base + SF_COL;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const WorkUnit wu = units[u];
+                const WorkUnit wu = make_unit(lm, pairs, u);
                 const int nsub = (wu.n_rows + BM - 1) / BM;
                 const int ntiles = (wu.t_end - wu.t_begin + BN - 1) / BN;
                 mbar_wait(a_full_bar + 8 * abuf, a_phase);
@@ -227,7 +268,7 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const int c0 = ((warp - kEpiWarp0) >> 2) * kEpiCols; // accumulator columns [c0, c0+80)
         uint32_t slot = 0, slot_phase = 0;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const WorkUnit wu = units[u];
+            const WorkUnit wu = make_unit(lm, pairs, u);
             const int nsub = (wu.n_rows + BM - 1) / BM;
             float best_val[MSUB];
             int best_dot[MSUB], best_idx[MSUB];
@@ -335,7 +376,6 @@ const char* fp4_last_error() { return g_err; }
 
 int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, int sm_count,
                        cudaStream_t st) {
-    (void)d_pairs;
     if (n_pairs <= 0) return 0;
     if (!load_encode()) return -1;
     int launches = 0;
@@ -391,65 +431,37 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled(B) failed (%d)", (int)r); return -1; }
     }
+    // work decomposition: pick the train-range split that minimises the static-schedule makespan
+    // ceil(units / #SM) / tsplit (small sub-batches of the pipelined host path otherwise lose a whole round)
     long long qblocks = 0;
-    int max_tiles = 1;
+    int min_tiles = 1 << 30;
     for (int p = 0; p < n_pairs; ++p) {
         if (h_pairs[p].n1 <= 0 || h_pairs[p].n2 <= 0) continue;
         qblocks += (h_pairs[p].n1 + BM * MSUB - 1) / (BM * MSUB);
         const int tiles = (h_pairs[p].n2 + BN - 1) / BN;
-        if (tiles > max_tiles) max_tiles = tiles;
+        if (tiles < min_tiles) min_tiles = tiles;
     }
     int tsplit = 1;
-    if (qblocks < 2LL * sm_count) {
-        long long t = (2LL * sm_count + qblocks - 1) / qblocks;
-        if (t > max_tiles) t = max_tiles;
-        tsplit = (int)(t < 1 ? 1 : t);
-    }
-    const size_t max_units = (size_t)qblocks * tsplit;
-    const size_t wbytes = (max_units * sizeof(WorkUnit) + 255) & ~(size_t)255;
-    if (s.work_used + wbytes > s.h_work_cap || s.work_used + wbytes > s.work_cap) {
-        if (cudaStreamSynchronize(st) != cudaSuccess) { snprintf(g_err, sizeof g_err, "stream sync failed"); return -1; }
-        s.work_used = 0;
-        if (16 * wbytes > s.h_work_cap) {
-            if (s.h_work) cudaFreeHost(s.h_work);
-            s.h_work = nullptr; s.h_work_cap = 0;
-            const size_t want = 16 * wbytes + (8u << 20);
-            if (cudaMallocHost(&s.h_work, want) != cudaSuccess) { snprintf(g_err, sizeof g_err, "cudaMallocHost failed"); return -1; }
-            s.h_work_cap = want;
-        }
-        if (!ensure_dev(s.d_work, s.work_cap, s.h_work_cap)) return -1;
-    }
-    WorkUnit* wu = reinterpret_cast<WorkUnit*>(static_cast<char*>(s.h_work) + s.work_used);
-    WorkUnit* d_wu = reinterpret_cast<WorkUnit*>(static_cast<char*>(s.d_work) + s.work_used);
-    size_t n_units = 0;
-    for (int p = 0; p < n_pairs; ++p) {
-        const PairDesc& pd = h_pairs[p];
-        if (pd.n1 <= 0 || pd.n2 <= 0) continue;
-        const uint32_t arow = (uint32_t)((pd.desc1 - lo) / 32), brow = (uint32_t)((pd.desc2 - lo) / 32);
-        const int tiles = (pd.n2 + BN - 1) / BN;
-        const int tper = (tiles + tsplit - 1) / tsplit;
-        for (int q0 = 0; q0 < pd.n1; q0 += BM * MSUB) {
-            for (int ts = 0; ts * tper < tiles; ++ts) {
-                WorkUnit& w = wu[n_units++];
-                w.a_row0 = arow + q0;
-                w.b_row0 = brow;
-                w.n_rows = (pd.n1 - q0 < BM * MSUB) ? pd.n1 - q0 : BM * MSUB;
-                w.t_begin = ts * tper * BN;
-                const int te = (ts + 1) * tper * BN;
-                w.t_end = te < pd.n2 ? te : pd.n2;
-                w.pad = 0;
-                w.key = pd.key + q0;
-            }
-        }
-    }
-    if (n_units == 0) return launches;
     {
-        const int n16 = (int)(n_units * sizeof(WorkUnit) / 16);
-        int blocks = (n16 + 255) / 256;
-        if (blocks > 64) blocks = 64;
-        pull_table_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(wu), reinterpret_cast<uint4*>(d_wu), n16);
-        ++launches;
+        double best = 1e30;
+        const int ts_max = qblocks < 2LL * sm_count ? 64 : 4;
+        for (int ts = 1; ts <= ts_max && ts <= (min_tiles > 0 ? min_tiles : 1); ++ts) {
+            const long long units = qblocks * ts;
+            const double makespan = (double)((units + sm_count - 1) / sm_count) / ts * (1.0 + 0.01 * (ts - 1));
+            if (makespan < best - 1e-9) { best = makespan; tsplit = ts; }
+        }
     }
+    if (n_pairs > kMaxPairsPerLaunch) { snprintf(g_err, sizeof g_err, "too many pairs per launch"); return -1; }
+    LaunchMap lm;
+    lm.lo = lo; lm.n_pairs = n_pairs; lm.tsplit = tsplit; lm.pad = 0;
+    int n_units = 0;
+    for (int p = 0; p < n_pairs; ++p) {
+        lm.prefix[p] = n_units;
+        n_units += units_of_pair(h_pairs[p].n1, h_pairs[p].n2, tsplit, nullptr);
+    }
+    lm.prefix[n_pairs] = n_units;
+    lm.n_units = n_units;
+    if (n_units == 0) return launches;
     static const int dbg = getenv("SFMGMS_TC_DEBUG") ? atoi(getenv("SFMGMS_TC_DEBUG")) : 0;   // timing experiments only
     auto kern = dbg == 1 ? hamming_fp4_kernel<1> : dbg == 3 ? hamming_fp4_kernel<3> : dbg == 4 ? hamming_fp4_kernel<4>
                                                                                                    : hamming_fp4_kernel<0>;
@@ -457,9 +469,8 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
         snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute(smem=%d) failed", SMEM_BYTES);
         return -1;
     }
-    const int grid = (int)(n_units < (size_t)sm_count ? n_units : (size_t)sm_count);
-    kern<<<grid, kThreads, SMEM_BYTES, st>>>(tmap, tmapB, d_wu, (int)n_units);
-    s.work_used += wbytes;
+    const int grid = n_units < sm_count ? n_units : sm_count;
+    kern<<<grid, kThreads, SMEM_BYTES, st>>>(tmap, tmapB, lm, d_pairs);
     return launches + 1;
 }
 
