@@ -841,12 +841,30 @@ int sfmgms_match_image_set(sfmgms_ctx* ctx, int n_images, const int64_t* kp_offs
     mark("pairs-uploaded");
     if (ctx->timing) { CU(cudaEventRecord(ctx->ev[0], st)); CU(cudaEventRecord(ctx->ev[1], st)); ctx->timing_mid_pending = false; }
     // ---- sub-batches in list order: wait for the chunk(s) they need, compute, hand results to the D2H stream ----
-    int n_ranges = n_pairs >= 64 ? 8 : (n_pairs >= 8 ? 4 : 1);
-    const int per = (n_pairs + n_ranges - 1) / (n_ranges > 0 ? n_ranges : 1);
+    // Sub-batch sizes DECREASE along the list: compute is faster than the H2D transfer, so every sub-batch ends up
+    // waiting for its images and the time after the last byte has arrived is one sub-batch of compute — keep that
+    // one small (1/32 of the list); the early ones are large to amortise launch overheads.
+    std::vector<int> range_begin;
+    {
+        static const int kNum[] = {8, 8, 6, 4, 3, 2, 1};   // 32nds of the pair list
+        int acc = 0;
+        range_begin.push_back(0);
+        if (n_pairs >= 64) {
+            for (int k = 0; k < 6; ++k) {
+                acc += kNum[k];
+                const int b = (int)((long long)n_pairs * acc / 32);
+                if (b > range_begin.back() && b < n_pairs) range_begin.push_back(b);
+            }
+        } else if (n_pairs >= 8) {
+            for (int k = 1; k < 4; ++k) range_begin.push_back(n_pairs * k / 4);
+        }
+        range_begin.push_back(n_pairs);
+    }
     int ham_launches = 0;
     size_t ev_k = (size_t)n_chunks;
-    for (int r0 = 0; r0 < n_pairs; r0 += per) {
-        const int rn = (n_pairs - r0 < per) ? n_pairs - r0 : per;
+    for (size_t ri = 0; ri + 1 < range_begin.size(); ++ri) {
+        const int r0 = range_begin[ri], rn = range_begin[ri + 1] - r0;
+        if (rn <= 0) continue;
         int need = 0;
         for (int p = r0; p < r0 + rn; ++p) {
             const int c = chunk_of_image[hp[p].img1] > chunk_of_image[hp[p].img2] ? chunk_of_image[hp[p].img1] : chunk_of_image[hp[p].img2];
