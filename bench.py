@@ -421,22 +421,5 @@ def main():
         dist.destroy_process_group()
 
 
-def _tc_built():
-    import ctypes
-
-    from sfm_gms_b200 import api
-    try:
-        c = api.Context(int(os.environ.get("LOCAL_RANK", "0")))
-        try:
-            c.set_option(api.OPT_HAMMING_KERNEL, api.HAMMING_TC)
-            ok = True
-        except api.SfmGmsError:
-            ok = False
-        c.close()
-        return ok
-    except Exception:
-        return False
-
-
 if __name__ == "__main__":
     main()
