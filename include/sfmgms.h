@@ -84,6 +84,14 @@ int sfmgms_bf_hamming(sfmgms_ctx* ctx, const uint8_t* query, int nq, const uint8
 int sfmgms_bf_hamming_crosscheck(sfmgms_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt,
                                  int desc_bytes, int32_t* train_idx, int32_t* dist, uint8_t* keep);
 
+/*  cv::BFMatcher(NORM_L2, crossCheck=false)::match for INTEGER-VALUED float descriptors with
+ * 128 columns — what OpenCV's SIFT produces and what the reference literally runs (FeatureMatchUtil.cpp:10, 66-68).
+ * For such data OpenCV's float accumulation of sum((a-b)^2) is exact, and so is this: train_idx[i] = lowest j
+ * minimising the squared distance, dist[i] = sqrtf((float)d2), bit-identical to cv2.  Any descriptor value that is
+ * not an integer in [0,255] -> SFMGMS_ERR_ARG (general float descriptors are not implemented).  dim must be 128. */
+int sfmgms_bf_l2(sfmgms_ctx* ctx, const float* query, int nq, const float* train, int nt, int dim,
+                 int32_t* train_idx, float* dist, int* n_matches);
+
 /* ---- stage 2: replaces cv::xfeatures2d::matchGMS ----------------------------------------------
  * (FeatureMatchUtil.cpp:69; DisparityUtil.cpp:149,299).  mask[i] (0/1) for each of the n_matches input
  * matches; *mask_len = n_matches, or 0 if rotation/scale search was requested and every hypothesis had

@@ -43,6 +43,8 @@ def lib():
                                                       ctypes.c_int, ctypes.c_int, ctypes.c_double, u8p, ip, ip,
                                                       ip, ip]
         L.oracle_gms.restype = ctypes.c_int
+        L.oracle_bf_l2.argtypes = [f32p, ctypes.c_int, f32p, ctypes.c_int, ctypes.c_int, i32p, f32p, ip]
+        L.oracle_bf_l2.restype = ctypes.c_int
         L.oracle_set_num_threads.argtypes = [ctypes.c_int]
         L.oracle_num_threads.restype = ctypes.c_int
         _LIB = L
@@ -70,6 +72,21 @@ def bf_hamming(q, t):
                                  _p(idx, ctypes.c_int32), _p(dist, ctypes.c_int32), ctypes.byref(n))
     if rc:
         raise ValueError("oracle_bf_hamming rc=%d" % rc)
+    return idx[: n.value], dist[: n.value]
+
+
+def bf_l2(q, t):
+    """cv2.BFMatcher(cv2.NORM_L2).match semantics -> (train_idx int32[n], dist float32[n])."""
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    t = np.ascontiguousarray(t, dtype=np.float32)
+    nq, nt = q.shape[0], t.shape[0]
+    idx = np.empty(nq, np.int32)
+    dist = np.empty(nq, np.float32)
+    n = ctypes.c_int(0)
+    rc = lib().oracle_bf_l2(_p(q, ctypes.c_float), nq, _p(t, ctypes.c_float), nt, q.shape[1], _p(idx, ctypes.c_int32),
+                            _p(dist, ctypes.c_float), ctypes.byref(n))
+    if rc:
+        raise ValueError("oracle_bf_l2 rc=%d" % rc)
     return idx[: n.value], dist[: n.value]
 
 

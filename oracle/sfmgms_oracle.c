@@ -320,6 +320,32 @@ done:
     return rc;
 }
 
+/* (f3) cv::BFMatcher(NORM_L2, crossCheck=false)::match on float descriptors (what the reference literally runs:
+ * SIFT + BFMatcher::create(), FeatureMatchUtil.cpp:10, 66-68).  OpenCV: dist = sqrt(sum (a-b)^2) accumulated in
+ * float, strict '<' scan on the float distance => lowest trainIdx among equal FLOAT distances.  For integer-valued
+ * descriptors (OpenCV SIFT) every partial sum is an integer < 2^24, so the float accumulation is exact whatever the
+ * SIMD order OpenCV uses; for other data this sequential sum is only one of the possible roundings (documented). */
+int oracle_bf_l2(const float* q, int nq, const float* t, int nt, int dim, int32_t* train_idx, float* dist, int* n_matches) {
+    if (nq < 0 || nt < 0 || dim <= 0 || nt >= (1 << 18)) return -1;
+    if (nt == 0) { if (n_matches) *n_matches = 0; return 0; }
+    for (int i = 0; i < nq; ++i) {
+        const float* a = q + (size_t)i * dim;
+        float best = INFINITY;
+        int bestj = -1;
+        for (int j = 0; j < nt; ++j) {
+            const float* b = t + (size_t)j * dim;
+            float s = 0.f;
+            for (int k = 0; k < dim; ++k) { float d = a[k] - b[k]; s += d * d; }
+            float d = sqrtf(s);
+            if (d < best) { best = d; bestj = j; }
+        }
+        train_idx[i] = bestj;
+        dist[i] = best;
+    }
+    if (n_matches) *n_matches = nq;
+    return 0;
+}
+
 /* (f2) cross-check helper for the "next" row: mutual nearest neighbours, as
  * BFMatcher(NORM_HAMMING, crossCheck=true) does (FeatureMatchUtil.cpp:22 uses crossCheck=true
  * with NORM_L2): keep (i, j*) iff i is also the NN of j* when the roles are swapped. */

@@ -7,6 +7,7 @@ library or without a B200 raises.
 """
 from .api import (  # noqa: F401
     NORM_HAMMING,
+    NORM_L2,
     BFMatcher,
     Context,
     DMatch,
@@ -17,5 +18,5 @@ from .api import (  # noqa: F401
     matchGMS,
 )
 
-__all__ = ["NORM_HAMMING", "BFMatcher", "Context", "DMatch", "SfmGmsError", "default_context", "gms_matcher",
+__all__ = ["NORM_HAMMING", "NORM_L2", "BFMatcher", "Context", "DMatch", "SfmGmsError", "default_context", "gms_matcher",
            "load_library", "matchGMS"]

@@ -16,6 +16,7 @@ from collections import namedtuple
 import numpy as np
 
 NORM_HAMMING = 6  # cv::NORM_HAMMING
+NORM_L2 = 4       # cv::NORM_L2
 
 SFMGMS_HOST, SFMGMS_DEVICE = 0, 1
 OPT_HAMMING_KERNEL, OPT_GMS_CHUNK_BYTES, OPT_TIMING, OPT_TC_OPERAND_CACHE = 1, 2, 3, 4
@@ -63,6 +64,7 @@ def load_library():
     L.sfmgms_stream.argtypes = [c_void_p]
     L.sfmgms_stream.restype = c_void_p
     L.sfmgms_bf_hamming.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, P(c_int)]
+    L.sfmgms_bf_l2.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, P(c_int)]
     L.sfmgms_bf_hamming_crosscheck.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p,
                                                c_void_p, c_void_p]
     L.sfmgms_gms.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
@@ -166,6 +168,19 @@ class Context:
         n = ctypes.c_int(0)
         self._check(self._lib.sfmgms_bf_hamming(self._h, _ptr(q), q.shape[0], _ptr(t), t.shape[0], 32, _ptr(idx),
                                                 _ptr(dist), ctypes.byref(n)))
+        return idx[: n.value], dist[: n.value]
+
+    def bf_l2(self, query, train):
+        """cv2.BFMatcher(cv2.NORM_L2).match on integer-valued float descriptors (SIFT): (train_idx, dist float32)."""
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        t = np.ascontiguousarray(train, dtype=np.float32)
+        if q.ndim != 2 or t.ndim != 2 or q.shape[1] != 128 or t.shape[1] != 128:
+            raise SfmGmsError(1, "L2 descriptors must be N x 128 float32 (SIFT)")
+        idx = np.empty(q.shape[0], np.int32)
+        dist = np.empty(q.shape[0], np.float32)
+        n = ctypes.c_int(0)
+        self._check(self._lib.sfmgms_bf_l2(self._h, _ptr(q), q.shape[0], _ptr(t), t.shape[0], 128, _ptr(idx), _ptr(dist),
+                                           ctypes.byref(n)))
         return idx[: n.value], dist[: n.value]
 
     def bf_hamming_crosscheck(self, query, train):
@@ -364,8 +379,10 @@ class BFMatcher:
     """cv::BFMatcher look-alike for NORM_HAMMING (FeatureMatchUtil.cpp:22, 66)."""
 
     def __init__(self, normType=NORM_HAMMING, crossCheck=False, ctx=None):
-        if normType != NORM_HAMMING:
-            raise SfmGmsError(1, "only NORM_HAMMING is implemented (north-star scope); got normType=%r" % (normType,))
+        if normType not in (NORM_HAMMING, NORM_L2) or (normType == NORM_L2 and crossCheck):
+            raise SfmGmsError(1, "implemented: NORM_HAMMING (with/without crossCheck), NORM_L2 (SIFT, no crossCheck); "
+                                 "got normType=%r crossCheck=%r" % (normType, crossCheck))
+        self.normType = normType
         self.crossCheck = bool(crossCheck)
         self._ctx = ctx
 
@@ -376,6 +393,9 @@ class BFMatcher:
     def match(self, queryDescriptors, trainDescriptors):
         """-> list[DMatch] exactly as cv2 returns it (query order; cross-check drops non-mutual rows)."""
         ctx = self._ctx or default_context()
+        if self.normType == NORM_L2:
+            idx, dist = ctx.bf_l2(queryDescriptors, trainDescriptors)
+            return [DMatch(i, int(idx[i]), 0, float(dist[i])) for i in range(len(idx))]
         if self.crossCheck:
             idx, dist, keep = ctx.bf_hamming_crosscheck(queryDescriptors, trainDescriptors)
             return [DMatch(int(i), int(idx[i]), 0, float(dist[i])) for i in np.nonzero(keep)[0]]

@@ -493,6 +493,38 @@ int sfmgms_bf_hamming_crosscheck(sfmgms_ctx* ctx, const uint8_t* query, int nq, 
     GUARD_END
 }
 
+int sfmgms_bf_l2(sfmgms_ctx* ctx, const float* query, int nq, const float* train, int nt, int dim, int32_t* train_idx,
+                 float* dist, int* n_matches) {
+    GUARD_BEGIN
+    if (nq < 0 || nt < 0) return fail(ctx, SFMGMS_ERR_ARG, "negative row count");
+    if (dim != 128) return fail(ctx, SFMGMS_ERR_ARG, "dim must be 128 (SIFT), got %d", dim);
+    if ((nq > 0 && !query) || (nt > 0 && !train)) return fail(ctx, SFMGMS_ERR_ARG, "null descriptor pointer");
+    if (nt >= SFMGMS_MAX_TRAIN_ROWS)
+        return fail(ctx, SFMGMS_ERR_TRAIN_ROWS, "train rows %d >= 2^18 (OpenCV BFMatcher: rows < IMGIDX_ONE)", nt);
+    if (n_matches) *n_matches = (nt == 0) ? 0 : nq;
+    if (nt == 0 || nq == 0) return SFMGMS_OK;
+    cudaStream_t st = ctx->stream;
+    CU(ctx->d_q.ensure((size_t)(nq + nt) * 512));
+    float* dq = (float*)ctx->d_q.p;
+    float* dt = dq + (size_t)nq * 128;
+    CU(ctx->d_hist.ensure(l2_scratch_bytes(nq, nt)));
+    CU(ctx->d_out_i32.ensure((size_t)nq * 8 + 16));
+    CU(cudaMemcpyAsync(dq, query, (size_t)nq * 512, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dt, train, (size_t)nt * 512, cudaMemcpyHostToDevice, st));
+    int32_t* o = (int32_t*)ctx->d_out_i32.p;
+    int* d_bad = (int*)(o + 2 * (size_t)nq);
+    ctx->launches += launch_l2_dp4a(dq, nq, dt, nt, ctx->d_hist.p, o, (float*)(o + nq), d_bad, ctx->sm_count, st);
+    CU(cudaGetLastError());
+    int bad = 0;
+    CU(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (train_idx) CU(cudaMemcpyAsync(train_idx, o, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    if (dist) CU(cudaMemcpyAsync(dist, o + nq, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (bad) return fail(ctx, SFMGMS_ERR_ARG, "descriptors must be integer-valued in [0,255] (OpenCV SIFT); general float L2 is not implemented");
+    return SFMGMS_OK;
+    GUARD_END
+}
+
 static int gms_args(sfmgms_ctx* ctx, int w1, int h1, int w2, int h2, int n1, int n2, int s1, int s2) {
     if (w1 <= 0 || h1 <= 0 || w2 <= 0 || h2 <= 0) return fail(ctx, SFMGMS_ERR_ARG, "image sizes must be positive");
     if (n1 < 0 || n2 < 0) return fail(ctx, SFMGMS_ERR_ARG, "negative keypoint count");

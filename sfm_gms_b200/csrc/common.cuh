@@ -64,4 +64,9 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
                double factor, PairResult* d_results, void* d_hist_scratch, size_t hist_scratch_bytes,
                void* d_match_scratch, cudaStream_t st);
 
+// L2 brute force for integer-valued float descriptors (OpenCV SIFT), l2_dp4a.cu
+size_t l2_scratch_bytes(int nq, int nt);
+int launch_l2_dp4a(const float* d_q, int nq, const float* d_t, int nt, void* d_scratch, int32_t* d_train_idx,
+                   float* d_dist, int* d_bad, int sm_count, cudaStream_t st);
+
 }  // namespace sfmgms

@@ -54,7 +54,7 @@ class Context {
 
 namespace cv {
 
-enum { NORM_HAMMING = 6 };
+enum { NORM_L2 = 4, NORM_HAMMING = 6 };
 
 // Layout-compatible with cv::Point2f / cv::Size / cv::KeyPoint (28 B) / cv::DMatch (16 B); strides verified
 // against the reference binary (0x1c and 0x10).
@@ -81,11 +81,27 @@ class BFMatcher {
    public:
     explicit BFMatcher(int normType = NORM_HAMMING, bool crossCheck = false, Context* ctx = nullptr)
         : cross_(crossCheck), ctx_(ctx) {
-        if (normType != NORM_HAMMING) throw Error(SFMGMS_ERR_ARG, "only NORM_HAMMING is implemented");
+        if (normType != NORM_HAMMING && !(normType == NORM_L2 && !crossCheck))
+            throw Error(SFMGMS_ERR_ARG, "implemented: NORM_HAMMING (with/without crossCheck) and NORM_L2 without crossCheck");
+        norm_ = normType;
+    }
+    // NORM_L2 on integer-valued float descriptors with 128 columns (OpenCV SIFT; FeatureMatchUtil.cpp:10, 66-68):
+    // distances are bit-identical to OpenCV's float results.
+    void match(const float* query, int nq, const float* train, int nt, std::vector<DMatch>& matches, int dim = 128) const {
+        if (norm_ != NORM_L2) throw Error(SFMGMS_ERR_ARG, "float descriptors need NORM_L2");
+        Context& c = ctx_ ? *ctx_ : Context::thread_default();
+        matches.clear();
+        std::vector<int32_t> idx((size_t)(nq > 0 ? nq : 0));
+        std::vector<float> dist(idx.size());
+        int n = 0;
+        c.check(sfmgms_bf_l2(c.get(), query, nq, train, nt, dim, idx.data(), dist.data(), &n));
+        matches.reserve((size_t)n);
+        for (int i = 0; i < n; ++i) matches.push_back(DMatch{i, idx[i], 0, dist[i]});
     }
     // matches.clear(); then one DMatch per query row in query order (cross-check: only the mutual ones)
     void match(const uint8_t* query, int nq, const uint8_t* train, int nt, std::vector<DMatch>& matches,
                int desc_bytes = 32) const {
+        if (norm_ != NORM_HAMMING) throw Error(SFMGMS_ERR_ARG, "uint8 descriptors need NORM_HAMMING");
         Context& c = ctx_ ? *ctx_ : Context::thread_default();
         matches.clear();
         std::vector<int32_t> idx((size_t)(nq > 0 ? nq : 0)), dist(idx.size());
@@ -106,6 +122,7 @@ class BFMatcher {
    private:
     bool cross_;
     Context* ctx_;
+    int norm_ = NORM_HAMMING;
 };
 
 namespace xfeatures2d {
@@ -197,10 +214,15 @@ inline void matchBFHammingGMS(const uint8_t* desc1, const uint8_t* desc2, const 
 #include <opencv2/features2d.hpp>
 namespace sfmgms {
 inline void match(const ::cv::Mat& desc1, const ::cv::Mat& desc2, std::vector<::cv::DMatch>& matches) {
-    CV_Assert(desc1.type() == CV_8U && desc2.type() == CV_8U && desc1.cols == 32 && desc2.cols == 32 &&
-              desc1.isContinuous() && desc2.isContinuous());
+    CV_Assert(desc1.type() == desc2.type() && desc1.isContinuous() && desc2.isContinuous());
     std::vector<cv::DMatch> m;
-    cv::BFMatcher().match(desc1.ptr<uint8_t>(), desc1.rows, desc2.ptr<uint8_t>(), desc2.rows, m);
+    if (desc1.type() == CV_32F) {   // SIFT: BFMatcher::create() = NORM_L2, exactly the reference's FeatureMatchUtil.cpp:66-68
+        CV_Assert(desc1.cols == 128 && desc2.cols == 128);
+        cv::BFMatcher(cv::NORM_L2).match(desc1.ptr<float>(), desc1.rows, desc2.ptr<float>(), desc2.rows, m);
+    } else {
+        CV_Assert(desc1.type() == CV_8U && desc1.cols == 32 && desc2.cols == 32);
+        cv::BFMatcher().match(desc1.ptr<uint8_t>(), desc1.rows, desc2.ptr<uint8_t>(), desc2.rows, m);
+    }
     matches.resize(m.size());
     if (!m.empty()) std::memcpy((void*)matches.data(), m.data(), m.size() * sizeof(cv::DMatch));
 }

@@ -98,6 +98,47 @@ def tie_case():
     print("bf_ties", max(x.trainIdx for x in m))
 
 
+def sift_case():
+    """The reference's literal main path (FeatureMatchUtil.cpp:10, 66-69): SIFT + BFMatcher(NORM_L2) + matchGMS(true,true).
+    cv2 pins stage 1 (trainIdx + float distance); descriptors are integer-valued, stored as uint8."""
+    i1, i2 = cv2.imread(R + "view0.png"), cv2.imread(R + "view1.png")
+    sift = cv2.SIFT_create(1500)
+    k1, d1 = sift.detectAndCompute(i1, None)
+    k2, d2 = sift.detectAndCompute(i2, None)
+    assert np.abs(d1 - np.round(d1)).max() == 0 and d1.max() <= 255 and d1.min() >= 0
+    m = cv2.BFMatcher(cv2.NORM_L2, False).match(d1, d2)
+    bt = np.array([x.trainIdx for x in m], np.int32)
+    bd = np.array([x.distance for x in m], np.float32)
+    p1 = np.array([k.pt for k in k1], np.float32)
+    p2 = np.array([k.pt for k in k2], np.float32)
+    s1, s2 = (i1.shape[1], i1.shape[0]), (i2.shape[1], i2.shape[0])
+    r = oracle.gms(s1, s2, p1, p2, np.arange(len(bt), dtype=np.int32), bt, True, True)
+    # float-tie case: d2 = n+1 at train row 0 and d2 = n at row 1 with sqrtf(n) == sqrtf(n+1) (n >= 2^22):
+    # OpenCV compares float distances with strict '<' and must answer row 0.
+    n = next(v for v in range(1 << 22, 1 << 23) if np.sqrt(np.float32(v)) == np.sqrt(np.float32(v + 1)))
+
+    def vec_with_norm2(target):
+        v = np.zeros(128, np.float32)
+        rem = target
+        for k in range(128):
+            x = min(255, int(np.floor(np.sqrt(rem))))
+            v[k] = x
+            rem -= x * x
+        assert rem == 0, rem
+        return v
+
+    tq = np.zeros((1, 128), np.float32)
+    tt = np.stack([vec_with_norm2(n + 1), vec_with_norm2(n), vec_with_norm2(n + 1)])
+    tm = cv2.BFMatcher(cv2.NORM_L2, False).match(tq, tt)
+    assert tm[0].trainIdx == 0, tm[0].trainIdx
+    np.savez_compressed(os.path.join(HERE, "sift_view01_1500.npz"), size1=np.array(s1, np.int32), size2=np.array(s2, np.int32),
+                        kp1=p1, kp2=p2, desc1=d1.astype(np.uint8), desc2=d2.astype(np.uint8), l2_train=bt, l2_dist=bd,
+                        gms_mask_11=np.packbits(r["mask"]), gms_n_11=np.int32(r["n_inliers"]), gms_best_11=np.int32(r["best_hyp"]),
+                        gms_len_11=np.int32(len(r["mask"])), tie_q=tq, tie_t=tt, tie_train=np.int32(tm[0].trainIdx),
+                        tie_dist=np.float32(tm[0].distance))
+    print("sift_view01_1500", len(bt), "gms(rot,scale)", r["n_inliers"], "tie n =", n)
+
+
 if __name__ == "__main__":
     oracle.build()
     oracle.set_num_threads(os.cpu_count())
@@ -106,3 +147,4 @@ if __name__ == "__main__":
     pack("view01_2k", *orb_pair("view0.png", "view1.png", 2000))
     pack("bun12_rot180_3k", *orb_pair("Bun1.jpg", "Bun2.jpg", 3000, rot180=True))
     tie_case()
+    sift_case()

@@ -396,3 +396,41 @@ def test_cxx_shim_demo_matches_golden(tmp_path, rot, sc, tag):
     exp = np.unpackbits(g["gms_mask_" + tag])[:n].astype(bool)
     assert ng == int(g["gms_n_" + tag]) and np.array_equal(gq, np.nonzero(exp)[0])
     assert nc == ng and np.array_equal(mk, exp) and nf == ng
+
+
+# ---- (§8f-3) the reference's literal main path: SIFT + BFMatcher(NORM_L2) + matchGMS(true, true) ----------------
+def test_sift_l2_pipeline_golden_cv2(ctx, oracle_mod):
+    import sfm_gms_b200 as sg
+
+    g = load_golden("sift_view01_1500")
+    d1, d2 = g["desc1"].astype(np.float32), g["desc2"].astype(np.float32)
+    idx, dist = ctx.bf_l2(d1, d2)
+    assert np.array_equal(idx, g["l2_train"]) and np.array_equal(dist, g["l2_dist"])   # bit-exact float distances
+    m = sg.BFMatcher(sg.NORM_L2).match(d1, d2)
+    out = sg.matchGMS(g["size1"], g["size2"], g["kp1"], g["kp2"], m, withRotation=True, withScale=True)
+    n = int(g["gms_len_11"])
+    exp = np.unpackbits(g["gms_mask_11"])[:n].astype(bool)
+    assert [x.queryIdx for x in out] == np.nonzero(exp)[0].tolist() and len(out) == int(g["gms_n_11"])
+    # float-tie: sqrtf(n) == sqrtf(n+1) above 2^22 -> the LOWER index wins although its exact d2 is larger
+    idx, dist = ctx.bf_l2(g["tie_q"], g["tie_t"])
+    assert idx[0] == 0 and dist[0] == g["tie_dist"]
+
+
+def test_l2_ragged_vs_oracle_and_errors(ctx, oracle_mod):
+    from sfm_gms_b200 import SfmGmsError
+
+    rng = np.random.default_rng(21)
+    for nq, nt in [(1, 1), (3, 700), (513, 257), (2000, 1999)]:
+        q = rng.integers(0, 256, (nq, 128)).astype(np.float32)
+        t = rng.integers(0, 256, (nt, 128)).astype(np.float32)
+        if nt > 4:
+            t[nt // 2] = t[1]; q[0] = t[1]
+        idx, dist = ctx.bf_l2(q, t)
+        oi, od = oracle_mod.bf_l2(q, t)
+        assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+    idx, dist = ctx.bf_l2(q, np.zeros((0, 128), np.float32))
+    assert len(idx) == 0
+    with pytest.raises(SfmGmsError):      # general float descriptors are not implemented (no silent approximation)
+        ctx.bf_l2(q + 0.5, t)
+    with pytest.raises(SfmGmsError):
+        ctx.bf_l2(q[:, :64], t[:, :64])
