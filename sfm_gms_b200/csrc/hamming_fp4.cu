@@ -61,6 +61,18 @@ static_assert(BTILE_BYTES % 1024 == 0 && kEpiCols == 80 && SF_COL + SF_COLS <= 5
 // |dot| <= 256 and the fraction has 7 bits: every key is exact in fp32.
 // (the addend is written as a compile-time literal so that it becomes an FADD immediate)
 
+// per pair of columns (2k, 2k+1): the index fractions added by one packed FADD2
+__constant__ float2 c_pairkey[40] = {{127.f / 128.f, 126.f / 128.f}, {125.f / 128.f, 124.f / 128.f}, {123.f / 128.f, 122.f / 128.f}, {121.f / 128.f, 120.f / 128.f}, {119.f / 128.f, 118.f / 128.f}, {117.f / 128.f, 116.f / 128.f}, {115.f / 128.f, 114.f / 128.f}, {113.f / 128.f, 112.f / 128.f}, {111.f / 128.f, 110.f / 128.f}, {109.f / 128.f, 108.f / 128.f}, {107.f / 128.f, 106.f / 128.f}, {105.f / 128.f, 104.f / 128.f}, {103.f / 128.f, 102.f / 128.f}, {101.f / 128.f, 100.f / 128.f}, {99.f / 128.f, 98.f / 128.f}, {97.f / 128.f, 96.f / 128.f}, {95.f / 128.f, 94.f / 128.f}, {93.f / 128.f, 92.f / 128.f}, {91.f / 128.f, 90.f / 128.f}, {89.f / 128.f, 88.f / 128.f}, {87.f / 128.f, 86.f / 128.f}, {85.f / 128.f, 84.f / 128.f}, {83.f / 128.f, 82.f / 128.f}, {81.f / 128.f, 80.f / 128.f}, {79.f / 128.f, 78.f / 128.f}, {77.f / 128.f, 76.f / 128.f}, {75.f / 128.f, 74.f / 128.f}, {73.f / 128.f, 72.f / 128.f}, {71.f / 128.f, 70.f / 128.f}, {69.f / 128.f, 68.f / 128.f}, {67.f / 128.f, 66.f / 128.f}, {65.f / 128.f, 64.f / 128.f}, {63.f / 128.f, 62.f / 128.f}, {61.f / 128.f, 60.f / 128.f}, {59.f / 128.f, 58.f / 128.f}, {57.f / 128.f, 56.f / 128.f}, {55.f / 128.f, 54.f / 128.f}, {53.f / 128.f, 52.f / 128.f}, {51.f / 128.f, 50.f / 128.f}, {49.f / 128.f, 48.f / 128.f}};
+
+// (lo, hi) + (c.x, c.y) with one packed fp32x2 add (sm_100: add.rn.f32x2 -> FADD2)
+__device__ __forceinline__ void add2(float lo, float hi, float2 c, float& out_lo, float& out_hi) {
+    unsigned long long x, cc, r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(lo), "f"(hi));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(c.x), "f"(c.y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(cc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(out_lo), "=f"(out_hi) : "l"(r));
+}
+
 struct WorkUnit {
     uint32_t a_row0, b_row0;   // operand rows (in the unpacked array) of the unit's first query / the train image's row 0
     int32_t n_rows, t_begin, t_end;
@@ -229,7 +241,8 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         }
     } else if (warp == kMmaWarp) {
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0, abuf = 0, a_phase = 0, slot = 0, slot_phase = 0;
+            // accumulator slot = sub-tile index & 1 (compile-time in the epilogue's unrolled loop); one phase bit per slot
+            uint32_t stage = 0, phase = 0, abuf = 0, a_phase = 0, slot_phase[ACC_SLOTS] = {0, 0};
             const uint32_t a_lo0 = sdesc_lo(a_smem), b_lo0 = sdesc_lo(b_smem);
             const uint32_t sf = tmem_base + SF_COL;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -241,8 +254,12 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 for (int ti = 0; ti < ntiles; ++ti) {
                     mbar_wait(full_bar + 8 * stage, phase);
                     const uint32_t b_lo = b_lo0 + stage * (BTILE_BYTES >> 4);
-                    for (int s = 0; s < nsub; ++s) {
-                        mbar_wait(tempty_bar + 8 * slot, slot_phase ^ 1);
+#pragma unroll
+                    for (int s = 0; s < MSUB; ++s) {
+                        if (s >= nsub) break;
+                        const int slot = s & 1;
+                        mbar_wait(tempty_bar + 8 * slot, slot_phase[slot] ^ 1);
+                        slot_phase[slot] ^= 1;
                         tc_fence_after();
                         const uint32_t d = tmem_base + slot * BN;
                         const uint32_t a_lo = a_lo_buf + s * (TILE_BYTES >> 4);
@@ -253,7 +270,6 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         tc_mma_mxf4<1>(d, a_lo + 6, b_lo + 6, kDescHi, kIdesc, sf, sf);
                         }
                         tc_commit(tfull_bar + 8 * slot);
-                        if (++slot == ACC_SLOTS) { slot = 0; slot_phase ^= 1; }
                     }
                     tc_commit(empty_bar + 8 * stage);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -266,20 +282,25 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         // ================= epilogue: 12 warps; warp = (lane quadrant, 80-column part) of every accumulator ==========
         const int quad = warp & 3;                        // TMEM lanes [32*quad, 32*quad+32)
         const int c0 = ((warp - kEpiWarp0) >> 2) * kEpiCols; // accumulator columns [c0, c0+80)
-        uint32_t slot = 0, slot_phase = 0;
+        const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + c0;
+        uint32_t slot_phase[ACC_SLOTS] = {0, 0};
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             const WorkUnit wu = make_unit(lm, pairs, u);
             const int nsub = (wu.n_rows + BM - 1) / BM;
-            float best_val[MSUB];
-            int best_dot[MSUB], best_idx[MSUB];
+            // per row: best key so far (dot + index fraction), the smallest key that would beat it (integer part + 1:
+            // strict '>' on the dot product keeps the earliest tile / part) and the column base it came from
+            float best_key[MSUB], beat[MSUB];
+            int best_base[MSUB];
 #pragma unroll
-            for (int s = 0; s < MSUB; ++s) { best_val[s] = -1.0e30f; best_dot[s] = -100000; best_idx[s] = dbg ? 0 : -1; }
+            for (int s = 0; s < MSUB; ++s) { best_key[s] = -1.0e30f; beat[s] = -1.0e29f; best_base[s] = -1; }
             for (int t = wu.t_begin; t < wu.t_end; t += BN) {
                 const int valid = wu.t_end - t;
 #pragma unroll
                 for (int s = 0; s < MSUB; ++s) {
                     if (s < nsub) {
-                        mbar_wait(tfull_bar + 8 * slot, slot_phase);
+                        const int slot = s & 1;                              // compile-time after unrolling
+                        mbar_wait(tfull_bar + 8 * slot, slot_phase[slot]);
+                        slot_phase[slot] ^= 1;
                         tc_fence_after();
                         int ra[64], rb[16];
                         if (dbg == 4) {    // DEBUG 4: no TMEM read, no ALU
@@ -288,22 +309,24 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 #pragma unroll
                             for (int j = 0; j < 16; ++j) rb[j] = 0;
                         } else {
-                            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * BN + c0;
-                            tc_ld64(taddr, ra);
-                            tc_ld16(taddr + 64, rb);
+                            tc_ld64(tbase + slot * BN, ra);
+                            tc_ld16(tbase + slot * BN + 64, rb);
                             tc_wait_ld();
                         }
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty_bar + 8 * slot);   // values are in registers now
-                        if (++slot == ACC_SLOTS) { slot = 0; slot_phase ^= 1; }
                         if (dbg == 4) continue;
+                        // index packing, two columns per instruction: (v_2k, v_2k+1) += ((127-2k)/128, (126-2k)/128)
                         float v[kEpiCols];
 #pragma unroll
-                        for (int j = 0; j < 64; ++j) v[j] = __int_as_float(ra[j]) + (float)(127 - j) * 0.0078125f;
+                        for (int k = 0; k < 32; ++k)
+                            add2(__int_as_float(ra[2 * k]), __int_as_float(ra[2 * k + 1]), c_pairkey[k], v[2 * k], v[2 * k + 1]);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[64 + j] = __int_as_float(rb[j]) + (float)(63 - j) * 0.0078125f;
-                        if (dbg == 1) { best_val[s] = fmaxf(best_val[s], v[0] + v[79]); continue; }   // DEBUG 1: no ALU
+                        for (int k = 0; k < 8; ++k)
+                            add2(__int_as_float(rb[2 * k]), __int_as_float(rb[2 * k + 1]), c_pairkey[32 + k], v[64 + 2 * k],
+                                 v[65 + 2 * k]);
+                        if (dbg == 1) { best_key[s] = fmaxf(best_key[s], v[0] + v[79]); continue; }   // DEBUG 1: no max tree
                         if (c0 + kEpiCols > valid) {                         // tail tile: mask columns outside the image
 #pragma unroll
                             for (int j = 0; j < kEpiCols; ++j)
@@ -312,12 +335,10 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         float m = v[0];
 #pragma unroll
                         for (int j = 1; j < kEpiCols; ++j) m = fmaxf(m, v[j]);
-                        // m = dot + (127 - j*)/128: strict '>' on the integer part keeps the earliest tile / part
-                        const float fl = floorf(m);
-                        const int dot = (int)fl;
-                        if (m > -1.0e29f && dot > best_dot[s]) {
-                            best_dot[s] = dot;
-                            best_idx[s] = t + c0 + 127 - (int)((m - fl) * 128.0f);
+                        if (m >= beat[s]) {                                  // integer part exceeds the best so far
+                            best_key[s] = m;
+                            beat[s] = floorf(m) + 1.0f;
+                            best_base[s] = t + c0;
                         }
                     }
                 }
@@ -325,9 +346,13 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 #pragma unroll
             for (int s = 0; s < MSUB; ++s) {
                 const int row = s * BM + quad * 32 + lane;
-                if (s < nsub && row < wu.n_rows && best_idx[s] >= 0) {
-                    const uint32_t dist = dbg ? 7u + (best_val[s] > 0.f) : (uint32_t)(256 - best_dot[s]) >> 1;   // <a,b> = 256 - 2*hamming
-                    atomicMin(wu.key + row, (dist << kTrainIdxBits) | (uint32_t)best_idx[s]);
+                if (s < nsub && row < wu.n_rows && (best_base[s] >= 0 || dbg)) {
+                    // key = dot + (127 - j)/128 : <a,b> = 256 - 2*hamming
+                    const float fl = floorf(best_key[s]);
+                    const int j = 127 - (int)((best_key[s] - fl) * 128.0f);
+                    const uint32_t dist = dbg ? 7u : (uint32_t)(256 - (int)fl) >> 1;
+                    const uint32_t idx = dbg ? 0u : (uint32_t)(best_base[s] + j);
+                    atomicMin(wu.key + row, (dist << kTrainIdxBits) | idx);
                 }
             }
         }
