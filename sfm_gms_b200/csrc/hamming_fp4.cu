@@ -8,9 +8,11 @@
 // Block scales: every scale byte this kernel could ever address is 0x7F, so the scale-factor layout in TMEM does
 // not matter: 32 TMEM columns are filled with 0x7F7F7F7F once per CTA.
 //
-// Kernel structure (persistent, warp-specialised, 1 CTA/SM, 384 threads): warp 0 TMA producer (query sub-tiles
-// double-buffered per work unit, train tiles through a ring), warp 1 MMA issuer, warp 2 TMEM allocator,
-// warps 4-11 epilogue (tcgen05.ld -> row max / first arg-max -> atomicMin(dist<<18|trainIdx)).
+// Kernel structure (persistent, warp-specialised, 1 CTA/SM, 512 threads): warps 0-11 epilogue (warp = TMEM lane
+// quadrant x 80-column part: tcgen05.ld -> index-packed keys -> max tree -> atomicMin(dist<<18|trainIdx)),
+// warp 12 TMA producer (query sub-tiles double-buffered per work unit, 240-row train tiles through a ring),
+// warp 13 MMA issuer (4 x M128 N240 K64 per accumulator, 2 accumulator slots in TMEM), warp 14 TMEM allocator.
+// The single-lane roles sit in the highest warp ids because the warp scheduler favours those.
 #include <cuda.h>
 
 #include <cstdio>
@@ -46,22 +48,22 @@ constexpr int ACC_SLOTS = 2;
 constexpr int SF_COL = ACC_SLOTS * BN;   // TMEM columns [480, 512): block scales (all 1.0)
 constexpr int SF_COLS = 32;
 constexpr int kEpiWarp0 = 0;            // epilogue warps first: the scheduler favours HIGH warp ids, which must be the
-constexpr int kEpiWarps = 12;           // 3 per TMEM lane quadrant, 80 accumulator columns each
-constexpr int kEpiCols = BN / 3;        // 80 = one x64 + one x16 tcgen05.ld
+#ifndef SFMGMS_FP4_EPIW
+#define SFMGMS_FP4_EPIW 12
+#endif
+constexpr int kEpiWarps = SFMGMS_FP4_EPIW;        // 12: 3 per TMEM lane quadrant x 80 columns; 16: 4 x 60 columns
+constexpr int kEpiCols = BN / (kEpiWarps / 4);    // 80 = x64 + x16 tcgen05.ld; 60 = x32 + x16 + x8 + x4
 constexpr int kProdWarp = kEpiWarps;     // latency-critical single-lane roles (TMA producer, MMA issuer)
 constexpr int kMmaWarp = kEpiWarps + 1;
 constexpr int kAllocWarp = kEpiWarps + 2;
 constexpr int kThreads = 32 * (kEpiWarps + 4);   // 512
 static_assert(STAGES >= 3, "B ring too shallow");
-static_assert(BTILE_BYTES % 1024 == 0 && kEpiCols == 80 && SF_COL + SF_COLS <= 512, "layout");
+static_assert(BTILE_BYTES % 1024 == 0 && (kEpiCols == 80 || kEpiCols == 60) && SF_COL + SF_COLS <= 512, "layout");
 
-// Epilogue index packing: key_j = <a,b_j> + (127 - j)/128 for column j < 80 of a warp's part.  One FADD per
-// element (FMA pipe; the addend is an immediate), then a plain max tree (ALU pipe): the maximum key
-// carries the maximum dot product (its integer part) AND the lowest column attaining it (its fraction).
-// |dot| <= 256 and the fraction has 7 bits: every key is exact in fp32.
-// (the addend is written as a compile-time literal so that it becomes an FADD immediate)
-
-// per pair of columns (2k, 2k+1): the index fractions added by one packed FADD2
+// Epilogue index packing: key_j = <a,b_j> + (127 - j)/128 for column j < 80 of a warp's part, then a plain max
+// tree (FMNMX3, ALU pipe): the maximum key carries the maximum dot product (its integer part) AND the lowest
+// column attaining it (its fraction).  |dot| <= 256 and the fraction has 7 bits: every key is exact in fp32.
+// The add runs on the FMA pipe, two columns per instruction (packed FADD2); per pair of columns (2k, 2k+1):
 __constant__ float2 c_pairkey[40] = {{127.f / 128.f, 126.f / 128.f}, {125.f / 128.f, 124.f / 128.f}, {123.f / 128.f, 122.f / 128.f}, {121.f / 128.f, 120.f / 128.f}, {119.f / 128.f, 118.f / 128.f}, {117.f / 128.f, 116.f / 128.f}, {115.f / 128.f, 114.f / 128.f}, {113.f / 128.f, 112.f / 128.f}, {111.f / 128.f, 110.f / 128.f}, {109.f / 128.f, 108.f / 128.f}, {107.f / 128.f, 106.f / 128.f}, {105.f / 128.f, 104.f / 128.f}, {103.f / 128.f, 102.f / 128.f}, {101.f / 128.f, 100.f / 128.f}, {99.f / 128.f, 98.f / 128.f}, {97.f / 128.f, 96.f / 128.f}, {95.f / 128.f, 94.f / 128.f}, {93.f / 128.f, 92.f / 128.f}, {91.f / 128.f, 90.f / 128.f}, {89.f / 128.f, 88.f / 128.f}, {87.f / 128.f, 86.f / 128.f}, {85.f / 128.f, 84.f / 128.f}, {83.f / 128.f, 82.f / 128.f}, {81.f / 128.f, 80.f / 128.f}, {79.f / 128.f, 78.f / 128.f}, {77.f / 128.f, 76.f / 128.f}, {75.f / 128.f, 74.f / 128.f}, {73.f / 128.f, 72.f / 128.f}, {71.f / 128.f, 70.f / 128.f}, {69.f / 128.f, 68.f / 128.f}, {67.f / 128.f, 66.f / 128.f}, {65.f / 128.f, 64.f / 128.f}, {63.f / 128.f, 62.f / 128.f}, {61.f / 128.f, 60.f / 128.f}, {59.f / 128.f, 58.f / 128.f}, {57.f / 128.f, 56.f / 128.f}, {55.f / 128.f, 54.f / 128.f}, {53.f / 128.f, 52.f / 128.f}, {51.f / 128.f, 50.f / 128.f}, {49.f / 128.f, 48.f / 128.f}};
 
 // (lo, hi) + (c.x, c.y) with one packed fp32x2 add (sm_100: add.rn.f32x2 -> FADD2)
@@ -71,6 +73,19 @@ __device__ __forceinline__ void add2(float lo, float hi, float2 c, float& out_lo
     asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(c.x), "f"(c.y));
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(cc));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(out_lo), "=f"(out_hi) : "l"(r));
+}
+
+// one warp's part of an accumulator row-quadrant: kEpiCols consecutive 32-bit TMEM columns -> registers
+__device__ __forceinline__ void ld_part(uint32_t taddr, int (&r)[kEpiCols]) {
+    if constexpr (kEpiCols == 80) {
+        tc_ld64(taddr, reinterpret_cast<int(&)[64]>(r[0]));
+        tc_ld16(taddr + 64, reinterpret_cast<int(&)[16]>(r[64]));
+    } else {
+        tc_ld32(taddr, reinterpret_cast<int(&)[32]>(r[0]));
+        tc_ld16(taddr + 32, reinterpret_cast<int(&)[16]>(r[32]));
+        tc_ld8(taddr + 48, reinterpret_cast<int(&)[8]>(r[48]));
+        tc_ld4(taddr + 56, reinterpret_cast<int(&)[4]>(r[56]));
+    }
 }
 
 struct WorkUnit {
@@ -302,15 +317,12 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         mbar_wait(tfull_bar + 8 * slot, slot_phase[slot]);
                         slot_phase[slot] ^= 1;
                         tc_fence_after();
-                        int ra[64], rb[16];
+                        int r[kEpiCols];
                         if (dbg == 4) {    // DEBUG 4: no TMEM read, no ALU
 #pragma unroll
-                            for (int j = 0; j < 64; ++j) ra[j] = 0;
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) rb[j] = 0;
+                            for (int j = 0; j < kEpiCols; ++j) r[j] = 0;
                         } else {
-                            tc_ld64(tbase + slot * BN, ra);
-                            tc_ld16(tbase + slot * BN + 64, rb);
+                            ld_part(tbase + slot * BN, r);
                             tc_wait_ld();
                         }
                         tc_fence_before();
@@ -320,13 +332,9 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         // index packing, two columns per instruction: (v_2k, v_2k+1) += ((127-2k)/128, (126-2k)/128)
                         float v[kEpiCols];
 #pragma unroll
-                        for (int k = 0; k < 32; ++k)
-                            add2(__int_as_float(ra[2 * k]), __int_as_float(ra[2 * k + 1]), c_pairkey[k], v[2 * k], v[2 * k + 1]);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            add2(__int_as_float(rb[2 * k]), __int_as_float(rb[2 * k + 1]), c_pairkey[32 + k], v[64 + 2 * k],
-                                 v[65 + 2 * k]);
-                        if (dbg == 1) { best_key[s] = fmaxf(best_key[s], v[0] + v[79]); continue; }   // DEBUG 1: no max tree
+                        for (int k = 0; k < kEpiCols / 2; ++k)
+                            add2(__int_as_float(r[2 * k]), __int_as_float(r[2 * k + 1]), c_pairkey[k], v[2 * k], v[2 * k + 1]);
+                        if (dbg == 1) { best_key[s] = fmaxf(best_key[s], v[0] + v[kEpiCols - 1]); continue; }   // DEBUG 1: no max tree
                         if (c0 + kEpiCols > valid) {                         // tail tile: mask columns outside the image
 #pragma unroll
                             for (int j = 0; j < kEpiCols; ++j)
