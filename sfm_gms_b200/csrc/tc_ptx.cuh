@@ -22,11 +22,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_%=:\n\t"
+#ifdef SFMGMS_MBAR_HINT_NS
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+#endif
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t"
+#ifdef SFMGMS_MBAR_HINT_NS
+        "}\n" ::"r"(bar), "r"(parity), "r"((uint32_t)SFMGMS_MBAR_HINT_NS) : "memory");
+#else
         "}\n" ::"r"(bar), "r"(parity) : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
     asm volatile(
