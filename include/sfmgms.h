@@ -53,6 +53,7 @@ extern "C" {
 #define SFMGMS_OPT_GMS_CHUNK_BYTES 2 /* scratch budget per GMS chunk (bytes), default 64 MiB */
 #define SFMGMS_OPT_TC_OPERAND_CACHE 4 /* 1 (default): keep the unpacked +-1 operands of the image set across
                                          sfmgms_match_pairs calls; 0: unpack again on every call */
+#define SFMGMS_OPT_L2_KERNEL 5        /* sfmgms_bf_l2: 0 auto (tcgen05), 1 DP4A CUDA-core kernel, 2 tcgen05 kind::i8 kernel */
 #define SFMGMS_OPT_TIMING 3          /* 1: record CUDA events around the Hamming and GMS stages of each batch */
 
 typedef struct sfmgms_ctx sfmgms_ctx;
@@ -88,7 +89,8 @@ int sfmgms_bf_hamming_crosscheck(sfmgms_ctx* ctx, const uint8_t* query, int nq, 
  * 128 columns — what OpenCV's SIFT produces and what the reference literally runs (FeatureMatchUtil.cpp:10, 66-68).
  * For such data OpenCV's float accumulation of sum((a-b)^2) is exact, and so is this: train_idx[i] = lowest j
  * minimising the squared distance, dist[i] = sqrtf((float)d2), bit-identical to cv2.  Any descriptor value that is
- * not an integer in [0,255] -> SFMGMS_ERR_ARG (general float descriptors are not implemented).  dim must be 128. */
+ * not an integer in [0,255] -> SFMGMS_ERR_ARG (general float descriptors are not implemented).  dim must be 128.
+ * Kernel: tcgen05 u8 x u8 GEMM with a fused row-argmin epilogue (l2_tc.cu); SFMGMS_OPT_L2_KERNEL selects the DP4A one. */
 int sfmgms_bf_l2(sfmgms_ctx* ctx, const float* query, int nq, const float* train, int nt, int dim,
                  int32_t* train_idx, float* dist, int* n_matches);
 

@@ -19,7 +19,7 @@ NORM_HAMMING = 6  # cv::NORM_HAMMING
 NORM_L2 = 4       # cv::NORM_L2
 
 SFMGMS_HOST, SFMGMS_DEVICE = 0, 1
-OPT_HAMMING_KERNEL, OPT_GMS_CHUNK_BYTES, OPT_TIMING, OPT_TC_OPERAND_CACHE = 1, 2, 3, 4
+OPT_HAMMING_KERNEL, OPT_GMS_CHUNK_BYTES, OPT_TIMING, OPT_TC_OPERAND_CACHE, OPT_L2_KERNEL = 1, 2, 3, 4, 5
 HAMMING_AUTO, HAMMING_POPC, HAMMING_TC, HAMMING_FP4 = 0, 1, 2, 3
 
 _ERR_NAMES = {1: "ERR_ARG", 2: "ERR_TRAIN_ROWS", 3: "ERR_DOMAIN", 4: "ERR_INDEX", 5: "ERR_CUDA", 6: "ERR_STATE"}

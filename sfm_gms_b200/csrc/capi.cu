@@ -63,6 +63,7 @@ struct sfmgms_ctx {
     int hamming_kernel = SFMGMS_HAMMING_AUTO;
     size_t gms_chunk_bytes = 64ull << 20;
     int timing = 0;
+    int l2_kernel = 0;   // 0 auto (tcgen05), 1 dp4a, 2 tcgen05
     bool timing_mid_pending = false;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // pipelined host<->device copies (match_image_set)
     std::vector<cudaEvent_t> events;                           // pool of timing-disabled events
@@ -391,6 +392,11 @@ int sfmgms_set_option(sfmgms_ctx* ctx, int key, int64_t value) {
         ctx->gms_chunk_bytes = (size_t)value;
         return SFMGMS_OK;
     }
+    if (key == SFMGMS_OPT_L2_KERNEL) {
+        if (value < 0 || value > 2) return fail(ctx, SFMGMS_ERR_ARG, "bad L2 kernel %lld", (long long)value);
+        ctx->l2_kernel = (int)value;
+        return SFMGMS_OK;
+    }
     if (key == SFMGMS_OPT_TC_OPERAND_CACHE) {
         ctx->tc.cache_enabled = value != 0;
         tc_invalidate(ctx->tc);
@@ -507,19 +513,30 @@ int sfmgms_bf_l2(sfmgms_ctx* ctx, const float* query, int nq, const float* train
     CU(ctx->d_q.ensure((size_t)(nq + nt) * 512));
     float* dq = (float*)ctx->d_q.p;
     float* dt = dq + (size_t)nq * 128;
-    CU(ctx->d_hist.ensure(l2_scratch_bytes(nq, nt)));
+    const bool use_tc = ctx->l2_kernel != 1;
+    CU(ctx->d_hist.ensure(use_tc ? l2_tc_scratch_bytes(nq, nt) : l2_scratch_bytes(nq, nt)));
     CU(ctx->d_out_i32.ensure((size_t)nq * 8 + 16));
     CU(cudaMemcpyAsync(dq, query, (size_t)nq * 512, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(dt, train, (size_t)nt * 512, cudaMemcpyHostToDevice, st));
     int32_t* o = (int32_t*)ctx->d_out_i32.p;
     int* d_bad = (int*)(o + 2 * (size_t)nq);
-    ctx->launches += launch_l2_dp4a(dq, nq, dt, nt, ctx->d_hist.p, o, (float*)(o + nq), d_bad, ctx->sm_count, st);
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[0], st));
+    const int nl = use_tc ? launch_l2_tc(dq, nq, dt, nt, ctx->d_hist.p, o, (float*)(o + nq), d_bad, ctx->sm_count, st)
+                          : launch_l2_dp4a(dq, nq, dt, nt, ctx->d_hist.p, o, (float*)(o + nq), d_bad, ctx->sm_count, st);
+    if (nl < 0) return fail(ctx, SFMGMS_ERR_CUDA, "L2 tensor-core launch setup failed");
+    ctx->launches += nl;
+    if (ctx->timing) { CU(cudaEventRecord(ctx->ev[1], st)); CU(cudaEventRecord(ctx->ev[2], st)); }
     CU(cudaGetLastError());
     int bad = 0;
     CU(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     if (train_idx) CU(cudaMemcpyAsync(train_idx, o, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
     if (dist) CU(cudaMemcpyAsync(dist, o + nq, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (ctx->timing) {
+        float a = 0.f;
+        CU(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
+        ctx->last_ms[0] = a; ctx->last_ms[1] = 0; ctx->last_ms[2] = nl;
+    }
     if (bad) return fail(ctx, SFMGMS_ERR_ARG, "descriptors must be integer-valued in [0,255] (OpenCV SIFT); general float L2 is not implemented");
     return SFMGMS_OK;
     GUARD_END

@@ -68,5 +68,9 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
 size_t l2_scratch_bytes(int nq, int nt);
 int launch_l2_dp4a(const float* d_q, int nq, const float* d_t, int nt, void* d_scratch, int32_t* d_train_idx,
                    float* d_dist, int* d_bad, int sm_count, cudaStream_t st);
+// tcgen05 (kind::i8, unsigned) variant, l2_tc.cu — same contract; returns -1 on a setup error
+size_t l2_tc_scratch_bytes(int nq, int nt);
+int launch_l2_tc(const float* d_q, int nq, const float* d_t, int nt, void* d_scratch, int32_t* d_train_idx,
+                 float* d_dist, int* d_bad, int sm_count, cudaStream_t st);
 
 }  // namespace sfmgms

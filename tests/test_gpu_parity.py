@@ -399,8 +399,19 @@ def test_cxx_shim_demo_matches_golden(tmp_path, rot, sc, tag):
 
 
 # ---- (§8f-3) the reference's literal main path: SIFT + BFMatcher(NORM_L2) + matchGMS(true, true) ----------------
-def test_sift_l2_pipeline_golden_cv2(ctx, oracle_mod):
+@pytest.fixture(params=["dp4a", "tcgen05"])
+def l2ctx(ctx, request):
+    from sfm_gms_b200 import api
+
+    ctx.set_option(api.OPT_L2_KERNEL, 1 if request.param == "dp4a" else 2)
+    yield ctx
+    ctx.set_option(api.OPT_L2_KERNEL, 0)
+
+
+def test_sift_l2_pipeline_golden_cv2(l2ctx, oracle_mod):
     import sfm_gms_b200 as sg
+
+    ctx = l2ctx
 
     g = load_golden("sift_view01_1500")
     d1, d2 = g["desc1"].astype(np.float32), g["desc2"].astype(np.float32)
@@ -416,13 +427,16 @@ def test_sift_l2_pipeline_golden_cv2(ctx, oracle_mod):
     assert idx[0] == 0 and dist[0] == g["tie_dist"]
 
 
-def test_l2_ragged_vs_oracle_and_errors(ctx, oracle_mod):
+def test_l2_ragged_vs_oracle_and_errors(l2ctx, oracle_mod):
     from sfm_gms_b200 import SfmGmsError
 
+    ctx = l2ctx
+
     rng = np.random.default_rng(21)
-    for nq, nt in [(1, 1), (3, 700), (513, 257), (2000, 1999)]:
-        q = rng.integers(0, 256, (nq, 128)).astype(np.float32)
-        t = rng.integers(0, 256, (nt, 128)).astype(np.float32)
+    for nq, nt in [(1, 1), (3, 700), (513, 257), (2000, 1999), (385, 241), (4000, 5000)]:
+        hi = 256 if nq % 2 else 40            # full-range values: squared distances above 2^22 (float-tie fixup path)
+        q = rng.integers(0, hi, (nq, 128)).astype(np.float32)
+        t = rng.integers(0, hi, (nt, 128)).astype(np.float32)
         if nt > 4:
             t[nt // 2] = t[1]; q[0] = t[1]
         idx, dist = ctx.bf_l2(q, t)
