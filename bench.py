@@ -96,14 +96,17 @@ class ClockSampler:
 
     def _run(self):
         nv = self.nv
+        k, pw = 0, 0.0
         while not self.stop_flag:
             try:
-                self.samples.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
-                                     nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                if k % 4 == 0:      # NVML queries cost milliseconds each: read the (1 s averaged) power less often
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), pw,
                                      nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
             except Exception:
                 pass
-            time.sleep(0.01)
+            k += 1
+            time.sleep(0.005)
 
     def stop(self):
         if self.t is None:
@@ -195,7 +198,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pairs", type=int, default=256, help="pairs per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
