@@ -60,11 +60,18 @@ constexpr int kThreads = 32 * (kEpiWarps + 4);   // 512
 static_assert(STAGES >= 3, "B ring too shallow");
 static_assert(BTILE_BYTES % 1024 == 0 && (kEpiCols == 80 || kEpiCols == 60) && SF_COL + SF_COLS <= 512, "layout");
 
-// Epilogue index packing: key_j = <a,b_j> + (127 - j)/128 for column j < 80 of a warp's part, then a plain max
-// tree (FMNMX3, ALU pipe): the maximum key carries the maximum dot product (its integer part) AND the lowest
-// column attaining it (its fraction).  |dot| <= 256 and the fraction has 7 bits: every key is exact in fp32.
-// The add runs on the FMA pipe, two columns per instruction (packed FADD2); per pair of columns (2k, 2k+1):
-__constant__ float2 c_pairkey[40] = {{127.f / 128.f, 126.f / 128.f}, {125.f / 128.f, 124.f / 128.f}, {123.f / 128.f, 122.f / 128.f}, {121.f / 128.f, 120.f / 128.f}, {119.f / 128.f, 118.f / 128.f}, {117.f / 128.f, 116.f / 128.f}, {115.f / 128.f, 114.f / 128.f}, {113.f / 128.f, 112.f / 128.f}, {111.f / 128.f, 110.f / 128.f}, {109.f / 128.f, 108.f / 128.f}, {107.f / 128.f, 106.f / 128.f}, {105.f / 128.f, 104.f / 128.f}, {103.f / 128.f, 102.f / 128.f}, {101.f / 128.f, 100.f / 128.f}, {99.f / 128.f, 98.f / 128.f}, {97.f / 128.f, 96.f / 128.f}, {95.f / 128.f, 94.f / 128.f}, {93.f / 128.f, 92.f / 128.f}, {91.f / 128.f, 90.f / 128.f}, {89.f / 128.f, 88.f / 128.f}, {87.f / 128.f, 86.f / 128.f}, {85.f / 128.f, 84.f / 128.f}, {83.f / 128.f, 82.f / 128.f}, {81.f / 128.f, 80.f / 128.f}, {79.f / 128.f, 78.f / 128.f}, {77.f / 128.f, 76.f / 128.f}, {75.f / 128.f, 74.f / 128.f}, {73.f / 128.f, 72.f / 128.f}, {71.f / 128.f, 70.f / 128.f}, {69.f / 128.f, 68.f / 128.f}, {67.f / 128.f, 66.f / 128.f}, {65.f / 128.f, 64.f / 128.f}, {63.f / 128.f, 62.f / 128.f}, {61.f / 128.f, 60.f / 128.f}, {59.f / 128.f, 58.f / 128.f}, {57.f / 128.f, 56.f / 128.f}, {55.f / 128.f, 54.f / 128.f}, {53.f / 128.f, 52.f / 128.f}, {51.f / 128.f, 50.f / 128.f}, {49.f / 128.f, 48.f / 128.f}};
+// Epilogue reduction.  A warp's 80 accumulator columns are 10 GROUPS of 8 consecutive columns.  Per group the
+// plain maximum of the 8 dot products (FMNMX3, ALU pipe), then key_g = groupmax_g + (15 - g)/16 (one packed FADD2
+// per two groups, FMA pipe) and the maximum of the 10 keys: its integer part is the best dot product of the part,
+// its fraction names the FIRST group that attains it.  |dot| <= 256 and the fraction has 4 bits: keys are exact
+// in fp32.  Which of the group's 8 train rows is the lowest-index minimum is settled afterwards by
+// hamming_resolve_kernel on the original descriptors (8 candidates per query row instead of n2).
+// This halves the epilogue's instruction count against tagging every column (80 adds -> 10).
+constexpr int kGroup = 8;
+constexpr int kGroups = kEpiCols / kGroup;
+static_assert(kEpiCols == 80 && kGroups == 10, "group tags below are written for 10 groups of 8");
+__constant__ float2 c_grouptag[kGroups / 2] = {{15.f / 16.f, 14.f / 16.f}, {13.f / 16.f, 12.f / 16.f}, {11.f / 16.f, 10.f / 16.f},
+                                               {9.f / 16.f, 8.f / 16.f}, {7.f / 16.f, 6.f / 16.f}};
 
 // (lo, hi) + (c.x, c.y) with one packed fp32x2 add (sm_100: add.rn.f32x2 -> FADD2)
 __device__ __forceinline__ void add2(float lo, float hi, float2 c, float& out_lo, float& out_hi) {
@@ -329,20 +336,28 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty_bar + 8 * slot);   // values are in registers now
                         if (dbg == 4) continue;
-                        // index packing, two columns per instruction: (v_2k, v_2k+1) += ((127-2k)/128, (126-2k)/128)
                         float v[kEpiCols];
 #pragma unroll
-                        for (int k = 0; k < kEpiCols / 2; ++k)
-                            add2(__int_as_float(r[2 * k]), __int_as_float(r[2 * k + 1]), c_pairkey[k], v[2 * k], v[2 * k + 1]);
+                        for (int j = 0; j < kEpiCols; ++j) v[j] = __int_as_float(r[j]);
                         if (dbg == 1) { best_key[s] = fmaxf(best_key[s], v[0] + v[kEpiCols - 1]); continue; }   // DEBUG 1: no max tree
                         if (c0 + kEpiCols > valid) {                         // tail tile: mask columns outside the image
 #pragma unroll
                             for (int j = 0; j < kEpiCols; ++j)
                                 if (c0 + j >= valid) v[j] = -1.0e30f;
                         }
-                        float m = v[0];
+                        float gm[kGroups];
 #pragma unroll
-                        for (int j = 1; j < kEpiCols; ++j) m = fmaxf(m, v[j]);
+                        for (int g = 0; g < kGroups; ++g) {
+                            const float* x = v + kGroup * g;
+                            const float a = fmaxf(fmaxf(x[0], x[1]), x[2]);
+                            const float b = fmaxf(fmaxf(x[3], x[4]), x[5]);
+                            gm[g] = fmaxf(fmaxf(fmaxf(x[6], x[7]), a), b);
+                        }
+#pragma unroll
+                        for (int k = 0; k < kGroups / 2; ++k) add2(gm[2 * k], gm[2 * k + 1], c_grouptag[k], gm[2 * k], gm[2 * k + 1]);
+                        float m = gm[0];
+#pragma unroll
+                        for (int g = 1; g < kGroups; ++g) m = fmaxf(m, gm[g]);
                         if (m >= beat[s]) {                                  // integer part exceeds the best so far
                             best_key[s] = m;
                             beat[s] = floorf(m) + 1.0f;
@@ -355,11 +370,11 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             for (int s = 0; s < MSUB; ++s) {
                 const int row = s * BM + quad * 32 + lane;
                 if (s < nsub && row < wu.n_rows && (best_base[s] >= 0 || dbg)) {
-                    // key = dot + (127 - j)/128 : <a,b> = 256 - 2*hamming
+                    // key = dot + (15 - g)/16 : <a,b> = 256 - 2*hamming; idx = first train row of the winning group
                     const float fl = floorf(best_key[s]);
-                    const int j = 127 - (int)((best_key[s] - fl) * 128.0f);
+                    const int g = 15 - (int)((best_key[s] - fl) * 16.0f);
                     const uint32_t dist = dbg ? 7u : (uint32_t)(256 - (int)fl) >> 1;
-                    const uint32_t idx = dbg ? 0u : (uint32_t)(best_base[s] + j);
+                    const uint32_t idx = dbg ? 0u : (uint32_t)(best_base[s] + kGroup * g);
                     atomicMin(wu.key + row, (dist << kTrainIdxBits) | idx);
                 }
             }
@@ -372,6 +387,42 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
     }
+}
+
+// After the tensor-core pass every key holds (distance << 18 | first train row of the winning group of 8).
+// Eight lanes per query row recompute the 8 candidates' Hamming distances on the original 256-bit descriptors
+// and the key becomes (distance << 18 | lowest train row attaining it) -- BFMatcher's tie rule.
+template <bool kVec>   // kVec: every descriptor row is 16-byte aligned (two 128-bit loads per row)
+__global__ void __launch_bounds__(256) hamming_resolve_kernel(const PairDesc* __restrict__ pairs) {
+    const PairDesc& pd = pairs[blockIdx.y];
+    const int row = blockIdx.x * 32 + (threadIdx.x >> 3);
+    const int l = threadIdx.x & 7;
+    if (pd.n1 <= 0 || pd.n2 <= 0 || row >= pd.n1) return;      // whole 8-lane groups leave together
+    const uint32_t key = pd.key[row];
+    const int cand = (int)(key & kTrainIdxMask) + l;
+    uint32_t d = 0x1FFFu;
+    if (cand < pd.n2) {
+        d = 0;
+        if constexpr (kVec) {
+            const uint4* q = reinterpret_cast<const uint4*>(pd.desc1) + (size_t)row * 2;
+            const uint4* t = reinterpret_cast<const uint4*>(pd.desc2) + (size_t)cand * 2;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint4 a = __ldg(q + h), b = __ldg(t + h);
+                d += __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z) + __popc(a.w ^ b.w);
+            }
+        } else {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(pd.desc1) + (size_t)row * kDescWords;
+            const uint32_t* t = reinterpret_cast<const uint32_t*>(pd.desc2) + (size_t)cand * kDescWords;
+#pragma unroll
+            for (int w = 0; w < kDescWords; ++w) d += __popc(__ldg(q + w) ^ __ldg(t + w));
+        }
+    }
+    uint32_t k = (d << 3) | (uint32_t)l;
+    const uint32_t mask = 0xFFu << (threadIdx.x & 24);
+#pragma unroll
+    for (int o = 1; o < kGroup; o <<= 1) k = min(k, __shfl_xor_sync(mask, k, o, kGroup));
+    if (l == 0) pd.key[row] = ((k >> 3) << kTrainIdxBits) | ((key & kTrainIdxMask) + (k & 7u));
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -415,10 +466,12 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
     const uint8_t* lo = nullptr;
     const uint8_t* hi = nullptr;
     long long ref_rows = 0;
+    bool aligned16 = true;   // descriptor rows are 32 bytes: a 16-byte aligned base keeps every row aligned
     for (int p = 0; p < n_pairs; ++p) {
         const PairDesc& pd = h_pairs[p];
         ref_rows += (long long)pd.n1 + pd.n2;
         if (pd.n1 <= 0 || pd.n2 <= 0) continue;
+        if ((reinterpret_cast<uintptr_t>(pd.desc1) | reinterpret_cast<uintptr_t>(pd.desc2)) & 15) aligned16 = false;
         const uint8_t* ends[2][2] = {{pd.desc1, pd.desc1 + (size_t)pd.n1 * 32}, {pd.desc2, pd.desc2 + (size_t)pd.n2 * 32}};
         for (auto& e : ends) {
             if (!lo || e[0] < lo) lo = e[0];
@@ -504,7 +557,14 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
     }
     const int grid = n_units < sm_count ? n_units : sm_count;
     kern<<<grid, kThreads, SMEM_BYTES, st>>>(tmap, tmapB, lm, d_pairs);
-    return launches + 1;
+    if (dbg) return launches + 1;
+    int max_n1 = 0;
+    for (int p = 0; p < n_pairs; ++p)
+        if (h_pairs[p].n2 > 0 && h_pairs[p].n1 > max_n1) max_n1 = h_pairs[p].n1;
+    const dim3 rgrid((unsigned)((max_n1 + 31) / 32), (unsigned)n_pairs);
+    if (aligned16) hamming_resolve_kernel<true><<<rgrid, 256, 0, st>>>(d_pairs);
+    else hamming_resolve_kernel<false><<<rgrid, 256, 0, st>>>(d_pairs);
+    return launches + 2;
 }
 
 }  // namespace sfmgms
