@@ -94,6 +94,29 @@ int sfmgms_bf_hamming_crosscheck(sfmgms_ctx* ctx, const uint8_t* query, int nq, 
 int sfmgms_bf_l2(sfmgms_ctx* ctx, const float* query, int nq, const float* train, int nt, int dim,
                  int32_t* train_idx, float* dist, int* n_matches);
 
+/*  cv::BFMatcher(NORM_L2, crossCheck=true)::match — the matcher bruteForceMatch constructs
+ * (FeatureMatchUtil.cpp:22-23).  Same data contract as sfmgms_bf_l2; keep[i] as in the Hamming cross-check
+ * (two tensor-core passes, query->train and train->query, joined on the device).  nq must be < 2^18 too. */
+int sfmgms_bf_l2_crosscheck(sfmgms_ctx* ctx, const float* query, int nq, const float* train, int nt, int dim,
+                            int32_t* train_idx, float* dist, uint8_t* keep);
+
+/*  The whole of bruteForceMatch (FeatureMatchUtil.cpp:20-31; cross_check = 1, the reference's
+ * constants are distance_coef = 4.0 = kDistanceCoef and max_matching_size = 500 = kMaxMatchingSize,
+ * FeatureMatchUtil.h:17-18) and of the inline match() (FeatureMatchUtil.cpp:38-50; cross_check = 0):
+ *   BFMatcher(norm_type, cross_check).match -> sort by distance -> while (front*coef < back) pop_back ->
+ *   while (size > max_matching_size) pop_back.
+ * norm_type: SFMGMS_NORM_L2 (query/train = const float*, width = 128, integer-valued as for sfmgms_bf_l2) or
+ * SFMGMS_NORM_HAMMING (const uint8_t*, width = 32).  Outputs: the surviving matches, ascending distance;
+ * *n_out = their number (<= capacity, else SFMGMS_ERR_ARG).  std::sort leaves the order of EQUAL distances
+ * unspecified; this library orders them by queryIdx (one of the orders std::sort may produce), so the output
+ * is deterministic.  An empty match list gives *n_out = 0 (the reference would dereference front() of an
+ * empty vector). */
+#define SFMGMS_NORM_L2 4       /* cv::NORM_L2 */
+#define SFMGMS_NORM_HAMMING 6  /* cv::NORM_HAMMING */
+int sfmgms_brute_force_match(sfmgms_ctx* ctx, int norm_type, int cross_check, const void* query, int nq,
+                             const void* train, int nt, int width, double distance_coef, int max_matching_size,
+                             int32_t* query_idx, int32_t* train_idx, float* dist, int capacity, int* n_out);
+
 /* ---- stage 2: replaces cv::xfeatures2d::matchGMS ----------------------------------------------
  * (FeatureMatchUtil.cpp:69; DisparityUtil.cpp:149,299).  mask[i] (0/1) for each of the n_matches input
  * matches; *mask_len = n_matches, or 0 if rotation/scale search was requested and every hypothesis had

@@ -105,6 +105,39 @@ def bf_hamming_crosscheck(q, t):
     return idx, dist, keep.astype(bool)
 
 
+def bf_l2_crosscheck(q, t):
+    """cv2.BFMatcher(cv2.NORM_L2, crossCheck=True).match (FeatureMatchUtil.cpp:22-23): the forward nearest
+    neighbour of every query is kept iff the nearest QUERY of that train row (lowest index on ties) is the
+    query itself.  -> (train_idx, dist float32, keep bool), all of length nq."""
+    idx, dist = bf_l2(q, t)
+    if len(idx) == 0:
+        return idx, dist, np.zeros(0, bool)
+    ridx, _ = bf_l2(t, q)
+    return idx, dist, ridx[idx] == np.arange(len(idx))
+
+
+def brute_force_match(q, t, norm="l2", cross_check=True, distance_coef=4.0, max_matching_size=500):
+    """bruteForceMatch (FeatureMatchUtil.cpp:20-31) / match (:38-50): (cross-checked) matches, sorted by
+    distance (stable: equal distances stay in queryIdx order -- std::sort leaves that order unspecified),
+    pruned while front*coef < back (double arithmetic on float distances), capped.
+    -> (query_idx int32, train_idx int32, dist float32)."""
+    if norm == "l2":
+        idx, dist, keep = bf_l2_crosscheck(q, t) if cross_check else bf_l2(q, t) + (None,)
+    else:
+        idx, dist, keep = bf_hamming_crosscheck(q, t) if cross_check else bf_hamming(q, t) + (None,)
+    qi = np.arange(len(idx), dtype=np.int32)
+    if keep is not None:
+        qi, idx, dist = qi[keep], idx[keep], dist[keep]
+    dist = dist.astype(np.float32)
+    order = np.argsort(dist, kind="stable")
+    qi, idx, dist = qi[order], idx[order], dist[order]
+    n = len(dist)
+    while n > 0 and np.float64(dist[0]) * distance_coef < np.float64(dist[n - 1]):
+        n -= 1
+    n = min(n, max_matching_size)
+    return qi[:n], idx[:n].astype(np.int32), dist[:n]
+
+
 def gms(size1, size2, kp1_xy, kp2_xy, query_idx, train_idx, with_rotation=False, with_scale=False,
         threshold_factor=6.0):
     """matchGMS semantics.  size = (width, height).  Returns dict(mask, n_inliers, hyp_counts, best_hyp).

@@ -12,11 +12,12 @@ from .api import (  # noqa: F401
     Context,
     DMatch,
     SfmGmsError,
+    bruteForceMatch,
     default_context,
     gms_matcher,
     load_library,
     matchGMS,
 )
 
-__all__ = ["NORM_HAMMING", "NORM_L2", "BFMatcher", "Context", "DMatch", "SfmGmsError", "default_context", "gms_matcher",
+__all__ = ["NORM_HAMMING", "NORM_L2", "BFMatcher", "Context", "DMatch", "SfmGmsError", "bruteForceMatch", "default_context", "gms_matcher",
            "load_library", "matchGMS"]

@@ -67,6 +67,10 @@ def load_library():
     L.sfmgms_bf_l2.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, P(c_int)]
     L.sfmgms_bf_hamming_crosscheck.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p,
                                                c_void_p, c_void_p]
+    L.sfmgms_bf_l2_crosscheck.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                          c_void_p]
+    L.sfmgms_brute_force_match.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_double,
+                                           c_int, c_void_p, c_void_p, c_void_p, c_int, P(c_int)]
     L.sfmgms_gms.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
                              c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p, P(c_int),
                              P(c_int), P(c_int)]
@@ -191,6 +195,42 @@ class Context:
         self._check(self._lib.sfmgms_bf_hamming_crosscheck(self._h, _ptr(q), q.shape[0], _ptr(t), t.shape[0], 32,
                                                            _ptr(idx), _ptr(dist), _ptr(keep)))
         return idx, dist, keep.astype(bool)
+
+    def bf_l2_crosscheck(self, query, train):
+        """cv2.BFMatcher(cv2.NORM_L2, crossCheck=True) (FeatureMatchUtil.cpp:22-23): (train_idx, dist f32, keep)."""
+        q, t = self._desc_l2(query), self._desc_l2(train)
+        idx = np.full(q.shape[0], -1, np.int32)
+        dist = np.full(q.shape[0], -1, np.float32)
+        keep = np.zeros(q.shape[0], np.uint8)
+        self._check(self._lib.sfmgms_bf_l2_crosscheck(self._h, _ptr(q), q.shape[0], _ptr(t), t.shape[0], 128, _ptr(idx),
+                                                      _ptr(dist), _ptr(keep)))
+        return idx, dist, keep.astype(bool)
+
+    def brute_force_match(self, query, train, norm_type=NORM_L2, cross_check=True, distance_coef=4.0,
+                          max_matching_size=500):
+        """bruteForceMatch (FeatureMatchUtil.cpp:20-31): cross-checked NN, sort by distance, prune while
+        front*coef < back, cap.  -> (query_idx, train_idx, dist float32), ascending distance (ties by queryIdx)."""
+        if norm_type == NORM_L2:
+            q, t, width = self._desc_l2(query), self._desc_l2(train), 128
+        else:
+            q, t, width = self._desc(query), self._desc(train), 32
+        cap = q.shape[0]
+        qi = np.empty(cap, np.int32)
+        ti = np.empty(cap, np.int32)
+        d = np.empty(cap, np.float32)
+        n = ctypes.c_int(0)
+        self._check(self._lib.sfmgms_brute_force_match(self._h, int(norm_type), int(bool(cross_check)), _ptr(q), q.shape[0],
+                                                       _ptr(t), t.shape[0], width, float(distance_coef),
+                                                       int(max_matching_size), _ptr(qi), _ptr(ti), _ptr(d), cap,
+                                                       ctypes.byref(n)))
+        return qi[: n.value], ti[: n.value], d[: n.value]
+
+    @staticmethod
+    def _desc_l2(d):
+        d = np.ascontiguousarray(d, dtype=np.float32)
+        if d.ndim != 2 or d.shape[1] != 128:
+            raise SfmGmsError(1, "L2 descriptors must be N x 128 float32 (SIFT)")
+        return d
 
     @staticmethod
     def _desc(d):
@@ -379,9 +419,9 @@ class BFMatcher:
     """cv::BFMatcher look-alike for NORM_HAMMING (FeatureMatchUtil.cpp:22, 66)."""
 
     def __init__(self, normType=NORM_HAMMING, crossCheck=False, ctx=None):
-        if normType not in (NORM_HAMMING, NORM_L2) or (normType == NORM_L2 and crossCheck):
-            raise SfmGmsError(1, "implemented: NORM_HAMMING (with/without crossCheck), NORM_L2 (SIFT, no crossCheck); "
-                                 "got normType=%r crossCheck=%r" % (normType, crossCheck))
+        if normType not in (NORM_HAMMING, NORM_L2):
+            raise SfmGmsError(1, "implemented: NORM_HAMMING and NORM_L2 (SIFT), with/without crossCheck; "
+                                 "got normType=%r" % (normType,))
         self.normType = normType
         self.crossCheck = bool(crossCheck)
         self._ctx = ctx
@@ -393,6 +433,9 @@ class BFMatcher:
     def match(self, queryDescriptors, trainDescriptors):
         """-> list[DMatch] exactly as cv2 returns it (query order; cross-check drops non-mutual rows)."""
         ctx = self._ctx or default_context()
+        if self.normType == NORM_L2 and self.crossCheck:
+            idx, dist, keep = ctx.bf_l2_crosscheck(queryDescriptors, trainDescriptors)
+            return [DMatch(int(i), int(idx[i]), 0, float(dist[i])) for i in np.nonzero(keep)[0]]
         if self.normType == NORM_L2:
             idx, dist = ctx.bf_l2(queryDescriptors, trainDescriptors)
             return [DMatch(i, int(idx[i]), 0, float(dist[i])) for i in range(len(idx))]
@@ -401,6 +444,25 @@ class BFMatcher:
             return [DMatch(int(i), int(idx[i]), 0, float(dist[i])) for i in np.nonzero(keep)[0]]
         idx, dist = ctx.bf_hamming(queryDescriptors, trainDescriptors)
         return [DMatch(i, int(idx[i]), 0, float(dist[i])) for i in range(len(idx))]
+
+
+def bruteForceMatch(desc1, desc2, ctx=None, kDistanceCoef=4.0, kMaxMatchingSize=500):
+    """The reference's bruteForceMatch(desc1, desc2, matches) (FeatureMatchUtil.cpp:20-31; constants from
+    FeatureMatchUtil.h:17-18): returns the list of DMatch it leaves in ``matches``.  float32 N x 128 descriptors
+    take the reference's NORM_L2 path; uint8 N x 32 descriptors the Hamming one."""
+    ctx = ctx or default_context()
+    norm = NORM_HAMMING if np.asarray(desc1).dtype == np.uint8 else NORM_L2
+    q, t, d = ctx.brute_force_match(desc1, desc2, norm, True, kDistanceCoef, kMaxMatchingSize)
+    return [DMatch(int(q[i]), int(t[i]), 0, float(d[i])) for i in range(len(q))]
+
+
+def match(desc1, desc2, kDistanceCoef, kMaxMatchingSize, ctx=None):
+    """The reference's inline match(desc1, desc2, matches, kDistanceCoef, kMaxMatchingSize)
+    (FeatureMatchUtil.cpp:38-50): BFMatcher::create() = NORM_L2 without cross-check, then the same sort/prune/cap."""
+    ctx = ctx or default_context()
+    norm = NORM_HAMMING if np.asarray(desc1).dtype == np.uint8 else NORM_L2
+    q, t, d = ctx.brute_force_match(desc1, desc2, norm, False, kDistanceCoef, kMaxMatchingSize)
+    return [DMatch(int(q[i]), int(t[i]), 0, float(d[i])) for i in range(len(q))]
 
 
 def matchGMS(size1, size2, keypoints1, keypoints2, matches1to2, withRotation=False, withScale=False,

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/sfmgms.h"
@@ -134,6 +135,15 @@ __global__ void crosscheck_kernel(const uint32_t* __restrict__ key, const uint32
     if (i >= nq) return;
     const uint32_t k = key[i];
     keep[i] = (k != kKeyInit) && ((rkey[k & kTrainIdxMask] & kTrainIdxMask) == (uint32_t)i);
+}
+
+// cross-check on plain index arrays (L2 path): keep[i] iff the nearest query of train row fwd[i] is i
+__global__ void crosscheck_idx_kernel(const int32_t* __restrict__ fwd, const int32_t* __restrict__ rev, int nq,
+                                      uint8_t* __restrict__ keep) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const int j = fwd[i];
+    keep[i] = j >= 0 && rev[j] == i;
 }
 
 // (§8f-1) ordered compaction of inlier coordinates for one pair: single CTA, chunked scan
@@ -540,6 +550,105 @@ int sfmgms_bf_l2(sfmgms_ctx* ctx, const float* query, int nq, const float* train
     if (bad) return fail(ctx, SFMGMS_ERR_ARG, "descriptors must be integer-valued in [0,255] (OpenCV SIFT); general float L2 is not implemented");
     return SFMGMS_OK;
     GUARD_END
+}
+
+int sfmgms_bf_l2_crosscheck(sfmgms_ctx* ctx, const float* query, int nq, const float* train, int nt, int dim,
+                            int32_t* train_idx, float* dist, uint8_t* keep) {
+    GUARD_BEGIN
+    if (nq < 0 || nt < 0) return fail(ctx, SFMGMS_ERR_ARG, "negative row count");
+    if (dim != 128) return fail(ctx, SFMGMS_ERR_ARG, "dim must be 128 (SIFT), got %d", dim);
+    if ((nq > 0 && !query) || (nt > 0 && !train)) return fail(ctx, SFMGMS_ERR_ARG, "null descriptor pointer");
+    if (nt >= SFMGMS_MAX_TRAIN_ROWS || nq >= SFMGMS_MAX_TRAIN_ROWS)
+        return fail(ctx, SFMGMS_ERR_TRAIN_ROWS, "rows %d / %d >= 2^18 (OpenCV BFMatcher: rows < IMGIDX_ONE)", nq, nt);
+    if (nt == 0 || nq == 0) return SFMGMS_OK;
+    cudaStream_t st = ctx->stream;
+    CU(ctx->d_q.ensure((size_t)(nq + nt) * 512));
+    float* dq = (float*)ctx->d_q.p;
+    float* dt = dq + (size_t)nq * 128;
+    const bool use_tc = ctx->l2_kernel != 1;
+    const size_t s_fwd = use_tc ? l2_tc_scratch_bytes(nq, nt) : l2_scratch_bytes(nq, nt);
+    const size_t s_rev = use_tc ? l2_tc_scratch_bytes(nt, nq) : l2_scratch_bytes(nt, nq);
+    CU(ctx->d_hist.ensure(s_fwd > s_rev ? s_fwd : s_rev));
+    CU(ctx->d_out_i32.ensure(((size_t)nq + nt) * 8 + 16));
+    CU(ctx->d_mask.ensure(nq));
+    CU(cudaMemcpyAsync(dq, query, (size_t)nq * 512, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dt, train, (size_t)nt * 512, cudaMemcpyHostToDevice, st));
+    int32_t* o = (int32_t*)ctx->d_out_i32.p;          // forward: idx[nq], dist[nq]
+    int32_t* r = o + 2 * (size_t)nq;                  // reverse: idx[nt], dist[nt]
+    int* d_bad = (int*)(r + 2 * (size_t)nt);          // one flag per pass
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[0], st));
+    int nl = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const float* a = pass ? dt : dq;
+        const float* b = pass ? dq : dt;
+        const int na = pass ? nt : nq, nb = pass ? nq : nt;
+        int32_t* out = pass ? r : o;
+        const int l = use_tc ? launch_l2_tc(a, na, b, nb, ctx->d_hist.p, out, (float*)(out + na), d_bad + pass, ctx->sm_count, st)
+                             : launch_l2_dp4a(a, na, b, nb, ctx->d_hist.p, out, (float*)(out + na), d_bad + pass, ctx->sm_count, st);
+        if (l < 0) return fail(ctx, SFMGMS_ERR_CUDA, "L2 tensor-core launch setup failed");
+        nl += l;
+    }
+    crosscheck_idx_kernel<<<(nq + 255) / 256, 256, 0, st>>>(o, r, nq, (uint8_t*)ctx->d_mask.p);
+    ctx->launches += nl + 1;
+    if (ctx->timing) { CU(cudaEventRecord(ctx->ev[1], st)); CU(cudaEventRecord(ctx->ev[2], st)); }
+    CU(cudaGetLastError());
+    int bad[2] = {0, 0};
+    CU(cudaMemcpyAsync(bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, st));
+    if (train_idx) CU(cudaMemcpyAsync(train_idx, o, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    if (dist) CU(cudaMemcpyAsync(dist, o + nq, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    if (keep) CU(cudaMemcpyAsync(keep, ctx->d_mask.p, (size_t)nq, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (ctx->timing) {
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]));
+        ctx->last_ms[0] = t; ctx->last_ms[1] = 0; ctx->last_ms[2] = nl;
+    }
+    if (bad[0] || bad[1]) return fail(ctx, SFMGMS_ERR_ARG, "descriptors must be integer-valued in [0,255] (OpenCV SIFT); general float L2 is not implemented");
+    return SFMGMS_OK;
+    GUARD_END
+}
+
+int sfmgms_brute_force_match(sfmgms_ctx* ctx, int norm_type, int cross_check, const void* query, int nq,
+                             const void* train, int nt, int width, double distance_coef, int max_matching_size,
+                             int32_t* query_idx, int32_t* train_idx, float* dist, int capacity, int* n_out) {
+    if (!ctx) return SFMGMS_ERR_ARG;
+    if (n_out) *n_out = 0;
+    if (norm_type != SFMGMS_NORM_L2 && norm_type != SFMGMS_NORM_HAMMING)
+        return fail(ctx, SFMGMS_ERR_ARG, "norm_type must be SFMGMS_NORM_L2 (4) or SFMGMS_NORM_HAMMING (6), got %d", norm_type);
+    if (nq < 0 || nt < 0 || capacity < 0 || max_matching_size < 0) return fail(ctx, SFMGMS_ERR_ARG, "negative size");
+    // stage 1 on the device: (cross-checked) nearest neighbours in query order
+    std::vector<int32_t> idx((size_t)nq), idist;
+    std::vector<float> fdist;
+    std::vector<uint8_t> keep((size_t)nq, 1);
+    int n = 0, rc;
+    if (norm_type == SFMGMS_NORM_L2) {
+        fdist.resize((size_t)nq);
+        rc = cross_check ? sfmgms_bf_l2_crosscheck(ctx, (const float*)query, nq, (const float*)train, nt, width, idx.data(), fdist.data(), keep.data())
+                         : sfmgms_bf_l2(ctx, (const float*)query, nq, (const float*)train, nt, width, idx.data(), fdist.data(), &n);
+    } else {
+        idist.resize((size_t)nq);
+        rc = cross_check ? sfmgms_bf_hamming_crosscheck(ctx, (const uint8_t*)query, nq, (const uint8_t*)train, nt, width, idx.data(), idist.data(), keep.data())
+                         : sfmgms_bf_hamming(ctx, (const uint8_t*)query, nq, (const uint8_t*)train, nt, width, idx.data(), idist.data(), &n);
+    }
+    if (rc) return rc;
+    if (nq == 0 || nt == 0) return SFMGMS_OK;
+    // the tail of FeatureMatchUtil.cpp:24-30 on the host, as in the reference: sort, ratio prune, cap
+    struct M { float d; int32_t q, t; };
+    std::vector<M> m;
+    m.reserve((size_t)nq);
+    for (int i = 0; i < nq; ++i)
+        if (keep[i]) m.push_back({norm_type == SFMGMS_NORM_L2 ? fdist[i] : (float)idist[i], i, idx[i]});
+    std::stable_sort(m.begin(), m.end(), [](const M& a, const M& b) { return a.d < b.d; });   // DMatch::operator<
+    while (!m.empty() && (double)m.front().d * distance_coef < (double)m.back().d) m.pop_back();
+    if (m.size() > (size_t)max_matching_size) m.resize((size_t)max_matching_size);
+    if (m.size() > (size_t)capacity) return fail(ctx, SFMGMS_ERR_ARG, "capacity %d < %zu surviving matches", capacity, m.size());
+    for (size_t k = 0; k < m.size(); ++k) {
+        if (query_idx) query_idx[k] = m[k].q;
+        if (train_idx) train_idx[k] = m[k].t;
+        if (dist) dist[k] = m[k].d;
+    }
+    if (n_out) *n_out = (int)m.size();
+    return SFMGMS_OK;
 }
 
 static int gms_args(sfmgms_ctx* ctx, int w1, int h1, int w2, int h2, int n1, int n2, int s1, int s2) {

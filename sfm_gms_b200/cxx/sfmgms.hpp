@@ -81,8 +81,8 @@ class BFMatcher {
    public:
     explicit BFMatcher(int normType = NORM_HAMMING, bool crossCheck = false, Context* ctx = nullptr)
         : cross_(crossCheck), ctx_(ctx) {
-        if (normType != NORM_HAMMING && !(normType == NORM_L2 && !crossCheck))
-            throw Error(SFMGMS_ERR_ARG, "implemented: NORM_HAMMING (with/without crossCheck) and NORM_L2 without crossCheck");
+        if (normType != NORM_HAMMING && normType != NORM_L2)
+            throw Error(SFMGMS_ERR_ARG, "implemented: NORM_HAMMING and NORM_L2, with/without crossCheck");
         norm_ = normType;
     }
     // NORM_L2 on integer-valued float descriptors with 128 columns (OpenCV SIFT; FeatureMatchUtil.cpp:10, 66-68):
@@ -93,6 +93,14 @@ class BFMatcher {
         matches.clear();
         std::vector<int32_t> idx((size_t)(nq > 0 ? nq : 0));
         std::vector<float> dist(idx.size());
+        if (cross_) {   // BFMatcher(NORM_L2, true): the matcher of bruteForceMatch (FeatureMatchUtil.cpp:22)
+            std::vector<uint8_t> keep(idx.size());
+            c.check(sfmgms_bf_l2_crosscheck(c.get(), query, nq, train, nt, dim, idx.data(), dist.data(), keep.data()));
+            if (nt == 0) return;
+            for (int i = 0; i < nq; ++i)
+                if (keep[i]) matches.push_back(DMatch{i, idx[i], 0, dist[i]});
+            return;
+        }
         int n = 0;
         c.check(sfmgms_bf_l2(c.get(), query, nq, train, nt, dim, idx.data(), dist.data(), &n));
         matches.reserve((size_t)n);
@@ -125,6 +133,43 @@ class BFMatcher {
     int norm_ = NORM_HAMMING;
 };
 
+namespace detail {
+inline void brute_force(int norm, bool cross, const void* d1, int n1, const void* d2, int n2, int width,
+                        std::vector<DMatch>& matches, double coef, int max_size, Context* ctx) {
+    Context& c = ctx ? *ctx : Context::thread_default();
+    matches.clear();
+    const size_t cap = (size_t)(n1 > 0 ? n1 : 0);
+    std::vector<int32_t> q(cap), t(cap);
+    std::vector<float> d(cap);
+    int n = 0;
+    c.check(sfmgms_brute_force_match(c.get(), norm, cross ? 1 : 0, d1, n1, d2, n2, width, coef, max_size, q.data(),
+                                     t.data(), d.data(), (int)cap, &n));
+    matches.reserve((size_t)n);
+    for (int i = 0; i < n; ++i) matches.push_back(DMatch{q[i], t[i], 0, d[i]});
+}
+}  // namespace detail
+
+}  // namespace cv
+
+// The reference's own helpers (FeatureMatchUtil.h:17-18, FeatureMatchUtil.cpp:20-31 and :38-50), same names:
+constexpr double kDistanceCoef = 4.0;
+constexpr int kMaxMatchingSize = 500;
+// bruteForceMatch(desc1, desc2, matches): BFMatcher(NORM_L2, true).match, sort, ratio prune, cap 500
+inline void bruteForceMatch(const float* desc1, int n1, const float* desc2, int n2, std::vector<cv::DMatch>& matches,
+                            Context* ctx = nullptr) {
+    cv::detail::brute_force(SFMGMS_NORM_L2, true, desc1, n1, desc2, n2, 128, matches, kDistanceCoef, kMaxMatchingSize, ctx);
+}
+inline void bruteForceMatch(const uint8_t* desc1, int n1, const uint8_t* desc2, int n2, std::vector<cv::DMatch>& matches,
+                            Context* ctx = nullptr) {   // ORB descriptors: the same flow under NORM_HAMMING
+    cv::detail::brute_force(SFMGMS_NORM_HAMMING, true, desc1, n1, desc2, n2, 32, matches, kDistanceCoef, kMaxMatchingSize, ctx);
+}
+// match(desc1, desc2, matches, kDistanceCoef, kMaxMatchingSize): BFMatcher::create() (NORM_L2, no cross-check)
+inline void match(const float* desc1, int n1, const float* desc2, int n2, std::vector<cv::DMatch>& matches,
+                  double distanceCoef, int maxMatchingSize, Context* ctx = nullptr) {
+    cv::detail::brute_force(SFMGMS_NORM_L2, false, desc1, n1, desc2, n2, 128, matches, distanceCoef, maxMatchingSize, ctx);
+}
+
+namespace cv {
 namespace xfeatures2d {
 
 // cv::xfeatures2d::matchGMS — exact OpenCV parameter order (…, withRotation, withScale, thresholdFactor).

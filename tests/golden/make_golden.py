@@ -139,6 +139,37 @@ def sift_case():
     print("sift_view01_1500", len(bt), "gms(rot,scale)", r["n_inliers"], "tie n =", n)
 
 
+def bruteforce_case():
+    """bruteForceMatch (FeatureMatchUtil.cpp:20-31): BFMatcher(NORM_L2, crossCheck=true).match, std::sort by
+    distance, prune while front*4 < back, cap 500.  cv2 pins the cross-checked match list; the sort/prune/cap tail
+    is restated here with a STABLE sort (std::sort leaves the order of equal distances unspecified; ties keep
+    query order).  Inputs are the descriptors already stored in sift_view01_1500.npz / view01_2k.npz."""
+    def tail(m, coef=4.0, cap=500):
+        m = sorted(m, key=lambda x: x[2])                     # stable: ties stay in queryIdx order
+        while m and np.float64(m[0][2]) * coef < np.float64(m[-1][2]):
+            m.pop()
+        return m[:cap]
+
+    out = {}
+    g = np.load(os.path.join(HERE, "sift_view01_1500.npz"))
+    d1, d2 = g["desc1"].astype(np.float32), g["desc2"].astype(np.float32)
+    h = np.load(os.path.join(HERE, "view01_2k.npz"))
+    for name, a, b, norm in (("l2", d1, d2, cv2.NORM_L2), ("l2_rev", d2[:700], d1, cv2.NORM_L2),
+                             ("ham", h["desc1"], h["desc2"], cv2.NORM_HAMMING)):
+        for xc in (True, False):
+            m = [(x.queryIdx, x.trainIdx, np.float32(x.distance)) for x in cv2.BFMatcher(norm, xc).match(a, b)]
+            key = "%s_%s" % (name, "xc" if xc else "nn")
+            out[key + "_full"] = np.array([(q, t) for q, t, _ in m], np.int32).reshape(-1, 2)
+            out[key + "_full_dist"] = np.array([d for _, _, d in m], np.float32)
+            for coef, cap in ((4.0, 500), (1.5, 100000), (4.0, 37)):
+                r = tail(m, coef, cap)
+                k2 = "%s_c%g_m%d" % (key, coef, cap)
+                out[k2] = np.array([(q, t) for q, t, _ in r], np.int32).reshape(-1, 2)
+                out[k2 + "_dist"] = np.array([d for _, _, d in r], np.float32)
+        print("bruteforce", name, len(out[name + "_xc_full"]), len(out[name + "_xc_c4_m500"]), len(out[name + "_xc_c1.5_m100000"]))
+    np.savez_compressed(os.path.join(HERE, "bruteforce.npz"), **out)
+
+
 if __name__ == "__main__":
     oracle.build()
     oracle.set_num_threads(os.cpu_count())
@@ -148,3 +179,4 @@ if __name__ == "__main__":
     pack("bun12_rot180_3k", *orb_pair("Bun1.jpg", "Bun2.jpg", 3000, rot180=True))
     tie_case()
     sift_case()
+    bruteforce_case()

@@ -448,3 +448,62 @@ def test_l2_ragged_vs_oracle_and_errors(l2ctx, oracle_mod):
         ctx.bf_l2(q + 0.5, t)
     with pytest.raises(SfmGmsError):
         ctx.bf_l2(q[:, :64], t[:, :64])
+
+
+# ---- (§8f-2) bruteForceMatch: BFMatcher(NORM_L2, crossCheck=true) + sort + ratio prune + cap (FeatureMatchUtil.cpp:20-31)
+BF_CASES = [("l2", "sift_view01_1500", False), ("l2_rev", "sift_view01_1500", True), ("ham", "view01_2k", False)]
+
+
+def _bruteforce_inputs(name, src, rev):
+    g = load_golden(src)
+    if name == "ham":
+        return g["desc1"], g["desc2"]
+    d1, d2 = g["desc1"].astype(np.float32), g["desc2"].astype(np.float32)
+    return (d2[:700], d1) if rev else (d1, d2)
+
+
+@pytest.mark.parametrize("name,src,rev", BF_CASES)
+def test_bruteforce_golden_cv2(l2ctx, name, src, rev):
+    import sfm_gms_b200 as sg
+
+    ctx = l2ctx
+    g = load_golden("bruteforce")
+    q, t = _bruteforce_inputs(name, src, rev)
+    norm = sg.NORM_HAMMING if name == "ham" else sg.NORM_L2
+    # the matcher bruteForceMatch constructs: cv2-pinned (queryIdx, trainIdx, distance) list
+    m = sg.BFMatcher(norm, True, ctx=ctx).match(q, t)
+    full = g[name + "_xc_full"]
+    assert [(x.queryIdx, x.trainIdx) for x in m] == [tuple(r) for r in full.tolist()]
+    assert np.array_equal(np.array([x.distance for x in m], np.float32), g[name + "_xc_full_dist"])
+    for xc in (True, False):
+        for coef, cap in ((4.0, 500), (1.5, 100000), (4.0, 37)):
+            key = "%s_%s_c%g_m%d" % (name, "xc" if xc else "nn", coef, cap)
+            qi, ti, d = ctx.brute_force_match(q, t, norm, xc, coef, cap)
+            assert np.array_equal(np.stack([qi, ti], 1).reshape(-1, 2), g[key]) and np.array_equal(d, g[key + "_dist"]), key
+    # the reference's own entry points, default constants (kDistanceCoef = 4, kMaxMatchingSize = 500)
+    out = sg.bruteForceMatch(q, t, ctx=ctx)
+    key = name + "_xc_c4_m500"
+    assert [(x.queryIdx, x.trainIdx) for x in out] == [tuple(r) for r in g[key].tolist()]
+    from sfm_gms_b200 import api
+    out = api.match(q, t, 1.5, 100000, ctx=ctx)
+    assert [(x.queryIdx, x.trainIdx) for x in out] == [tuple(r) for r in g[name + "_nn_c1.5_m100000"].tolist()]
+
+
+def test_l2_crosscheck_vs_oracle_ragged(l2ctx, oracle_mod):
+    ctx = l2ctx
+    rng = np.random.default_rng(33)
+    for nq, nt in [(1, 1), (5, 300), (700, 129), (1500, 1501)]:
+        q = rng.integers(0, 60, (nq, 128)).astype(np.float32)
+        t = rng.integers(0, 60, (nt, 128)).astype(np.float32)
+        k = min(nq, nt) // 2
+        t[:k] = q[:k]                       # mutual pairs ...
+        if nt > 3 and nq > 3:
+            t[nt - 1] = q[0]; q[nq - 1] = q[1]   # ... and duplicates that the tie rules must break the same way
+        idx, dist, keep = ctx.bf_l2_crosscheck(q, t)
+        oi, od, ok = oracle_mod.bf_l2_crosscheck(q, t)
+        assert np.array_equal(keep, ok) and np.array_equal(idx, oi) and np.array_equal(dist, od), (nq, nt)
+        a = ctx.brute_force_match(q, t, 4, True, 4.0, 500)
+        b = oracle_mod.brute_force_match(q, t, "l2", True, 4.0, 500)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b)), (nq, nt)
+    qi, ti, d = ctx.brute_force_match(q, np.zeros((0, 128), np.float32))
+    assert len(qi) == 0
