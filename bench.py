@@ -349,8 +349,53 @@ def main():
     t0 = time.perf_counter()
     ms_e2e_dev = timed(step_e2e, args.steps)
     wall_e2e = time.perf_counter() - t0
-    e2e_value = total_pairs * args.steps / (ms_e2e_dev * 1e-3)
+    e2e_single = total_pairs * args.steps / (ms_e2e_dev * 1e-3)
     assert np.array_equal(h_ninl.numpy(), n_inl_dev), "e2e and resident arms disagree"
+
+    # ---- e2e, streaming: the same call from TWO host threads, one context each (the library's threading model:
+    # one ctx per host thread), alternating steps -- one thread's H2D overlaps the other's compute tail and D2H.
+    # Every step still copies its inputs from pinned host memory and its results back inside the timed region.
+    import threading
+
+    ctx2 = sg.Context(local_rank)
+    if args.kernel != "auto":
+        ctx2.set_option(api.OPT_HAMMING_KERNEL, {"popc": api.HAMMING_POPC, "tc": api.HAMMING_TC, "fp4": api.HAMMING_FP4}[args.kernel])
+    ctx2.set_option(api.OPT_TC_OPERAND_CACHE, 0)
+    outs2 = [torch.zeros(P, dtype=torch.int32).pin_memory() for _ in range(3)] + \
+            [torch.zeros(tot_m, dtype=torch.int32).pin_memory() for _ in range(2)] + [torch.zeros(tot_m, dtype=torch.uint8).pin_memory()]
+    outs1 = [h_ninl, h_bh, h_ml, h_ti, h_di, h_mk]
+
+    def worker(c, outs, n):
+        for _ in range(n):
+            c.match_image_set_raw(loc_off, h_desc.data_ptr(), h_kp.data_ptr(), loc_sizes, loc_pairs, 0, 0, 6.0,
+                                  *[o.data_ptr() for o in outs])
+
+    def run_streaming(steps):
+        n1 = (steps + 1) // 2
+        th = [threading.Thread(target=worker, args=(ctx, outs1, n1)), threading.Thread(target=worker, args=(ctx2, outs2, steps - n1))]
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()                       # device idle: stamps "now"
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), wall
+
+    l1 = ctx.kernel_launches + ctx2.kernel_launches
+    run_streaming(4)
+    ms_stream, wall_stream = run_streaming(args.steps)
+    e2e_value = total_pairs * args.steps / (ms_stream * 1e-3)
+    assert np.array_equal(h_ninl.numpy(), n_inl_dev) and (args.steps < 2 or np.array_equal(outs2[0].numpy(), n_inl_dev)), \
+        "streaming e2e and resident arms disagree"
 
     # ---- gather per-rank inlier totals on the host (no data-path collective; just the report) ---------
     inl_total = torch.tensor([int(n_inl_dev.sum())], device=dev, dtype=torch.int64)
@@ -381,11 +426,17 @@ def main():
             ops = 2.0 * 256 * dists               # 2 x MACs on the unpacked +-1 operands
             achieved = ops / per_launch_s / 1e12
             mult = 4.0 if kind == "fp4" else 2.0  # dense fp4 (kind::mxf4) = 4x, int8 = 2x the bf16 rate on sm_100a
-            peak = mult * peaks.get("bf16_tflops_sustained", 1413.3)
+            # Denominator: mult x the measured BURST bf16 rate.  The sustained cuBLAS bf16 figure in
+            # MEASURED_PEAKS.json is power-limited (its SM clock sags to ~1.34 GHz); this kernel holds 1.965 GHz and
+            # EXCEEDS mult x sustained, so that figure is reported beside it rather than used as the ceiling.
+            peak = mult * peaks.get("bf16_tflops", 1660.1)
+            sustained = mult * peaks.get("bf16_tflops_sustained", 1413.3)
             roof = {"bound": "tensor", "kernel": "hamming_%s_kernel" % kind, "achieved": achieved, "peak": peak,
                     "unit": "TOP/s", "frac": achieved / peak,
-                    "peak_source": "%gx measured sustained bf16 TFLOP/s (MEASURED_PEAKS.json); %s dense rate = %gx bf16 on "
+                    "peak_source": "%gx measured burst bf16 TFLOP/s (MEASURED_PEAKS.json); %s dense rate = %gx bf16 on "
                                    "sm_100a" % (mult, "mxf4" if kind == "fp4" else "int8", mult),
+                    "frac_of_%gx_sustained_bf16" % mult: achieved / sustained,
+                    "frac_of_nominal": achieved / (mult * 2250.0),
                     "traffic": None, "algorithmic_units_per_launch": dists, "avg_launch_ms": per_launch_s * 1e3}
         try:   # DRAM bytes of the dominant kernel from the committed ncu --set full capture (same command, P pairs/launch)
             tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
@@ -405,8 +456,11 @@ def main():
                            "parallelism": "pair-sharded x%d, one NCCL broadcast of the shared set (%.1f ms, untimed)"
                                           % (world, bcast_ms)},
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e_dev / args.steps,
-                        "wall_ms_per_step": 1e3 * wall_e2e / args.steps},
+                        "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_stream / args.steps,
+                        "wall_ms_per_step": 1e3 * wall_stream / args.steps,
+                        "mode": "2 host threads x 1 context each, alternating steps (H2D of one overlaps compute/D2H of the other)",
+                        "single_thread": {"value": e2e_single, "ms_per_step": ms_e2e_dev / args.steps,
+                                          "wall_ms_per_step": 1e3 * wall_e2e / args.steps}},
                 "gpu_launches": int(launches), "roofline": roof,
                 "stage_ms_per_step": {"hamming": float(np.mean(ham_ms)), "gms": float(np.mean(gms_ms))},
                 "clocks": clocks, "inliers_total": int(inl_total.item())}
