@@ -53,7 +53,8 @@ extern "C" {
 #define SFMGMS_OPT_GMS_CHUNK_BYTES 2 /* scratch budget per GMS chunk (bytes), default 64 MiB */
 #define SFMGMS_OPT_TC_OPERAND_CACHE 4 /* 1 (default): keep the unpacked +-1 operands of the image set across
                                          sfmgms_match_pairs calls; 0: unpack again on every call */
-#define SFMGMS_OPT_L2_KERNEL 5        /* sfmgms_bf_l2: 0 auto (tcgen05), 1 DP4A CUDA-core kernel, 2 tcgen05 kind::i8 kernel */
+#define SFMGMS_OPT_L2_KERNEL 5        /* sfmgms_bf_l2: 0 auto, 1 DP4A CUDA-core kernel, 2 tcgen05 kind::i8 kernel (1, 2: integer-valued
+                                         data, else the fp32 kernel takes over), 3 always the order-exact fp32 kernel */
 #define SFMGMS_OPT_TIMING 3          /* 1: record CUDA events around the Hamming and GMS stages of each batch */
 
 typedef struct sfmgms_ctx sfmgms_ctx;
@@ -85,12 +86,16 @@ int sfmgms_bf_hamming(sfmgms_ctx* ctx, const uint8_t* query, int nq, const uint8
 int sfmgms_bf_hamming_crosscheck(sfmgms_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt,
                                  int desc_bytes, int32_t* train_idx, int32_t* dist, uint8_t* keep);
 
-/*  cv::BFMatcher(NORM_L2, crossCheck=false)::match for INTEGER-VALUED float descriptors with
- * 128 columns — what OpenCV's SIFT produces and what the reference literally runs (FeatureMatchUtil.cpp:10, 66-68).
- * For such data OpenCV's float accumulation of sum((a-b)^2) is exact, and so is this: train_idx[i] = lowest j
- * minimising the squared distance, dist[i] = sqrtf((float)d2), bit-identical to cv2.  Any descriptor value that is
- * not an integer in [0,255] -> SFMGMS_ERR_ARG (general float descriptors are not implemented).  dim must be 128.
- * Kernel: tcgen05 u8 x u8 GEMM with a fused row-argmin epilogue (l2_tc.cu); SFMGMS_OPT_L2_KERNEL selects the DP4A one. */
+/*  cv::BFMatcher(NORM_L2, crossCheck=false)::match on CV_32F descriptors — what the reference
+ * literally runs (SIFT, FeatureMatchUtil.cpp:10, 66-68).  train_idx[i] = lowest j minimising the FLOAT distance
+ * sqrtf(normL2Sqr(q_i, t_j)), dist[i] = that float.  Two kernels behind one call:
+ *  - dim == 128 and every value an integer in [0,255] (OpenCV SIFT): OpenCV's float accumulation is exact in any
+ *    order; tcgen05 u8 x u8 GEMM with a fused row-argmin epilogue (l2_tc.cu; SFMGMS_OPT_L2_KERNEL = 1: DP4A).
+ *    Bit-identical to cv2, including OpenCV's float-tie rule for d2 >= 2^22.
+ *  - anything else (RootSIFT, normalised or learned descriptors, other widths; 1 <= dim <= 256): the fp32 kernel
+ *    l2_f32.cu restates OpenCV's hal::normL2Sqr_ addition order (4 accumulators x 4 lanes, no FMA, scalar tail) and
+ *    is bit-identical to cv2 built with the 4-lane (SSE) baseline — the stock x86-64 packages; a build whose
+ *    normL2Sqr_ uses wider vectors may differ in the last ulp of a distance. */
 int sfmgms_bf_l2(sfmgms_ctx* ctx, const float* query, int nq, const float* train, int nt, int dim,
                  int32_t* train_idx, float* dist, int* n_matches);
 

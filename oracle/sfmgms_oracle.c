@@ -320,11 +320,28 @@ done:
     return rc;
 }
 
+/* OpenCV core hal::normL2Sqr_(const float* a, const float* b, int n) (modules/core/src/norm.cpp), universal-
+ * intrinsics build with 4 float lanes (the SSE baseline of the stock x86-64 packages): four vector accumulators,
+ * 16 elements per iteration, d_k = t*t + d_k with mul and add rounded separately; lanes combined as
+ * ((d0+d1)+d2)+d3, then v_reduce_sum = (s0+s2)+(s1+s3); the n%16 tail is added element by element.
+ * Pinned: bit-exact against cv2 4.13 here (tests/test_oracle.py::test_l2_oracle_general_float_vs_cv2). */
+static float norm_l2_sqr_cv(const float* a, const float* b, int n) {
+    float acc[16];
+    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+    int j = 0;
+    for (; j <= n - 16; j += 16)
+        for (int c = 0; c < 16; ++c) { float t = a[j + c] - b[j + c]; float m = t * t; acc[c] = m + acc[c]; }
+    float s[4];
+    for (int l = 0; l < 4; ++l) { float x = acc[l] + acc[4 + l]; x = x + acc[8 + l]; s[l] = x + acc[12 + l]; }
+    float x = s[0] + s[2], y = s[1] + s[3];
+    float d = x + y;
+    for (; j < n; ++j) { float t = a[j] - b[j]; float m = t * t; d = d + m; }
+    return d;
+}
+
 /* (f3) cv::BFMatcher(NORM_L2, crossCheck=false)::match on float descriptors (what the reference literally runs:
- * SIFT + BFMatcher::create(), FeatureMatchUtil.cpp:10, 66-68).  OpenCV: dist = sqrt(sum (a-b)^2) accumulated in
- * float, strict '<' scan on the float distance => lowest trainIdx among equal FLOAT distances.  For integer-valued
- * descriptors (OpenCV SIFT) every partial sum is an integer < 2^24, so the float accumulation is exact whatever the
- * SIMD order OpenCV uses; for other data this sequential sum is only one of the possible roundings (documented). */
+ * SIFT + BFMatcher::create(), FeatureMatchUtil.cpp:10, 66-68).  OpenCV: dist = sqrt(normL2Sqr_(a, b)) in float,
+ * strict '<' scan on the float distance => lowest trainIdx among equal FLOAT distances. */
 int oracle_bf_l2(const float* q, int nq, const float* t, int nt, int dim, int32_t* train_idx, float* dist, int* n_matches) {
     if (nq < 0 || nt < 0 || dim <= 0 || nt >= (1 << 18)) return -1;
     if (nt == 0) { if (n_matches) *n_matches = 0; return 0; }
@@ -333,10 +350,7 @@ int oracle_bf_l2(const float* q, int nq, const float* t, int nt, int dim, int32_
         float best = INFINITY;
         int bestj = -1;
         for (int j = 0; j < nt; ++j) {
-            const float* b = t + (size_t)j * dim;
-            float s = 0.f;
-            for (int k = 0; k < dim; ++k) { float d = a[k] - b[k]; s += d * d; }
-            float d = sqrtf(s);
+            float d = sqrtf(norm_l2_sqr_cv(a, t + (size_t)j * dim, dim));
             if (d < best) { best = d; bestj = j; }
         }
         train_idx[i] = bestj;

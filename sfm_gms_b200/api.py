@@ -175,16 +175,14 @@ class Context:
         return idx[: n.value], dist[: n.value]
 
     def bf_l2(self, query, train):
-        """cv2.BFMatcher(cv2.NORM_L2).match on integer-valued float descriptors (SIFT): (train_idx, dist float32)."""
-        q = np.ascontiguousarray(query, dtype=np.float32)
-        t = np.ascontiguousarray(train, dtype=np.float32)
-        if q.ndim != 2 or t.ndim != 2 or q.shape[1] != 128 or t.shape[1] != 128:
-            raise SfmGmsError(1, "L2 descriptors must be N x 128 float32 (SIFT)")
+        """cv2.BFMatcher(cv2.NORM_L2).match on float32 descriptors: (train_idx, dist float32), bit-identical to cv2
+        (integer-valued SIFT rows on the tensor cores, any other float data on the order-exact fp32 kernel)."""
+        q, t = self._desc_l2(query), self._desc_l2(train, q_like=query)
         idx = np.empty(q.shape[0], np.int32)
         dist = np.empty(q.shape[0], np.float32)
         n = ctypes.c_int(0)
-        self._check(self._lib.sfmgms_bf_l2(self._h, _ptr(q), q.shape[0], _ptr(t), t.shape[0], 128, _ptr(idx), _ptr(dist),
-                                           ctypes.byref(n)))
+        self._check(self._lib.sfmgms_bf_l2(self._h, _ptr(q), q.shape[0], _ptr(t), t.shape[0], q.shape[1], _ptr(idx),
+                                           _ptr(dist), ctypes.byref(n)))
         return idx[: n.value], dist[: n.value]
 
     def bf_hamming_crosscheck(self, query, train):
@@ -198,11 +196,11 @@ class Context:
 
     def bf_l2_crosscheck(self, query, train):
         """cv2.BFMatcher(cv2.NORM_L2, crossCheck=True) (FeatureMatchUtil.cpp:22-23): (train_idx, dist f32, keep)."""
-        q, t = self._desc_l2(query), self._desc_l2(train)
+        q, t = self._desc_l2(query), self._desc_l2(train, q_like=query)
         idx = np.full(q.shape[0], -1, np.int32)
         dist = np.full(q.shape[0], -1, np.float32)
         keep = np.zeros(q.shape[0], np.uint8)
-        self._check(self._lib.sfmgms_bf_l2_crosscheck(self._h, _ptr(q), q.shape[0], _ptr(t), t.shape[0], 128, _ptr(idx),
+        self._check(self._lib.sfmgms_bf_l2_crosscheck(self._h, _ptr(q), q.shape[0], _ptr(t), t.shape[0], q.shape[1], _ptr(idx),
                                                       _ptr(dist), _ptr(keep)))
         return idx, dist, keep.astype(bool)
 
@@ -211,7 +209,8 @@ class Context:
         """bruteForceMatch (FeatureMatchUtil.cpp:20-31): cross-checked NN, sort by distance, prune while
         front*coef < back, cap.  -> (query_idx, train_idx, dist float32), ascending distance (ties by queryIdx)."""
         if norm_type == NORM_L2:
-            q, t, width = self._desc_l2(query), self._desc_l2(train), 128
+            q, t = self._desc_l2(query), self._desc_l2(train, q_like=query)
+            width = q.shape[1]
         else:
             q, t, width = self._desc(query), self._desc(train), 32
         cap = q.shape[0]
@@ -226,10 +225,12 @@ class Context:
         return qi[: n.value], ti[: n.value], d[: n.value]
 
     @staticmethod
-    def _desc_l2(d):
+    def _desc_l2(d, q_like=None):
         d = np.ascontiguousarray(d, dtype=np.float32)
-        if d.ndim != 2 or d.shape[1] != 128:
-            raise SfmGmsError(1, "L2 descriptors must be N x 128 float32 (SIFT)")
+        if d.ndim != 2 or d.shape[1] < 1:
+            raise SfmGmsError(1, "L2 descriptors must be N x dim float32")
+        if q_like is not None and np.ndim(q_like) == 2 and np.shape(q_like)[1] != d.shape[1]:
+            raise SfmGmsError(1, "query and train descriptors differ in width")   # OpenCV asserts equal cols
         return d
 
     @staticmethod

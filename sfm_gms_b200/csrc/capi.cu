@@ -64,7 +64,7 @@ struct sfmgms_ctx {
     int hamming_kernel = SFMGMS_HAMMING_AUTO;
     size_t gms_chunk_bytes = 64ull << 20;
     int timing = 0;
-    int l2_kernel = 0;   // 0 auto (tcgen05), 1 dp4a, 2 tcgen05
+    int l2_kernel = 0;   // 0 auto (tcgen05, fp32 fallback), 1 dp4a, 2 tcgen05, 3 fp32 order-exact
     bool timing_mid_pending = false;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // pipelined host<->device copies (match_image_set)
     std::vector<cudaEvent_t> events;                           // pool of timing-disabled events
@@ -403,7 +403,7 @@ int sfmgms_set_option(sfmgms_ctx* ctx, int key, int64_t value) {
         return SFMGMS_OK;
     }
     if (key == SFMGMS_OPT_L2_KERNEL) {
-        if (value < 0 || value > 2) return fail(ctx, SFMGMS_ERR_ARG, "bad L2 kernel %lld", (long long)value);
+        if (value < 0 || value > 3) return fail(ctx, SFMGMS_ERR_ARG, "bad L2 kernel %lld", (long long)value);
         ctx->l2_kernel = (int)value;
         return SFMGMS_OK;
     }
@@ -509,36 +509,73 @@ int sfmgms_bf_hamming_crosscheck(sfmgms_ctx* ctx, const uint8_t* query, int nq, 
     GUARD_END
 }
 
+// Nearest train row of every row of a[na] in b[nb] -> out = idx[na] | dist[na] (device, on ctx->stream).
+// dim 128 first tries the integer tensor-core / DP4A path (OpenCV SIFT data: exact in any order); rows that are not
+// integer-valued in [0,255] raise its flag and the pass is redone by the order-exact fp32 kernel (l2_f32.cu).
+// Synchronises the stream when it has to read the flag.
+static int l2_nn(sfmgms_ctx* ctx, const float* a, int na, const float* b, int nb, int dim, int32_t* out, int* d_bad,
+                 int* n_launches) {
+    cudaStream_t st = ctx->stream;
+    const int mode = ctx->l2_kernel;            // 0 auto, 1 dp4a, 2 tcgen05, 3 fp32 order-exact
+    bool need_f32 = (dim != 128) || mode == 3;
+    if (!need_f32) {
+        const int l = mode == 1 ? launch_l2_dp4a(a, na, b, nb, ctx->d_hist.p, out, (float*)(out + na), d_bad, ctx->sm_count, st)
+                                : launch_l2_tc(a, na, b, nb, ctx->d_hist.p, out, (float*)(out + na), d_bad, ctx->sm_count, st);
+        if (l < 0) return fail(ctx, SFMGMS_ERR_CUDA, "L2 tensor-core launch setup failed");
+        *n_launches += l;
+        int bad = 0;
+        CU(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        need_f32 = bad != 0;
+    }
+    if (need_f32) {
+        const int l = launch_l2_f32(a, na, b, nb, dim, ctx->d_hist.p, out, (float*)(out + na), st);
+        if (l < 0) return fail(ctx, SFMGMS_ERR_CUDA, "L2 fp32 launch setup failed");
+        *n_launches += l;
+    }
+    return SFMGMS_OK;
+}
+
+static size_t l2_scratch_need(sfmgms_ctx* ctx, int na, int nb) {
+    const size_t x = ctx->l2_kernel == 1 ? l2_scratch_bytes(na, nb) : l2_tc_scratch_bytes(na, nb);
+    const size_t y = l2_f32_scratch_bytes(na);
+    return x > y ? x : y;
+}
+
+static int l2_args(sfmgms_ctx* ctx, const float* query, int nq, const float* train, int nt, int dim, bool cross) {
+    if (nq < 0 || nt < 0) return fail(ctx, SFMGMS_ERR_ARG, "negative row count");
+    if (dim < 1 || dim > l2_f32_max_dim()) return fail(ctx, SFMGMS_ERR_ARG, "dim must be in [1, %d], got %d", l2_f32_max_dim(), dim);
+    if ((nq > 0 && !query) || (nt > 0 && !train)) return fail(ctx, SFMGMS_ERR_ARG, "null descriptor pointer");
+    if (nt >= SFMGMS_MAX_TRAIN_ROWS || (cross && nq >= SFMGMS_MAX_TRAIN_ROWS))
+        return fail(ctx, SFMGMS_ERR_TRAIN_ROWS, "rows %d / %d >= 2^18 (OpenCV BFMatcher: rows < IMGIDX_ONE)", nq, nt);
+    return SFMGMS_OK;
+}
+
 int sfmgms_bf_l2(sfmgms_ctx* ctx, const float* query, int nq, const float* train, int nt, int dim, int32_t* train_idx,
                  float* dist, int* n_matches) {
     GUARD_BEGIN
-    if (nq < 0 || nt < 0) return fail(ctx, SFMGMS_ERR_ARG, "negative row count");
-    if (dim != 128) return fail(ctx, SFMGMS_ERR_ARG, "dim must be 128 (SIFT), got %d", dim);
-    if ((nq > 0 && !query) || (nt > 0 && !train)) return fail(ctx, SFMGMS_ERR_ARG, "null descriptor pointer");
-    if (nt >= SFMGMS_MAX_TRAIN_ROWS)
-        return fail(ctx, SFMGMS_ERR_TRAIN_ROWS, "train rows %d >= 2^18 (OpenCV BFMatcher: rows < IMGIDX_ONE)", nt);
+    int rc = l2_args(ctx, query, nq, train, nt, dim, false);
+    if (rc) return rc;
     if (n_matches) *n_matches = (nt == 0) ? 0 : nq;
     if (nt == 0 || nq == 0) return SFMGMS_OK;
     cudaStream_t st = ctx->stream;
-    CU(ctx->d_q.ensure((size_t)(nq + nt) * 512));
+    const size_t rowb = (size_t)dim * 4;
+    CU(ctx->d_q.ensure((size_t)(nq + nt) * rowb));
     float* dq = (float*)ctx->d_q.p;
-    float* dt = dq + (size_t)nq * 128;
-    const bool use_tc = ctx->l2_kernel != 1;
-    CU(ctx->d_hist.ensure(use_tc ? l2_tc_scratch_bytes(nq, nt) : l2_scratch_bytes(nq, nt)));
+    float* dt = dq + (size_t)nq * dim;
+    CU(ctx->d_hist.ensure(l2_scratch_need(ctx, nq, nt)));
     CU(ctx->d_out_i32.ensure((size_t)nq * 8 + 16));
-    CU(cudaMemcpyAsync(dq, query, (size_t)nq * 512, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(dt, train, (size_t)nt * 512, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dq, query, (size_t)nq * rowb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dt, train, (size_t)nt * rowb, cudaMemcpyHostToDevice, st));
     int32_t* o = (int32_t*)ctx->d_out_i32.p;
     int* d_bad = (int*)(o + 2 * (size_t)nq);
     if (ctx->timing) CU(cudaEventRecord(ctx->ev[0], st));
-    const int nl = use_tc ? launch_l2_tc(dq, nq, dt, nt, ctx->d_hist.p, o, (float*)(o + nq), d_bad, ctx->sm_count, st)
-                          : launch_l2_dp4a(dq, nq, dt, nt, ctx->d_hist.p, o, (float*)(o + nq), d_bad, ctx->sm_count, st);
-    if (nl < 0) return fail(ctx, SFMGMS_ERR_CUDA, "L2 tensor-core launch setup failed");
+    int nl = 0;
+    rc = l2_nn(ctx, dq, nq, dt, nt, dim, o, d_bad, &nl);
+    if (rc) return rc;
     ctx->launches += nl;
     if (ctx->timing) { CU(cudaEventRecord(ctx->ev[1], st)); CU(cudaEventRecord(ctx->ev[2], st)); }
     CU(cudaGetLastError());
-    int bad = 0;
-    CU(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     if (train_idx) CU(cudaMemcpyAsync(train_idx, o, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
     if (dist) CU(cudaMemcpyAsync(dist, o + nq, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -547,7 +584,6 @@ int sfmgms_bf_l2(sfmgms_ctx* ctx, const float* query, int nq, const float* train
         CU(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
         ctx->last_ms[0] = a; ctx->last_ms[1] = 0; ctx->last_ms[2] = nl;
     }
-    if (bad) return fail(ctx, SFMGMS_ERR_ARG, "descriptors must be integer-valued in [0,255] (OpenCV SIFT); general float L2 is not implemented");
     return SFMGMS_OK;
     GUARD_END
 }
@@ -555,45 +591,33 @@ int sfmgms_bf_l2(sfmgms_ctx* ctx, const float* query, int nq, const float* train
 int sfmgms_bf_l2_crosscheck(sfmgms_ctx* ctx, const float* query, int nq, const float* train, int nt, int dim,
                             int32_t* train_idx, float* dist, uint8_t* keep) {
     GUARD_BEGIN
-    if (nq < 0 || nt < 0) return fail(ctx, SFMGMS_ERR_ARG, "negative row count");
-    if (dim != 128) return fail(ctx, SFMGMS_ERR_ARG, "dim must be 128 (SIFT), got %d", dim);
-    if ((nq > 0 && !query) || (nt > 0 && !train)) return fail(ctx, SFMGMS_ERR_ARG, "null descriptor pointer");
-    if (nt >= SFMGMS_MAX_TRAIN_ROWS || nq >= SFMGMS_MAX_TRAIN_ROWS)
-        return fail(ctx, SFMGMS_ERR_TRAIN_ROWS, "rows %d / %d >= 2^18 (OpenCV BFMatcher: rows < IMGIDX_ONE)", nq, nt);
+    int rc = l2_args(ctx, query, nq, train, nt, dim, true);
+    if (rc) return rc;
     if (nt == 0 || nq == 0) return SFMGMS_OK;
     cudaStream_t st = ctx->stream;
-    CU(ctx->d_q.ensure((size_t)(nq + nt) * 512));
+    const size_t rowb = (size_t)dim * 4;
+    CU(ctx->d_q.ensure((size_t)(nq + nt) * rowb));
     float* dq = (float*)ctx->d_q.p;
-    float* dt = dq + (size_t)nq * 128;
-    const bool use_tc = ctx->l2_kernel != 1;
-    const size_t s_fwd = use_tc ? l2_tc_scratch_bytes(nq, nt) : l2_scratch_bytes(nq, nt);
-    const size_t s_rev = use_tc ? l2_tc_scratch_bytes(nt, nq) : l2_scratch_bytes(nt, nq);
+    float* dt = dq + (size_t)nq * dim;
+    const size_t s_fwd = l2_scratch_need(ctx, nq, nt), s_rev = l2_scratch_need(ctx, nt, nq);
     CU(ctx->d_hist.ensure(s_fwd > s_rev ? s_fwd : s_rev));
     CU(ctx->d_out_i32.ensure(((size_t)nq + nt) * 8 + 16));
     CU(ctx->d_mask.ensure(nq));
-    CU(cudaMemcpyAsync(dq, query, (size_t)nq * 512, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(dt, train, (size_t)nt * 512, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dq, query, (size_t)nq * rowb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dt, train, (size_t)nt * rowb, cudaMemcpyHostToDevice, st));
     int32_t* o = (int32_t*)ctx->d_out_i32.p;          // forward: idx[nq], dist[nq]
     int32_t* r = o + 2 * (size_t)nq;                  // reverse: idx[nt], dist[nt]
-    int* d_bad = (int*)(r + 2 * (size_t)nt);          // one flag per pass
+    int* d_bad = (int*)(r + 2 * (size_t)nt);
     if (ctx->timing) CU(cudaEventRecord(ctx->ev[0], st));
     int nl = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-        const float* a = pass ? dt : dq;
-        const float* b = pass ? dq : dt;
-        const int na = pass ? nt : nq, nb = pass ? nq : nt;
-        int32_t* out = pass ? r : o;
-        const int l = use_tc ? launch_l2_tc(a, na, b, nb, ctx->d_hist.p, out, (float*)(out + na), d_bad + pass, ctx->sm_count, st)
-                             : launch_l2_dp4a(a, na, b, nb, ctx->d_hist.p, out, (float*)(out + na), d_bad + pass, ctx->sm_count, st);
-        if (l < 0) return fail(ctx, SFMGMS_ERR_CUDA, "L2 tensor-core launch setup failed");
-        nl += l;
-    }
+    rc = l2_nn(ctx, dq, nq, dt, nt, dim, o, d_bad, &nl);
+    if (rc) return rc;
+    rc = l2_nn(ctx, dt, nt, dq, nq, dim, r, d_bad, &nl);
+    if (rc) return rc;
     crosscheck_idx_kernel<<<(nq + 255) / 256, 256, 0, st>>>(o, r, nq, (uint8_t*)ctx->d_mask.p);
     ctx->launches += nl + 1;
     if (ctx->timing) { CU(cudaEventRecord(ctx->ev[1], st)); CU(cudaEventRecord(ctx->ev[2], st)); }
     CU(cudaGetLastError());
-    int bad[2] = {0, 0};
-    CU(cudaMemcpyAsync(bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, st));
     if (train_idx) CU(cudaMemcpyAsync(train_idx, o, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
     if (dist) CU(cudaMemcpyAsync(dist, o + nq, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
     if (keep) CU(cudaMemcpyAsync(keep, ctx->d_mask.p, (size_t)nq, cudaMemcpyDeviceToHost, st));
@@ -603,7 +627,6 @@ int sfmgms_bf_l2_crosscheck(sfmgms_ctx* ctx, const float* query, int nq, const f
         CU(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]));
         ctx->last_ms[0] = t; ctx->last_ms[1] = 0; ctx->last_ms[2] = nl;
     }
-    if (bad[0] || bad[1]) return fail(ctx, SFMGMS_ERR_ARG, "descriptors must be integer-valued in [0,255] (OpenCV SIFT); general float L2 is not implemented");
     return SFMGMS_OK;
     GUARD_END
 }

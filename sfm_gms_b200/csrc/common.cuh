@@ -68,6 +68,11 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
 size_t l2_scratch_bytes(int nq, int nt);
 int launch_l2_dp4a(const float* d_q, int nq, const float* d_t, int nt, void* d_scratch, int32_t* d_train_idx,
                    float* d_dist, int* d_bad, int sm_count, cudaStream_t st);
+// order-exact fp32 kernel for general float descriptors, l2_f32.cu (dim in [1, l2_f32_max_dim()])
+size_t l2_f32_scratch_bytes(int nq);
+int l2_f32_max_dim();
+int launch_l2_f32(const float* d_q, int nq, const float* d_t, int nt, int dim, void* d_scratch, int32_t* d_train_idx,
+                  float* d_dist, cudaStream_t st);
 // tcgen05 (kind::i8, unsigned) variant, l2_tc.cu — same contract; returns -1 on a setup error
 size_t l2_tc_scratch_bytes(int nq, int nt);
 int launch_l2_tc(const float* d_q, int nq, const float* d_t, int nt, void* d_scratch, int32_t* d_train_idx,

@@ -170,6 +170,27 @@ def bruteforce_case():
     np.savez_compressed(os.path.join(HERE, "bruteforce.npz"), **out)
 
 
+def l2_float_case():
+    """General float descriptors (not integer-valued): cv2.BFMatcher(NORM_L2) pins trainIdx and the float distance,
+    which depend on the addition order inside OpenCV's normL2Sqr_.  RootSIFT of the SIFT fixture (dim 128), a
+    64-wide slice, and a width with a scalar tail (dim 70); cross-check list for RootSIFT."""
+    g = np.load(os.path.join(HERE, "sift_view01_1500.npz"))
+    d1, d2 = g["desc1"].astype(np.float32), g["desc2"].astype(np.float32)
+    r1 = np.sqrt(d1 / np.maximum(d1.sum(1, keepdims=True), 1e-7)).astype(np.float32)
+    r2 = np.sqrt(d2 / np.maximum(d2.sum(1, keepdims=True), 1e-7)).astype(np.float32)
+    out = {}
+    for name, a, b in (("root128", r1, r2), ("root64", np.ascontiguousarray(r1[:, :64]), np.ascontiguousarray(r2[:, :64])),
+                       ("root70", np.ascontiguousarray(r1[:600, 3:73]), np.ascontiguousarray(r2[:900, 3:73]))):
+        m = cv2.BFMatcher(cv2.NORM_L2, False).match(a, b)
+        out[name + "_train"] = np.array([x.trainIdx for x in m], np.int32)
+        out[name + "_dist"] = np.array([x.distance for x in m], np.float32)
+    m = cv2.BFMatcher(cv2.NORM_L2, True).match(r1, r2)
+    out["root128_xc"] = np.array([(x.queryIdx, x.trainIdx) for x in m], np.int32)
+    out["root128_xc_dist"] = np.array([x.distance for x in m], np.float32)
+    np.savez_compressed(os.path.join(HERE, "l2_float.npz"), **out)
+    print("l2_float", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     oracle.build()
     oracle.set_num_threads(os.cpu_count())
@@ -180,3 +201,4 @@ if __name__ == "__main__":
     tie_case()
     sift_case()
     bruteforce_case()
+    l2_float_case()

@@ -444,10 +444,58 @@ def test_l2_ragged_vs_oracle_and_errors(l2ctx, oracle_mod):
         assert np.array_equal(idx, oi) and np.array_equal(dist, od)
     idx, dist = ctx.bf_l2(q, np.zeros((0, 128), np.float32))
     assert len(idx) == 0
-    with pytest.raises(SfmGmsError):      # general float descriptors are not implemented (no silent approximation)
-        ctx.bf_l2(q + 0.5, t)
+    with pytest.raises(SfmGmsError):      # OpenCV asserts equal widths
+        ctx.bf_l2(q[:, :64], t)
     with pytest.raises(SfmGmsError):
-        ctx.bf_l2(q[:, :64], t[:, :64])
+        ctx.bf_l2(np.zeros((4, 300), np.float32), np.zeros((4, 300), np.float32))   # dim > 256
+
+
+def _rootsift(g):
+    d1, d2 = g["desc1"].astype(np.float32), g["desc2"].astype(np.float32)
+    r1 = np.sqrt(d1 / np.maximum(d1.sum(1, keepdims=True), 1e-7)).astype(np.float32)
+    r2 = np.sqrt(d2 / np.maximum(d2.sum(1, keepdims=True), 1e-7)).astype(np.float32)
+    return {"root128": (r1, r2), "root64": (np.ascontiguousarray(r1[:, :64]), np.ascontiguousarray(r2[:, :64])),
+            "root70": (np.ascontiguousarray(r1[:600, 3:73]), np.ascontiguousarray(r2[:900, 3:73]))}
+
+
+def test_l2_general_float_golden_cv2(l2ctx):
+    """(§8f-3) non-integer float descriptors (RootSIFT; widths 128, 64 and 70 = scalar tail): trainIdx AND the float
+    distances bit-identical to cv2 -- the fp32 kernel restates OpenCV's normL2Sqr_ addition order."""
+    import sfm_gms_b200 as sg
+
+    ctx = l2ctx
+    g = load_golden("l2_float")
+    data = _rootsift(load_golden("sift_view01_1500"))
+    for name, (a, b) in data.items():
+        idx, dist = ctx.bf_l2(a, b)
+        assert np.array_equal(idx, g[name + "_train"]) and np.array_equal(dist, g[name + "_dist"]), name
+    a, b = data["root128"]
+    m = sg.BFMatcher(sg.NORM_L2, True, ctx=ctx).match(a, b)
+    assert np.array_equal(np.array([(x.queryIdx, x.trainIdx) for x in m], np.int32), g["root128_xc"])
+    assert np.array_equal(np.array([x.distance for x in m], np.float32), g["root128_xc_dist"])
+
+
+def test_l2_general_float_vs_oracle_ragged(ctx, oracle_mod):
+    from sfm_gms_b200 import api
+
+    rng = np.random.default_rng(77)
+    for nq, nt, dim in [(1, 1, 128), (3, 700, 128), (513, 257, 64), (130, 1999, 33), (385, 241, 7), (64, 64, 16),
+                        (1000, 1500, 256), (200, 300, 1)]:
+        q = (rng.standard_normal((nq, dim)) * 11).astype(np.float32)
+        t = (rng.standard_normal((nt, dim)) * 11).astype(np.float32)
+        if nt > 4:
+            t[nt // 2] = t[1]; q[0] = t[1]          # exact ties: lowest train index must win
+        idx, dist = ctx.bf_l2(q, t)
+        oi, od = oracle_mod.bf_l2(q, t)
+        assert np.array_equal(idx, oi) and np.array_equal(dist, od), (nq, nt, dim)
+    # forcing the fp32 kernel on integer-valued SIFT data gives the same bits as the tensor-core path
+    g = load_golden("sift_view01_1500")
+    ctx.set_option(api.OPT_L2_KERNEL, 3)
+    try:
+        idx, dist = ctx.bf_l2(g["desc1"].astype(np.float32), g["desc2"].astype(np.float32))
+    finally:
+        ctx.set_option(api.OPT_L2_KERNEL, 0)
+    assert np.array_equal(idx, g["l2_train"]) and np.array_equal(dist, g["l2_dist"])
 
 
 # ---- (§8f-2) bruteForceMatch: BFMatcher(NORM_L2, crossCheck=true) + sort + ratio prune + cap (FeatureMatchUtil.cpp:20-31)
