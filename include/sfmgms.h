@@ -122,6 +122,22 @@ int sfmgms_brute_force_match(sfmgms_ctx* ctx, int norm_type, int cross_check, co
                              const void* train, int nt, int width, double distance_coef, int max_matching_size,
                              int32_t* query_idx, int32_t* train_idx, float* dist, int capacity, int* n_out);
 
+/* (first half) cv::ORB::compute(image, keypoints, descriptors) for keypoints on pyramid level 0 —
+ * `f2d = ORB::create()` (DisparityUtil.cpp:107, all defaults: patchSize 31, edgeThreshold 31, WTA_K 2) and
+ * `f2d->compute(img, keypoints, descriptors)` at every pixel (DisparityUtil.cpp:127-134).  Steps, as OpenCV's
+ * detectAndCompute(useProvidedKeypoints = true): BGR -> gray, drop keypoints whose rounded position is within 31
+ * pixels of the border (input order kept), 7x7 sigma-2 Gaussian blur, rotated-BRIEF bits with each keypoint's OWN
+ * angle (degrees; OpenCV does not re-estimate it on this path; a default KeyPoint carries -1).
+ * image: 8-bit, channels 1 (gray) or 3 (BGR), rows stride_bytes apart.  keypoints: (x, y) floats at offset 0 of every
+ * kp_stride_bytes; angle float at angle_offset_bytes (12 in cv::KeyPoint; -1 = every angle is -1); octave int32 at
+ * octave_offset_bytes (20 in cv::KeyPoint; -1 = not given, assumed 0); a non-zero octave -> SFMGMS_ERR_ARG (the scale
+ * pyramid and the FAST/Harris detector of detectAndCompute are not implemented yet).
+ * Out: kept_index[r] = input index of output row r, descriptors[r*32 .. r*32+31], *n_kept = rows (<= n_keypoints;
+ * both arrays must have room for n_keypoints rows). */
+int sfmgms_orb_compute(sfmgms_ctx* ctx, const uint8_t* image, int width, int height, int channels, int stride_bytes,
+                       const void* keypoints, int n_keypoints, int kp_stride_bytes, int angle_offset_bytes,
+                       int octave_offset_bytes, int32_t* kept_index, uint8_t* descriptors, int* n_kept);
+
 /* ---- stage 2: replaces cv::xfeatures2d::matchGMS ----------------------------------------------
  * (FeatureMatchUtil.cpp:69; DisparityUtil.cpp:149,299).  mask[i] (0/1) for each of the n_matches input
  * matches; *mask_len = n_matches, or 0 if rotation/scale search was requested and every hypothesis had

@@ -8,6 +8,8 @@ library or without a B200 raises.
 from .api import (  # noqa: F401
     NORM_HAMMING,
     NORM_L2,
+    ORB,
+    ORB_create,
     BFMatcher,
     Context,
     DMatch,
@@ -19,5 +21,5 @@ from .api import (  # noqa: F401
     matchGMS,
 )
 
-__all__ = ["NORM_HAMMING", "NORM_L2", "BFMatcher", "Context", "DMatch", "SfmGmsError", "bruteForceMatch", "default_context", "gms_matcher",
+__all__ = ["NORM_HAMMING", "NORM_L2", "ORB", "ORB_create", "BFMatcher", "Context", "DMatch", "SfmGmsError", "bruteForceMatch", "default_context", "gms_matcher",
            "load_library", "matchGMS"]

@@ -71,6 +71,8 @@ def load_library():
                                           c_void_p]
     L.sfmgms_brute_force_match.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_double,
                                            c_int, c_void_p, c_void_p, c_void_p, c_int, P(c_int)]
+    L.sfmgms_orb_compute.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, P(c_int)]
     L.sfmgms_gms.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
                              c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p, P(c_int),
                              P(c_int), P(c_int)]
@@ -243,6 +245,30 @@ class Context:
         if d.ndim != 2 or d.shape[1] != 32:
             raise SfmGmsError(1, "descriptors must be N x 32 bytes (256-bit), got %s" % (d.shape,))
         return d
+
+    # -- (f4, first half) ORB descriptors on provided level-0 keypoints -----------------------------------
+    def orb_compute(self, image, pts, angles=None, octaves=None):
+        """cv2.ORB_create().compute(image, keypoints) for level-0 keypoints (DisparityUtil.cpp:107, 127-134).
+        image: HxW (gray) or HxWx3 (BGR) uint8; pts (N, 2) float32 (x, y); angles (N,) degrees (None: all -1, the
+        default KeyPoint angle).  -> (kept int32[n] = surviving input indices, desc uint8[n, 32])."""
+        img = np.ascontiguousarray(image)
+        if img.dtype != np.uint8 or img.ndim not in (2, 3) or (img.ndim == 3 and img.shape[2] != 3):
+            raise SfmGmsError(1, "image must be HxW or HxWx3 uint8")
+        h, w = img.shape[:2]
+        ch = 1 if img.ndim == 2 else 3
+        pts = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1, 2)
+        n = pts.shape[0]
+        rec = np.zeros((n, 4), np.float32)                    # x, y, angle, octave (int32 bits)
+        rec[:, :2] = pts
+        rec[:, 2] = -1.0 if angles is None else np.asarray(angles, np.float32).reshape(-1)
+        if octaves is not None:
+            rec[:, 3] = np.asarray(octaves, np.int32).reshape(-1).view(np.float32)
+        kept = np.empty(n, np.int32)
+        desc = np.empty((n, 32), np.uint8)
+        nk = ctypes.c_int(0)
+        self._check(self._lib.sfmgms_orb_compute(self._h, _ptr(img), w, h, ch, w * ch, _ptr(rec), n, 16, 8, 12, _ptr(kept),
+                                                 _ptr(desc), ctypes.byref(nk)))
+        return kept[: nk.value], desc[: nk.value]
 
     # -- stage 2 ------------------------------------------------------------------------------------
     def gms(self, size1, size2, kp1, kp2, query_idx, train_idx, with_rotation=False, with_scale=False,
@@ -445,6 +471,39 @@ class BFMatcher:
             return [DMatch(int(i), int(idx[i]), 0, float(dist[i])) for i in np.nonzero(keep)[0]]
         idx, dist = ctx.bf_hamming(queryDescriptors, trainDescriptors)
         return [DMatch(i, int(idx[i]), 0, float(dist[i])) for i in range(len(idx))]
+
+
+class ORB:
+    """cv::ORB look-alike for the descriptor side: ``ORB_create().compute(image, keypoints)`` with the defaults of
+    ``ORB::create()`` (DisparityUtil.cpp:107).  detect / detectAndCompute (FAST + Harris + pyramid) are not built."""
+
+    def __init__(self, ctx=None):
+        self._ctx = ctx
+
+    @staticmethod
+    def create():
+        return ORB()
+
+    def descriptorSize(self):
+        return 32
+
+    def compute(self, image, keypoints):
+        """-> (kept keypoints, descriptors) as cv2 returns them.  keypoints: list of cv2.KeyPoint-like objects
+        (.pt, .angle, .octave) -> a list comes back; or a tuple (pts[, angles]) of arrays -> the kept indices."""
+        ctx = self._ctx or default_context()
+        if isinstance(keypoints, tuple):
+            pts = keypoints[0]
+            ang = keypoints[1] if len(keypoints) > 1 else None
+            return ctx.orb_compute(image, pts, ang)
+        pts = np.array([k.pt for k in keypoints], np.float32).reshape(-1, 2)
+        ang = np.array([k.angle for k in keypoints], np.float32)
+        octv = np.array([getattr(k, "octave", 0) for k in keypoints], np.int32)
+        kept, desc = ctx.orb_compute(image, pts, ang, octv)
+        return [keypoints[i] for i in kept], desc
+
+
+def ORB_create(ctx=None):
+    return ORB(ctx)
 
 
 def bruteForceMatch(desc1, desc2, ctx=None, kDistanceCoef=4.0, kMaxMatchingSize=500):

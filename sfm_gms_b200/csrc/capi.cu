@@ -3,6 +3,7 @@
 // returns an error code.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <ctime>
@@ -672,6 +673,66 @@ int sfmgms_brute_force_match(sfmgms_ctx* ctx, int norm_type, int cross_check, co
     }
     if (n_out) *n_out = (int)m.size();
     return SFMGMS_OK;
+}
+
+// ---- (§8f-4, first half) cv::ORB::compute on provided level-0 keypoints ---------------------------------
+int sfmgms_orb_compute(sfmgms_ctx* ctx, const uint8_t* image, int width, int height, int channels, int stride_bytes,
+                       const void* keypoints, int n_keypoints, int kp_stride_bytes, int angle_offset_bytes,
+                       int octave_offset_bytes, int32_t* kept_index, uint8_t* descriptors, int* n_kept) {
+    GUARD_BEGIN
+    if (n_kept) *n_kept = 0;
+    if (!image || width <= 0 || height <= 0) return fail(ctx, SFMGMS_ERR_ARG, "empty image");
+    if (channels != 1 && channels != 3) return fail(ctx, SFMGMS_ERR_ARG, "channels must be 1 (gray) or 3 (BGR), got %d", channels);
+    if (stride_bytes < width * channels) return fail(ctx, SFMGMS_ERR_ARG, "row stride %d < %d", stride_bytes, width * channels);
+    if (n_keypoints < 0 || (n_keypoints > 0 && !keypoints) || kp_stride_bytes < 8)
+        return fail(ctx, SFMGMS_ERR_ARG, "bad keypoint array");
+    if (n_keypoints == 0) return SFMGMS_OK;
+    // KeyPointsFilter::runByImageBorder(keypoints, image.size(), edgeThreshold = 31): a host loop, as in OpenCV.
+    // Rect(31, 31, w-62, h-62).contains(Point(pt)): Point2f -> Point rounds with cvRound (half to even).
+    const int kEdge = 31;
+    CU(ctx->h_stage.ensure((size_t)n_keypoints * 12));
+    float* xya = (float*)ctx->h_stage.p;
+    int n = 0;
+    const char* base = (const char*)keypoints;
+    for (int i = 0; i < n_keypoints; ++i) {
+        const char* kp = base + (size_t)i * kp_stride_bytes;
+        float x, y, ang = -1.f;
+        memcpy(&x, kp, 4); memcpy(&y, kp + 4, 4);
+        if (angle_offset_bytes >= 0) memcpy(&ang, kp + angle_offset_bytes, 4);
+        if (octave_offset_bytes >= 0) {
+            int32_t oct; memcpy(&oct, kp + octave_offset_bytes, 4);
+            if (oct != 0) return fail(ctx, SFMGMS_ERR_ARG, "keypoint %d has octave %d: only pyramid level 0 is implemented", i, oct);
+        }
+        const long cx = lrintf(x), cy = lrintf(y);
+        if (!(cx >= kEdge && cx < width - kEdge && cy >= kEdge && cy < height - kEdge)) continue;
+        xya[3 * n] = x; xya[3 * n + 1] = y; xya[3 * n + 2] = ang;
+        if (kept_index) kept_index[n] = i;
+        ++n;
+    }
+    if (n_kept) *n_kept = n;
+    if (n == 0) return SFMGMS_OK;
+    cudaStream_t st = ctx->stream;
+    const size_t img_bytes = (size_t)stride_bytes * height, plane = (size_t)width * height;
+    CU(ctx->d_q.ensure(img_bytes)); CU(ctx->d_kp1.ensure(plane)); CU(ctx->d_kp2.ensure(plane));
+    CU(ctx->d_mq.ensure((size_t)n * 12)); CU(ctx->d_mt.ensure((size_t)n * orb_kp_bytes())); CU(ctx->d_out_i32.ensure((size_t)n * 32));
+    CU(cudaMemcpyAsync(ctx->d_q.p, image, img_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_mq.p, xya, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[0], st));
+    const int nl = launch_orb_compute((const uint8_t*)ctx->d_q.p, width, height, channels, stride_bytes, (const float*)ctx->d_mq.p, n,
+                                      (uint8_t*)ctx->d_kp1.p, (uint8_t*)ctx->d_kp2.p, ctx->d_mt.p, (uint8_t*)ctx->d_out_i32.p,
+                                      ctx->sm_count, st);
+    ctx->launches += nl;
+    if (ctx->timing) { CU(cudaEventRecord(ctx->ev[1], st)); CU(cudaEventRecord(ctx->ev[2], st)); }
+    CU(cudaGetLastError());
+    if (descriptors) CU(cudaMemcpyAsync(descriptors, ctx->d_out_i32.p, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (ctx->timing) {
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]));
+        ctx->last_ms[0] = t; ctx->last_ms[1] = 0; ctx->last_ms[2] = nl;
+    }
+    return SFMGMS_OK;
+    GUARD_END
 }
 
 static int gms_args(sfmgms_ctx* ctx, int w1, int h1, int w2, int h2, int n1, int n2, int s1, int s2) {

@@ -68,6 +68,10 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
 size_t l2_scratch_bytes(int nq, int nt);
 int launch_l2_dp4a(const float* d_q, int nq, const float* d_t, int nt, void* d_scratch, int32_t* d_train_idx,
                    float* d_dist, int* d_bad, int sm_count, cudaStream_t st);
+// ORB descriptors on provided level-0 keypoints, orb.cu
+size_t orb_kp_bytes();
+int launch_orb_compute(const uint8_t* d_image, int w, int h, int channels, int stride, const float* d_xya, int n,
+                       uint8_t* d_gray, uint8_t* d_blur, void* d_prep, uint8_t* d_desc, int sm_count, cudaStream_t st);
 // order-exact fp32 kernel for general float descriptors, l2_f32.cu (dim in [1, l2_f32_max_dim()])
 size_t l2_f32_scratch_bytes(int nq);
 int l2_f32_max_dim();

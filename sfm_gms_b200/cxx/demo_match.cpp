@@ -6,6 +6,7 @@
 // out.bin  : int32 n_matches | int32 trainIdx[n] | int32 dist[n] | int32 n_gms | int32 gms_queryIdx[n_gms]
 //            | int32 n_gms_class | uint8 mask_class[n_matches] (gms_matcher::GetInlierMask, same flags)
 //            | int32 n_fused (matchBFHammingGMS, must equal n_gms)
+//            | int32 n_bf | int32 bf_queryIdx[n_bf] | int32 bf_trainIdx[n_bf]   (bruteForceMatch, FeatureMatchUtil.cpp:20-31)
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -48,6 +49,9 @@ int main(int argc, char** argv) {
         // fused one-call form
         std::vector<cv::DMatch> m2, g2;
         matchBFHammingGMS(d1.data(), d2.data(), kpts1, kpts2, cv::Size(w1, h1), cv::Size(w2, h2), m2, g2, rot, sc);
+        // the reference's brute-force helper: cross-checked match, sort, ratio prune, cap 500
+        std::vector<cv::DMatch> mbf;
+        bruteForceMatch(d1.data(), n1, d2.data(), n2, mbf);
         std::printf("matches %zu  GMS %zu  class %d  fused %zu  (%.3f s for BF+GMS incl. first-call setup)\n", matches.size(),
                     matchesGMS.size(), n_class, g2.size(), std::chrono::duration<double>(t1 - t0).count());
         if (argc > 4) {
@@ -64,6 +68,10 @@ int main(int argc, char** argv) {
             for (int i = 0; i < n; ++i) { uint8_t b = (i < (int)vbInliers.size() && vbInliers[i]) ? 1 : 0; std::fwrite(&b, 1, 1, o); }
             int32_t nf = (int32_t)g2.size();
             std::fwrite(&nf, 4, 1, o);
+            int32_t nb = (int32_t)mbf.size();
+            std::fwrite(&nb, 4, 1, o);
+            for (auto& m : mbf) std::fwrite(&m.queryIdx, 4, 1, o);
+            for (auto& m : mbf) std::fwrite(&m.trainIdx, 4, 1, o);
             std::fclose(o);
         }
     } catch (const Error& e) {

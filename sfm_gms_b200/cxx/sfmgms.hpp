@@ -133,6 +133,35 @@ class BFMatcher {
     int norm_ = NORM_HAMMING;
 };
 
+// cv::ORB, descriptor side only: ORB::create() defaults, compute() on level-0 keypoints as
+// DisparityUtil.cpp:107 + 127-134 use it.  Like OpenCV, compute() REMOVES the keypoints it cannot describe (within
+// 31 pixels of the border) from `keypoints` and writes one 32-byte row per surviving keypoint.
+class ORB {
+   public:
+    explicit ORB(Context* ctx = nullptr) : ctx_(ctx) {}
+    static ORB create() { return ORB(); }
+    int descriptorSize() const { return 32; }
+    // image: 8-bit, `channels` 1 (gray) or 3 (BGR), rows `stride_bytes` apart (0 = packed)
+    void compute(const uint8_t* image, Size size, int channels, std::vector<KeyPoint>& keypoints,
+                 std::vector<uint8_t>& descriptors, int stride_bytes = 0) const {
+        Context& c = ctx_ ? *ctx_ : Context::thread_default();
+        const int n = (int)keypoints.size();
+        std::vector<int32_t> kept((size_t)n);
+        descriptors.assign((size_t)n * 32, 0);
+        int nk = 0;
+        c.check(sfmgms_orb_compute(c.get(), image, size.width, size.height, channels,
+                                   stride_bytes ? stride_bytes : size.width * channels, n ? &keypoints[0].pt.x : nullptr, n,
+                                   (int)sizeof(KeyPoint), 12, 20, kept.data(), descriptors.data(), &nk));
+        std::vector<KeyPoint> out((size_t)nk);
+        for (int i = 0; i < nk; ++i) out[(size_t)i] = keypoints[(size_t)kept[(size_t)i]];
+        keypoints.swap(out);
+        descriptors.resize((size_t)nk * 32);
+    }
+
+   private:
+    Context* ctx_;
+};
+
 namespace detail {
 inline void brute_force(int norm, bool cross, const void* d1, int n1, const void* d2, int n2, int width,
                         std::vector<DMatch>& matches, double coef, int max_size, Context* ctx) {

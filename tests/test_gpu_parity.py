@@ -363,7 +363,7 @@ def test_cv2_shaped_api(ctx):
 
 # ---- the C++ shim (sfmgms.hpp): BFMatcher::match + matchGMS exactly as FeatureMatchUtil.cpp:66-69 calls them ----
 @pytest.mark.parametrize("rot,sc,tag", [(0, 0, "00"), (1, 1, "11")])
-def test_cxx_shim_demo_matches_golden(tmp_path, rot, sc, tag):
+def test_cxx_shim_demo_matches_golden(tmp_path, oracle_mod, rot, sc, tag):
     import os
     import subprocess
 
@@ -391,7 +391,12 @@ def test_cxx_shim_demo_matches_golden(tmp_path, rot, sc, tag):
     gq = raw[o:o + 4 * ng].view(np.int32); o += 4 * ng
     nc = int(raw[o:o + 4].view(np.int32)[0]); o += 4
     mk = raw[o:o + n].astype(bool); o += n
-    nf = int(raw[o:o + 4].view(np.int32)[0])
+    nf = int(raw[o:o + 4].view(np.int32)[0]); o += 4
+    nb = int(raw[o:o + 4].view(np.int32)[0]); o += 4
+    bq = raw[o:o + 4 * nb].view(np.int32); o += 4 * nb
+    bt = raw[o:o + 4 * nb].view(np.int32)
+    eq, et, _ = oracle_mod.brute_force_match(g["desc1"], g["desc2"], "hamming", True, 4.0, 500)
+    assert np.array_equal(bq, eq) and np.array_equal(bt, et)          # sfmgms::bruteForceMatch (C++ shim)
     assert n == n1 and np.array_equal(ti, g["bf_train"]) and np.array_equal(di, g["bf_dist"])
     exp = np.unpackbits(g["gms_mask_" + tag])[:n].astype(bool)
     assert ng == int(g["gms_n_" + tag]) and np.array_equal(gq, np.nonzero(exp)[0])
@@ -555,3 +560,43 @@ def test_l2_crosscheck_vs_oracle_ragged(l2ctx, oracle_mod):
         assert all(np.array_equal(x, y) for x, y in zip(a, b)), (nq, nt)
     qi, ti, d = ctx.brute_force_match(q, np.zeros((0, 128), np.float32))
     assert len(qi) == 0
+
+
+# ---- (§8f-4, first half) ORB descriptors on provided level-0 keypoints (DisparityUtil.cpp:107, 127-134) ----------
+@pytest.mark.parametrize("name", ["view0_bgr", "disp_gray"])
+def test_orb_compute_golden_cv2(ctx, name):
+    import sfm_gms_b200 as sg
+
+    g = load_golden("orb_compute")
+    kept, desc = ctx.orb_compute(g[name + "_img"], g[name + "_pts"], g[name + "_ang"])
+    assert np.array_equal(kept, g[name + "_kept"]) and np.array_equal(desc, g[name + "_desc"])   # every bit, vs cv2
+
+    class KP:                                   # cv2.KeyPoint-shaped objects through the ORB look-alike
+        def __init__(self, p, a):
+            self.pt, self.angle, self.octave = (float(p[0]), float(p[1])), float(a), 0
+
+    kps = [KP(p, a) for p, a in zip(g[name + "_pts"][:400], g[name + "_ang"][:400])]
+    out_k, out_d = sg.ORB_create(ctx).compute(g[name + "_img"], kps)
+    n = int((g[name + "_kept"] < 400).sum())
+    assert len(out_k) == n and np.array_equal(out_d, g[name + "_desc"][:n])
+    assert [kps.index(k) for k in out_k] == g[name + "_kept"][:n].tolist()
+
+
+def test_orb_compute_vs_oracle_edges(ctx):
+    from oracle import orb
+    from sfm_gms_b200 import SfmGmsError
+
+    rng = np.random.default_rng(5)
+    for (h, w, ch) in [(63, 63, 1), (64, 70, 3), (97, 65, 1), (200, 333, 3)]:
+        img = rng.integers(0, 256, (h, w) if ch == 1 else (h, w, 3), dtype=np.uint8)
+        n = 500
+        pts = np.stack([rng.uniform(-2, w + 2, n), rng.uniform(-2, h + 2, n)], 1).astype(np.float32)
+        pts[:40] = np.round(pts[:40]) + 0.5                       # half-way positions: cvRound is half-to-even
+        ang = rng.uniform(-10, 370, n).astype(np.float32)
+        kept, desc = ctx.orb_compute(img, pts, ang)
+        ok, od = orb.orb_compute(img, pts, ang)
+        assert np.array_equal(kept, ok) and np.array_equal(desc, od), (h, w, ch)
+    kept, desc = ctx.orb_compute(img, np.zeros((0, 2), np.float32))
+    assert len(kept) == 0 and desc.shape == (0, 32)
+    with pytest.raises(SfmGmsError):                              # pyramid levels > 0: not implemented, said loudly
+        ctx.orb_compute(img, pts, ang, octaves=np.ones(n, np.int32))
