@@ -122,21 +122,33 @@ int sfmgms_brute_force_match(sfmgms_ctx* ctx, int norm_type, int cross_check, co
                              const void* train, int nt, int width, double distance_coef, int max_matching_size,
                              int32_t* query_idx, int32_t* train_idx, float* dist, int capacity, int* n_out);
 
-/* (first half) cv::ORB::compute(image, keypoints, descriptors) for keypoints on pyramid level 0 —
- * `f2d = ORB::create()` (DisparityUtil.cpp:107, all defaults: patchSize 31, edgeThreshold 31, WTA_K 2) and
- * `f2d->compute(img, keypoints, descriptors)` at every pixel (DisparityUtil.cpp:127-134).  Steps, as OpenCV's
- * detectAndCompute(useProvidedKeypoints = true): BGR -> gray, drop keypoints whose rounded position is within 31
- * pixels of the border (input order kept), 7x7 sigma-2 Gaussian blur, rotated-BRIEF bits with each keypoint's OWN
- * angle (degrees; OpenCV does not re-estimate it on this path; a default KeyPoint carries -1).
+/*  cv::ORB — `f2d = ORB::create()` (DisparityUtil.cpp:107; defaults scaleFactor 1.2f, 8 levels,
+ * edgeThreshold 31, firstLevel 0, WTA_K 2, HARRIS_SCORE, patchSize 31).
+ *
+ * sfmgms_orb_compute = f2d->compute(img, keypoints, descriptors) (DisparityUtil.cpp:127-134, a KeyPoint at every
+ * pixel): BGR -> gray, scale pyramid up to the highest octave present, drop keypoints whose rounded position is
+ * within 31 pixels of the image border, regroup by octave if the input is not sorted by octave (input order kept
+ * inside an octave), 7x7 sigma-2 Gaussian per level, rotated-BRIEF bits with each keypoint's OWN angle (degrees;
+ * OpenCV does not re-estimate it on this path; a default KeyPoint carries -1).
  * image: 8-bit, channels 1 (gray) or 3 (BGR), rows stride_bytes apart.  keypoints: (x, y) floats at offset 0 of every
  * kp_stride_bytes; angle float at angle_offset_bytes (12 in cv::KeyPoint; -1 = every angle is -1); octave int32 at
- * octave_offset_bytes (20 in cv::KeyPoint; -1 = not given, assumed 0); a non-zero octave -> SFMGMS_ERR_ARG (the scale
- * pyramid and the FAST/Harris detector of detectAndCompute are not implemented yet).
+ * octave_offset_bytes (20 in cv::KeyPoint; -1 = every octave is 0); octaves 0..15.
  * Out: kept_index[r] = input index of output row r, descriptors[r*32 .. r*32+31], *n_kept = rows (<= n_keypoints;
  * both arrays must have room for n_keypoints rows). */
 int sfmgms_orb_compute(sfmgms_ctx* ctx, const uint8_t* image, int width, int height, int channels, int stride_bytes,
                        const void* keypoints, int n_keypoints, int kp_stride_bytes, int angle_offset_bytes,
                        int octave_offset_bytes, int32_t* kept_index, uint8_t* descriptors, int* n_kept);
+
+/* sfmgms_orb_detect_and_compute = ORB::create(nfeatures) [+ setFastThreshold(fast_threshold)] ->
+ * detectAndCompute(img, noArray(), keypoints, descriptors) (DisparityUtil.cpp:139-140 with the defaults 500 / 20;
+ * BASELINE config 1 uses 10000 / 0).  FAST-9/16 + non-max suppression per pyramid level, border filter, retainBest by
+ * FAST score then by Harris response, intensity-centroid angle, descriptors.  keypoints: `capacity` records in
+ * cv::KeyPoint layout (28 bytes: pt.x, pt.y, size, angle, response, octave, class_id = -1), in OpenCV's output
+ * order; descriptors: capacity x 32 bytes (may be NULL: detect only).  *n_keypoints = count; it can exceed nfeatures
+ * by ties at a level's cut (OpenCV keeps them) -- capacity too small -> SFMGMS_ERR_ARG with *n_keypoints = needed. */
+int sfmgms_orb_detect_and_compute(sfmgms_ctx* ctx, const uint8_t* image, int width, int height, int channels, int stride_bytes,
+                                  int nfeatures, int fast_threshold, void* keypoints, uint8_t* descriptors, int capacity,
+                                  int* n_keypoints);
 
 /* ---- stage 2: replaces cv::xfeatures2d::matchGMS ----------------------------------------------
  * (FeatureMatchUtil.cpp:69; DisparityUtil.cpp:149,299).  mask[i] (0/1) for each of the n_matches input

@@ -13,6 +13,7 @@ from .api import (  # noqa: F401
     BFMatcher,
     Context,
     DMatch,
+    KeyPoint,
     SfmGmsError,
     bruteForceMatch,
     default_context,
@@ -21,5 +22,5 @@ from .api import (  # noqa: F401
     matchGMS,
 )
 
-__all__ = ["NORM_HAMMING", "NORM_L2", "ORB", "ORB_create", "BFMatcher", "Context", "DMatch", "SfmGmsError", "bruteForceMatch", "default_context", "gms_matcher",
+__all__ = ["NORM_HAMMING", "NORM_L2", "ORB", "ORB_create", "BFMatcher", "Context", "DMatch", "KeyPoint", "SfmGmsError", "bruteForceMatch", "default_context", "gms_matcher",
            "load_library", "matchGMS"]

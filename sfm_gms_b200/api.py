@@ -73,6 +73,8 @@ def load_library():
                                            c_int, c_void_p, c_void_p, c_void_p, c_int, P(c_int)]
     L.sfmgms_orb_compute.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, P(c_int)]
+    L.sfmgms_orb_detect_and_compute.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                                c_void_p, c_int, P(c_int)]
     L.sfmgms_gms.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
                              c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p, P(c_int),
                              P(c_int), P(c_int)]
@@ -269,6 +271,31 @@ class Context:
         self._check(self._lib.sfmgms_orb_compute(self._h, _ptr(img), w, h, ch, w * ch, _ptr(rec), n, 16, 8, 12, _ptr(kept),
                                                  _ptr(desc), ctypes.byref(nk)))
         return kept[: nk.value], desc[: nk.value]
+
+    def orb_detect_and_compute(self, image, nfeatures=500, fast_threshold=20, with_descriptors=True):
+        """cv2.ORB_create(nfeatures) [+ setFastThreshold] .detectAndCompute(image, None) (DisparityUtil.cpp:107, 139-140).
+        -> (kp float32[n, 6] = x, y, size, angle, response, octave in OpenCV's output order, desc uint8[n, 32] | None)"""
+        img = np.ascontiguousarray(image)
+        if img.dtype != np.uint8 or img.ndim not in (2, 3) or (img.ndim == 3 and img.shape[2] != 3):
+            raise SfmGmsError(1, "image must be HxW or HxWx3 uint8")
+        h, w = img.shape[:2]
+        ch = 1 if img.ndim == 2 else 3
+        cap = max(2 * int(nfeatures), 64)
+        for _ in range(2):
+            rec = np.zeros((cap, 7), np.float32)              # cv::KeyPoint records (28 bytes)
+            desc = np.zeros((cap, 32), np.uint8) if with_descriptors else None
+            n = ctypes.c_int(0)
+            rc = self._lib.sfmgms_orb_detect_and_compute(self._h, _ptr(img), w, h, ch, w * ch, int(nfeatures), int(fast_threshold),
+                                                         _ptr(rec), _ptr(desc) if with_descriptors else None, cap, ctypes.byref(n))
+            if rc == 1 and n.value > cap:                      # ties at a level's cut: retry with the reported size
+                cap = n.value
+                continue
+            self._check(rc)
+            break
+        kp = np.empty((n.value, 6), np.float32)
+        kp[:, :5] = rec[: n.value, :5]
+        kp[:, 5] = rec[: n.value, 5].view(np.int32)
+        return kp, (desc[: n.value] if with_descriptors else None)
 
     # -- stage 2 ------------------------------------------------------------------------------------
     def gms(self, size1, size2, kp1, kp2, query_idx, train_idx, with_rotation=False, with_scale=False,
@@ -473,28 +500,63 @@ class BFMatcher:
         return [DMatch(i, int(idx[i]), 0, float(dist[i])) for i in range(len(idx))]
 
 
-class ORB:
-    """cv::ORB look-alike for the descriptor side: ``ORB_create().compute(image, keypoints)`` with the defaults of
-    ``ORB::create()`` (DisparityUtil.cpp:107).  detect / detectAndCompute (FAST + Harris + pyramid) are not built."""
+class KeyPoint:
+    """cv2.KeyPoint-shaped record returned by ORB.detect / detectAndCompute."""
+    __slots__ = ("pt", "size", "angle", "response", "octave", "class_id")
 
-    def __init__(self, ctx=None):
+    def __init__(self, x, y, size, angle=-1.0, response=0.0, octave=0, class_id=-1):
+        self.pt, self.size, self.angle, self.response, self.octave, self.class_id = (x, y), size, angle, response, octave, class_id
+
+    def __repr__(self):
+        return "KeyPoint(pt=%r, size=%r, angle=%r, response=%r, octave=%r)" % (self.pt, self.size, self.angle, self.response, self.octave)
+
+
+class ORB:
+    """cv::ORB look-alike: ``ORB_create(nfeatures)`` with the other defaults of ``ORB::create()`` (DisparityUtil.cpp:107:
+    scaleFactor 1.2, 8 levels, edgeThreshold 31, HARRIS_SCORE, patchSize 31), ``setFastThreshold``, ``detect``,
+    ``compute`` and ``detectAndCompute`` -- bit-identical to cv2 (keypoint order included)."""
+
+    def __init__(self, nfeatures=500, ctx=None):
         self._ctx = ctx
+        self._nfeatures = int(nfeatures)
+        self._fast = 20
 
     @staticmethod
-    def create():
-        return ORB()
+    def create(nfeatures=500):
+        return ORB(nfeatures)
+
+    def setFastThreshold(self, t):
+        self._fast = int(t)
+
+    def getFastThreshold(self):
+        return self._fast
 
     def descriptorSize(self):
         return 32
 
+    def detectAndCompute(self, image, mask=None):
+        if mask is not None:
+            raise SfmGmsError(1, "masks are not implemented")
+        ctx = self._ctx or default_context()
+        kp, desc = ctx.orb_detect_and_compute(image, self._nfeatures, self._fast, True)
+        return [KeyPoint(float(r[0]), float(r[1]), float(r[2]), float(r[3]), float(r[4]), int(r[5])) for r in kp], desc
+
+    def detect(self, image, mask=None):
+        if mask is not None:
+            raise SfmGmsError(1, "masks are not implemented")
+        ctx = self._ctx or default_context()
+        kp, _ = ctx.orb_detect_and_compute(image, self._nfeatures, self._fast, False)
+        return [KeyPoint(float(r[0]), float(r[1]), float(r[2]), float(r[3]), float(r[4]), int(r[5])) for r in kp]
+
     def compute(self, image, keypoints):
         """-> (kept keypoints, descriptors) as cv2 returns them.  keypoints: list of cv2.KeyPoint-like objects
-        (.pt, .angle, .octave) -> a list comes back; or a tuple (pts[, angles]) of arrays -> the kept indices."""
+        (.pt, .angle, .octave) -> a list comes back; or a tuple (pts[, angles[, octaves]]) of arrays -> the kept indices."""
         ctx = self._ctx or default_context()
         if isinstance(keypoints, tuple):
             pts = keypoints[0]
             ang = keypoints[1] if len(keypoints) > 1 else None
-            return ctx.orb_compute(image, pts, ang)
+            octv = keypoints[2] if len(keypoints) > 2 else None
+            return ctx.orb_compute(image, pts, ang, octv)
         pts = np.array([k.pt for k in keypoints], np.float32).reshape(-1, 2)
         ang = np.array([k.angle for k in keypoints], np.float32)
         octv = np.array([getattr(k, "octave", 0) for k in keypoints], np.int32)
@@ -502,8 +564,8 @@ class ORB:
         return [keypoints[i] for i in kept], desc
 
 
-def ORB_create(ctx=None):
-    return ORB(ctx)
+def ORB_create(nfeatures=500, ctx=None):
+    return ORB(nfeatures, ctx)
 
 
 def bruteForceMatch(desc1, desc2, ctx=None, kDistanceCoef=4.0, kMaxMatchingSize=500):

@@ -77,6 +77,7 @@ struct sfmgms_ctx {
     DevBuf d_set_desc, d_set_kp;
     HostBuf h_stage, h_pairs_pinned, h_results;
     TcState tc;   // tensor-core Hamming operand cache (hamming_tc.cu)
+    OrbWorkspace* orb = nullptr;   // ORB pyramid + scratch (orb.cu), created on first use
 
     // image set
     int n_images = 0;
@@ -378,6 +379,7 @@ void sfmgms_destroy(sfmgms_ctx* ctx) {
                       &ctx->d_set_desc, &ctx->d_set_kp};
     for (DevBuf* b : bufs) b->release();
     tc_release(ctx->tc);
+    if (ctx->orb) orb_ws_destroy(ctx->orb);
     ctx->h_stage.release(); ctx->h_pairs_pinned.release(); ctx->h_results.release();
     for (int k = 0; k < 3; ++k) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
@@ -675,58 +677,100 @@ int sfmgms_brute_force_match(sfmgms_ctx* ctx, int norm_type, int cross_check, co
     return SFMGMS_OK;
 }
 
-// ---- (§8f-4, first half) cv::ORB::compute on provided level-0 keypoints ---------------------------------
+// ---- (§8f-4) cv::ORB: compute on provided keypoints, detectAndCompute -----------------------------------
+static int orb_image_args(sfmgms_ctx* ctx, const uint8_t* image, int width, int height, int channels, int stride_bytes) {
+    if (!image || width <= 0 || height <= 0) return fail(ctx, SFMGMS_ERR_ARG, "empty image");
+    if (channels != 1 && channels != 3) return fail(ctx, SFMGMS_ERR_ARG, "channels must be 1 (gray) or 3 (BGR), got %d", channels);
+    if (stride_bytes < width * channels) return fail(ctx, SFMGMS_ERR_ARG, "row stride %d < %d", stride_bytes, width * channels);
+    if (!ctx->orb) ctx->orb = orb_ws_create();
+    return SFMGMS_OK;
+}
+
 int sfmgms_orb_compute(sfmgms_ctx* ctx, const uint8_t* image, int width, int height, int channels, int stride_bytes,
                        const void* keypoints, int n_keypoints, int kp_stride_bytes, int angle_offset_bytes,
                        int octave_offset_bytes, int32_t* kept_index, uint8_t* descriptors, int* n_kept) {
     GUARD_BEGIN
     if (n_kept) *n_kept = 0;
-    if (!image || width <= 0 || height <= 0) return fail(ctx, SFMGMS_ERR_ARG, "empty image");
-    if (channels != 1 && channels != 3) return fail(ctx, SFMGMS_ERR_ARG, "channels must be 1 (gray) or 3 (BGR), got %d", channels);
-    if (stride_bytes < width * channels) return fail(ctx, SFMGMS_ERR_ARG, "row stride %d < %d", stride_bytes, width * channels);
+    int rc = orb_image_args(ctx, image, width, height, channels, stride_bytes);
+    if (rc) return rc;
     if (n_keypoints < 0 || (n_keypoints > 0 && !keypoints) || kp_stride_bytes < 8)
         return fail(ctx, SFMGMS_ERR_ARG, "bad keypoint array");
     if (n_keypoints == 0) return SFMGMS_OK;
     // KeyPointsFilter::runByImageBorder(keypoints, image.size(), edgeThreshold = 31): a host loop, as in OpenCV.
     // Rect(31, 31, w-62, h-62).contains(Point(pt)): Point2f -> Point rounds with cvRound (half to even).
     const int kEdge = 31;
-    CU(ctx->h_stage.ensure((size_t)n_keypoints * 12));
-    float* xya = (float*)ctx->h_stage.p;
-    int n = 0;
+    struct K { float x, y, ang; int32_t oct; int32_t idx; };
+    std::vector<K> kept;
+    kept.reserve((size_t)n_keypoints);
     const char* base = (const char*)keypoints;
+    int max_oct = 0;
+    int32_t prev_oct = 0;
+    bool sorted = true;
     for (int i = 0; i < n_keypoints; ++i) {
         const char* kp = base + (size_t)i * kp_stride_bytes;
-        float x, y, ang = -1.f;
-        memcpy(&x, kp, 4); memcpy(&y, kp + 4, 4);
-        if (angle_offset_bytes >= 0) memcpy(&ang, kp + angle_offset_bytes, 4);
-        if (octave_offset_bytes >= 0) {
-            int32_t oct; memcpy(&oct, kp + octave_offset_bytes, 4);
-            if (oct != 0) return fail(ctx, SFMGMS_ERR_ARG, "keypoint %d has octave %d: only pyramid level 0 is implemented", i, oct);
-        }
-        const long cx = lrintf(x), cy = lrintf(y);
+        K k; k.ang = -1.f; k.oct = 0; k.idx = i;
+        memcpy(&k.x, kp, 4); memcpy(&k.y, kp + 4, 4);
+        if (angle_offset_bytes >= 0) memcpy(&k.ang, kp + angle_offset_bytes, 4);
+        if (octave_offset_bytes >= 0) memcpy(&k.oct, kp + octave_offset_bytes, 4);
+        if (k.oct < 0 || k.oct > 15) return fail(ctx, SFMGMS_ERR_ARG, "keypoint %d has octave %d (supported: 0..15)", i, k.oct);
+        // the level count and the sortedness test look at ALL keypoints, before the border filter (orb.cpp)
+        if (i > 0 && k.oct < prev_oct) sorted = false;
+        prev_oct = k.oct;
+        if (k.oct > max_oct) max_oct = k.oct;
+        const long cx = lrintf(k.x), cy = lrintf(k.y);
         if (!(cx >= kEdge && cx < width - kEdge && cy >= kEdge && cy < height - kEdge)) continue;
-        xya[3 * n] = x; xya[3 * n + 1] = y; xya[3 * n + 2] = ang;
-        if (kept_index) kept_index[n] = i;
-        ++n;
+        kept.push_back(k);
     }
+    // keypoints not sorted by level are regrouped level by level, input order kept inside a level (orb.cpp)
+    if (!sorted) std::stable_sort(kept.begin(), kept.end(), [](const K& a, const K& b) { return a.oct < b.oct; });
+    const int n = (int)kept.size();
     if (n_kept) *n_kept = n;
     if (n == 0) return SFMGMS_OK;
+    std::vector<float> xyao((size_t)n * 4);
+    for (int i = 0; i < n; ++i) {
+        xyao[4 * (size_t)i] = kept[(size_t)i].x; xyao[4 * (size_t)i + 1] = kept[(size_t)i].y; xyao[4 * (size_t)i + 2] = kept[(size_t)i].ang;
+        memcpy(&xyao[4 * (size_t)i + 3], &kept[(size_t)i].oct, 4);
+        if (kept_index) kept_index[i] = kept[(size_t)i].idx;
+    }
     cudaStream_t st = ctx->stream;
-    const size_t img_bytes = (size_t)stride_bytes * height, plane = (size_t)width * height;
-    CU(ctx->d_q.ensure(img_bytes)); CU(ctx->d_kp1.ensure(plane)); CU(ctx->d_kp2.ensure(plane));
-    CU(ctx->d_mq.ensure((size_t)n * 12)); CU(ctx->d_mt.ensure((size_t)n * orb_kp_bytes())); CU(ctx->d_out_i32.ensure((size_t)n * 32));
-    CU(cudaMemcpyAsync(ctx->d_q.p, image, img_bytes, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->d_mq.p, xya, (size_t)n * 12, cudaMemcpyHostToDevice, st));
     if (ctx->timing) CU(cudaEventRecord(ctx->ev[0], st));
-    const int nl = launch_orb_compute((const uint8_t*)ctx->d_q.p, width, height, channels, stride_bytes, (const float*)ctx->d_mq.p, n,
-                                      (uint8_t*)ctx->d_kp1.p, (uint8_t*)ctx->d_kp2.p, ctx->d_mt.p, (uint8_t*)ctx->d_out_i32.p,
-                                      ctx->sm_count, st);
+    int nl = 0;
+    const int got = orb_compute_provided(ctx->orb, image, width, height, channels, stride_bytes, xyao.data(), n, max_oct + 1, descriptors,
+                                         ctx->sm_count, st, &nl);
     ctx->launches += nl;
-    if (ctx->timing) { CU(cudaEventRecord(ctx->ev[1], st)); CU(cudaEventRecord(ctx->ev[2], st)); }
-    CU(cudaGetLastError());
-    if (descriptors) CU(cudaMemcpyAsync(descriptors, ctx->d_out_i32.p, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    if (got < 0) return fail(ctx, SFMGMS_ERR_CUDA, "%s", orb_ws_error(ctx->orb));
     if (ctx->timing) {
+        CU(cudaEventRecord(ctx->ev[1], st)); CU(cudaEventRecord(ctx->ev[2], st));
+        CU(cudaStreamSynchronize(st));
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]));
+        ctx->last_ms[0] = t; ctx->last_ms[1] = 0; ctx->last_ms[2] = nl;
+    }
+    return SFMGMS_OK;
+    GUARD_END
+}
+
+int sfmgms_orb_detect_and_compute(sfmgms_ctx* ctx, const uint8_t* image, int width, int height, int channels, int stride_bytes,
+                                  int nfeatures, int fast_threshold, void* keypoints, uint8_t* descriptors, int capacity,
+                                  int* n_keypoints) {
+    GUARD_BEGIN
+    if (n_keypoints) *n_keypoints = 0;
+    int rc = orb_image_args(ctx, image, width, height, channels, stride_bytes);
+    if (rc) return rc;
+    if (nfeatures < 0 || capacity < 0 || fast_threshold < 0 || fast_threshold > 255)
+        return fail(ctx, SFMGMS_ERR_ARG, "bad nfeatures / capacity / fast_threshold");
+    cudaStream_t st = ctx->stream;
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[0], st));
+    int nl = 0, needed = 0;
+    const int got = orb_detect_and_compute(ctx->orb, image, width, height, channels, stride_bytes, nfeatures, fast_threshold, 8, keypoints,
+                                           descriptors, capacity, &needed, ctx->sm_count, st, &nl);
+    ctx->launches += nl;
+    if (got == -2) { if (n_keypoints) *n_keypoints = needed; return fail(ctx, SFMGMS_ERR_ARG, "capacity %d < %d keypoints", capacity, needed); }
+    if (got < 0) return fail(ctx, SFMGMS_ERR_CUDA, "%s", orb_ws_error(ctx->orb));
+    if (n_keypoints) *n_keypoints = got;
+    if (ctx->timing) {
+        CU(cudaEventRecord(ctx->ev[1], st)); CU(cudaEventRecord(ctx->ev[2], st));
+        CU(cudaStreamSynchronize(st));
         float t = 0.f;
         CU(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]));
         ctx->last_ms[0] = t; ctx->last_ms[1] = 0; ctx->last_ms[2] = nl;

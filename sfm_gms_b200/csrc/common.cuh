@@ -68,10 +68,16 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
 size_t l2_scratch_bytes(int nq, int nt);
 int launch_l2_dp4a(const float* d_q, int nq, const float* d_t, int nt, void* d_scratch, int32_t* d_train_idx,
                    float* d_dist, int* d_bad, int sm_count, cudaStream_t st);
-// ORB descriptors on provided level-0 keypoints, orb.cu
-size_t orb_kp_bytes();
-int launch_orb_compute(const uint8_t* d_image, int w, int h, int channels, int stride, const float* d_xya, int n,
-                       uint8_t* d_gray, uint8_t* d_blur, void* d_prep, uint8_t* d_desc, int sm_count, cudaStream_t st);
+// cv::ORB (detectAndCompute / compute), orb.cu.  The workspace owns the pyramid and every scratch buffer.
+struct OrbWorkspace;
+OrbWorkspace* orb_ws_create();
+void orb_ws_destroy(OrbWorkspace* w);
+const char* orb_ws_error(const OrbWorkspace* w);
+int orb_compute_provided(OrbWorkspace* ws, const uint8_t* h_image, int w, int h, int channels, int stride, const float* h_xyao,
+                         int n, int nlevels, uint8_t* h_desc, int sm_count, cudaStream_t st, int* launches);
+int orb_detect_and_compute(OrbWorkspace* ws, const uint8_t* h_image, int w, int h, int channels, int stride, int nfeatures,
+                           int fast_threshold, int nlevels, void* h_kp, uint8_t* h_desc, int capacity, int* needed, int sm_count,
+                           cudaStream_t st, int* launches);
 // order-exact fp32 kernel for general float descriptors, l2_f32.cu (dim in [1, l2_f32_max_dim()])
 size_t l2_f32_scratch_bytes(int nq);
 int l2_f32_max_dim();

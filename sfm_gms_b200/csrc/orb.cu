@@ -1,23 +1,63 @@
-// orb.cu — cv::ORB::compute on provided level-0 keypoints (first half): the descriptor side of ORB,
-// as DisparityUtil.cpp:127-134 runs it at every pixel (`ORB::create()` defaults, DisparityUtil.cpp:107).
-//
-// Restates OpenCV features2d orb.cpp (detectAndCompute with useProvidedKeypoints = true; un-vendored dependency):
-//   gray = (B*3735 + G*19235 + R*9798 + 2^14) >> 15                      (cvtColor BGR2GRAY, 8-bit)
-//   blurred = GaussianBlur(gray, 7x7, sigma 2, reflect-101): Gaussian-weighted sum rounded to nearest (the pyramid
-//             sub-matrix takes OpenCV's floating-point path, not its 8-bit fixed-point one; oracle/orb.py has the pin)
-//   per keypoint: a = (float)cos(angle_rad), b = (float)sin(angle_rad); 512 pattern points rotated in float with
-//             separately rounded products, cvRound (half to even), 256 pixel comparisons -> 32 bytes.
-// The border filter (KeyPointsFilter::runByImageBorder, edgeThreshold 31) is the caller's host loop in capi.cu, as it
-// is a host loop in OpenCV.  HBM-bound byte work: one pass over the image per stage, descriptors gather from L1/L2.
+// orb.cu — cv::ORB: `ORB::create()` + detectAndCompute / compute as DisparityUtil.cpp:107, 127-140 use
+// them.  Restates OpenCV features2d orb.cpp / fast.cpp / keypoint.cpp and imgproc resize (un-vendored dependency of the
+// reference; every step is pinned bit-exactly against cv2 4.13 by oracle/orb.py and tests/golden/orb_*.npz):
+//   gray     = (B*3735 + G*19235 + R*9798 + 2^14) >> 15                          cvtColor(BGR2GRAY), 8-bit
+//   pyramid  : level l has scale s_l = (float)pow((double)1.2f, l), size cvRound(w / s_l) x cvRound(h / s_l), and is
+//              resize(level l-1, INTER_LINEAR_EXACT): 8.8 fixed-point weights round((frac)*256) from
+//              f = (1/(dst/src))*(d + 0.5) - 0.5 in double, result (h0*(256-cy) + h1*cy + 2^15) >> 16
+//   FAST     : FAST-9/16, threshold t, score = largest t' keeping the pixel a corner, 3x3 strict non-max suppression,
+//              row-major order; KeyPointsFilter::runByImageBorder(31); retainBest(2 n_l) by FAST score
+//   Harris   : 7x7 block of 3x3 Sobel-like sums (int), response = ((float)a*b - (float)c*c - 0.04f*(a+b)^2) * scale^4
+//              with every float op rounded separately; retainBest(n_l) per level
+//   retainBest = std::nth_element + std::partition on the host, exactly as OpenCV does it: the ORDER of the returned
+//              keypoints is the order those two library calls leave (libstdc++ here and in the stock cv2 packages)
+//   angle    : intensity centroid over the radius-15 disc (integer moments), cv::fastAtan2's float polynomial
+//   blur     : 7x7 sigma-2 Gaussian, floating point, rounded to nearest (OpenCV sends the pyramid SUB-matrix to its
+//              float path, not to the 8-bit fixed-point kernel; see oracle/orb.py for the pin and its one caveat)
+//   BRIEF    : a = (float)cos(angle), b = (float)sin(angle); 512 pattern points rotated in float with separately
+//              rounded products, cvRound, 256 comparisons -> 32 bytes
+// HBM/L2-bound byte and integer work: one coalesced pass over the pyramid per stage; the per-keypoint stages gather.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
 #include "common.cuh"
 
 namespace sfmgms {
 
 namespace {
 
+constexpr int kMaxLevels = 16;
+constexpr int kEdge = 31;            // edgeThreshold
+constexpr int kPatch = 31;           // patchSize
+constexpr int kHalfPatch = 15;
+
+struct Level {
+    long long off;   // byte offset of the level image in the pyramid buffers (dense rows, stride = w)
+    int w, h;
+    float scale;     // layerScale
+    int row0;        // first row of this level in the concatenated row index
+};
+struct LevelTable {
+    Level l[kMaxLevels];
+    int n;
+    int total_rows;
+    int max_w;
+};
+
 __constant__ signed char c_pattern[512][2] = {
 #include "orb_pattern.inc"
 };
+// end of each row of the radius-15 disc (orb.cpp: umax)
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+__device__ __forceinline__ int level_of_row(const LevelTable& T, int row) {
+    int l = 0;
+    while (l + 1 < T.n && row >= T.l[l + 1].row0) ++l;
+    return l;
+}
 
 __global__ void orb_gray_kernel(const uint8_t* __restrict__ bgr, int stride, int w, int h, uint8_t* __restrict__ gray) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
@@ -26,7 +66,265 @@ __global__ void orb_gray_kernel(const uint8_t* __restrict__ bgr, int stride, int
     gray[(size_t)y * w + x] = (uint8_t)((p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + (1 << 14)) >> 15);
 }
 
-__device__ __forceinline__ int reflect101(int i, int n) {   // BORDER_REFLECT_101, |offset| <= 3
+__global__ void orb_copy_kernel(const uint8_t* __restrict__ src, int stride, int w, int h, uint8_t* __restrict__ dst) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x < w) dst[(size_t)y * w + x] = src[(size_t)y * stride + x];
+}
+
+// resize(INTER_LINEAR_EXACT), 8-bit: xo/xc/yo/yc = source offset and 8-bit weight of the second tap per column / row
+__global__ void orb_resize_kernel(const uint8_t* __restrict__ src, int sw, int sh, uint8_t* __restrict__ dst, int dw, int dh,
+                                  const int* __restrict__ xo, const int* __restrict__ xc, const int* __restrict__ yo,
+                                  const int* __restrict__ yc) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dw) return;
+    const int x0 = xo[x], x1 = min(x0 + 1, sw - 1), cx = xc[x];
+    const int y0 = yo[y], y1 = min(y0 + 1, sh - 1), cy = yc[y];
+    const uint8_t* r0 = src + (size_t)y0 * sw;
+    const uint8_t* r1 = src + (size_t)y1 * sw;
+    const int h0 = r0[x0] * (256 - cx) + r0[x1] * cx;          // 8.8 fixed point
+    const int h1 = r1[x0] * (256 - cx) + r1[x1] * cx;
+    dst[(size_t)y * dw + x] = (uint8_t)((h0 * (256 - cy) + h1 * cy + (1 << 15)) >> 16);
+}
+
+// FAST-9/16 score of every pixel of every level (0 = not a corner).  One thread per pixel, rows of all levels
+// concatenated in blockIdx.y.
+__global__ void __launch_bounds__(128) orb_fast_score_kernel(LevelTable T, const uint8_t* __restrict__ pyr,
+                                                             uint8_t* __restrict__ score, int thr) {
+    const int row = blockIdx.y;
+    const int l = level_of_row(T, row);
+    const int w = T.l[l].w, h = T.l[l].h;
+    const int y = row - T.l[l].row0, x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    uint8_t* out = score + T.l[l].off + (size_t)y * w + x;
+    if (x < 3 || x >= w - 3 || y < 3 || y >= h - 3) { *out = 0; return; }
+    const uint8_t* p = pyr + T.l[l].off + (size_t)y * w + x;
+    const int v = p[0];
+    // the 16-pixel Bresenham circle of radius 3, clockwise from (0, 3) as fast.cpp's makeOffsets lists it
+    const int d[16] = {v - p[3 * w],      v - p[3 * w + 1],  v - p[2 * w + 2],  v - p[w + 3],      v - p[3],          v - p[-w + 3],
+                       v - p[-2 * w + 2], v - p[-3 * w + 1], v - p[-3 * w],     v - p[-3 * w - 1], v - p[-2 * w - 2], v - p[-w - 3],
+                       v - p[-3],         v - p[w - 3],      v - p[2 * w - 2],  v - p[3 * w - 1]};
+    int amin = -1000, amax = 1000;       // max over the 16 arcs of 9 of min(d);  min over arcs of max(d)
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        int mn = d[s], mx = d[s];
+#pragma unroll
+        for (int j = 1; j < 9; ++j) { mn = min(mn, d[(s + j) & 15]); mx = max(mx, d[(s + j) & 15]); }
+        amin = max(amin, mn);
+        amax = min(amax, mx);
+    }
+    const bool corner = amin > thr || amax < -thr;
+    *out = corner ? (uint8_t)(max(max(amin, thr), -min(amax, -thr)) - 1) : (uint8_t)0;
+}
+
+__device__ __forceinline__ bool nms_keep(const uint8_t* s, int w, int h, int x, int y) {
+    if (x < kEdge || x >= w - kEdge || y < kEdge || y >= h - kEdge) return false;      // runByImageBorder
+    const uint8_t* p = s + (size_t)y * w + x;
+    const int v = p[0];
+    return v > 0 && v > p[-1] && v > p[1] && v > p[-w - 1] && v > p[-w] && v > p[-w + 1] && v > p[w - 1] && v > p[w] &&
+           v > p[w + 1];
+}
+
+__global__ void __launch_bounds__(256) orb_nms_count_kernel(LevelTable T, const uint8_t* __restrict__ score,
+                                                            int* __restrict__ rowcount) {
+    const int row = blockIdx.x;
+    const int l = level_of_row(T, row);
+    const int w = T.l[l].w, h = T.l[l].h, y = row - T.l[l].row0;
+    const uint8_t* s = score + T.l[l].off;
+    int c = 0;
+    for (int x = threadIdx.x; x < w; x += 256) c += nms_keep(s, w, h, x, y) ? 1 : 0;
+    __shared__ int tot;
+    if (threadIdx.x == 0) tot = 0;
+    __syncthreads();
+    if (c) atomicAdd(&tot, c);
+    __syncthreads();
+    if (threadIdx.x == 0) rowcount[row] = tot;
+}
+
+// exclusive scan of rowcount[n] -> rowoff[n], total -> rowoff[n]; single CTA
+__global__ void __launch_bounds__(1024) orb_scan_kernel(const int* __restrict__ cnt, int n, int* __restrict__ off) {
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n ? cnt[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) wsum[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int s = wsum[lane], si = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, si, o); if (lane >= o) si += t; }
+            wsum[lane] = si - s;
+        }
+        __syncthreads();
+        const int c0 = carry;
+        if (i < n) off[i] = c0 + wsum[wid] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c0 + wsum[wid] + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) off[n] = carry;
+}
+
+struct Cand { int x, y, score, level; };
+
+// corners that survive NMS + border filter, in row-major order per level (levels in order): FAST's output order
+__global__ void __launch_bounds__(256) orb_nms_write_kernel(LevelTable T, const uint8_t* __restrict__ score,
+                                                            const int* __restrict__ rowoff, Cand* __restrict__ out) {
+    const int row = blockIdx.x;
+    if (rowoff[row + 1] == rowoff[row]) return;
+    const int l = level_of_row(T, row);
+    const int w = T.l[l].w, h = T.l[l].h, y = row - T.l[l].row0;
+    const uint8_t* s = score + T.l[l].off;
+    __shared__ int wcnt[8];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = rowoff[row];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int x0 = 0; x0 < w; x0 += 256) {
+        const int x = x0 + threadIdx.x;
+        const bool k = x < w && nms_keep(s, w, h, x, y);
+        const unsigned m = __ballot_sync(0xffffffffu, k);
+        if (lane == 0) wcnt[wid] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { if (j < wid) before += wcnt[j]; total += wcnt[j]; }
+        if (k) out[base + before + __popc(m & ((1u << lane) - 1))] = Cand{x, y, (int)s[(size_t)y * w + x], l};
+        __syncthreads();
+        if (threadIdx.x == 0) base += total;
+        __syncthreads();
+    }
+}
+
+struct Pt { int x, y, level; };
+
+// HarrisResponses (orb.cpp), blockSize 7, k = 0.04f: one warp per keypoint
+__global__ void __launch_bounds__(256) orb_harris_kernel(LevelTable T, const uint8_t* __restrict__ pyr, const Pt* __restrict__ pts,
+                                                         int n, float* __restrict__ resp) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const Pt p = pts[i];
+    const int w = T.l[p.level].w;
+    const uint8_t* img = pyr + T.l[p.level].off;
+    int a = 0, b = 0, c = 0;
+    for (int k = lane; k < 49; k += 32) {
+        const uint8_t* q = img + (size_t)(p.y - 3 + k / 7) * w + (p.x - 3 + k % 7);
+        const int Ix = (q[1] - q[-1]) * 2 + (q[-w + 1] - q[-w - 1]) + (q[w + 1] - q[w - 1]);
+        const int Iy = (q[w] - q[-w]) * 2 + (q[w - 1] - q[-w - 1]) + (q[w + 1] - q[-w + 1]);
+        a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0) {
+        const float scale = __fdiv_rn(1.f, __fmul_rn((float)(4 * 7), 255.f));
+        const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+        const float fa = (float)a, fb = (float)b, fc = (float)c;
+        const float t = __fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc));
+        const float u = __fadd_rn(fa, fb);
+        resp[i] = __fmul_rn(__fsub_rn(t, __fmul_rn(__fmul_rn(0.04f, u), u)), s4);
+    }
+}
+
+// cv::fastAtan2 (mathfuncs_core): degrees in [0, 360)
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float p1 = 57.283626556396484f, p3 = -18.66744613647461f, p5 = 8.914000511169434f, p7 = -2.539724588394165f;
+    const float eps = 2.220446049250313e-16f;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a;
+    if (ax >= ay) {
+        const float c = __fdiv_rn(ay, __fadd_rn(ax, eps)), c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        const float c = __fdiv_rn(ax, __fadd_rn(ay, eps)), c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0.f) a = __fsub_rn(180.f, a);
+    if (y < 0.f) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+struct KpOut {      // cv::KeyPoint layout (28 bytes)
+    float x, y, size, angle, response;
+    int octave, class_id;
+};
+struct OrbKp {      // prepared keypoint for the descriptor kernel
+    int cx, cy, level;
+    float a, b;
+};
+
+// ICAngles + the final scaling of computeKeyPoints; also prepares the descriptor centre exactly as
+// computeOrbDescriptors recomputes it from the scaled point.  16 lanes per keypoint (one disc row pair each).
+__global__ void __launch_bounds__(256) orb_angle_kernel(LevelTable T, const uint8_t* __restrict__ pyr, const Pt* __restrict__ pts,
+                                                        const float* __restrict__ resp, int n, KpOut* __restrict__ out,
+                                                        OrbKp* __restrict__ prep) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, v = threadIdx.x & 15;
+    const bool valid = i < n;                 // both 16-lane halves of a warp stay in the shuffles below
+    const Pt p = pts[valid ? i : n - 1];
+    const int w = T.l[p.level].w;
+    const uint8_t* c = pyr + T.l[p.level].off + (size_t)p.y * w + p.x;
+    int m10 = 0, m01 = 0;
+    if (v == 0) {
+        for (int u = -kHalfPatch; u <= kHalfPatch; ++u) m10 += u * c[u];
+    } else {
+        const int d = c_umax[v];
+        int vs = 0;
+        for (int u = -d; u <= d; ++u) {
+            const int plus = c[u + v * w], minus = c[u - v * w];
+            vs += plus - minus;
+            m10 += u * (plus + minus);
+        }
+        m01 = v * vs;
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o, 16); m01 += __shfl_xor_sync(0xffffffffu, m01, o, 16); }
+    if (v == 0 && valid) {
+        const float sc = T.l[p.level].scale;
+        KpOut k;
+        k.x = __fmul_rn((float)p.x, sc);
+        k.y = __fmul_rn((float)p.y, sc);
+        k.size = __fmul_rn((float)kPatch, sc);
+        k.angle = fast_atan2_deg((float)m01, (float)m10);
+        k.response = resp[i];
+        k.octave = p.level;
+        k.class_id = -1;
+        out[i] = k;
+        const float inv = __fdiv_rn(1.f, sc);
+        const float rad = __fmul_rn(k.angle, (float)(3.1415926535897932384626433832795 / 180.f));
+        OrbKp q;
+        q.cx = __float2int_rn(__fmul_rn(k.x, inv));
+        q.cy = __float2int_rn(__fmul_rn(k.y, inv));
+        q.level = p.level;
+        q.a = (float)cos((double)rad);
+        q.b = (float)sin((double)rad);
+        prep[i] = q;
+    }
+}
+
+// provided keypoints (x, y, angle_deg, octave) -> descriptor centre and rotation
+__global__ void orb_prepare_kernel(LevelTable T, const float* __restrict__ xyao, int n, OrbKp* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int level = __float_as_int(xyao[4 * i + 3]);
+    const float inv = __fdiv_rn(1.f, T.l[level].scale);
+    const float rad = __fmul_rn(xyao[4 * i + 2], (float)(3.1415926535897932384626433832795 / 180.f));
+    OrbKp k;
+    k.cx = __float2int_rn(__fmul_rn(xyao[4 * i], inv));
+    k.cy = __float2int_rn(__fmul_rn(xyao[4 * i + 1], inv));
+    k.level = level;
+    k.a = (float)cos((double)rad);
+    k.b = (float)sin((double)rad);
+    out[i] = k;
+}
+
+__device__ __forceinline__ int reflect101(int i, int n) {   // BORDER_REFLECT_101
     if (n == 1) return 0;
     while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
     return i;
@@ -34,10 +332,9 @@ __device__ __forceinline__ int reflect101(int i, int n) {   // BORDER_REFLECT_10
 
 constexpr int BW = 32, BH = 16, R = 3;
 
-// exp(-x^2 / 8) / sum, x = -3..3 (cv::getGaussianKernel(7, 2.0)), summed in the oracle's order
-__global__ void __launch_bounds__(BW * BH) orb_blur_kernel(const uint8_t* __restrict__ src, int stride, int w, int h,
-                                                           uint8_t* __restrict__ dst, double k0, double k1, double k2,
-                                                           double k3) {
+// 7x7 sigma-2 Gaussian of one level (taps k0..k3 = cv::getGaussianKernel(7, 2.0)), summed in the oracle's order
+__global__ void __launch_bounds__(BW * BH) orb_blur_kernel(const uint8_t* __restrict__ src, int w, int h, uint8_t* __restrict__ dst,
+                                                           double k0, double k1, double k2, double k3) {
     __shared__ uint8_t tile[BH + 2 * R][BW + 2 * R];
     __shared__ double rows[BH + 2 * R][BW];
     const double k[7] = {k0, k1, k2, k3, k2, k1, k0};
@@ -45,7 +342,7 @@ __global__ void __launch_bounds__(BW * BH) orb_blur_kernel(const uint8_t* __rest
     const int tid = threadIdx.y * BW + threadIdx.x;
     for (int i = tid; i < (BH + 2 * R) * (BW + 2 * R); i += BW * BH) {
         const int ty = i / (BW + 2 * R), tx = i - ty * (BW + 2 * R);
-        tile[ty][tx] = src[(size_t)reflect101(y0 + ty - R, h) * stride + reflect101(x0 + tx - R, w)];
+        tile[ty][tx] = src[(size_t)reflect101(y0 + ty - R, h) * w + reflect101(x0 + tx - R, w)];
     }
     __syncthreads();
     for (int i = tid; i < (BH + 2 * R) * BW; i += BW * BH) {
@@ -66,27 +363,11 @@ __global__ void __launch_bounds__(BW * BH) orb_blur_kernel(const uint8_t* __rest
     }
 }
 
-struct OrbKp {    // prepared keypoint: patch centre and rotation
-    int cx, cy;
-    float a, b;
-};
-
-__global__ void orb_prepare_kernel(const float* __restrict__ xya, int n, OrbKp* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float x = xya[3 * i], y = xya[3 * i + 1];
-    const float rad = __fmul_rn(xya[3 * i + 2], (float)(3.1415926535897932384626433832795 / 180.f));
-    OrbKp k;
-    k.cx = __float2int_rn(x);
-    k.cy = __float2int_rn(y);
-    k.a = (float)cos((double)rad);
-    k.b = (float)sin((double)rad);
-    out[i] = k;
-}
-
-// one warp per keypoint (grid-stride); lane = descriptor byte, its 16 pattern points stay in registers
-__global__ void __launch_bounds__(256) orb_desc_kernel(const uint8_t* __restrict__ img, int w, const OrbKp* __restrict__ kps,
-                                                       int n, uint8_t* __restrict__ desc) {
+// one warp per keypoint (grid-stride); lane = descriptor byte, its 16 pattern points stay in registers.
+// A sample outside the level image (possible only for caller-provided keypoints on coarse levels) reads what OpenCV's
+// pyramid holds there: the reflect-101 border of the UNBLURRED level.
+__global__ void __launch_bounds__(256) orb_desc_kernel(LevelTable T, const uint8_t* __restrict__ blur, const uint8_t* __restrict__ raw,
+                                                       const OrbKp* __restrict__ kps, int n, uint8_t* __restrict__ desc) {
     const int lane = threadIdx.x & 31;
     float px[16], py[16];
 #pragma unroll
@@ -94,13 +375,16 @@ __global__ void __launch_bounds__(256) orb_desc_kernel(const uint8_t* __restrict
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
         const OrbKp k = kps[i];
-        const uint8_t* centre = img + (size_t)k.cy * w + k.cx;
+        const int w = T.l[k.level].w, h = T.l[k.level].h;
+        const uint8_t* img = blur + T.l[k.level].off;
         int v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const float x = __fsub_rn(__fmul_rn(px[j], k.a), __fmul_rn(py[j], k.b));
             const float y = __fadd_rn(__fmul_rn(px[j], k.b), __fmul_rn(py[j], k.a));
-            v[j] = __ldg(centre + __float2int_rn(y) * w + __float2int_rn(x));
+            const int xx = k.cx + __float2int_rn(x), yy = k.cy + __float2int_rn(y);
+            if (xx >= 0 && xx < w && yy >= 0 && yy < h) v[j] = __ldg(img + (size_t)yy * w + xx);
+            else v[j] = raw[T.l[k.level].off + (size_t)reflect101(yy, h) * w + reflect101(xx, w)];
         }
         unsigned val = 0;
 #pragma unroll
@@ -109,36 +393,258 @@ __global__ void __launch_bounds__(256) orb_desc_kernel(const uint8_t* __restrict
     }
 }
 
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t bytes) {
+        if (bytes <= cap) return true;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) return false;
+        cap = want;
+        return true;
+    }
+    ~Buf() { if (p) cudaFree(p); }
+};
+
+// KeyPointsFilter::retainBest (features2d keypoint.cpp): nth_element + partition; the resulting order is the output order
+struct Rec { float response; int id; };
+void retain_best(std::vector<Rec>& v, int n_points) {
+    if (n_points < 0 || v.size() <= (size_t)n_points) return;
+    if (n_points == 0) { v.clear(); return; }
+    std::nth_element(v.begin(), v.begin() + n_points - 1, v.end(), [](const Rec& a, const Rec& b) { return a.response > b.response; });
+    const float ambiguous = v[(size_t)n_points - 1].response;
+    auto new_end = std::partition(v.begin() + n_points, v.end(), [ambiguous](const Rec& a) { return a.response >= ambiguous; });
+    v.resize((size_t)(new_end - v.begin()));
+}
+
+// interpolationLinear<uint8_t>::getCoeffs (imgproc resize.cpp, bit-exact path): offset and 8-bit weight per output index
+void linear_exact_coeffs(int ssize, int dsize, std::vector<int>& ofs, std::vector<int>& c1) {
+    ofs.assign((size_t)dsize, 0); c1.assign((size_t)dsize, 0);
+    const double inv_scale = (double)dsize / (double)ssize;
+    const double scale = 1.0 / inv_scale;
+    for (int v = 0; v < dsize; ++v) {
+        const double f = scale * ((double)v + 0.5) - 0.5;
+        const int i = (int)std::floor(f);
+        if (i >= 0 && ssize > 1) {
+            if (i < ssize - 1) { ofs[(size_t)v] = i; c1[(size_t)v] = (int)std::nearbyint((f - i) * 256.0); }
+            else ofs[(size_t)v] = ssize - 1;      // right border: the last pixel with full weight
+        }                                         // left border: pixel 0 with full weight (ofs 0, c1 0)
+    }
+}
+
 }  // namespace
 
-size_t orb_kp_bytes() { return sizeof(OrbKp); }
+struct OrbWorkspace {
+    Buf img, pyr, blur, score, rowcnt, rowoff, cand, pts, resp, kpout, prep, desc, coef, xyao;
+    LevelTable T;
+    char err[256] = "";
+};
 
-// image on the device (channels 1 or 3, row stride `stride`); d_xya: n x (x, y, angle_deg) already border-filtered;
-// d_gray / d_blur: w*h bytes each; d_prep: n * orb_kp_bytes().  Returns the number of kernel launches.
-int launch_orb_compute(const uint8_t* d_image, int w, int h, int channels, int stride, const float* d_xya, int n,
-                       uint8_t* d_gray, uint8_t* d_blur, void* d_prep, uint8_t* d_desc, int sm_count, cudaStream_t st) {
-    int launches = 0;
-    const uint8_t* gray = d_image;
-    int gstride = stride;
-    if (channels == 3) {
-        orb_gray_kernel<<<dim3((unsigned)((w + 255) / 256), (unsigned)h), 256, 0, st>>>(d_image, stride, w, h, d_gray);
-        gray = d_gray; gstride = w; ++launches;
+OrbWorkspace* orb_ws_create() { return new OrbWorkspace(); }
+void orb_ws_destroy(OrbWorkspace* w) { delete w; }
+const char* orb_ws_error(const OrbWorkspace* w) { return w->err; }
+
+namespace {
+
+bool fail_ws(OrbWorkspace* ws, const char* msg) { snprintf(ws->err, sizeof ws->err, "%s", msg); return false; }
+
+// gray level 0 + the scale pyramid (levels 1..n-1) on the device; fills ws->T.  Host image in, any stride.
+bool build_pyramid(OrbWorkspace* ws, const uint8_t* h_image, int w, int h, int channels, int stride, int nlevels,
+                   cudaStream_t st, int* launches) {
+    LevelTable& T = ws->T;
+    T.n = nlevels;
+    long long off = 0;
+    int row = 0, max_w = 0;
+    for (int l = 0; l < nlevels; ++l) {
+        const float scale = (float)std::pow((double)1.2f, (double)l);     // getScale(level, firstLevel = 0, scaleFactor)
+        const float inv = 1.0f / scale;
+        Level& L = T.l[l];
+        L.scale = scale;
+        L.w = (int)lrintf((float)w * inv);
+        L.h = (int)lrintf((float)h * inv);
+        if (L.w < 1 || L.h < 1) return fail_ws(ws, "image too small for the requested pyramid level");
+        L.off = off; L.row0 = row;
+        off += (long long)L.w * L.h;
+        off = (off + 255) & ~255ll;
+        row += L.h;
+        max_w = std::max(max_w, L.w);
     }
+    T.total_rows = row; T.max_w = max_w;
+    const size_t img_bytes = (size_t)stride * h;
+    if (!ws->img.ensure(img_bytes) || !ws->pyr.ensure((size_t)off) || !ws->blur.ensure((size_t)off) || !ws->score.ensure((size_t)off))
+        return fail_ws(ws, "cudaMalloc failed (pyramid)");
+    if (cudaMemcpyAsync(ws->img.p, h_image, img_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return fail_ws(ws, "H2D failed");
+    uint8_t* pyr = (uint8_t*)ws->pyr.p;
+    const dim3 g0((unsigned)((w + 255) / 256), (unsigned)h);
+    if (channels == 3) orb_gray_kernel<<<g0, 256, 0, st>>>((const uint8_t*)ws->img.p, stride, w, h, pyr);
+    else orb_copy_kernel<<<g0, 256, 0, st>>>((const uint8_t*)ws->img.p, stride, w, h, pyr);
+    ++*launches;
+    if (nlevels > 1) {
+        // resize coefficients of every level, one upload
+        std::vector<int> all, xo, xc, yo, yc;
+        std::vector<size_t> pos((size_t)nlevels * 4, 0);
+        for (int l = 1; l < nlevels; ++l) {
+            linear_exact_coeffs(T.l[l - 1].w, T.l[l].w, xo, xc);
+            linear_exact_coeffs(T.l[l - 1].h, T.l[l].h, yo, yc);
+            const std::vector<int>* v[4] = {&xo, &xc, &yo, &yc};
+            for (int k = 0; k < 4; ++k) { pos[(size_t)l * 4 + k] = all.size(); all.insert(all.end(), v[k]->begin(), v[k]->end()); }
+        }
+        if (!ws->coef.ensure(all.size() * 4)) return fail_ws(ws, "cudaMalloc failed (coefficients)");
+        // pageable source: the copy is staged before the call returns, so `all` may go out of scope afterwards
+        if (cudaMemcpyAsync(ws->coef.p, all.data(), all.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) return fail_ws(ws, "H2D failed");
+        const int* c = (const int*)ws->coef.p;
+        for (int l = 1; l < nlevels; ++l) {
+            const Level& S = T.l[l - 1];
+            const Level& D = T.l[l];
+            orb_resize_kernel<<<dim3((unsigned)((D.w + 255) / 256), (unsigned)D.h), 256, 0, st>>>(
+                pyr + S.off, S.w, S.h, pyr + D.off, D.w, D.h, c + pos[(size_t)l * 4], c + pos[(size_t)l * 4 + 1], c + pos[(size_t)l * 4 + 2],
+                c + pos[(size_t)l * 4 + 3]);
+            ++*launches;
+        }
+    }
+    return true;
+}
+
+void blur_levels(OrbWorkspace* ws, cudaStream_t st, int* launches) {
     double k[7], sum = 0.0;
-    for (int i = 0; i < 7; ++i) { const double x = i - 3.0; k[i] = exp(-(x * x) / 8.0); sum += k[i]; }
+    for (int i = 0; i < 7; ++i) { const double x = i - 3.0; k[i] = std::exp(-(x * x) / 8.0); sum += k[i]; }
     for (int i = 0; i < 7; ++i) k[i] /= sum;
-    orb_blur_kernel<<<dim3((unsigned)((w + BW - 1) / BW), (unsigned)((h + BH - 1) / BH)), dim3(BW, BH), 0, st>>>(
-        gray, gstride, w, h, d_blur, k[0], k[1], k[2], k[3]);
-    ++launches;
-    if (n > 0) {
-        OrbKp* prep = static_cast<OrbKp*>(d_prep);
-        orb_prepare_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_xya, n, prep);
-        long long blocks = ((long long)n + 7) / 8;
-        if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
-        orb_desc_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_blur, w, prep, n, d_desc);
-        launches += 2;
+    for (int l = 0; l < ws->T.n; ++l) {
+        const Level& L = ws->T.l[l];
+        orb_blur_kernel<<<dim3((unsigned)((L.w + BW - 1) / BW), (unsigned)((L.h + BH - 1) / BH)), dim3(BW, BH), 0, st>>>(
+            (const uint8_t*)ws->pyr.p + L.off, L.w, L.h, (uint8_t*)ws->blur.p + L.off, k[0], k[1], k[2], k[3]);
+        ++*launches;
     }
-    return launches;
+}
+
+bool describe(OrbWorkspace* ws, int n, uint8_t* h_desc, int sm_count, cudaStream_t st, int* launches) {
+    if (!ws->desc.ensure((size_t)n * 32)) return fail_ws(ws, "cudaMalloc failed (descriptors)");
+    long long blocks = ((long long)n + 7) / 8;
+    if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
+    orb_desc_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws->T, (const uint8_t*)ws->blur.p, (const uint8_t*)ws->pyr.p,
+                                                      (const OrbKp*)ws->prep.p, n, (uint8_t*)ws->desc.p);
+    ++*launches;
+    if (h_desc && cudaMemcpyAsync(h_desc, ws->desc.p, (size_t)n * 32, cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail_ws(ws, "D2H failed");
+    return true;
+}
+
+}  // namespace
+
+// cv::ORB::compute on provided keypoints.  h_xyao: n records (x, y, angle_deg, octave as int bits), already
+// border-filtered and grouped by level by the caller; nlevels = max octave + 1.
+int orb_compute_provided(OrbWorkspace* ws, const uint8_t* h_image, int w, int h, int channels, int stride, const float* h_xyao,
+                         int n, int nlevels, uint8_t* h_desc, int sm_count, cudaStream_t st, int* launches) {
+    if (nlevels < 1 || nlevels > kMaxLevels) { fail_ws(ws, "octave out of range (0..15)"); return -1; }
+    if (!build_pyramid(ws, h_image, w, h, channels, stride, nlevels, st, launches)) return -1;
+    blur_levels(ws, st, launches);
+    if (!ws->xyao.ensure((size_t)n * 16) || !ws->prep.ensure((size_t)n * sizeof(OrbKp))) { fail_ws(ws, "cudaMalloc failed"); return -1; }
+    if (cudaMemcpyAsync(ws->xyao.p, h_xyao, (size_t)n * 16, cudaMemcpyHostToDevice, st) != cudaSuccess) { fail_ws(ws, "H2D failed"); return -1; }
+    orb_prepare_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws->T, (const float*)ws->xyao.p, n, (OrbKp*)ws->prep.p);
+    ++*launches;
+    if (!describe(ws, n, h_desc, sm_count, st, launches)) return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { fail_ws(ws, "CUDA error in ORB compute"); return -1; }
+    return n;
+}
+
+// cv::ORB::detectAndCompute with ORB::create() defaults except nfeatures / fastThreshold.
+// h_kp: capacity records in cv::KeyPoint layout (28 B); h_desc: capacity x 32.  Returns the number of keypoints,
+// -1 on error, -2 when capacity is too small (*needed is set).
+int orb_detect_and_compute(OrbWorkspace* ws, const uint8_t* h_image, int w, int h, int channels, int stride, int nfeatures,
+                           int fast_threshold, int nlevels, void* h_kp, uint8_t* h_desc, int capacity, int* needed, int sm_count,
+                           cudaStream_t st, int* launches) {
+    if (nlevels < 1 || nlevels > kMaxLevels) { fail_ws(ws, "nlevels out of range (1..16)"); return -1; }
+    if (!build_pyramid(ws, h_image, w, h, channels, stride, nlevels, st, launches)) return -1;
+    const LevelTable& T = ws->T;
+    // features per level (computeKeyPoints): geometric split in float, remainder to the last level
+    std::vector<int> n_per((size_t)nlevels);
+    {
+        const float factor = (float)(1.0 / (double)1.2f);
+        float nd = nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nlevels));
+        int sum = 0;
+        for (int l = 0; l < nlevels - 1; ++l) {
+            n_per[(size_t)l] = (int)lrintf(nd);
+            sum += n_per[(size_t)l];
+            nd *= factor;
+        }
+        n_per[(size_t)nlevels - 1] = std::max(nfeatures - sum, 0);
+    }
+    // FAST scores, NMS, ordered compaction
+    const int rows = T.total_rows;
+    if (!ws->rowcnt.ensure((size_t)rows * 4) || !ws->rowoff.ensure((size_t)(rows + 1) * 4)) { fail_ws(ws, "cudaMalloc failed"); return -1; }
+    orb_fast_score_kernel<<<dim3((unsigned)((T.max_w + 127) / 128), (unsigned)rows), 128, 0, st>>>(T, (const uint8_t*)ws->pyr.p,
+                                                                                                  (uint8_t*)ws->score.p, fast_threshold);
+    orb_nms_count_kernel<<<rows, 256, 0, st>>>(T, (const uint8_t*)ws->score.p, (int*)ws->rowcnt.p);
+    orb_scan_kernel<<<1, 1024, 0, st>>>((const int*)ws->rowcnt.p, rows, (int*)ws->rowoff.p);
+    *launches += 3;
+    int total = 0;
+    if (cudaMemcpyAsync(&total, (const int*)ws->rowoff.p + rows, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) { fail_ws(ws, "CUDA error in FAST"); return -1; }
+    std::vector<Cand> cand((size_t)total);
+    if (total > 0) {
+        if (!ws->cand.ensure((size_t)total * sizeof(Cand))) { fail_ws(ws, "cudaMalloc failed"); return -1; }
+        orb_nms_write_kernel<<<rows, 256, 0, st>>>(T, (const uint8_t*)ws->score.p, (const int*)ws->rowoff.p, (Cand*)ws->cand.p);
+        ++*launches;
+        if (cudaMemcpyAsync(cand.data(), ws->cand.p, (size_t)total * sizeof(Cand), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) { fail_ws(ws, "CUDA error in NMS"); return -1; }
+    }
+    // per level: retainBest(2 * n_level) by FAST score (HARRIS_SCORE keeps twice as many for the second ranking)
+    std::vector<Pt> sel;
+    std::vector<int> counters((size_t)nlevels, 0);
+    {
+        size_t pos = 0;
+        std::vector<Rec> v;
+        for (int l = 0; l < nlevels; ++l) {
+            v.clear();
+            const size_t first = pos;
+            while (pos < cand.size() && cand[pos].level == l) { v.push_back(Rec{(float)cand[pos].score, (int)(pos - first)}); ++pos; }
+            retain_best(v, 2 * n_per[(size_t)l]);
+            counters[(size_t)l] = (int)v.size();
+            for (const Rec& r : v) sel.push_back(Pt{cand[first + (size_t)r.id].x, cand[first + (size_t)r.id].y, l});
+        }
+    }
+    const int nsel = (int)sel.size();
+    if (nsel == 0) { if (needed) *needed = 0; return 0; }
+    // Harris responses of the selected corners, then retainBest(n_level) per level
+    if (!ws->pts.ensure((size_t)nsel * sizeof(Pt)) || !ws->resp.ensure((size_t)nsel * 4)) { fail_ws(ws, "cudaMalloc failed"); return -1; }
+    std::vector<float> resp((size_t)nsel);
+    if (cudaMemcpyAsync(ws->pts.p, sel.data(), (size_t)nsel * sizeof(Pt), cudaMemcpyHostToDevice, st) != cudaSuccess) { fail_ws(ws, "H2D failed"); return -1; }
+    orb_harris_kernel<<<(nsel + 7) / 8, 256, 0, st>>>(T, (const uint8_t*)ws->pyr.p, (const Pt*)ws->pts.p, nsel, (float*)ws->resp.p);
+    ++*launches;
+    if (cudaMemcpyAsync(resp.data(), ws->resp.p, (size_t)nsel * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) { fail_ws(ws, "CUDA error in Harris"); return -1; }
+    std::vector<Pt> fin;
+    std::vector<float> fin_resp;
+    {
+        size_t offset = 0;
+        std::vector<Rec> v;
+        for (int l = 0; l < nlevels; ++l) {
+            v.clear();
+            for (int i = 0; i < counters[(size_t)l]; ++i) v.push_back(Rec{resp[offset + (size_t)i], i});
+            retain_best(v, n_per[(size_t)l]);
+            for (const Rec& r : v) { fin.push_back(sel[offset + (size_t)r.id]); fin_resp.push_back(r.response); }
+            offset += (size_t)counters[(size_t)l];
+        }
+    }
+    const int n = (int)fin.size();
+    if (needed) *needed = n;
+    if (n > capacity) return -2;
+    if (n == 0) return 0;
+    // orientation, final coordinates, descriptors
+    if (!ws->kpout.ensure((size_t)n * sizeof(KpOut)) || !ws->prep.ensure((size_t)n * sizeof(OrbKp))) { fail_ws(ws, "cudaMalloc failed"); return -1; }
+    if (cudaMemcpyAsync(ws->pts.p, fin.data(), (size_t)n * sizeof(Pt), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(ws->resp.p, fin_resp.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { fail_ws(ws, "H2D failed"); return -1; }
+    orb_angle_kernel<<<(n + 15) / 16, 256, 0, st>>>(T, (const uint8_t*)ws->pyr.p, (const Pt*)ws->pts.p, (const float*)ws->resp.p, n,
+                                                    (KpOut*)ws->kpout.p, (OrbKp*)ws->prep.p);
+    ++*launches;
+    if (h_kp && cudaMemcpyAsync(h_kp, ws->kpout.p, (size_t)n * sizeof(KpOut), cudaMemcpyDeviceToHost, st) != cudaSuccess) { fail_ws(ws, "D2H failed"); return -1; }
+    if (h_desc) {
+        blur_levels(ws, st, launches);
+        if (!describe(ws, n, h_desc, sm_count, st, launches)) return -1;
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { fail_ws(ws, "CUDA error in ORB"); return -1; }
+    return n;
 }
 
 }  // namespace sfmgms

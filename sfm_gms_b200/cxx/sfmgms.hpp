@@ -133,15 +133,24 @@ class BFMatcher {
     int norm_ = NORM_HAMMING;
 };
 
-// cv::ORB, descriptor side only: ORB::create() defaults, compute() on level-0 keypoints as
-// DisparityUtil.cpp:107 + 127-134 use it.  Like OpenCV, compute() REMOVES the keypoints it cannot describe (within
-// 31 pixels of the border) from `keypoints` and writes one 32-byte row per surviving keypoint.
+// cv::ORB: ORB::create(nfeatures) with OpenCV's other defaults, as DisparityUtil.cpp:107 builds it.
+// detectAndCompute / detect / compute return what OpenCV returns, keypoint order included.  Like OpenCV, compute()
+// REMOVES the keypoints it cannot describe (within 31 pixels of the border) from `keypoints`.
 class ORB {
    public:
-    explicit ORB(Context* ctx = nullptr) : ctx_(ctx) {}
-    static ORB create() { return ORB(); }
+    explicit ORB(int nfeatures = 500, Context* ctx = nullptr) : nfeatures_(nfeatures), ctx_(ctx) {}
+    static ORB create(int nfeatures = 500) { return ORB(nfeatures); }
+    void setFastThreshold(int t) { fast_ = t; }
+    int getFastThreshold() const { return fast_; }
     int descriptorSize() const { return 32; }
     // image: 8-bit, `channels` 1 (gray) or 3 (BGR), rows `stride_bytes` apart (0 = packed)
+    void detectAndCompute(const uint8_t* image, Size size, int channels, std::vector<KeyPoint>& keypoints,
+                          std::vector<uint8_t>& descriptors, int stride_bytes = 0) const {
+        run(image, size, channels, keypoints, &descriptors, stride_bytes);
+    }
+    void detect(const uint8_t* image, Size size, int channels, std::vector<KeyPoint>& keypoints, int stride_bytes = 0) const {
+        run(image, size, channels, keypoints, nullptr, stride_bytes);
+    }
     void compute(const uint8_t* image, Size size, int channels, std::vector<KeyPoint>& keypoints,
                  std::vector<uint8_t>& descriptors, int stride_bytes = 0) const {
         Context& c = ctx_ ? *ctx_ : Context::thread_default();
@@ -159,6 +168,24 @@ class ORB {
     }
 
    private:
+    void run(const uint8_t* image, Size size, int channels, std::vector<KeyPoint>& keypoints, std::vector<uint8_t>* descriptors,
+             int stride_bytes) const {
+        Context& c = ctx_ ? *ctx_ : Context::thread_default();
+        int cap = 2 * nfeatures_ + 64, n = 0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            keypoints.assign((size_t)cap, KeyPoint{});
+            if (descriptors) descriptors->assign((size_t)cap * 32, 0);
+            const int rc = sfmgms_orb_detect_and_compute(c.get(), image, size.width, size.height, channels,
+                                                         stride_bytes ? stride_bytes : size.width * channels, nfeatures_, fast_,
+                                                         keypoints.data(), descriptors ? descriptors->data() : nullptr, cap, &n);
+            if (rc == SFMGMS_ERR_ARG && n > cap) { cap = n; continue; }    // ties at a level's cut: retry once
+            c.check(rc);
+            break;
+        }
+        keypoints.resize((size_t)n);
+        if (descriptors) descriptors->resize((size_t)n * 32);
+    }
+    int nfeatures_, fast_ = 20;
     Context* ctx_;
 };
 

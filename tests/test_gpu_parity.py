@@ -576,7 +576,7 @@ def test_orb_compute_golden_cv2(ctx, name):
             self.pt, self.angle, self.octave = (float(p[0]), float(p[1])), float(a), 0
 
     kps = [KP(p, a) for p, a in zip(g[name + "_pts"][:400], g[name + "_ang"][:400])]
-    out_k, out_d = sg.ORB_create(ctx).compute(g[name + "_img"], kps)
+    out_k, out_d = sg.ORB_create(ctx=ctx).compute(g[name + "_img"], kps)
     n = int((g[name + "_kept"] < 400).sum())
     assert len(out_k) == n and np.array_equal(out_d, g[name + "_desc"][:n])
     assert [kps.index(k) for k in out_k] == g[name + "_kept"][:n].tolist()
@@ -598,5 +598,53 @@ def test_orb_compute_vs_oracle_edges(ctx):
         assert np.array_equal(kept, ok) and np.array_equal(desc, od), (h, w, ch)
     kept, desc = ctx.orb_compute(img, np.zeros((0, 2), np.float32))
     assert len(kept) == 0 and desc.shape == (0, 32)
-    with pytest.raises(SfmGmsError):                              # pyramid levels > 0: not implemented, said loudly
-        ctx.orb_compute(img, pts, ang, octaves=np.ones(n, np.int32))
+    with pytest.raises(SfmGmsError):
+        ctx.orb_compute(img, pts, ang, octaves=np.full(n, 16, np.int32))      # octaves above 15 are refused
+
+
+def test_orb_compute_octaves_golden_cv2(ctx):
+    """provided keypoints on pyramid levels 0..3, not sorted by octave: OpenCV regroups them level by level and
+    samples coarse-level patches that may stick out of the level into its reflected border"""
+    from oracle import orb
+
+    g = load_golden("orb_compute_octaves")
+    kept, desc = ctx.orb_compute(g["img"], g["pts"], g["ang"], g["oct"])
+    assert np.array_equal(kept, g["kept"]) and np.array_equal(desc, g["desc"])
+    o = np.sort(g["oct"])                                          # sorted input: order kept as given
+    kept, desc = ctx.orb_compute(g["img"], g["pts"], g["ang"], o)
+    ok, od = orb.orb_compute(g["img"], g["pts"], g["ang"], o)
+    assert np.array_equal(kept, ok) and np.array_equal(desc, od)
+
+
+@pytest.mark.parametrize("name", ["view0_bgr", "pika_gray"])
+@pytest.mark.parametrize("nf,thr", [(500, 20), (3000, 0)])
+def test_orb_detect_and_compute_golden_cv2(ctx, name, nf, thr):
+    """(§8f-4) ORB::create(nf) + detectAndCompute: the keypoint LIST (order, pt, size, angle, response, octave) and
+    every descriptor bit equal cv2 (DisparityUtil.cpp:107,139-140 defaults; BASELINE config 1's generator settings)."""
+    import sfm_gms_b200 as sg
+
+    g = load_golden("orb_detect")
+    key = "%s_%d_%d" % (name, nf, thr)
+    kp, desc = ctx.orb_detect_and_compute(g[name + "_img"], nf, thr)
+    assert kp.shape == g[key + "_kp"].shape and np.array_equal(kp, g[key + "_kp"])
+    assert np.array_equal(desc, g[key + "_desc"])
+    orb = sg.ORB_create(nf, ctx=ctx)
+    orb.setFastThreshold(thr)
+    kps = orb.detect(g[name + "_img"])
+    assert len(kps) == len(kp) and kps[0].pt == (float(kp[0, 0]), float(kp[0, 1])) and kps[-1].octave == int(kp[-1, 5])
+
+
+def test_orb_detect_vs_oracle_random_images(ctx):
+    from oracle import orb
+
+    rng = np.random.default_rng(9)
+    for (h, w, ch, nf, thr) in [(240, 320, 1, 300, 20), (200, 260, 3, 800, 5), (150, 150, 1, 100, 40), (90, 400, 1, 50, 10)]:
+        base = rng.integers(0, 256, (h // 8 + 2, w // 8 + 2) if ch == 1 else (h // 8 + 2, w // 8 + 2, 3), dtype=np.uint8)
+        img = np.kron(base, np.ones((8, 8) if ch == 1 else (8, 8, 1), np.uint8))[:h, :w].copy()   # blocky: many corners, many ties
+        img = (img.astype(np.int32) + rng.integers(-6, 7, img.shape)).clip(0, 255).astype(np.uint8)
+        kp, desc = ctx.orb_detect_and_compute(img, nf, thr)
+        okp, od = orb.orb_detect_and_compute(img, nf, thr)
+        assert kp.shape == okp.shape and np.array_equal(kp.astype(np.float64), okp), (h, w, ch, nf, thr)
+        assert np.array_equal(desc, od), (h, w, ch, nf, thr)
+    kp, desc = ctx.orb_detect_and_compute(np.full((100, 100), 7, np.uint8))      # nothing to detect
+    assert kp.shape == (0, 6) and desc.shape == (0, 32)
