@@ -1,6 +1,6 @@
 // orb.cu — cv::ORB: `ORB::create()` + detectAndCompute / compute as DisparityUtil.cpp:107, 127-140 use
 // them.  Restates OpenCV features2d orb.cpp / fast.cpp / keypoint.cpp and imgproc resize (un-vendored dependency of the
-// reference; every step is pinned bit-exactly against cv2 4.13 by oracle/orb.py and tests/golden/orb_*.npz):
+// reference; every step is pinned bit-exactly against cv2 4.13 by the CPU restatement in the test tree and tests/golden/orb_*.npz):
 //   gray     = (B*3735 + G*19235 + R*9798 + 2^14) >> 15                          cvtColor(BGR2GRAY), 8-bit
 //   pyramid  : level l has scale s_l = (float)pow((double)1.2f, l), size cvRound(w / s_l) x cvRound(h / s_l), and is
 //              resize(level l-1, INTER_LINEAR_EXACT): 8.8 fixed-point weights round((frac)*256) from
@@ -13,7 +13,7 @@
 //              keypoints is the order those two library calls leave (libstdc++ here and in the stock cv2 packages)
 //   angle    : intensity centroid over the radius-15 disc (integer moments), cv::fastAtan2's float polynomial
 //   blur     : 7x7 sigma-2 Gaussian, floating point, rounded to nearest (OpenCV sends the pyramid SUB-matrix to its
-//              float path, not to the 8-bit fixed-point kernel; see oracle/orb.py for the pin and its one caveat)
+//              float path, not to the 8-bit fixed-point kernel; DESIGN.md has the pin and its one caveat)
 //   BRIEF    : a = (float)cos(angle), b = (float)sin(angle); 512 pattern points rotated in float with separately
 //              rounded products, cvRound, 256 comparisons -> 32 bytes
 // HBM/L2-bound byte and integer work: one coalesced pass over the pyramid per stage; the per-keypoint stages gather.
