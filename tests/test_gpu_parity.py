@@ -648,3 +648,26 @@ def test_orb_detect_vs_oracle_random_images(ctx):
         assert np.array_equal(desc, od), (h, w, ch, nf, thr)
     kp, desc = ctx.orb_detect_and_compute(np.full((100, 100), 7, np.uint8))      # nothing to detect
     assert kp.shape == (0, 6) and desc.shape == (0, 32)
+
+
+def test_full_pipeline_image_to_inliers(ctx, oracle_mod):
+    """image pair -> ORB -> BF-Hamming -> GMS, the whole chain on the device, against the whole chain of oracles:
+    DisparityUtil.cpp:107,139-149 with the brute-force matcher of FeatureMatchUtil.cpp:66-69."""
+    from oracle import orb as orb_oracle
+
+    g = load_golden("orb_detect")
+    img1 = g["view0_bgr_img"]
+    img2 = np.ascontiguousarray(img1[7:, 11:])               # a translated view of the same scene
+    out = []
+    for fn, bf, gms in ((ctx.orb_detect_and_compute, ctx.bf_hamming, ctx.gms),
+                        (orb_oracle.orb_detect_and_compute, oracle_mod.bf_hamming, oracle_mod.gms)):
+        k1, d1 = fn(img1, 1500, 5)
+        k2, d2 = fn(img2, 1500, 5)
+        idx, dist = bf(d1, d2)
+        s1, s2 = (img1.shape[1], img1.shape[0]), (img2.shape[1], img2.shape[0])
+        r = gms(s1, s2, np.asarray(k1)[:, :2].astype(np.float32), np.asarray(k2)[:, :2].astype(np.float32),
+                np.arange(len(idx), dtype=np.int32), idx, False, False)
+        out.append((np.asarray(k1, np.float64), d1, idx, dist, np.asarray(r["mask"]), r["n_inliers"]))
+    a, b = out
+    assert all(np.array_equal(x, y) for x, y in zip(a[:5], b[:5])) and a[5] == b[5]
+    assert a[5] > 200                                         # the translation is found: most matches are inliers
