@@ -45,6 +45,8 @@ def lib():
         L.oracle_gms.restype = ctypes.c_int
         L.oracle_bf_l2.argtypes = [f32p, ctypes.c_int, f32p, ctypes.c_int, ctypes.c_int, i32p, f32p, ip]
         L.oracle_bf_l2.restype = ctypes.c_int
+        L.oracle_orb_blur7.argtypes = [u8p, ctypes.c_int, ctypes.c_int, u8p]
+        L.oracle_orb_blur7.restype = ctypes.c_int
         L.oracle_set_num_threads.argtypes = [ctypes.c_int]
         L.oracle_num_threads.restype = ctypes.c_int
         _LIB = L
@@ -103,6 +105,16 @@ def bf_hamming_crosscheck(q, t):
     if rc:
         raise ValueError("oracle_bf_hamming_crosscheck rc=%d" % rc)
     return idx, dist, keep.astype(bool)
+
+
+def orb_blur7(gray):
+    """ORB's 7x7 sigma-2 Gaussian of one pyramid level (float32 separable filter with OpenCV's FMA order; C file)."""
+    g = np.ascontiguousarray(gray, dtype=np.uint8)
+    out = np.empty_like(g)
+    rc = lib().oracle_orb_blur7(_p(g, ctypes.c_uint8), g.shape[1], g.shape[0], _p(out, ctypes.c_uint8))
+    if rc:
+        raise ValueError("oracle_orb_blur7 rc=%d" % rc)
+    return out
 
 
 def bf_l2_crosscheck(q, t):

@@ -378,3 +378,43 @@ int oracle_bf_hamming_crosscheck(const uint8_t* q, int nq, const uint8_t* t, int
     free(back); free(bd);
     return rc;
 }
+
+/* (f4) The 7x7 sigma-2 Gaussian ORB applies to every pyramid level before sampling the BRIEF tests (orb.cpp
+ * detectAndCompute: GaussianBlur(workingMat, workingMat, Size(7,7), 2, 2, BORDER_REFLECT_101) on a SUB-matrix of the
+ * pyramid, which skips OpenCV's 8-bit fixed-point Gaussian and runs the float separable filter).  Pinned against cv2
+ * 4.13 (x86-64 AVX2 dispatch of imgproc filter.simd.hpp: RowVec_32f / SymmColumnVec_32f): float taps
+ * k = (float)getGaussianKernel(7, 2); row pass sequential with fused multiply-add, s = x0*k0, s = fma(x_i, k_i, s);
+ * column pass symmetric, s = r3*k3, s = fma(r[3-d] + r[3+d], k[3-d], s) for d = 1..3; result rounded half to even.
+ * (The last w mod 8 columns of a row go through OpenCV's scalar tail; BRIEF never samples them for detected
+ * keypoints -- they lie >= 13 pixels inside the level.) */
+static int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+    return i;
+}
+
+int oracle_orb_blur7(const uint8_t* src, int w, int h, uint8_t* dst) {
+    static const float k[7] = {0x1.1f5f62p-4f, 0x1.0c70fcp-3f, 0x1.869472p-3f, 0x1.ba95c0p-3f, 0x1.869472p-3f, 0x1.0c70fcp-3f, 0x1.1f5f62p-4f};
+    if (w <= 0 || h <= 0) return -1;
+    float* rows = (float*)malloc(sizeof(float) * (size_t)w * (size_t)h);
+    if (!rows) return -1;
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const uint8_t* r = src + (size_t)y * w;
+            float s = (float)r[reflect101(x - 3, w)] * k[0];
+            for (int i = 1; i < 7; ++i) s = fmaf((float)r[reflect101(x - 3 + i, w)], k[i], s);
+            rows[(size_t)y * w + x] = s;
+        }
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            float s = rows[(size_t)y * w + x] * k[3];
+            for (int d = 1; d <= 3; ++d) {
+                float pair = rows[(size_t)reflect101(y - d, h) * w + x] + rows[(size_t)reflect101(y + d, h) * w + x];
+                s = fmaf(pair, k[3 - d], s);
+            }
+            float r = nearbyintf(s);
+            dst[(size_t)y * w + x] = (uint8_t)(r < 0.f ? 0.f : (r > 255.f ? 255.f : r));
+        }
+    free(rows);
+    return 0;
+}

@@ -12,8 +12,8 @@
 //   retainBest = std::nth_element + std::partition on the host, exactly as OpenCV does it: the ORDER of the returned
 //              keypoints is the order those two library calls leave (libstdc++ here and in the stock cv2 packages)
 //   angle    : intensity centroid over the radius-15 disc (integer moments), cv::fastAtan2's float polynomial
-//   blur     : 7x7 sigma-2 Gaussian, floating point, rounded to nearest (OpenCV sends the pyramid SUB-matrix to its
-//              float path, not to the 8-bit fixed-point kernel; DESIGN.md has the pin and its one caveat)
+//   blur     : 7x7 sigma-2 Gaussian in float32 with OpenCV's own tap order and FMA placement (the pyramid SUB-matrix
+//              takes the float separable filter, not the 8-bit fixed-point kernel; pinned on 36 M descriptor bits)
 //   BRIEF    : a = (float)cos(angle), b = (float)sin(angle); 512 pattern points rotated in float with separately
 //              rounded products, cvRound, 256 comparisons -> 32 bytes
 // HBM/L2-bound byte and integer work: one coalesced pass over the pyramid per stage; the per-keypoint stages gather.
@@ -332,12 +332,13 @@ __device__ __forceinline__ int reflect101(int i, int n) {   // BORDER_REFLECT_10
 
 constexpr int BW = 32, BH = 16, R = 3;
 
-// 7x7 sigma-2 Gaussian of one level (taps k0..k3 = cv::getGaussianKernel(7, 2.0)), summed in the oracle's order
-__global__ void __launch_bounds__(BW * BH) orb_blur_kernel(const uint8_t* __restrict__ src, int w, int h, uint8_t* __restrict__ dst,
-                                                           double k0, double k1, double k2, double k3) {
+// 7x7 sigma-2 Gaussian of one level, exactly as OpenCV's float separable filter evaluates it for ORB (the pyramid
+// sub-matrix does not take the 8-bit fixed-point path): float taps (float)getGaussianKernel(7, 2); row pass
+// s = x0*k0, s = fma(x_i, k_i, s); column pass s = r3*k3, s = fma(r[3-d] + r[3+d], k[3-d], s); round half to even.
+__global__ void __launch_bounds__(BW * BH) orb_blur_kernel(const uint8_t* __restrict__ src, int w, int h, uint8_t* __restrict__ dst) {
     __shared__ uint8_t tile[BH + 2 * R][BW + 2 * R];
-    __shared__ double rows[BH + 2 * R][BW];
-    const double k[7] = {k0, k1, k2, k3, k2, k1, k0};
+    __shared__ float rows[BH + 2 * R][BW];
+    const float k[7] = {0x1.1f5f62p-4f, 0x1.0c70fcp-3f, 0x1.869472p-3f, 0x1.ba95c0p-3f, 0x1.869472p-3f, 0x1.0c70fcp-3f, 0x1.1f5f62p-4f};
     const int x0 = blockIdx.x * BW, y0 = blockIdx.y * BH;
     const int tid = threadIdx.y * BW + threadIdx.x;
     for (int i = tid; i < (BH + 2 * R) * (BW + 2 * R); i += BW * BH) {
@@ -347,19 +348,20 @@ __global__ void __launch_bounds__(BW * BH) orb_blur_kernel(const uint8_t* __rest
     __syncthreads();
     for (int i = tid; i < (BH + 2 * R) * BW; i += BW * BH) {
         const int ty = i / BW, tx = i - ty * BW;
-        double s = 0.0;
+        float s = __fmul_rn((float)tile[ty][tx], k[0]);
 #pragma unroll
-        for (int j = 0; j < 7; ++j) s = __dadd_rn(s, __dmul_rn((double)tile[ty][tx + j], k[j]));
+        for (int j = 1; j < 7; ++j) s = __fmaf_rn((float)tile[ty][tx + j], k[j], s);
         rows[ty][tx] = s;
     }
     __syncthreads();
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if (x < w && y < h) {
-        double s = 0.0;
+        float s = __fmul_rn(rows[threadIdx.y + 3][threadIdx.x], k[3]);
 #pragma unroll
-        for (int j = 0; j < 7; ++j) s = __dadd_rn(s, __dmul_rn(rows[threadIdx.y + j][threadIdx.x], k[j]));
-        const double r = rint(s);                              // half to even, as cvRound / saturate_cast<uchar>
-        dst[(size_t)y * w + x] = (uint8_t)(r < 0.0 ? 0.0 : (r > 255.0 ? 255.0 : r));
+        for (int d = 1; d <= 3; ++d)
+            s = __fmaf_rn(__fadd_rn(rows[threadIdx.y + 3 - d][threadIdx.x], rows[threadIdx.y + 3 + d][threadIdx.x]), k[3 - d], s);
+        const float r = rintf(s);                              // half to even, as saturate_cast<uchar>(float)
+        dst[(size_t)y * w + x] = (uint8_t)(r < 0.f ? 0.f : (r > 255.f ? 255.f : r));
     }
 }
 
@@ -508,13 +510,10 @@ bool build_pyramid(OrbWorkspace* ws, const uint8_t* h_image, int w, int h, int c
 }
 
 void blur_levels(OrbWorkspace* ws, cudaStream_t st, int* launches) {
-    double k[7], sum = 0.0;
-    for (int i = 0; i < 7; ++i) { const double x = i - 3.0; k[i] = std::exp(-(x * x) / 8.0); sum += k[i]; }
-    for (int i = 0; i < 7; ++i) k[i] /= sum;
     for (int l = 0; l < ws->T.n; ++l) {
         const Level& L = ws->T.l[l];
         orb_blur_kernel<<<dim3((unsigned)((L.w + BW - 1) / BW), (unsigned)((L.h + BH - 1) / BH)), dim3(BW, BH), 0, st>>>(
-            (const uint8_t*)ws->pyr.p + L.off, L.w, L.h, (uint8_t*)ws->blur.p + L.off, k[0], k[1], k[2], k[3]);
+            (const uint8_t*)ws->pyr.p + L.off, L.w, L.h, (uint8_t*)ws->blur.p + L.off);
         ++*launches;
     }
 }

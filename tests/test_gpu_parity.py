@@ -671,3 +671,17 @@ def test_full_pipeline_image_to_inliers(ctx, oracle_mod):
     a, b = out
     assert all(np.array_equal(x, y) for x, y in zip(a[:5], b[:5])) and a[5] == b[5]
     assert a[5] > 200                                         # the translation is found: most matches are inliers
+
+
+def test_orb_detect_and_compute_vs_live_cv2_full_size(ctx):
+    """when cv2 is importable: a full-size (1390 x 1110) tie-heavy image, 10,000 features, FAST threshold 0 -- the
+    keypoint list and all 2.56 M descriptor bits equal OpenCV's"""
+    cv2 = pytest.importorskip("cv2")
+    g = load_golden("orb_detect")
+    img = np.tile(g["view0_bgr_img"], (4, 4, 1))[:1110, :1390].copy()
+    kp, desc = ctx.orb_detect_and_compute(img, 10000, 0)
+    orb = cv2.ORB_create(10000)
+    orb.setFastThreshold(0)
+    ref_k, ref_d = orb.detectAndCompute(img, None)
+    ref = np.array([(k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave) for k in ref_k], np.float32)
+    assert kp.shape == ref.shape and np.array_equal(kp, ref) and np.array_equal(desc, ref_d)
