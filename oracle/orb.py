@@ -9,10 +9,9 @@ arithmetic lives in OpenCV features2d `orb.cpp` (un-vendored dependency, 4.5.x i
     2. level 0 of the pyramid = the image with a reflect-101 border (keypoints with octave 0 use no other level)
     3. KeyPointsFilter::runByImageBorder(kp, size, edgeThreshold=31): keep 31 <= cvRound(x) < w-31, same for y
     4. GaussianBlur(level, 7x7, sigma 2, BORDER_REFLECT_101) -- on the pyramid SUB-matrix, which OpenCV does not send
-       to its fixed-point 8-bit kernel but to the float separable filter: float32 taps, row pass sequential with FMA,
-       column pass symmetric with FMA, rounded half to even (oracle_orb_blur7 in sfmgms_oracle.c).  Pinned against
-       cv2: 0 differing descriptor bits over 7 full-size images x 20,000 keypoints (36 M bits), where e.g. the
-       exactly-rounded (double) Gaussian differs in 1-5 bits per image.
+       to its fixed-point 8-bit kernel but to the float separable filter: float32 taps, row pass sequential (FMA in
+       the 32-pixel vector loop, two roundings in its scalar remainder), column pass symmetric with FMA, rounded half
+       to even (oracle_orb_blur7 in sfmgms_oracle.c, which also lists the evidence).
     5. computeOrbDescriptors: angle (degrees, as given: -1 for a default KeyPoint) -> radians in float,
        a = (float)cos, b = (float)sin; for each of the 512 pattern points  x = px*a - py*b, y = px*b + py*a  in float
        (products and sum rounded separately), sample blurred[cy + cvRound(y), cx + cvRound(x)] around

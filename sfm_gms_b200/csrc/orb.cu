@@ -334,12 +334,14 @@ constexpr int BW = 32, BH = 16, R = 3;
 
 // 7x7 sigma-2 Gaussian of one level, exactly as OpenCV's float separable filter evaluates it for ORB (the pyramid
 // sub-matrix does not take the 8-bit fixed-point path): float taps (float)getGaussianKernel(7, 2); row pass
-// s = x0*k0, s = fma(x_i, k_i, s); column pass s = r3*k3, s = fma(r[3-d] + r[3+d], k[3-d], s); round half to even.
+// s = x0*k0, s = fma(x_i, k_i, s) in the first 32*floor(w/32) columns and s = s + x_i*k_i (two roundings) in the
+// rest; column pass s = r3*k3, s = fma(r[3-d] + r[3+d], k[3-d], s); round half to even.
 __global__ void __launch_bounds__(BW * BH) orb_blur_kernel(const uint8_t* __restrict__ src, int w, int h, uint8_t* __restrict__ dst) {
     __shared__ uint8_t tile[BH + 2 * R][BW + 2 * R];
     __shared__ float rows[BH + 2 * R][BW];
     const float k[7] = {0x1.1f5f62p-4f, 0x1.0c70fcp-3f, 0x1.869472p-3f, 0x1.ba95c0p-3f, 0x1.869472p-3f, 0x1.0c70fcp-3f, 0x1.1f5f62p-4f};
     const int x0 = blockIdx.x * BW, y0 = blockIdx.y * BH;
+    const int row_vec_end = w & ~31;
     const int tid = threadIdx.y * BW + threadIdx.x;
     for (int i = tid; i < (BH + 2 * R) * (BW + 2 * R); i += BW * BH) {
         const int ty = i / (BW + 2 * R), tx = i - ty * (BW + 2 * R);
@@ -349,8 +351,13 @@ __global__ void __launch_bounds__(BW * BH) orb_blur_kernel(const uint8_t* __rest
     for (int i = tid; i < (BH + 2 * R) * BW; i += BW * BH) {
         const int ty = i / BW, tx = i - ty * BW;
         float s = __fmul_rn((float)tile[ty][tx], k[0]);
+        if (x0 + tx < row_vec_end) {     // OpenCV's 32-pixel vector loop of the uchar->float row filter: fused
 #pragma unroll
-        for (int j = 1; j < 7; ++j) s = __fmaf_rn((float)tile[ty][tx + j], k[j], s);
+            for (int j = 1; j < 7; ++j) s = __fmaf_rn((float)tile[ty][tx + j], k[j], s);
+        } else {                         // its scalar remainder: product and sum rounded separately
+#pragma unroll
+            for (int j = 1; j < 7; ++j) s = __fadd_rn(s, __fmul_rn((float)tile[ty][tx + j], k[j]));
+        }
         rows[ty][tx] = s;
     }
     __syncthreads();
