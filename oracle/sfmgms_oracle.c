@@ -387,8 +387,10 @@ int oracle_bf_hamming_crosscheck(const uint8_t* q, int nq, const uint8_t* t, int
  * 32*floor(w/32) columns (the vector loop) and s = s + x_i*k_i with two roundings in the remaining columns (its scalar
  * remainder); column pass symmetric with FMA, s = r3*k3, s = fma(r[3-d] + r[3+d], k[3-d], s) for d = 1..3; result
  * rounded half to even.  Evidence: descriptor bits of cv2.ORB on 7 full-size images x 20,000 keypoints and a
- * randomised live-cv2 stress (scripts/orb_stress.py); the float-source variant of the same filter is visible
- * directly through cv2.GaussianBlur(float32). */
+ * randomised live-cv2 stress (scripts/orb_stress.py: 0 mismatches in 14,714 trials); the float-source variant of the
+ * same filter is visible directly through cv2.GaussianBlur(float32).  The loop width was settled on 319 images whose
+ * blurred pyramids differ between a 32- and a 64-column vector loop: 32 columns 0 differing descriptor bits, 64
+ * columns 80; fusing everywhere: 1-5 bits on about every second such image. */
 static int reflect101(int i, int n) {
     if (n == 1) return 0;
     while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;

@@ -481,6 +481,7 @@ bool build_pyramid(OrbWorkspace* ws, const uint8_t* h_image, int w, int h, int c
         max_w = std::max(max_w, L.w);
     }
     T.total_rows = row; T.max_w = max_w;
+    if (row > 65535) return fail_ws(ws, "image too tall: the pyramid has more than 65535 rows in total");
     const size_t img_bytes = (size_t)stride * h;
     if (!ws->img.ensure(img_bytes) || !ws->pyr.ensure((size_t)off) || !ws->blur.ensure((size_t)off) || !ws->score.ensure((size_t)off))
         return fail_ws(ws, "cudaMalloc failed (pyramid)");
