@@ -685,3 +685,34 @@ def test_orb_detect_and_compute_vs_live_cv2_full_size(ctx):
     ref_k, ref_d = orb.detectAndCompute(img, None)
     ref = np.array([(k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave) for k in ref_k], np.float32)
     assert kp.shape == ref.shape and np.array_equal(kp, ref) and np.array_equal(desc, ref_d)
+
+
+def test_new_entry_points_report_errors(ctx):
+    """error behaviour of the §8f entry points through the raw C ABI (no exceptions across the boundary)"""
+    import ctypes
+
+    lib, h = ctx._lib, ctx._h
+    g = load_golden("orb_detect")
+    img = np.ascontiguousarray(g["pika_gray_img"])
+    hh, ww = img.shape
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rec = np.zeros((8, 7), np.float32)
+    desc = np.zeros((8, 32), np.uint8)
+    n = ctypes.c_int(0)
+    # capacity too small: SFMGMS_ERR_ARG and the needed count comes back
+    rc = lib.sfmgms_orb_detect_and_compute(h, p(img), ww, hh, 1, ww, 500, 20, p(rec), p(desc), 8, ctypes.byref(n))
+    assert rc == 1 and n.value == len(g["pika_gray_500_20_kp"]) and b"capacity" in lib.sfmgms_last_error(h)
+    assert lib.sfmgms_orb_detect_and_compute(h, p(img), ww, hh, 2, 2 * ww, 500, 20, p(rec), p(desc), 8, ctypes.byref(n)) == 1
+    assert lib.sfmgms_orb_detect_and_compute(h, p(img), ww, hh, 1, ww - 1, 500, 20, p(rec), p(desc), 8, ctypes.byref(n)) == 1
+    assert lib.sfmgms_orb_detect_and_compute(h, None, ww, hh, 1, ww, 500, 20, p(rec), p(desc), 8, ctypes.byref(n)) == 1
+    # detect only (descriptors = NULL) is allowed
+    big = np.zeros((2000, 7), np.float32)
+    assert lib.sfmgms_orb_detect_and_compute(h, p(img), ww, hh, 1, ww, 500, 20, p(big), None, 2000, ctypes.byref(n)) == 0
+    assert n.value == len(g["pika_gray_500_20_kp"]) and np.array_equal(big[: n.value, :5], g["pika_gray_500_20_kp"][:, :5])
+    # bruteForceMatch: unknown norm, capacity too small
+    q = np.zeros((4, 32), np.uint8)
+    out = np.zeros(4, np.int32)
+    d = np.zeros(4, np.float32)
+    assert lib.sfmgms_brute_force_match(h, 5, 1, p(q), 4, p(q), 4, 32, 4.0, 500, p(out), p(out), p(d), 4, ctypes.byref(n)) == 1
+    assert lib.sfmgms_brute_force_match(h, 6, 0, p(q), 4, p(q), 4, 32, 4.0, 500, p(out), p(out), p(d), 2, ctypes.byref(n)) == 1
+    assert lib.sfmgms_brute_force_match(h, 6, 0, p(q), 4, p(q), 4, 32, 4.0, 500, p(out), p(out), p(d), 4, ctypes.byref(n)) == 0 and n.value == 4
