@@ -18,7 +18,9 @@
 //              rounded products, cvRound, 256 comparisons -> 32 bytes
 // HBM/L2-bound byte and integer work: one coalesced pass over the pyramid per stage; the per-keypoint stages gather.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -445,6 +447,18 @@ void linear_exact_coeffs(int ssize, int dsize, std::vector<int>& ofs, std::vecto
 
 }  // namespace
 
+// SFMGMS_ORB_TRACE=1: wall time between the host synchronisation points of detectAndCompute (stderr)
+struct StageTimer {
+    bool on = getenv("SFMGMS_ORB_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void mark(const char* what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[orb] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+
 struct OrbWorkspace {
     Buf img, pyr, blur, score, rowcnt, rowoff, cand, pts, resp, kpout, prep, desc, coef, xyao;
     LevelTable T;
@@ -562,7 +576,9 @@ int orb_detect_and_compute(OrbWorkspace* ws, const uint8_t* h_image, int w, int 
                            int fast_threshold, int nlevels, void* h_kp, uint8_t* h_desc, int capacity, int* needed, int sm_count,
                            cudaStream_t st, int* launches) {
     if (nlevels < 1 || nlevels > kMaxLevels) { fail_ws(ws, "nlevels out of range (1..16)"); return -1; }
+    StageTimer tm;
     if (!build_pyramid(ws, h_image, w, h, channels, stride, nlevels, st, launches)) return -1;
+    tm.mark("enqueue H2D + pyramid");
     const LevelTable& T = ws->T;
     // features per level (computeKeyPoints): geometric split in float, remainder to the last level
     std::vector<int> n_per((size_t)nlevels);
@@ -588,6 +604,7 @@ int orb_detect_and_compute(OrbWorkspace* ws, const uint8_t* h_image, int w, int 
     int total = 0;
     if (cudaMemcpyAsync(&total, (const int*)ws->rowoff.p + rows, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess) { fail_ws(ws, "CUDA error in FAST"); return -1; }
+    tm.mark("pyramid + FAST + count (sync)");
     std::vector<Cand> cand((size_t)total);
     if (total > 0) {
         if (!ws->cand.ensure((size_t)total * sizeof(Cand))) { fail_ws(ws, "cudaMalloc failed"); return -1; }
@@ -596,12 +613,15 @@ int orb_detect_and_compute(OrbWorkspace* ws, const uint8_t* h_image, int w, int 
         if (cudaMemcpyAsync(cand.data(), ws->cand.p, (size_t)total * sizeof(Cand), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
             cudaStreamSynchronize(st) != cudaSuccess) { fail_ws(ws, "CUDA error in NMS"); return -1; }
     }
+    tm.mark("NMS write + D2H (sync)");
     // per level: retainBest(2 * n_level) by FAST score (HARRIS_SCORE keeps twice as many for the second ranking)
     std::vector<Pt> sel;
     std::vector<int> counters((size_t)nlevels, 0);
     {
         size_t pos = 0;
         std::vector<Rec> v;
+        v.reserve(cand.size());
+        sel.reserve(cand.size() < (size_t)4 * (size_t)nfeatures + 64 ? cand.size() : (size_t)4 * (size_t)nfeatures + 64);
         for (int l = 0; l < nlevels; ++l) {
             v.clear();
             const size_t first = pos;
@@ -612,6 +632,7 @@ int orb_detect_and_compute(OrbWorkspace* ws, const uint8_t* h_image, int w, int 
         }
     }
     const int nsel = (int)sel.size();
+    tm.mark("host retainBest (FAST)");
     if (nsel == 0) { if (needed) *needed = 0; return 0; }
     // Harris responses of the selected corners, then retainBest(n_level) per level
     if (!ws->pts.ensure((size_t)nsel * sizeof(Pt)) || !ws->resp.ensure((size_t)nsel * 4)) { fail_ws(ws, "cudaMalloc failed"); return -1; }
@@ -621,6 +642,7 @@ int orb_detect_and_compute(OrbWorkspace* ws, const uint8_t* h_image, int w, int 
     ++*launches;
     if (cudaMemcpyAsync(resp.data(), ws->resp.p, (size_t)nsel * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess) { fail_ws(ws, "CUDA error in Harris"); return -1; }
+    tm.mark("Harris + D2H (sync)");
     std::vector<Pt> fin;
     std::vector<float> fin_resp;
     {
@@ -635,6 +657,7 @@ int orb_detect_and_compute(OrbWorkspace* ws, const uint8_t* h_image, int w, int 
         }
     }
     const int n = (int)fin.size();
+    tm.mark("host retainBest (Harris)");
     if (needed) *needed = n;
     if (n > capacity) return -2;
     if (n == 0) return 0;
@@ -651,6 +674,7 @@ int orb_detect_and_compute(OrbWorkspace* ws, const uint8_t* h_image, int w, int 
         if (!describe(ws, n, h_desc, sm_count, st, launches)) return -1;
     }
     if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { fail_ws(ws, "CUDA error in ORB"); return -1; }
+    tm.mark("angle + blur + BRIEF + D2H");
     return n;
 }
 
