@@ -150,6 +150,25 @@ int sfmgms_orb_detect_and_compute(sfmgms_ctx* ctx, const uint8_t* image, int wid
                                   int nfeatures, int fast_threshold, void* keypoints, uint8_t* descriptors, int capacity,
                                   int* n_keypoints);
 
+/* The arguments of ORB::create(nfeatures, scaleFactor, nlevels, edgeThreshold, firstLevel, WTA_K, scoreType, patchSize,
+ * fastThreshold), in that order.  Implemented: any nfeatures, scaleFactor > 1, nlevels 1..16, edgeThreshold >= 19,
+ * scoreType 0 (HARRIS_SCORE) or 1 (FAST_SCORE), any fastThreshold; firstLevel must be 0, WTA_K 2, patchSize 31 (the
+ * learned BRIEF pattern exists for that patch only) -- anything else -> SFMGMS_ERR_ARG. */
+typedef struct sfmgms_orb_params {
+    int nfeatures;        /* 500 */
+    float scale_factor;   /* 1.2f */
+    int nlevels;          /* 8 */
+    int edge_threshold;   /* 31 */
+    int first_level;      /* 0 */
+    int wta_k;            /* 2 */
+    int score_type;       /* 0 = ORB::HARRIS_SCORE */
+    int patch_size;       /* 31 */
+    int fast_threshold;   /* 20 */
+} sfmgms_orb_params;
+int sfmgms_orb_detect_and_compute_ex(sfmgms_ctx* ctx, const uint8_t* image, int width, int height, int channels, int stride_bytes,
+                                     const sfmgms_orb_params* params, void* keypoints, uint8_t* descriptors, int capacity,
+                                     int* n_keypoints);
+
 /* ---- stage 2: replaces cv::xfeatures2d::matchGMS ----------------------------------------------
  * (FeatureMatchUtil.cpp:69; DisparityUtil.cpp:149,299).  mask[i] (0/1) for each of the n_matches input
  * matches; *mask_len = n_matches, or 0 if rotation/scale search was requested and every hypothesis had

@@ -145,15 +145,16 @@ def resize_linear_exact(src, dw, dh):
     return ((v + 32768) >> 16).astype(np.uint8)
 
 
-def level_scale(level):
-    return np.float32(np.float64(SCALE_FACTOR) ** np.float64(level))
+def level_scale(level, scale_factor=SCALE_FACTOR):
+    """getScale(level, firstLevel = 0, scaleFactor) = (float)pow(scaleFactor, level), scaleFactor held as double"""
+    return np.float32(np.float64(scale_factor) ** np.float64(level))
 
 
-def build_pyramid(gray, nlevels=N_LEVELS):
+def build_pyramid(gray, nlevels=N_LEVELS, scale_factor=SCALE_FACTOR):
     h, w = gray.shape
     levels, prev = [], gray
     for l in range(nlevels):
-        inv = np.float32(1.0) / level_scale(l)
+        inv = np.float32(1.0) / level_scale(l, scale_factor)
         dw, dh = int(np.rint(np.float32(w) * inv)), int(np.rint(np.float32(h) * inv))
         cur = gray if l == 0 else resize_linear_exact(prev, dw, dh)
         levels.append(cur)
@@ -187,9 +188,9 @@ def fast_detect(img, threshold):
     return xs, ys, smap[ys, xs]
 
 
-def features_per_level(nfeatures, nlevels=N_LEVELS):
+def features_per_level(nfeatures, nlevels=N_LEVELS, scale_factor=SCALE_FACTOR):
     f = np.float32
-    factor = f(1.0 / np.float64(SCALE_FACTOR))
+    factor = f(1.0 / np.float64(scale_factor))
     nd = f(f(nfeatures) * (f(1) - factor)) / (f(1) - f(np.float64(factor) ** np.float64(nlevels)))
     out, total = [], 0
     for _ in range(nlevels - 1):
@@ -269,26 +270,33 @@ def ic_angle(img, x, y, um, half=PATCH // 2):
     return fast_atan2(np.float32(m01), np.float32(m10))
 
 
-def orb_detect_and_compute(image, nfeatures=500, fast_threshold=20, nlevels=N_LEVELS, with_descriptors=True):
-    """-> (kp float64[n, 6] = x, y, size, angle, response, octave  (float32 values), desc uint8[n, 32] or None)"""
+def orb_detect_and_compute(image, nfeatures=500, fast_threshold=20, nlevels=N_LEVELS, with_descriptors=True,
+                           scale_factor=1.2, edge_threshold=EDGE_THRESHOLD, score_type=0):
+    """ORB::create(nfeatures, scaleFactor, nlevels, edgeThreshold, 0, 2, scoreType, 31, fastThreshold)
+    .detectAndCompute.  score_type 0 = HARRIS_SCORE, 1 = FAST_SCORE.  edge_threshold >= 19 (every sample inside).
+    -> (kp float64[n, 6] = x, y, size, angle, response, octave  (float32 values), desc uint8[n, 32] or None)"""
     f = np.float32
+    sf = float(np.float32(scale_factor))                     # create() takes a float, the class keeps a double
     image = np.asarray(image)
     gray = gray_from_bgr(image) if image.ndim == 3 else image
-    levels = build_pyramid(gray, nlevels)
-    scales = [level_scale(l) for l in range(nlevels)]
-    nper = features_per_level(nfeatures, nlevels)
+    levels = build_pyramid(gray, nlevels, sf)
+    scales = [level_scale(l, sf) for l in range(nlevels)]
+    nper = features_per_level(nfeatures, nlevels, sf)
     um = umax_table()
     picked = []
     for l, img in enumerate(levels):
         h, w = img.shape
         xs, ys, sc = fast_detect(img, fast_threshold)
-        m = (xs >= EDGE_THRESHOLD) & (xs < w - EDGE_THRESHOLD) & (ys >= EDGE_THRESHOLD) & (ys < h - EDGE_THRESHOLD)
+        m = (xs >= edge_threshold) & (xs < w - edge_threshold) & (ys >= edge_threshold) & (ys < h - edge_threshold)
         xs, ys, sc = xs[m], ys[m], sc[m]
-        _, ids = retain_best(sc.astype(np.float32), 2 * nper[l])
-        picked.append((xs[ids], ys[ids]))
-    rows, centres = [], []
-    for l, (xs, ys) in enumerate(picked):
-        resp, ids = retain_best(harris_responses(levels[l], xs, ys), nper[l])
+        resp, ids = retain_best(sc.astype(np.float32), (2 if score_type == 0 else 1) * nper[l])
+        picked.append((xs[ids], ys[ids], resp))
+    rows = []
+    for l, (xs, ys, fast_resp) in enumerate(picked):
+        if score_type == 0:
+            resp, ids = retain_best(harris_responses(levels[l], xs, ys), nper[l])
+        else:
+            resp, ids = fast_resp, np.arange(len(xs))
         for r, i in zip(resp, ids):
             x, y = int(xs[i]), int(ys[i])
             rows.append((f(f(x) * scales[l]), f(f(y) * scales[l]), f(f(PATCH) * scales[l]), ic_angle(levels[l], x, y, um), r, l))

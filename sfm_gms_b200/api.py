@@ -75,6 +75,8 @@ def load_library():
                                      c_void_p, c_void_p, P(c_int)]
     L.sfmgms_orb_detect_and_compute.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                                 c_void_p, c_int, P(c_int)]
+    L.sfmgms_orb_detect_and_compute_ex.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                                   c_void_p, c_int, P(c_int)]
     L.sfmgms_gms.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
                              c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p, P(c_int),
                              P(c_int), P(c_int)]
@@ -272,21 +274,27 @@ class Context:
                                                  _ptr(desc), ctypes.byref(nk)))
         return kept[: nk.value], desc[: nk.value]
 
-    def orb_detect_and_compute(self, image, nfeatures=500, fast_threshold=20, with_descriptors=True):
-        """cv2.ORB_create(nfeatures) [+ setFastThreshold] .detectAndCompute(image, None) (DisparityUtil.cpp:107, 139-140).
+    def orb_detect_and_compute(self, image, nfeatures=500, fast_threshold=20, with_descriptors=True, scale_factor=1.2,
+                               nlevels=8, edge_threshold=31, score_type=0, first_level=0, wta_k=2, patch_size=31):
+        """cv2.ORB_create(nfeatures, scaleFactor, nlevels, edgeThreshold, firstLevel, WTA_K, scoreType, patchSize,
+        fastThreshold).detectAndCompute(image, None) (DisparityUtil.cpp:107, 139-140 use the defaults).
         -> (kp float32[n, 6] = x, y, size, angle, response, octave in OpenCV's output order, desc uint8[n, 32] | None)"""
         img = np.ascontiguousarray(image)
         if img.dtype != np.uint8 or img.ndim not in (2, 3) or (img.ndim == 3 and img.shape[2] != 3):
             raise SfmGmsError(1, "image must be HxW or HxWx3 uint8")
         h, w = img.shape[:2]
         ch = 1 if img.ndim == 2 else 3
+        prm = np.zeros(9, np.int32)
+        prm[:] = [int(nfeatures), 0, int(nlevels), int(edge_threshold), int(first_level), int(wta_k), int(score_type),
+                  int(patch_size), int(fast_threshold)]
+        prm[1:2] = np.array([scale_factor], np.float32).view(np.int32)
         cap = max(2 * int(nfeatures), 64)
         for _ in range(2):
             rec = np.zeros((cap, 7), np.float32)              # cv::KeyPoint records (28 bytes)
             desc = np.zeros((cap, 32), np.uint8) if with_descriptors else None
             n = ctypes.c_int(0)
-            rc = self._lib.sfmgms_orb_detect_and_compute(self._h, _ptr(img), w, h, ch, w * ch, int(nfeatures), int(fast_threshold),
-                                                         _ptr(rec), _ptr(desc) if with_descriptors else None, cap, ctypes.byref(n))
+            rc = self._lib.sfmgms_orb_detect_and_compute_ex(self._h, _ptr(img), w, h, ch, w * ch, _ptr(prm), _ptr(rec),
+                                                            _ptr(desc) if with_descriptors else None, cap, ctypes.byref(n))
             if rc == 1 and n.value > cap:                      # ties at a level's cut: retry with the reported size
                 cap = n.value
                 continue
@@ -516,14 +524,20 @@ class ORB:
     scaleFactor 1.2, 8 levels, edgeThreshold 31, HARRIS_SCORE, patchSize 31), ``setFastThreshold``, ``detect``,
     ``compute`` and ``detectAndCompute`` -- bit-identical to cv2 (keypoint order included)."""
 
-    def __init__(self, nfeatures=500, ctx=None):
+    HARRIS_SCORE, FAST_SCORE = 0, 1
+
+    def __init__(self, nfeatures=500, scaleFactor=1.2, nlevels=8, edgeThreshold=31, firstLevel=0, WTA_K=2, scoreType=0,
+                 patchSize=31, fastThreshold=20, ctx=None):
         self._ctx = ctx
         self._nfeatures = int(nfeatures)
-        self._fast = 20
+        self._fast = int(fastThreshold)
+        self._kw = dict(scale_factor=scaleFactor, nlevels=nlevels, edge_threshold=edgeThreshold, score_type=scoreType,
+                        first_level=firstLevel, wta_k=WTA_K, patch_size=patchSize)
 
     @staticmethod
-    def create(nfeatures=500):
-        return ORB(nfeatures)
+    def create(nfeatures=500, scaleFactor=1.2, nlevels=8, edgeThreshold=31, firstLevel=0, WTA_K=2, scoreType=0, patchSize=31,
+               fastThreshold=20):
+        return ORB(nfeatures, scaleFactor, nlevels, edgeThreshold, firstLevel, WTA_K, scoreType, patchSize, fastThreshold)
 
     def setFastThreshold(self, t):
         self._fast = int(t)
@@ -538,14 +552,14 @@ class ORB:
         if mask is not None:
             raise SfmGmsError(1, "masks are not implemented")
         ctx = self._ctx or default_context()
-        kp, desc = ctx.orb_detect_and_compute(image, self._nfeatures, self._fast, True)
+        kp, desc = ctx.orb_detect_and_compute(image, self._nfeatures, self._fast, True, **self._kw)
         return [KeyPoint(float(r[0]), float(r[1]), float(r[2]), float(r[3]), float(r[4]), int(r[5])) for r in kp], desc
 
     def detect(self, image, mask=None):
         if mask is not None:
             raise SfmGmsError(1, "masks are not implemented")
         ctx = self._ctx or default_context()
-        kp, _ = ctx.orb_detect_and_compute(image, self._nfeatures, self._fast, False)
+        kp, _ = ctx.orb_detect_and_compute(image, self._nfeatures, self._fast, False, **self._kw)
         return [KeyPoint(float(r[0]), float(r[1]), float(r[2]), float(r[3]), float(r[4]), int(r[5])) for r in kp]
 
     def compute(self, image, keypoints):
@@ -564,8 +578,9 @@ class ORB:
         return [keypoints[i] for i in kept], desc
 
 
-def ORB_create(nfeatures=500, ctx=None):
-    return ORB(nfeatures, ctx)
+def ORB_create(nfeatures=500, scaleFactor=1.2, nlevels=8, edgeThreshold=31, firstLevel=0, WTA_K=2, scoreType=0, patchSize=31,
+               fastThreshold=20, ctx=None):
+    return ORB(nfeatures, scaleFactor, nlevels, edgeThreshold, firstLevel, WTA_K, scoreType, patchSize, fastThreshold, ctx)
 
 
 def bruteForceMatch(desc1, desc2, ctx=None, kDistanceCoef=4.0, kMaxMatchingSize=500):

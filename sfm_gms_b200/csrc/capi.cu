@@ -750,20 +750,28 @@ int sfmgms_orb_compute(sfmgms_ctx* ctx, const uint8_t* image, int width, int hei
     GUARD_END
 }
 
-int sfmgms_orb_detect_and_compute(sfmgms_ctx* ctx, const uint8_t* image, int width, int height, int channels, int stride_bytes,
-                                  int nfeatures, int fast_threshold, void* keypoints, uint8_t* descriptors, int capacity,
-                                  int* n_keypoints) {
+int sfmgms_orb_detect_and_compute_ex(sfmgms_ctx* ctx, const uint8_t* image, int width, int height, int channels, int stride_bytes,
+                                     const sfmgms_orb_params* prm, void* keypoints, uint8_t* descriptors, int capacity,
+                                     int* n_keypoints) {
     GUARD_BEGIN
     if (n_keypoints) *n_keypoints = 0;
     int rc = orb_image_args(ctx, image, width, height, channels, stride_bytes);
     if (rc) return rc;
-    if (nfeatures < 0 || capacity < 0 || fast_threshold < 0 || fast_threshold > 255)
+    if (!prm) return fail(ctx, SFMGMS_ERR_ARG, "null parameter block");
+    if (prm->nfeatures < 0 || capacity < 0 || prm->fast_threshold < 0 || prm->fast_threshold > 255)
         return fail(ctx, SFMGMS_ERR_ARG, "bad nfeatures / capacity / fast_threshold");
+    if (!(prm->scale_factor > 1.0f) || prm->nlevels < 1 || prm->nlevels > 16)
+        return fail(ctx, SFMGMS_ERR_ARG, "scale_factor must be > 1 and nlevels in 1..16");
+    if (prm->first_level != 0 || prm->wta_k != 2 || prm->patch_size != 31 || (prm->score_type != 0 && prm->score_type != 1))
+        return fail(ctx, SFMGMS_ERR_ARG, "implemented: firstLevel 0, WTA_K 2, patchSize 31, scoreType HARRIS_SCORE (0) or FAST_SCORE (1)");
+    if (prm->edge_threshold < 19)
+        return fail(ctx, SFMGMS_ERR_ARG, "edge_threshold %d < 19: patches that leave the level image are not implemented", prm->edge_threshold);
     cudaStream_t st = ctx->stream;
     if (ctx->timing) CU(cudaEventRecord(ctx->ev[0], st));
     int nl = 0, needed = 0;
-    const int got = orb_detect_and_compute(ctx->orb, image, width, height, channels, stride_bytes, nfeatures, fast_threshold, 8, keypoints,
-                                           descriptors, capacity, &needed, ctx->sm_count, st, &nl);
+    const int got = orb_detect_and_compute(ctx->orb, image, width, height, channels, stride_bytes, prm->nfeatures, prm->fast_threshold,
+                                           prm->nlevels, prm->scale_factor, prm->edge_threshold, prm->score_type, keypoints, descriptors,
+                                           capacity, &needed, ctx->sm_count, st, &nl);
     ctx->launches += nl;
     if (got == -2) { if (n_keypoints) *n_keypoints = needed; return fail(ctx, SFMGMS_ERR_ARG, "capacity %d < %d keypoints", capacity, needed); }
     if (got < 0) return fail(ctx, SFMGMS_ERR_CUDA, "%s", orb_ws_error(ctx->orb));
@@ -777,6 +785,14 @@ int sfmgms_orb_detect_and_compute(sfmgms_ctx* ctx, const uint8_t* image, int wid
     }
     return SFMGMS_OK;
     GUARD_END
+}
+
+int sfmgms_orb_detect_and_compute(sfmgms_ctx* ctx, const uint8_t* image, int width, int height, int channels, int stride_bytes,
+                                  int nfeatures, int fast_threshold, void* keypoints, uint8_t* descriptors, int capacity,
+                                  int* n_keypoints) {
+    const sfmgms_orb_params prm = {nfeatures, 1.2f, 8, 31, 0, 2, 0, 31, fast_threshold};   // ORB::create() defaults
+    return sfmgms_orb_detect_and_compute_ex(ctx, image, width, height, channels, stride_bytes, &prm, keypoints, descriptors, capacity,
+                                            n_keypoints);
 }
 
 static int gms_args(sfmgms_ctx* ctx, int w1, int h1, int w2, int h2, int n1, int n2, int s1, int s2) {

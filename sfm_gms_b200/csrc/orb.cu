@@ -32,7 +32,6 @@ namespace sfmgms {
 namespace {
 
 constexpr int kMaxLevels = 16;
-constexpr int kEdge = 31;            // edgeThreshold
 constexpr int kPatch = 31;           // patchSize
 constexpr int kHalfPatch = 15;
 
@@ -47,6 +46,7 @@ struct LevelTable {
     int n;
     int total_rows;
     int max_w;
+    int edge;        // edgeThreshold (ORB::create default 31)
 };
 
 __constant__ signed char c_pattern[512][2] = {
@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(128) orb_fast_score_kernel(LevelTable T, const
     *out = corner ? (uint8_t)(max(max(amin, thr), -min(amax, -thr)) - 1) : (uint8_t)0;
 }
 
-__device__ __forceinline__ bool nms_keep(const uint8_t* s, int w, int h, int x, int y) {
-    if (x < kEdge || x >= w - kEdge || y < kEdge || y >= h - kEdge) return false;      // runByImageBorder
+__device__ __forceinline__ bool nms_keep(const uint8_t* s, int w, int h, int x, int y, int edge) {
+    if (x < edge || x >= w - edge || y < edge || y >= h - edge) return false;      // runByImageBorder
     const uint8_t* p = s + (size_t)y * w + x;
     const int v = p[0];
     return v > 0 && v > p[-1] && v > p[1] && v > p[-w - 1] && v > p[-w] && v > p[-w + 1] && v > p[w - 1] && v > p[w] &&
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) orb_nms_count_kernel(LevelTable T, const 
     const int w = T.l[l].w, h = T.l[l].h, y = row - T.l[l].row0;
     const uint8_t* s = score + T.l[l].off;
     int c = 0;
-    for (int x = threadIdx.x; x < w; x += 256) c += nms_keep(s, w, h, x, y) ? 1 : 0;
+    for (int x = threadIdx.x; x < w; x += 256) c += nms_keep(s, w, h, x, y, T.edge) ? 1 : 0;
     __shared__ int tot;
     if (threadIdx.x == 0) tot = 0;
     __syncthreads();
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256) orb_nms_write_kernel(LevelTable T, const 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int x0 = 0; x0 < w; x0 += 256) {
         const int x = x0 + threadIdx.x;
-        const bool k = x < w && nms_keep(s, w, h, x, y);
+        const bool k = x < w && nms_keep(s, w, h, x, y, T.edge);
         const unsigned m = __ballot_sync(0xffffffffu, k);
         if (lane == 0) wcnt[wid] = __popc(m);
         __syncthreads();
@@ -475,13 +475,14 @@ bool fail_ws(OrbWorkspace* ws, const char* msg) { snprintf(ws->err, sizeof ws->e
 
 // gray level 0 + the scale pyramid (levels 1..n-1) on the device; fills ws->T.  Host image in, any stride.
 bool build_pyramid(OrbWorkspace* ws, const uint8_t* h_image, int w, int h, int channels, int stride, int nlevels,
-                   cudaStream_t st, int* launches) {
+                   double scale_factor, int edge, cudaStream_t st, int* launches) {
     LevelTable& T = ws->T;
     T.n = nlevels;
+    T.edge = edge;
     long long off = 0;
     int row = 0, max_w = 0;
     for (int l = 0; l < nlevels; ++l) {
-        const float scale = (float)std::pow((double)1.2f, (double)l);     // getScale(level, firstLevel = 0, scaleFactor)
+        const float scale = (float)std::pow(scale_factor, (double)l);     // getScale(level, firstLevel = 0, scaleFactor)
         const float inv = 1.0f / scale;
         Level& L = T.l[l];
         L.scale = scale;
@@ -558,7 +559,7 @@ bool describe(OrbWorkspace* ws, int n, uint8_t* h_desc, int sm_count, cudaStream
 int orb_compute_provided(OrbWorkspace* ws, const uint8_t* h_image, int w, int h, int channels, int stride, const float* h_xyao,
                          int n, int nlevels, uint8_t* h_desc, int sm_count, cudaStream_t st, int* launches) {
     if (nlevels < 1 || nlevels > kMaxLevels) { fail_ws(ws, "octave out of range (0..15)"); return -1; }
-    if (!build_pyramid(ws, h_image, w, h, channels, stride, nlevels, st, launches)) return -1;
+    if (!build_pyramid(ws, h_image, w, h, channels, stride, nlevels, (double)1.2f, 31, st, launches)) return -1;
     blur_levels(ws, st, launches);
     if (!ws->xyao.ensure((size_t)n * 16) || !ws->prep.ensure((size_t)n * sizeof(OrbKp))) { fail_ws(ws, "cudaMalloc failed"); return -1; }
     if (cudaMemcpyAsync(ws->xyao.p, h_xyao, (size_t)n * 16, cudaMemcpyHostToDevice, st) != cudaSuccess) { fail_ws(ws, "H2D failed"); return -1; }
@@ -573,17 +574,18 @@ int orb_compute_provided(OrbWorkspace* ws, const uint8_t* h_image, int w, int h,
 // h_kp: capacity records in cv::KeyPoint layout (28 B); h_desc: capacity x 32.  Returns the number of keypoints,
 // -1 on error, -2 when capacity is too small (*needed is set).
 int orb_detect_and_compute(OrbWorkspace* ws, const uint8_t* h_image, int w, int h, int channels, int stride, int nfeatures,
-                           int fast_threshold, int nlevels, void* h_kp, uint8_t* h_desc, int capacity, int* needed, int sm_count,
-                           cudaStream_t st, int* launches) {
+                           int fast_threshold, int nlevels, float scale_factor_f, int edge, int score_type, void* h_kp,
+                           uint8_t* h_desc, int capacity, int* needed, int sm_count, cudaStream_t st, int* launches) {
+    const double scale_factor = (double)scale_factor_f;     // ORB::create takes a float, the class keeps a double
     if (nlevels < 1 || nlevels > kMaxLevels) { fail_ws(ws, "nlevels out of range (1..16)"); return -1; }
     StageTimer tm;
-    if (!build_pyramid(ws, h_image, w, h, channels, stride, nlevels, st, launches)) return -1;
+    if (!build_pyramid(ws, h_image, w, h, channels, stride, nlevels, scale_factor, edge, st, launches)) return -1;
     tm.mark("enqueue H2D + pyramid");
     const LevelTable& T = ws->T;
     // features per level (computeKeyPoints): geometric split in float, remainder to the last level
     std::vector<int> n_per((size_t)nlevels);
     {
-        const float factor = (float)(1.0 / (double)1.2f);
+        const float factor = (float)(1.0 / scale_factor);
         float nd = nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nlevels));
         int sum = 0;
         for (int l = 0; l < nlevels - 1; ++l) {
@@ -616,6 +618,7 @@ int orb_detect_and_compute(OrbWorkspace* ws, const uint8_t* h_image, int w, int 
     tm.mark("NMS write + D2H (sync)");
     // per level: retainBest(2 * n_level) by FAST score (HARRIS_SCORE keeps twice as many for the second ranking)
     std::vector<Pt> sel;
+    std::vector<float> sel_resp;      // FAST scores of the selection (the final response under FAST_SCORE)
     std::vector<int> counters((size_t)nlevels, 0);
     {
         size_t pos = 0;
@@ -626,26 +629,26 @@ int orb_detect_and_compute(OrbWorkspace* ws, const uint8_t* h_image, int w, int 
             v.clear();
             const size_t first = pos;
             while (pos < cand.size() && cand[pos].level == l) { v.push_back(Rec{(float)cand[pos].score, (int)(pos - first)}); ++pos; }
-            retain_best(v, 2 * n_per[(size_t)l]);
+            retain_best(v, (score_type == 0 ? 2 : 1) * n_per[(size_t)l]);   // HARRIS_SCORE keeps twice as many for its own ranking
             counters[(size_t)l] = (int)v.size();
-            for (const Rec& r : v) sel.push_back(Pt{cand[first + (size_t)r.id].x, cand[first + (size_t)r.id].y, l});
+            for (const Rec& r : v) { sel.push_back(Pt{cand[first + (size_t)r.id].x, cand[first + (size_t)r.id].y, l}); sel_resp.push_back(r.response); }
         }
     }
     const int nsel = (int)sel.size();
     tm.mark("host retainBest (FAST)");
     if (nsel == 0) { if (needed) *needed = 0; return 0; }
-    // Harris responses of the selected corners, then retainBest(n_level) per level
-    if (!ws->pts.ensure((size_t)nsel * sizeof(Pt)) || !ws->resp.ensure((size_t)nsel * 4)) { fail_ws(ws, "cudaMalloc failed"); return -1; }
-    std::vector<float> resp((size_t)nsel);
-    if (cudaMemcpyAsync(ws->pts.p, sel.data(), (size_t)nsel * sizeof(Pt), cudaMemcpyHostToDevice, st) != cudaSuccess) { fail_ws(ws, "H2D failed"); return -1; }
-    orb_harris_kernel<<<(nsel + 7) / 8, 256, 0, st>>>(T, (const uint8_t*)ws->pyr.p, (const Pt*)ws->pts.p, nsel, (float*)ws->resp.p);
-    ++*launches;
-    if (cudaMemcpyAsync(resp.data(), ws->resp.p, (size_t)nsel * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-        cudaStreamSynchronize(st) != cudaSuccess) { fail_ws(ws, "CUDA error in Harris"); return -1; }
-    tm.mark("Harris + D2H (sync)");
     std::vector<Pt> fin;
     std::vector<float> fin_resp;
-    {
+    if (!ws->pts.ensure((size_t)nsel * sizeof(Pt)) || !ws->resp.ensure((size_t)nsel * 4)) { fail_ws(ws, "cudaMalloc failed"); return -1; }
+    if (score_type == 0) {
+        // Harris responses of the selected corners, then retainBest(n_level) per level
+        std::vector<float> resp((size_t)nsel);
+        if (cudaMemcpyAsync(ws->pts.p, sel.data(), (size_t)nsel * sizeof(Pt), cudaMemcpyHostToDevice, st) != cudaSuccess) { fail_ws(ws, "H2D failed"); return -1; }
+        orb_harris_kernel<<<(nsel + 7) / 8, 256, 0, st>>>(T, (const uint8_t*)ws->pyr.p, (const Pt*)ws->pts.p, nsel, (float*)ws->resp.p);
+        ++*launches;
+        if (cudaMemcpyAsync(resp.data(), ws->resp.p, (size_t)nsel * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) { fail_ws(ws, "CUDA error in Harris"); return -1; }
+        tm.mark("Harris + D2H (sync)");
         size_t offset = 0;
         std::vector<Rec> v;
         for (int l = 0; l < nlevels; ++l) {
@@ -655,6 +658,9 @@ int orb_detect_and_compute(OrbWorkspace* ws, const uint8_t* h_image, int w, int 
             for (const Rec& r : v) { fin.push_back(sel[offset + (size_t)r.id]); fin_resp.push_back(r.response); }
             offset += (size_t)counters[(size_t)l];
         }
+    } else {                                   // FAST_SCORE: the first selection is final
+        fin = sel;
+        fin_resp = sel_resp;
     }
     const int n = (int)fin.size();
     tm.mark("host retainBest (Harris)");

@@ -716,3 +716,28 @@ def test_new_entry_points_report_errors(ctx):
     assert lib.sfmgms_brute_force_match(h, 5, 1, p(q), 4, p(q), 4, 32, 4.0, 500, p(out), p(out), p(d), 4, ctypes.byref(n)) == 1
     assert lib.sfmgms_brute_force_match(h, 6, 0, p(q), 4, p(q), 4, 32, 4.0, 500, p(out), p(out), p(d), 2, ctypes.byref(n)) == 1
     assert lib.sfmgms_brute_force_match(h, 6, 0, p(q), 4, p(q), 4, 32, 4.0, 500, p(out), p(out), p(d), 4, ctypes.byref(n)) == 0 and n.value == 4
+
+
+ORB_PARAM_SETS = [(800, 1.5, 4, 31, 0, 10), (300, 1.1, 12, 19, 0, 20), (700, 1.2, 8, 31, 1, 20), (400, 1.3, 1, 25, 1, 5),
+                  (2000, 2.0, 3, 40, 0, 0)]
+
+
+@pytest.mark.parametrize("i", range(len(ORB_PARAM_SETS)))
+def test_orb_non_default_parameters_golden_cv2(ctx, i):
+    """ORB::create(nfeatures, scaleFactor, nlevels, edgeThreshold, 0, 2, scoreType, 31, fastThreshold): pyramids of 1-12
+    levels, scale factors 1.1-2.0, FAST_SCORE ranking, other border widths -- keypoint list and descriptors equal cv2"""
+    import sfm_gms_b200 as sg
+    from sfm_gms_b200 import SfmGmsError
+
+    g = load_golden("orb_detect")
+    nf, sf, nl, edge, score, thr = ORB_PARAM_SETS[i]
+    orb = sg.ORB_create(nf, sf, nl, edge, 0, 2, score, 31, thr, ctx=ctx)
+    kps, desc = orb.detectAndCompute(g["view0_bgr_img"])
+    ref = g["params%d_kp" % i]
+    got = np.array([(k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave) for k in kps], np.float32).reshape(-1, 6)
+    assert np.array_equal(got, ref) and np.array_equal(desc, g["params%d_desc" % i])
+    if i == 0:
+        for bad in (dict(WTA_K=3), dict(firstLevel=1), dict(patchSize=21), dict(edgeThreshold=5), dict(scaleFactor=1.0),
+                    dict(nlevels=0), dict(scoreType=2)):
+            with pytest.raises(SfmGmsError):                   # refused loudly, never approximated
+                sg.ORB_create(100, ctx=ctx, **bad).detectAndCompute(g["view0_bgr_img"])
