@@ -65,13 +65,26 @@ static_assert(BTILE_BYTES % 1024 == 0 && (kEpiCols == 80 || kEpiCols == 60) && S
 // per two groups, FMA pipe) and the maximum of the 10 keys: its integer part is the best dot product of the part,
 // its fraction names the FIRST group that attains it.  |dot| <= 256 and the fraction has 4 bits: keys are exact
 // in fp32.  Which of the group's 8 train rows is the lowest-index minimum is settled afterwards by
-// hamming_resolve_kernel on the original descriptors (8 candidates per query row instead of n2).
+// hamming_resolve_kernel on the original descriptors (8 candidates per query row instead of n2).  Group size 4
+// (-DSFMGMS_FP4_GROUP=4: 20 tags, half the resolve traffic) measured 3 % slower overall, 16 would double the resolve.
 // This halves the epilogue's instruction count against tagging every column (80 adds -> 10).
-constexpr int kGroup = 8;
+#ifndef SFMGMS_FP4_GROUP
+#define SFMGMS_FP4_GROUP 8
+#endif
+constexpr int kGroup = SFMGMS_FP4_GROUP;                 // 8 (default) or 4 columns per tagged group
+constexpr int kGroupShift = kGroup == 8 ? 3 : 2;
 constexpr int kGroups = kEpiCols / kGroup;
-static_assert(kEpiCols == 80 && kGroups == 10, "group tags below are written for 10 groups of 8");
+constexpr int kTagDen = kGroups <= 16 ? 16 : 32;         // tag of group g = (kTagDen - 1 - g) / kTagDen
+static_assert(kEpiCols == 80 && (kGroup == 8 || kGroup == 4), "group tags below are written for 10 groups of 8 / 20 of 4");
+#if SFMGMS_FP4_GROUP == 8
 __constant__ float2 c_grouptag[kGroups / 2] = {{15.f / 16.f, 14.f / 16.f}, {13.f / 16.f, 12.f / 16.f}, {11.f / 16.f, 10.f / 16.f},
                                                {9.f / 16.f, 8.f / 16.f}, {7.f / 16.f, 6.f / 16.f}};
+#else
+__constant__ float2 c_grouptag[kGroups / 2] = {{31.f / 32.f, 30.f / 32.f}, {29.f / 32.f, 28.f / 32.f}, {27.f / 32.f, 26.f / 32.f},
+                                               {25.f / 32.f, 24.f / 32.f}, {23.f / 32.f, 22.f / 32.f}, {21.f / 32.f, 20.f / 32.f},
+                                               {19.f / 32.f, 18.f / 32.f}, {17.f / 32.f, 16.f / 32.f}, {15.f / 32.f, 14.f / 32.f},
+                                               {13.f / 32.f, 12.f / 32.f}};
+#endif
 
 // (lo, hi) + (c.x, c.y) with one packed fp32x2 add (sm_100: add.rn.f32x2 -> FADD2)
 __device__ __forceinline__ void add2(float lo, float hi, float2 c, float& out_lo, float& out_hi) {
@@ -349,9 +362,13 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 #pragma unroll
                         for (int g = 0; g < kGroups; ++g) {
                             const float* x = v + kGroup * g;
-                            const float a = fmaxf(fmaxf(x[0], x[1]), x[2]);
-                            const float b = fmaxf(fmaxf(x[3], x[4]), x[5]);
-                            gm[g] = fmaxf(fmaxf(fmaxf(x[6], x[7]), a), b);
+                            if constexpr (kGroup == 8) {
+                                const float a = fmaxf(fmaxf(x[0], x[1]), x[2]);
+                                const float b = fmaxf(fmaxf(x[3], x[4]), x[5]);
+                                gm[g] = fmaxf(fmaxf(fmaxf(x[6], x[7]), a), b);
+                            } else {
+                                gm[g] = fmaxf(fmaxf(fmaxf(x[0], x[1]), x[2]), x[3]);
+                            }
                         }
 #pragma unroll
                         for (int k = 0; k < kGroups / 2; ++k) add2(gm[2 * k], gm[2 * k + 1], c_grouptag[k], gm[2 * k], gm[2 * k + 1]);
@@ -372,7 +389,7 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 if (s < nsub && row < wu.n_rows && (best_base[s] >= 0 || dbg)) {
                     // key = dot + (15 - g)/16 : <a,b> = 256 - 2*hamming; idx = first train row of the winning group
                     const float fl = floorf(best_key[s]);
-                    const int g = 15 - (int)((best_key[s] - fl) * 16.0f);
+                    const int g = kTagDen - 1 - (int)((best_key[s] - fl) * (float)kTagDen);
                     const uint32_t dist = dbg ? 7u : (uint32_t)(256 - (int)fl) >> 1;
                     const uint32_t idx = dbg ? 0u : (uint32_t)(best_base[s] + kGroup * g);
                     atomicMin(wu.key + row, (dist << kTrainIdxBits) | idx);
@@ -395,8 +412,8 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 template <bool kVec>   // kVec: every descriptor row is 16-byte aligned (two 128-bit loads per row)
 __global__ void __launch_bounds__(256) hamming_resolve_kernel(const PairDesc* __restrict__ pairs) {
     const PairDesc& pd = pairs[blockIdx.y];
-    const int row = blockIdx.x * 32 + (threadIdx.x >> 3);
-    const int l = threadIdx.x & 7;
+    const int row = blockIdx.x * (256 / kGroup) + (threadIdx.x >> kGroupShift);
+    const int l = threadIdx.x & (kGroup - 1);
     if (pd.n1 <= 0 || pd.n2 <= 0 || row >= pd.n1) return;      // whole 8-lane groups leave together
     const uint32_t key = pd.key[row];
     const int cand = (int)(key & kTrainIdxMask) + l;
@@ -418,11 +435,11 @@ __global__ void __launch_bounds__(256) hamming_resolve_kernel(const PairDesc* __
             for (int w = 0; w < kDescWords; ++w) d += __popc(__ldg(q + w) ^ __ldg(t + w));
         }
     }
-    uint32_t k = (d << 3) | (uint32_t)l;
-    const uint32_t mask = 0xFFu << (threadIdx.x & 24);
+    uint32_t k = (d << kGroupShift) | (uint32_t)l;
+    const uint32_t mask = ((1u << kGroup) - 1u) << (threadIdx.x & 31 & ~(kGroup - 1));
 #pragma unroll
     for (int o = 1; o < kGroup; o <<= 1) k = min(k, __shfl_xor_sync(mask, k, o, kGroup));
-    if (l == 0) pd.key[row] = ((k >> 3) << kTrainIdxBits) | ((key & kTrainIdxMask) + (k & 7u));
+    if (l == 0) pd.key[row] = ((k >> kGroupShift) << kTrainIdxBits) | ((key & kTrainIdxMask) + (k & (uint32_t)(kGroup - 1)));
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -561,7 +578,8 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
     int max_n1 = 0;
     for (int p = 0; p < n_pairs; ++p)
         if (h_pairs[p].n2 > 0 && h_pairs[p].n1 > max_n1) max_n1 = h_pairs[p].n1;
-    const dim3 rgrid((unsigned)((max_n1 + 31) / 32), (unsigned)n_pairs);
+    const int rows_per_block = 256 / kGroup;
+    const dim3 rgrid((unsigned)((max_n1 + rows_per_block - 1) / rows_per_block), (unsigned)n_pairs);
     if (aligned16) hamming_resolve_kernel<true><<<rgrid, 256, 0, st>>>(d_pairs);
     else hamming_resolve_kernel<false><<<rgrid, 256, 0, st>>>(d_pairs);
     return launches + 2;
