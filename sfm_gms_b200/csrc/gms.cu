@@ -376,7 +376,10 @@ size_t gms_match_scratch_bytes(long long n_matches_total, int n_scales) {
 }
 
 // Left-grid rows per shared-memory band for scale s: (rows + 2 halo) * 20 cells * (G_r u16 + one int) must fit.
-static int smem_band_rows(int s) { return s == 0 ? 5 : s == 1 ? 20 : s == 2 ? 10 : s == 3 ? 4 : 1; }
+static int smem_band_rows(int s) {
+    static const int b0 = getenv("SFMGMS_GMS_BAND0") ? atoi(getenv("SFMGMS_GMS_BAND0")) : 5;   // tuning experiments only
+    return s == 0 ? b0 : s == 1 ? 20 : s == 2 ? 10 : s == 3 ? 4 : 1;
+}
 static size_t smem_band_bytes(int s) {
     const int w = right_grid_w(s), gr = w * w, b = smem_band_rows(s);
     const int rows = b >= kGridL ? kGridL : b + 2;
