@@ -151,9 +151,9 @@ int sfmgms_orb_detect_and_compute(sfmgms_ctx* ctx, const uint8_t* image, int wid
                                   int* n_keypoints);
 
 /* The arguments of ORB::create(nfeatures, scaleFactor, nlevels, edgeThreshold, firstLevel, WTA_K, scoreType, patchSize,
- * fastThreshold), in that order.  Implemented: any nfeatures, scaleFactor > 1, nlevels 1..16, edgeThreshold >= 19,
- * scoreType 0 (HARRIS_SCORE) or 1 (FAST_SCORE), any fastThreshold; firstLevel must be 0, WTA_K 2, patchSize 31 (the
- * learned BRIEF pattern exists for that patch only) -- anything else -> SFMGMS_ERR_ARG. */
+ * fastThreshold), in that order.  Implemented: any nfeatures, scaleFactor > 1, nlevels 1..16, edgeThreshold >= 0,
+ * WTA_K 2 / 3 / 4, scoreType 0 (HARRIS_SCORE) or 1 (FAST_SCORE), patchSize 2..63 (31: the learned pattern, else
+ * OpenCV's seeded random pattern), any fastThreshold; firstLevel must be 0 -- anything else -> SFMGMS_ERR_ARG. */
 typedef struct sfmgms_orb_params {
     int nfeatures;        /* 500 */
     float scale_factor;   /* 1.2f */

@@ -270,19 +270,72 @@ def ic_angle(img, x, y, um, half=PATCH // 2):
     return fast_atan2(np.float32(m01), np.float32(m10))
 
 
+class CvRng:
+    """cv::RNG: multiply-with-carry; uniform(a, b) = a + next() % (b - a)."""
+
+    def __init__(self, state):
+        self.state = state if state else 0xFFFFFFFF
+
+    def next(self):
+        self.state = ((self.state & 0xFFFFFFFF) * 4164903690 + (self.state >> 32)) & 0xFFFFFFFFFFFFFFFF
+        return self.state & 0xFFFFFFFF
+
+    def uniform(self, a, b):
+        return a if a == b else int(self.next() % (b - a) + a)
+
+
+def sample_pattern(patch=PATCH, wta_k=2):
+    """The BRIEF sample points of a configuration (orb.cpp): bit_pattern_31_ for patchSize 31, else makeRandomPattern
+    (RNG 0x34985739); WTA_K 3 / 4: initializeOrbPattern draws 128 tuples of distinct points from that pool (RNG 0x12345678)."""
+    if patch == PATCH:
+        pool = PATTERN
+    else:
+        rng = CvRng(0x34985739)
+        pool = np.array([(rng.uniform(-(patch // 2), patch // 2 + 1), rng.uniform(-(patch // 2), patch // 2 + 1))
+                         for _ in range(512)], np.int32)
+    if wta_k == 2:
+        return pool
+    rng = CvRng(0x12345678)
+    pat = np.zeros((128 * wta_k, 2), np.int32)
+    for i in range(128):
+        for k in range(wta_k):
+            while True:
+                pt = pool[rng.uniform(0, 512)]
+                if not any((pat[wta_k * i + k1] == pt).all() for k1 in range(k)):
+                    pat[wta_k * i + k] = pt
+                    break
+    return pat
+
+
+def _pad_reflect101(img, pad):
+    def idx(n):
+        i = np.arange(-pad, n + pad)
+        if n == 1:
+            return np.zeros_like(i)
+        for _ in range(8):
+            i = np.where(i < 0, -i, i)
+            i = np.where(i >= n, 2 * n - 2 - i, i)
+        return i
+    return img[np.ix_(idx(img.shape[0]), idx(img.shape[1]))]
+
+
 def orb_detect_and_compute(image, nfeatures=500, fast_threshold=20, nlevels=N_LEVELS, with_descriptors=True,
-                           scale_factor=1.2, edge_threshold=EDGE_THRESHOLD, score_type=0):
-    """ORB::create(nfeatures, scaleFactor, nlevels, edgeThreshold, 0, 2, scoreType, 31, fastThreshold)
-    .detectAndCompute.  score_type 0 = HARRIS_SCORE, 1 = FAST_SCORE.  edge_threshold >= 19 (every sample inside).
+                           scale_factor=1.2, edge_threshold=EDGE_THRESHOLD, score_type=0, wta_k=2, patch_size=PATCH):
+    """ORB::create(nfeatures, scaleFactor, nlevels, edgeThreshold, 0, WTA_K, scoreType, patchSize, fastThreshold)
+    .detectAndCompute.  score_type 0 = HARRIS_SCORE, 1 = FAST_SCORE.  Reads that leave a level (small edgeThreshold)
+    see what OpenCV's pyramid buffer holds there: the reflect-101 border of the unblurred level.
     -> (kp float64[n, 6] = x, y, size, angle, response, octave  (float32 values), desc uint8[n, 32] or None)"""
     f = np.float32
+    B = 48                                                     # >= ceil(31 * sqrt(2)): the widest excursion of any read
     sf = float(np.float32(scale_factor))                     # create() takes a float, the class keeps a double
     image = np.asarray(image)
     gray = gray_from_bgr(image) if image.ndim == 3 else image
     levels = build_pyramid(gray, nlevels, sf)
     scales = [level_scale(l, sf) for l in range(nlevels)]
     nper = features_per_level(nfeatures, nlevels, sf)
-    um = umax_table()
+    half = patch_size // 2
+    um = umax_table(half)
+    padded = [_pad_reflect101(img, B) for img in levels]
     picked = []
     for l, img in enumerate(levels):
         h, w = img.shape
@@ -293,18 +346,26 @@ def orb_detect_and_compute(image, nfeatures=500, fast_threshold=20, nlevels=N_LE
         picked.append((xs[ids], ys[ids], resp))
     rows = []
     for l, (xs, ys, fast_resp) in enumerate(picked):
+        if len(xs) == 0:
+            continue
         if score_type == 0:
-            resp, ids = retain_best(harris_responses(levels[l], xs, ys), nper[l])
+            resp, ids = retain_best(harris_responses(padded[l], xs + B, ys + B), nper[l])
         else:
             resp, ids = fast_resp, np.arange(len(xs))
         for r, i in zip(resp, ids):
             x, y = int(xs[i]), int(ys[i])
-            rows.append((f(f(x) * scales[l]), f(f(y) * scales[l]), f(f(PATCH) * scales[l]), ic_angle(levels[l], x, y, um), r, l))
+            rows.append((f(f(x) * scales[l]), f(f(y) * scales[l]), f(f(patch_size) * scales[l]),
+                         ic_angle(padded[l], x + B, y + B, um, half), r, l))
     kp = np.array(rows, np.float64).reshape(-1, 6)
     if not with_descriptors or len(rows) == 0:
         return kp, (np.zeros((0, 32), np.uint8) if with_descriptors else None)
-    blurred = [gaussian_blur_7(img) for img in levels]
-    px, py = PATTERN[:, 0].astype(f), PATTERN[:, 1].astype(f)
+    blurred = []
+    for l, img in enumerate(levels):
+        b = padded[l].copy()
+        b[B:-B, B:-B] = gaussian_blur_7(img)                   # only the level itself is blurred, its border is not
+        blurred.append(b)
+    pat = sample_pattern(patch_size, wta_k)
+    px, py = pat[:, 0].astype(f), pat[:, 1].astype(f)
     desc = np.zeros((len(rows), 32), np.uint8)
     for r, (x, y, _, ang, _, l) in enumerate(rows):
         inv = f(1) / scales[l]
@@ -313,6 +374,17 @@ def orb_detect_and_compute(image, nfeatures=500, fast_threshold=20, nlevels=N_LE
         a, b = f(np.cos(np.float64(rad))), f(np.sin(np.float64(rad)))
         ix = np.rint((px * a).astype(f) - (py * b).astype(f)).astype(np.int64)
         iy = np.rint((px * b).astype(f) + (py * a).astype(f)).astype(np.int64)
-        vals = blurred[l][cy + iy, cx + ix].astype(np.int32)
-        desc[r] = np.packbits((vals[0::2] < vals[1::2]).astype(np.uint8).reshape(32, 8)[:, ::-1], axis=1).ravel()
+        v = blurred[l][cy + iy + B, cx + ix + B].astype(np.int32)
+        if wta_k == 2:
+            desc[r] = np.packbits((v[0::2] < v[1::2]).astype(np.uint8).reshape(32, 8)[:, ::-1], axis=1).ravel()
+        elif wta_k == 3:                                       # index of the maximum of 3 (orb.cpp's tie rules)
+            t = v.reshape(32, 4, 3)
+            t0, t1, t2 = t[..., 0], t[..., 1], t[..., 2]
+            k = np.where(t2 > t1, np.where(t2 > t0, 2, 0), (t1 > t0).astype(np.int64))
+            desc[r] = (k[:, 0] | (k[:, 1] << 2) | (k[:, 2] << 4) | (k[:, 3] << 6)).astype(np.uint8)
+        else:                                                  # index of the maximum of 4
+            t = v.reshape(32, 4, 4)
+            t0, t1, t2, t3 = t[..., 0], t[..., 1], t[..., 2], t[..., 3]
+            k = np.where(np.maximum(t0, t1) > np.maximum(t2, t3), (t1 > t0).astype(np.int64), np.where(t3 > t2, 3, 2))
+            desc[r] = (k[:, 0] | (k[:, 1] << 2) | (k[:, 2] << 4) | (k[:, 3] << 6)).astype(np.uint8)
     return kp, desc

@@ -24,12 +24,27 @@ while time.time() - t0 < budget:
         img = cv2.GaussianBlur(img.astype(np.uint8), (5, 5), 1.2)
     img = np.ascontiguousarray(img.astype(np.uint8))
     nf, thr = int(rng.choice([1, 50, 500, 3000, 20000])), int(rng.choice([0, 5, 20, 60]))
-    orb = cv2.ORB_create(nf)
-    orb.setFastThreshold(thr)
-    rk, rd = orb.detectAndCompute(img, None)
+    full = os.environ.get("ORB_STRESS_FULL") is not None       # also randomise the other ORB::create arguments
+    sf = float(rng.choice([1.2, 1.1, 1.5, 2.0])) if full else 1.2
+    nl = int(rng.choice([8, 1, 3, 12])) if full else 8
+    edge = int(rng.choice([31, 0, 3, 7, 19, 40])) if full else 31
+    wta = int(rng.choice([2, 3, 4])) if full else 2
+    score = int(rng.choice([0, 1])) if full else 0
+    patch = int(rng.choice([31, 9, 21, 45, 63])) if full else 31
+    orb = cv2.ORB_create(nf, sf, nl, edge, 0, wta, score, patch, thr)
+    try:
+        rk, rd = orb.detectAndCompute(img, None)
+    except cv2.error:                                          # a pyramid level of size 0: OpenCV asserts, we must refuse too
+        try:
+            ctx.orb_detect_and_compute(img, nf, thr, True, sf, nl, edge, score, 0, wta, patch)
+            bad += 1
+            print("MISMATCH: cv2 raised, the library did not", (sf, nl, w, h), flush=True)
+        except sg.SfmGmsError:
+            pass
+        continue
     ref = np.array([(k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave) for k in rk], np.float32).reshape(-1, 6)
-    kp, desc = ctx.orb_detect_and_compute(img, nf, thr)
-    ok = kp.shape == ref.shape and np.array_equal(kp, ref) and (len(rk) == 0 or np.array_equal(desc, rd))
+    kp, desc = ctx.orb_detect_and_compute(img, nf, thr, True, sf, nl, edge, score, 0, wta, patch)
+    ok = kp.shape == ref.shape and np.array_equal(kp, ref) and (len(rk) == 0 or (rd is not None and np.array_equal(desc, rd)))
     # provided keypoints: random positions / angles / octaves
     n = 400
     pts = np.stack([rng.uniform(0, w, n), rng.uniform(0, h, n)], 1).astype(np.float32)
@@ -44,6 +59,6 @@ while time.time() - t0 < budget:
         bad += 1
         nbits = int(np.unpackbits(desc ^ rd).sum()) if ok is False and desc is not None and rd is not None and desc.shape == rd.shape else -1
         nb2 = int(np.unpackbits(cd ^ d2).sum()) if (ck and cd.shape == d2.shape) else -1
-        print("MISMATCH it=%d %dx%dx%d cell=%d noise=%d nf=%d thr=%d detect_ok=%s (n %d vs %d, bits %d) compute_ok=%s (bits %d)" % (
-            it, w, h, ch, cell, noise, nf, thr, ok, len(kp), len(ref), nbits, ok2, nb2), flush=True)
+        print("MISMATCH it=%d params=%r %dx%dx%d cell=%d noise=%d nf=%d thr=%d detect_ok=%s (n %d vs %d, bits %d) compute_ok=%s (bits %d)" % (
+            it, (sf, nl, edge, wta, score, patch), w, h, ch, cell, noise, nf, thr, ok, len(kp), len(ref), nbits, ok2, nb2), flush=True)
 print("orb stress: %d iterations, %d mismatching in %.0f s" % (it, bad, time.time() - t0))

@@ -762,15 +762,16 @@ int sfmgms_orb_detect_and_compute_ex(sfmgms_ctx* ctx, const uint8_t* image, int 
         return fail(ctx, SFMGMS_ERR_ARG, "bad nfeatures / capacity / fast_threshold");
     if (!(prm->scale_factor > 1.0f) || prm->nlevels < 1 || prm->nlevels > 16)
         return fail(ctx, SFMGMS_ERR_ARG, "scale_factor must be > 1 and nlevels in 1..16");
-    if (prm->first_level != 0 || prm->wta_k != 2 || prm->patch_size != 31 || (prm->score_type != 0 && prm->score_type != 1))
-        return fail(ctx, SFMGMS_ERR_ARG, "implemented: firstLevel 0, WTA_K 2, patchSize 31, scoreType HARRIS_SCORE (0) or FAST_SCORE (1)");
-    if (prm->edge_threshold < 19)
-        return fail(ctx, SFMGMS_ERR_ARG, "edge_threshold %d < 19: patches that leave the level image are not implemented", prm->edge_threshold);
+    if (prm->first_level != 0) return fail(ctx, SFMGMS_ERR_ARG, "firstLevel %d: only 0 is implemented", prm->first_level);
+    if (prm->wta_k < 2 || prm->wta_k > 4 || prm->patch_size < 2 || prm->patch_size > 63 || (prm->score_type != 0 && prm->score_type != 1) ||
+        prm->edge_threshold < 0)
+        return fail(ctx, SFMGMS_ERR_ARG, "need WTA_K in 2..4, patchSize in 2..63, scoreType 0 (HARRIS_SCORE) or 1 (FAST_SCORE), edgeThreshold >= 0");
     cudaStream_t st = ctx->stream;
     if (ctx->timing) CU(cudaEventRecord(ctx->ev[0], st));
     int nl = 0, needed = 0;
     const int got = orb_detect_and_compute(ctx->orb, image, width, height, channels, stride_bytes, prm->nfeatures, prm->fast_threshold,
-                                           prm->nlevels, prm->scale_factor, prm->edge_threshold, prm->score_type, keypoints, descriptors,
+                                           prm->nlevels, prm->scale_factor, prm->edge_threshold, prm->score_type, prm->wta_k, prm->patch_size,
+                                           keypoints, descriptors,
                                            capacity, &needed, ctx->sm_count, st, &nl);
     ctx->launches += nl;
     if (got == -2) { if (n_keypoints) *n_keypoints = needed; return fail(ctx, SFMGMS_ERR_ARG, "capacity %d < %d keypoints", capacity, needed); }

@@ -76,8 +76,8 @@ const char* orb_ws_error(const OrbWorkspace* w);
 int orb_compute_provided(OrbWorkspace* ws, const uint8_t* h_image, int w, int h, int channels, int stride, const float* h_xyao,
                          int n, int nlevels, uint8_t* h_desc, int sm_count, cudaStream_t st, int* launches);
 int orb_detect_and_compute(OrbWorkspace* ws, const uint8_t* h_image, int w, int h, int channels, int stride, int nfeatures,
-                           int fast_threshold, int nlevels, float scale_factor, int edge, int score_type, void* h_kp,
-                           uint8_t* h_desc, int capacity, int* needed, int sm_count, cudaStream_t st, int* launches);
+                           int fast_threshold, int nlevels, float scale_factor, int edge, int score_type, int wta_k, int patch,
+                           void* h_kp, uint8_t* h_desc, int capacity, int* needed, int sm_count, cudaStream_t st, int* launches);
 // order-exact fp32 kernel for general float descriptors, l2_f32.cu (dim in [1, l2_f32_max_dim()])
 size_t l2_f32_scratch_bytes(int nq);
 int l2_f32_max_dim();

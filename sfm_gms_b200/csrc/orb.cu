@@ -32,8 +32,7 @@ namespace sfmgms {
 namespace {
 
 constexpr int kMaxLevels = 16;
-constexpr int kPatch = 31;           // patchSize
-constexpr int kHalfPatch = 15;
+constexpr int kMaxHalfPatch = 31;    // patchSize <= 63 (ORB::create default 31)
 
 struct Level {
     long long off;   // byte offset of the level image in the pyramid buffers (dense rows, stride = w)
@@ -49,11 +48,28 @@ struct LevelTable {
     int edge;        // edgeThreshold (ORB::create default 31)
 };
 
-__constant__ signed char c_pattern[512][2] = {
+// bit_pattern_31_: the learned test pairs for patchSize 31 (host copy; the device reads the pattern of the current
+// configuration from the workspace)
+const signed char h_pattern31[512][2] = {
 #include "orb_pattern.inc"
 };
-// end of each row of the radius-15 disc (orb.cpp: umax)
-__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+struct OrbCfg {      // per-call configuration of the keypoint kernels
+    int patch, half;                  // patchSize, patchSize / 2
+    int umax[kMaxHalfPatch + 2];      // end of each row of the radius-`half` disc (orb.cpp: umax)
+};
+
+__device__ __forceinline__ int reflect101(int i, int n) {   // BORDER_REFLECT_101
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+    return i;
+}
+// pixel of a level image; outside the image: what OpenCV's pyramid buffer holds there (reflect-101 border)
+template <bool kInside>
+__device__ __forceinline__ int pix(const uint8_t* img, int w, int h, int x, int y) {
+    if (kInside) return img[(size_t)y * w + x];
+    return img[(size_t)reflect101(y, h) * w + reflect101(x, w)];
+}
 
 __device__ __forceinline__ int level_of_row(const LevelTable& T, int row) {
     int l = 0;
@@ -207,20 +223,29 @@ __global__ void __launch_bounds__(256) orb_nms_write_kernel(LevelTable T, const 
 struct Pt { int x, y, level; };
 
 // HarrisResponses (orb.cpp), blockSize 7, k = 0.04f: one warp per keypoint
+template <bool kInside>
+__device__ __forceinline__ void harris_sums(const uint8_t* img, int w, int h, int px0, int py0, int lane, int& a, int& b, int& c) {
+    for (int k = lane; k < 49; k += 32) {
+        const int x = px0 - 3 + k % 7, y = py0 - 3 + k / 7;
+        const int nw = pix<kInside>(img, w, h, x - 1, y - 1), nn = pix<kInside>(img, w, h, x, y - 1), ne = pix<kInside>(img, w, h, x + 1, y - 1);
+        const int ww = pix<kInside>(img, w, h, x - 1, y), ee = pix<kInside>(img, w, h, x + 1, y);
+        const int sw = pix<kInside>(img, w, h, x - 1, y + 1), ss = pix<kInside>(img, w, h, x, y + 1), se = pix<kInside>(img, w, h, x + 1, y + 1);
+        const int Ix = (ee - ww) * 2 + (ne - nw) + (se - sw);
+        const int Iy = (ss - nn) * 2 + (sw - nw) + (se - ne);
+        a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
+    }
+}
+
 __global__ void __launch_bounds__(256) orb_harris_kernel(LevelTable T, const uint8_t* __restrict__ pyr, const Pt* __restrict__ pts,
                                                          int n, float* __restrict__ resp) {
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n) return;
     const Pt p = pts[i];
-    const int w = T.l[p.level].w;
+    const int w = T.l[p.level].w, h = T.l[p.level].h;
     const uint8_t* img = pyr + T.l[p.level].off;
     int a = 0, b = 0, c = 0;
-    for (int k = lane; k < 49; k += 32) {
-        const uint8_t* q = img + (size_t)(p.y - 3 + k / 7) * w + (p.x - 3 + k % 7);
-        const int Ix = (q[1] - q[-1]) * 2 + (q[-w + 1] - q[-w - 1]) + (q[w + 1] - q[w - 1]);
-        const int Iy = (q[w] - q[-w]) * 2 + (q[w - 1] - q[-w - 1]) + (q[w + 1] - q[-w + 1]);
-        a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
-    }
+    if (p.x >= 4 && p.x < w - 4 && p.y >= 4 && p.y < h - 4) harris_sums<true>(img, w, h, p.x, p.y, lane, a, b, c);
+    else harris_sums<false>(img, w, h, p.x, p.y, lane, a, b, c);      // edgeThreshold < 4: the block leaves the level
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -263,36 +288,42 @@ struct OrbKp {      // prepared keypoint for the descriptor kernel
 };
 
 // ICAngles + the final scaling of computeKeyPoints; also prepares the descriptor centre exactly as
-// computeOrbDescriptors recomputes it from the scaled point.  16 lanes per keypoint (one disc row pair each).
-__global__ void __launch_bounds__(256) orb_angle_kernel(LevelTable T, const uint8_t* __restrict__ pyr, const Pt* __restrict__ pts,
-                                                        const float* __restrict__ resp, int n, KpOut* __restrict__ out,
-                                                        OrbKp* __restrict__ prep) {
-    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, v = threadIdx.x & 15;
-    const bool valid = i < n;                 // both 16-lane halves of a warp stay in the shuffles below
-    const Pt p = pts[valid ? i : n - 1];
-    const int w = T.l[p.level].w;
-    const uint8_t* c = pyr + T.l[p.level].off + (size_t)p.y * w + p.x;
-    int m10 = 0, m01 = 0;
+// computeOrbDescriptors recomputes it from the scaled point.  One warp per keypoint, lane v = disc rows +-v.
+template <bool kInside>
+__device__ __forceinline__ void ic_moments(const uint8_t* img, int w, int h, int x0, int y0, int v, const OrbCfg& cfg, int& m10, int& m01) {
     if (v == 0) {
-        for (int u = -kHalfPatch; u <= kHalfPatch; ++u) m10 += u * c[u];
-    } else {
-        const int d = c_umax[v];
+        for (int u = -cfg.half; u <= cfg.half; ++u) m10 += u * pix<kInside>(img, w, h, x0 + u, y0);
+    } else if (v <= cfg.half) {
+        const int d = cfg.umax[v];
         int vs = 0;
         for (int u = -d; u <= d; ++u) {
-            const int plus = c[u + v * w], minus = c[u - v * w];
+            const int plus = pix<kInside>(img, w, h, x0 + u, y0 + v), minus = pix<kInside>(img, w, h, x0 + u, y0 - v);
             vs += plus - minus;
             m10 += u * (plus + minus);
         }
         m01 = v * vs;
     }
+}
+
+__global__ void __launch_bounds__(256) orb_angle_kernel(LevelTable T, OrbCfg cfg, const uint8_t* __restrict__ pyr,
+                                                        const Pt* __restrict__ pts, const float* __restrict__ resp, int n,
+                                                        KpOut* __restrict__ out, OrbKp* __restrict__ prep) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, v = threadIdx.x & 31;
+    if (i >= n) return;                        // whole warps leave together
+    const Pt p = pts[i];
+    const int w = T.l[p.level].w, h = T.l[p.level].h;
+    const uint8_t* img = pyr + T.l[p.level].off;
+    int m10 = 0, m01 = 0;
+    if (p.x >= cfg.half && p.x < w - cfg.half && p.y >= cfg.half && p.y < h - cfg.half) ic_moments<true>(img, w, h, p.x, p.y, v, cfg, m10, m01);
+    else ic_moments<false>(img, w, h, p.x, p.y, v, cfg, m10, m01);      // small edgeThreshold: the disc leaves the level
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o, 16); m01 += __shfl_xor_sync(0xffffffffu, m01, o, 16); }
-    if (v == 0 && valid) {
+    for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
+    if (v == 0) {
         const float sc = T.l[p.level].scale;
         KpOut k;
         k.x = __fmul_rn((float)p.x, sc);
         k.y = __fmul_rn((float)p.y, sc);
-        k.size = __fmul_rn((float)kPatch, sc);
+        k.size = __fmul_rn((float)cfg.patch, sc);
         k.angle = fast_atan2_deg((float)m01, (float)m10);
         k.response = resp[i];
         k.octave = p.level;
@@ -324,12 +355,6 @@ __global__ void orb_prepare_kernel(LevelTable T, const float* __restrict__ xyao,
     k.a = (float)cos((double)rad);
     k.b = (float)sin((double)rad);
     out[i] = k;
-}
-
-__device__ __forceinline__ int reflect101(int i, int n) {   // BORDER_REFLECT_101
-    if (n == 1) return 0;
-    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
-    return i;
 }
 
 constexpr int BW = 32, BH = 16, R = 3;
@@ -374,23 +399,26 @@ __global__ void __launch_bounds__(BW * BH) orb_blur_kernel(const uint8_t* __rest
     }
 }
 
-// one warp per keypoint (grid-stride); lane = descriptor byte, its 16 pattern points stay in registers.
-// A sample outside the level image (possible only for caller-provided keypoints on coarse levels) reads what OpenCV's
-// pyramid holds there: the reflect-101 border of the UNBLURRED level.
-__global__ void __launch_bounds__(256) orb_desc_kernel(LevelTable T, const uint8_t* __restrict__ blur, const uint8_t* __restrict__ raw,
-                                                       const OrbKp* __restrict__ kps, int n, uint8_t* __restrict__ desc) {
+// one warp per keypoint (grid-stride); lane = descriptor byte, its pattern points (16 for WTA_K 2 and 4, 12 for
+// WTA_K 3) stay in registers.  A sample outside the level image (small edgeThreshold, or caller-provided keypoints on
+// coarse levels) reads what OpenCV's pyramid holds there: the reflect-101 border of the UNBLURRED level.
+template <int kWta>
+__global__ void __launch_bounds__(256) orb_desc_kernel(LevelTable T, const signed char* __restrict__ pattern, const uint8_t* __restrict__ blur,
+                                                       const uint8_t* __restrict__ raw, const OrbKp* __restrict__ kps, int n,
+                                                       uint8_t* __restrict__ desc) {
+    constexpr int kPts = kWta == 3 ? 12 : 16;
     const int lane = threadIdx.x & 31;
-    float px[16], py[16];
+    float px[kPts], py[kPts];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { px[j] = (float)c_pattern[16 * lane + j][0]; py[j] = (float)c_pattern[16 * lane + j][1]; }
+    for (int j = 0; j < kPts; ++j) { px[j] = (float)pattern[2 * (kPts * lane + j)]; py[j] = (float)pattern[2 * (kPts * lane + j) + 1]; }
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
         const OrbKp k = kps[i];
         const int w = T.l[k.level].w, h = T.l[k.level].h;
         const uint8_t* img = blur + T.l[k.level].off;
-        int v[16];
+        int v[kPts];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < kPts; ++j) {
             const float x = __fsub_rn(__fmul_rn(px[j], k.a), __fmul_rn(py[j], k.b));
             const float y = __fadd_rn(__fmul_rn(px[j], k.b), __fmul_rn(py[j], k.a));
             const int xx = k.cx + __float2int_rn(x), yy = k.cy + __float2int_rn(y);
@@ -398,8 +426,26 @@ __global__ void __launch_bounds__(256) orb_desc_kernel(LevelTable T, const uint8
             else v[j] = raw[T.l[k.level].off + (size_t)reflect101(yy, h) * w + reflect101(xx, w)];
         }
         unsigned val = 0;
+        if (kWta == 2) {
 #pragma unroll
-        for (int b = 0; b < 8; ++b) val |= (unsigned)(v[2 * b] < v[2 * b + 1]) << b;
+            for (int b = 0; b < 8; ++b) val |= (unsigned)(v[2 * b] < v[2 * b + 1]) << b;
+        } else if (kWta == 3) {              // index of the maximum of 3, ties as orb.cpp resolves them
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int t0 = v[3 * g], t1 = v[3 * g + 1], t2 = v[3 * g + 2];
+                val |= (unsigned)(t2 > t1 ? (t2 > t0 ? 2 : 0) : (t1 > t0 ? 1 : 0)) << (2 * g);
+            }
+        } else {                             // index of the maximum of 4
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                int t0 = v[4 * g], t2 = v[4 * g + 2];
+                const int t1 = v[4 * g + 1], t3 = v[4 * g + 3];
+                int u = 0, vv = 2;
+                if (t1 > t0) { t0 = t1; u = 1; }
+                if (t3 > t2) { t2 = t3; vv = 3; }
+                val |= (unsigned)(t0 > t2 ? u : vv) << (2 * g);
+            }
+        }
         desc[(size_t)i * 32 + lane] = (uint8_t)val;
     }
 }
@@ -460,8 +506,9 @@ struct StageTimer {
 };
 
 struct OrbWorkspace {
-    Buf img, pyr, blur, score, rowcnt, rowoff, cand, pts, resp, kpout, prep, desc, coef, xyao;
+    Buf img, pyr, blur, score, rowcnt, rowoff, cand, pts, resp, kpout, prep, desc, coef, xyao, pattern;
     LevelTable T;
+    int pattern_patch = 0, pattern_wta = 0;     // configuration the device pattern was built for
     char err[256] = "";
 };
 
@@ -541,12 +588,82 @@ void blur_levels(OrbWorkspace* ws, cudaStream_t st, int* launches) {
     }
 }
 
-bool describe(OrbWorkspace* ws, int n, uint8_t* h_desc, int sm_count, cudaStream_t st, int* launches) {
+// cv::RNG (core/operations.hpp): multiply-with-carry generator; uniform(a, b) = a + next() % (b - a)
+struct CvRng {
+    unsigned long long state;
+    explicit CvRng(unsigned long long s) : state(s ? s : 0xffffffffull) {}
+    unsigned next() { state = (unsigned long long)(unsigned)state * 4164903690ull + (unsigned)(state >> 32); return (unsigned)state; }
+    int uniform(int a, int b) { return a == b ? a : (int)(next() % (unsigned)(b - a) + a); }
+};
+
+// the sample pattern of a configuration, as orb.cpp builds it: bit_pattern_31_ for patchSize 31, else
+// makeRandomPattern (RNG 0x34985739); for WTA_K 3 / 4 initializeOrbPattern draws 128 tuples of distinct points from
+// that pool (RNG 0x12345678)
+bool upload_pattern(OrbWorkspace* ws, int patch, int wta, cudaStream_t st) {
+    if (ws->pattern.p && ws->pattern_patch == patch && ws->pattern_wta == wta) return true;
+    signed char pool[512][2];
+    if (patch == 31) {
+        memcpy(pool, h_pattern31, sizeof pool);
+    } else {
+        CvRng rng(0x34985739ull);
+        for (int i = 0; i < 512; ++i) {
+            pool[i][0] = (signed char)rng.uniform(-patch / 2, patch / 2 + 1);
+            pool[i][1] = (signed char)rng.uniform(-patch / 2, patch / 2 + 1);
+        }
+    }
+    signed char pat[512][2];
+    int npts = 512;
+    if (wta == 2) {
+        memcpy(pat, pool, sizeof pat);
+    } else {
+        CvRng rng(0x12345678ull);
+        const int ntuples = 32 * 4;
+        npts = ntuples * wta;
+        for (int i = 0; i < ntuples; ++i)
+            for (int k = 0; k < wta; ++k)
+                for (;;) {
+                    const int idx = rng.uniform(0, 512);
+                    int k1 = 0;
+                    for (; k1 < k; ++k1)
+                        if (pat[wta * i + k1][0] == pool[idx][0] && pat[wta * i + k1][1] == pool[idx][1]) break;
+                    if (k1 == k) { pat[wta * i + k][0] = pool[idx][0]; pat[wta * i + k][1] = pool[idx][1]; break; }
+                }
+    }
+    if (!ws->pattern.ensure(sizeof pat)) return fail_ws(ws, "cudaMalloc failed (pattern)");
+    if (cudaMemcpyAsync(ws->pattern.p, pat, (size_t)npts * 2, cudaMemcpyHostToDevice, st) != cudaSuccess) return fail_ws(ws, "H2D failed");
+    ws->pattern_patch = patch; ws->pattern_wta = wta;
+    return true;
+}
+
+// umax (orb.cpp computeKeyPoints): row ends of the radius-`half` disc, made symmetric
+void make_cfg(int patch, OrbCfg& cfg) {
+    cfg.patch = patch;
+    const int half = patch / 2;
+    cfg.half = half;
+    for (int& u : cfg.umax) u = 0;
+    const int vmax = (int)std::floor(half * std::sqrt(2.f) / 2 + 1);
+    const int vmin = (int)std::ceil(half * std::sqrt(2.f) / 2);
+    for (int v = 0; v <= vmax; ++v) cfg.umax[v] = (int)std::nearbyint(std::sqrt((double)half * half - (double)v * v));
+    for (int v = half, v0 = 0; v >= vmin; --v) {
+        while (cfg.umax[v0] == cfg.umax[v0 + 1]) ++v0;
+        cfg.umax[v] = v0;
+        ++v0;
+    }
+}
+
+bool describe(OrbWorkspace* ws, int n, int patch, int wta, uint8_t* h_desc, int sm_count, cudaStream_t st, int* launches) {
     if (!ws->desc.ensure((size_t)n * 32)) return fail_ws(ws, "cudaMalloc failed (descriptors)");
+    if (!upload_pattern(ws, patch, wta, st)) return false;
     long long blocks = ((long long)n + 7) / 8;
     if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
-    orb_desc_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws->T, (const uint8_t*)ws->blur.p, (const uint8_t*)ws->pyr.p,
-                                                      (const OrbKp*)ws->prep.p, n, (uint8_t*)ws->desc.p);
+    const signed char* pat = (const signed char*)ws->pattern.p;
+    const uint8_t* blur = (const uint8_t*)ws->blur.p;
+    const uint8_t* raw = (const uint8_t*)ws->pyr.p;
+    const OrbKp* prep = (const OrbKp*)ws->prep.p;
+    uint8_t* d = (uint8_t*)ws->desc.p;
+    if (wta == 2) orb_desc_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(ws->T, pat, blur, raw, prep, n, d);
+    else if (wta == 3) orb_desc_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(ws->T, pat, blur, raw, prep, n, d);
+    else orb_desc_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(ws->T, pat, blur, raw, prep, n, d);
     ++*launches;
     if (h_desc && cudaMemcpyAsync(h_desc, ws->desc.p, (size_t)n * 32, cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail_ws(ws, "D2H failed");
     return true;
@@ -565,7 +682,7 @@ int orb_compute_provided(OrbWorkspace* ws, const uint8_t* h_image, int w, int h,
     if (cudaMemcpyAsync(ws->xyao.p, h_xyao, (size_t)n * 16, cudaMemcpyHostToDevice, st) != cudaSuccess) { fail_ws(ws, "H2D failed"); return -1; }
     orb_prepare_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws->T, (const float*)ws->xyao.p, n, (OrbKp*)ws->prep.p);
     ++*launches;
-    if (!describe(ws, n, h_desc, sm_count, st, launches)) return -1;
+    if (!describe(ws, n, 31, 2, h_desc, sm_count, st, launches)) return -1;
     if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { fail_ws(ws, "CUDA error in ORB compute"); return -1; }
     return n;
 }
@@ -574,8 +691,11 @@ int orb_compute_provided(OrbWorkspace* ws, const uint8_t* h_image, int w, int h,
 // h_kp: capacity records in cv::KeyPoint layout (28 B); h_desc: capacity x 32.  Returns the number of keypoints,
 // -1 on error, -2 when capacity is too small (*needed is set).
 int orb_detect_and_compute(OrbWorkspace* ws, const uint8_t* h_image, int w, int h, int channels, int stride, int nfeatures,
-                           int fast_threshold, int nlevels, float scale_factor_f, int edge, int score_type, void* h_kp,
-                           uint8_t* h_desc, int capacity, int* needed, int sm_count, cudaStream_t st, int* launches) {
+                           int fast_threshold, int nlevels, float scale_factor_f, int edge, int score_type, int wta_k, int patch,
+                           void* h_kp, uint8_t* h_desc, int capacity, int* needed, int sm_count, cudaStream_t st, int* launches) {
+    if (patch < 2 || patch > 2 * kMaxHalfPatch + 1 || wta_k < 2 || wta_k > 4) { fail_ws(ws, "patchSize (2..63) / WTA_K (2..4) out of range"); return -1; }
+    OrbCfg cfg;
+    make_cfg(patch, cfg);
     const double scale_factor = (double)scale_factor_f;     // ORB::create takes a float, the class keeps a double
     if (nlevels < 1 || nlevels > kMaxLevels) { fail_ws(ws, "nlevels out of range (1..16)"); return -1; }
     StageTimer tm;
@@ -671,13 +791,13 @@ int orb_detect_and_compute(OrbWorkspace* ws, const uint8_t* h_image, int w, int 
     if (!ws->kpout.ensure((size_t)n * sizeof(KpOut)) || !ws->prep.ensure((size_t)n * sizeof(OrbKp))) { fail_ws(ws, "cudaMalloc failed"); return -1; }
     if (cudaMemcpyAsync(ws->pts.p, fin.data(), (size_t)n * sizeof(Pt), cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(ws->resp.p, fin_resp.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { fail_ws(ws, "H2D failed"); return -1; }
-    orb_angle_kernel<<<(n + 15) / 16, 256, 0, st>>>(T, (const uint8_t*)ws->pyr.p, (const Pt*)ws->pts.p, (const float*)ws->resp.p, n,
+    orb_angle_kernel<<<(n + 7) / 8, 256, 0, st>>>(T, cfg, (const uint8_t*)ws->pyr.p, (const Pt*)ws->pts.p, (const float*)ws->resp.p, n,
                                                     (KpOut*)ws->kpout.p, (OrbKp*)ws->prep.p);
     ++*launches;
     if (h_kp && cudaMemcpyAsync(h_kp, ws->kpout.p, (size_t)n * sizeof(KpOut), cudaMemcpyDeviceToHost, st) != cudaSuccess) { fail_ws(ws, "D2H failed"); return -1; }
     if (h_desc) {
         blur_levels(ws, st, launches);
-        if (!describe(ws, n, h_desc, sm_count, st, launches)) return -1;
+        if (!describe(ws, n, patch, wta_k, h_desc, sm_count, st, launches)) return -1;
     }
     if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { fail_ws(ws, "CUDA error in ORB"); return -1; }
     tm.mark("angle + blur + BRIEF + D2H");

@@ -719,25 +719,28 @@ def test_new_entry_points_report_errors(ctx):
 
 
 ORB_PARAM_SETS = [(800, 1.5, 4, 31, 0, 10), (300, 1.1, 12, 19, 0, 20), (700, 1.2, 8, 31, 1, 20), (400, 1.3, 1, 25, 1, 5),
-                  (2000, 2.0, 3, 40, 0, 0)]
+                  (2000, 2.0, 3, 40, 0, 0), (500, 1.2, 8, 31, 0, 20, 3, 31), (500, 1.2, 8, 31, 0, 20, 4, 31), (600, 1.2, 6, 31, 0, 10, 2, 21),
+                  (600, 1.3, 5, 25, 1, 10, 3, 41), (800, 1.2, 8, 5, 0, 20, 2, 31), (800, 1.2, 4, 0, 0, 5, 4, 15), (300, 1.2, 8, 12, 0, 20, 2, 31)]
 
 
 @pytest.mark.parametrize("i", range(len(ORB_PARAM_SETS)))
 def test_orb_non_default_parameters_golden_cv2(ctx, i):
-    """ORB::create(nfeatures, scaleFactor, nlevels, edgeThreshold, 0, 2, scoreType, 31, fastThreshold): pyramids of 1-12
-    levels, scale factors 1.1-2.0, FAST_SCORE ranking, other border widths -- keypoint list and descriptors equal cv2"""
+    """ORB::create(nfeatures, scaleFactor, nlevels, edgeThreshold, 0, WTA_K, scoreType, patchSize, fastThreshold):
+    pyramids of 1-12 levels, scale factors 1.1-2.0, FAST_SCORE ranking, border widths 0-40 (reads that leave the
+    level), WTA_K 3 and 4, random patterns for other patch sizes -- keypoint list and descriptors equal cv2"""
     import sfm_gms_b200 as sg
     from sfm_gms_b200 import SfmGmsError
 
     g = load_golden("orb_detect")
-    nf, sf, nl, edge, score, thr = ORB_PARAM_SETS[i]
-    orb = sg.ORB_create(nf, sf, nl, edge, 0, 2, score, 31, thr, ctx=ctx)
+    nf, sf, nl, edge, score, thr = ORB_PARAM_SETS[i][:6]
+    wta, patch = ORB_PARAM_SETS[i][6:] if len(ORB_PARAM_SETS[i]) > 6 else (2, 31)
+    orb = sg.ORB_create(nf, sf, nl, edge, 0, wta, score, patch, thr, ctx=ctx)
     kps, desc = orb.detectAndCompute(g["view0_bgr_img"])
     ref = g["params%d_kp" % i]
     got = np.array([(k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave) for k in kps], np.float32).reshape(-1, 6)
     assert np.array_equal(got, ref) and np.array_equal(desc, g["params%d_desc" % i])
     if i == 0:
-        for bad in (dict(WTA_K=3), dict(firstLevel=1), dict(patchSize=21), dict(edgeThreshold=5), dict(scaleFactor=1.0),
+        for bad in (dict(WTA_K=5), dict(firstLevel=1), dict(patchSize=64), dict(edgeThreshold=-1), dict(scaleFactor=1.0),
                     dict(nlevels=0), dict(scoreType=2)):
             with pytest.raises(SfmGmsError):                   # refused loudly, never approximated
                 sg.ORB_create(100, ctx=ctx, **bad).detectAndCompute(g["view0_bgr_img"])
