@@ -385,8 +385,10 @@ int oracle_bf_hamming_crosscheck(const uint8_t* q, int nq, const uint8_t* t, int
  * 4.13 (x86-64 AVX2 dispatch of imgproc filter.simd.hpp: RowVec_32f / SymmColumnVec_32f): float taps
  * k = (float)getGaussianKernel(7, 2); row pass sequential, s = x0*k0 then s = fma(x_i, k_i, s) in the first
  * 32*floor(w/32) columns (the vector loop) and s = s + x_i*k_i with two roundings in the remaining columns (its scalar
- * remainder); column pass symmetric with FMA, s = r3*k3, s = fma(r[3-d] + r[3+d], k[3-d], s) for d = 1..3; result
- * rounded half to even.  Evidence: descriptor bits of cv2.ORB on 7 full-size images x 20,000 keypoints and a
+ * remainder); column pass symmetric, s = r3*k3, s = fma(r[3-d] + r[3+d], k[3-d], s) for d = 1..3 (two roundings
+ * instead of the fma in the last w mod 4 columns, the column filter's scalar tail -- thin evidence: two events of the
+ * randomised stress with edgeThreshold 0 and the float-source filter's visible tail; only reachable with
+ * edgeThreshold < 13); result rounded half to even.  Evidence: descriptor bits of cv2.ORB on 7 full-size images x 20,000 keypoints and a
  * randomised live-cv2 stress (scripts/orb_stress.py: 0 mismatches in 14,714 trials); the float-source variant of the
  * same filter is visible directly through cv2.GaussianBlur(float32).  The loop width was settled on 319 images whose
  * blurred pyramids differ between a 32- and a 64-column vector loop: 32 columns 0 differing descriptor bits, 64
@@ -418,7 +420,8 @@ int oracle_orb_blur7(const uint8_t* src, int w, int h, uint8_t* dst) {
             float s = rows[(size_t)y * w + x] * k[3];
             for (int d = 1; d <= 3; ++d) {
                 float pair = rows[(size_t)reflect101(y - d, h) * w + x] + rows[(size_t)reflect101(y + d, h) * w + x];
-                s = fmaf(pair, k[3 - d], s);
+                if (x < (w & ~3)) s = fmaf(pair, k[3 - d], s);          /* vector loops of the column filter (8, 4 lanes) */
+                else { float m = pair * k[3 - d]; s = s + m; }          /* its scalar tail: two roundings */
             }
             float r = nearbyintf(s);
             dst[(size_t)y * w + x] = (uint8_t)(r < 0.f ? 0.f : (r > 255.f ? 255.f : r));

@@ -362,7 +362,8 @@ constexpr int BW = 32, BH = 16, R = 3;
 // 7x7 sigma-2 Gaussian of one level, exactly as OpenCV's float separable filter evaluates it for ORB (the pyramid
 // sub-matrix does not take the 8-bit fixed-point path): float taps (float)getGaussianKernel(7, 2); row pass
 // s = x0*k0, s = fma(x_i, k_i, s) in the first 32*floor(w/32) columns and s = s + x_i*k_i (two roundings) in the
-// rest; column pass s = r3*k3, s = fma(r[3-d] + r[3+d], k[3-d], s); round half to even.
+// rest; column pass s = r3*k3, s = fma(r[3-d] + r[3+d], k[3-d], s) (two roundings in the last w mod 4 columns);
+// round half to even.
 __global__ void __launch_bounds__(BW * BH) orb_blur_kernel(const uint8_t* __restrict__ src, int w, int h, uint8_t* __restrict__ dst) {
     __shared__ uint8_t tile[BH + 2 * R][BW + 2 * R];
     __shared__ float rows[BH + 2 * R][BW];
@@ -391,9 +392,15 @@ __global__ void __launch_bounds__(BW * BH) orb_blur_kernel(const uint8_t* __rest
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if (x < w && y < h) {
         float s = __fmul_rn(rows[threadIdx.y + 3][threadIdx.x], k[3]);
+        if (x < (w & ~3)) {              // the vector loops of the column filter (8 and 4 lanes): fused
 #pragma unroll
-        for (int d = 1; d <= 3; ++d)
-            s = __fmaf_rn(__fadd_rn(rows[threadIdx.y + 3 - d][threadIdx.x], rows[threadIdx.y + 3 + d][threadIdx.x]), k[3 - d], s);
+            for (int d = 1; d <= 3; ++d)
+                s = __fmaf_rn(__fadd_rn(rows[threadIdx.y + 3 - d][threadIdx.x], rows[threadIdx.y + 3 + d][threadIdx.x]), k[3 - d], s);
+        } else {                         // its scalar tail (last w mod 4 columns): two roundings
+#pragma unroll
+            for (int d = 1; d <= 3; ++d)
+                s = __fadd_rn(s, __fmul_rn(__fadd_rn(rows[threadIdx.y + 3 - d][threadIdx.x], rows[threadIdx.y + 3 + d][threadIdx.x]), k[3 - d]));
+        }
         const float r = rintf(s);                              // half to even, as saturate_cast<uchar>(float)
         dst[(size_t)y * w + x] = (uint8_t)(r < 0.f ? 0.f : (r > 255.f ? 255.f : r));
     }
