@@ -7,7 +7,7 @@ arithmetic lives in OpenCV features2d `orb.cpp` (un-vendored dependency, 4.5.x i
   detectAndCompute(image, noArray(), keypoints, descriptors, useProvidedKeypoints=true)
     1. non-gray input -> cvtColor(BGR2GRAY): (B*3735 + G*19235 + R*9798 + 2^14) >> 15
     2. level 0 of the pyramid = the image with a reflect-101 border (keypoints with octave 0 use no other level)
-    3. KeyPointsFilter::runByImageBorder(kp, size, edgeThreshold=31): keep 31 <= cvRound(x) < w-31, same for y
+    3. KeyPointsFilter::runByImageBorder(kp, size, edgeThreshold): keep edge <= cvRound(x) < w-edge, same for y
     4. GaussianBlur(level, 7x7, sigma 2, BORDER_REFLECT_101) -- on the pyramid SUB-matrix, which OpenCV does not send
        to its fixed-point 8-bit kernel but to the float separable filter: float32 taps, row pass sequential (FMA in
        the 32-pixel vector loop, two roundings in its scalar remainder), column pass symmetric with FMA, rounded half
