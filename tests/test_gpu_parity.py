@@ -744,3 +744,18 @@ def test_orb_non_default_parameters_golden_cv2(ctx, i):
                     dict(nlevels=0), dict(scoreType=2)):
             with pytest.raises(SfmGmsError):                   # refused loudly, never approximated
                 sg.ORB_create(100, ctx=ctx, **bad).detectAndCompute(g["view0_bgr_img"])
+
+
+def test_device_descriptors_must_be_16_byte_aligned(ctx):
+    """caller-owned DEVICE arrays: the documented alignment (16 bytes for descriptors) is enforced, not assumed"""
+    torch = pytest.importorskip("torch")
+    from sfm_gms_b200 import SfmGmsError, api
+
+    dev = torch.device("cuda", 0)
+    raw = torch.zeros(100 * 32 + 4, dtype=torch.uint8, device=dev)
+    kp = torch.zeros(100, 2, dtype=torch.float32, device=dev)
+    off = np.array([0, 60, 100], np.int64)
+    sizes = np.tile(np.array([[320, 240]], np.int32), (2, 1))
+    with pytest.raises(SfmGmsError):
+        ctx.set_images_raw(off, raw.data_ptr() + 4, kp.data_ptr(), sizes, api.SFMGMS_DEVICE, keepalive=(raw, kp))
+    ctx.set_images_raw(off, raw.data_ptr(), kp.data_ptr(), sizes, api.SFMGMS_DEVICE, keepalive=(raw, kp))     # aligned: accepted
