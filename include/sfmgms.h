@@ -169,6 +169,17 @@ int sfmgms_orb_detect_and_compute_ex(sfmgms_ctx* ctx, const uint8_t* image, int 
                                      const sfmgms_orb_params* params, void* keypoints, uint8_t* descriptors, int capacity,
                                      int* n_keypoints);
 
+/* Pixels in, image set out: runs ORB (the parameters above) on every image and makes the result the image set of
+ * sfmgms_match_pairs / sfmgms_match_offsets / sfmgms_inlier_points -- the whole per-pair flow of
+ * DisparityUtil.cpp:139-149 (detectAndCompute on both images, match, matchGMS) for a sequence of images.
+ * images[i]: 8-bit, channels[i] in {1, 3}, rows strides[i] bytes apart (strides == NULL: packed).
+ * kp_offsets_out (n_images + 1, may be NULL): keypoint range of every image.  The keypoints themselves (cv::KeyPoint
+ * records, OpenCV's order) are read back with sfmgms_get_image_keypoints. */
+int sfmgms_set_images_from_pixels(sfmgms_ctx* ctx, int n_images, const uint8_t* const* images, const int32_t* widths,
+                                  const int32_t* heights, const int32_t* channels, const int32_t* strides,
+                                  const sfmgms_orb_params* params, int64_t* kp_offsets_out);
+int sfmgms_get_image_keypoints(sfmgms_ctx* ctx, int image, void* keypoints /* capacity x 28 bytes */, int capacity, int* n_out);
+
 /* ---- stage 2: replaces cv::xfeatures2d::matchGMS ----------------------------------------------
  * (FeatureMatchUtil.cpp:69; DisparityUtil.cpp:149,299).  mask[i] (0/1) for each of the n_matches input
  * matches; *mask_len = n_matches, or 0 if rotation/scale search was requested and every hypothesis had

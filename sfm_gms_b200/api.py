@@ -77,6 +77,9 @@ def load_library():
                                                 c_void_p, c_int, P(c_int)]
     L.sfmgms_orb_detect_and_compute_ex.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                                    c_void_p, c_int, P(c_int)]
+    L.sfmgms_set_images_from_pixels.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                c_void_p]
+    L.sfmgms_get_image_keypoints.argtypes = [c_void_p, c_int, c_void_p, c_int, P(c_int)]
     L.sfmgms_gms.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
                              c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p, P(c_int),
                              P(c_int), P(c_int)]
@@ -415,6 +418,40 @@ class Context:
                                                 ctypes.c_void_p(int(kp_ptr)), _ptr(s), int(location)))
         self._offsets = off
         self._keep = keepalive
+
+    def set_images_from_pixels(self, images, nfeatures=500, fast_threshold=20, scale_factor=1.2, nlevels=8,
+                               edge_threshold=31, score_type=0, wta_k=2, patch_size=31):
+        """ORB on every image (HxW or HxWx3 uint8 arrays) -> the image set of match_pairs.  -> kp_offsets int64[n+1]"""
+        imgs = [np.ascontiguousarray(im) for im in images]
+        for im in imgs:
+            if im.dtype != np.uint8 or im.ndim not in (2, 3) or (im.ndim == 3 and im.shape[2] != 3):
+                raise SfmGmsError(1, "images must be HxW or HxWx3 uint8")
+        n = len(imgs)
+        ptrs = (ctypes.c_void_p * max(n, 1))(*[im.ctypes.data for im in imgs])
+        w = np.array([im.shape[1] for im in imgs], np.int32)
+        h = np.array([im.shape[0] for im in imgs], np.int32)
+        ch = np.array([1 if im.ndim == 2 else 3 for im in imgs], np.int32)
+        prm = np.zeros(9, np.int32)
+        prm[:] = [int(nfeatures), 0, int(nlevels), int(edge_threshold), 0, int(wta_k), int(score_type), int(patch_size),
+                  int(fast_threshold)]
+        prm[1:2] = np.array([scale_factor], np.float32).view(np.int32)
+        off = np.zeros(n + 1, np.int64)
+        self._check(self._lib.sfmgms_set_images_from_pixels(self._h, n, ctypes.cast(ptrs, ctypes.c_void_p), _ptr(w), _ptr(h), _ptr(ch),
+                                                            None, _ptr(prm), _ptr(off)))
+        self._offsets = off
+        self._keep = None
+        return off
+
+    def get_image_keypoints(self, image):
+        """-> float32[n, 6] = x, y, size, angle, response, octave of one image of the last set_images_from_pixels"""
+        n = ctypes.c_int(0)
+        self._lib.sfmgms_get_image_keypoints(self._h, int(image), None, 0, ctypes.byref(n))
+        rec = np.zeros((max(n.value, 1), 7), np.float32)
+        self._check(self._lib.sfmgms_get_image_keypoints(self._h, int(image), _ptr(rec), max(n.value, 1), ctypes.byref(n)))
+        kp = np.empty((n.value, 6), np.float32)
+        kp[:, :5] = rec[: n.value, :5]
+        kp[:, 5] = rec[: n.value, 5].view(np.int32)
+        return kp
 
     def match_image_set(self, kp_offsets, desc, kp_xy, sizes_wh, pairs, with_rotation=False, with_scale=False,
                         threshold_factor=6.0):

@@ -78,6 +78,7 @@ struct sfmgms_ctx {
     HostBuf h_stage, h_pairs_pinned, h_results;
     TcState tc;   // tensor-core Hamming operand cache (hamming_tc.cu)
     OrbWorkspace* orb = nullptr;   // ORB pyramid + scratch (orb.cu), created on first use
+    std::vector<uint8_t> orb_keypoints;   // cv::KeyPoint records of the last sfmgms_set_images_from_pixels
 
     // image set
     int n_images = 0;
@@ -921,12 +922,69 @@ int sfmgms_set_images(sfmgms_ctx* ctx, int n_images, const int64_t* kp_offsets, 
         return fail(ctx, SFMGMS_ERR_ARG, "bad location %d", location);
     }
     ctx->n_images = n_images;
+    if (ctx->orb_keypoints.size() != (size_t)total * 28) ctx->orb_keypoints.clear();
     ctx->offsets.assign(kp_offsets, kp_offsets + n_images + 1);
     ctx->sizes.assign(sizes_wh, sizes_wh + 2 * (size_t)n_images);
     ctx->set_version++;
     tc_invalidate(ctx->tc);
     return SFMGMS_OK;
     GUARD_END
+}
+
+// pixels -> ORB -> image set: the caller side of the path (DisparityUtil.cpp:139-149 per pair; an SfM sequence does
+// it once per image).  Keypoints stay available through sfmgms_get_image_keypoints.
+int sfmgms_set_images_from_pixels(sfmgms_ctx* ctx, int n_images, const uint8_t* const* images, const int32_t* widths,
+                                  const int32_t* heights, const int32_t* channels, const int32_t* strides,
+                                  const sfmgms_orb_params* prm, int64_t* kp_offsets_out) {
+    if (!ctx) return SFMGMS_ERR_ARG;
+    if (n_images < 0 || (n_images > 0 && (!images || !widths || !heights || !channels || !prm)))
+        return fail(ctx, SFMGMS_ERR_ARG, "bad image list");
+    std::vector<uint8_t> desc;
+    std::vector<float> xy;
+    std::vector<int64_t> off((size_t)n_images + 1, 0);
+    std::vector<int32_t> sizes((size_t)n_images * 2);
+    ctx->orb_keypoints.clear();
+    std::vector<uint8_t> kbuf, dbuf;
+    for (int i = 0; i < n_images; ++i) {
+        int cap = 2 * prm->nfeatures + 64, n = 0, rc = SFMGMS_OK;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            kbuf.resize((size_t)cap * 28); dbuf.resize((size_t)cap * 32);
+            rc = sfmgms_orb_detect_and_compute_ex(ctx, images[i], widths[i], heights[i], channels[i],
+                                                  strides ? strides[i] : widths[i] * channels[i], prm, kbuf.data(), dbuf.data(), cap, &n);
+            if (rc == SFMGMS_ERR_ARG && n > cap) { cap = n; continue; }      // ties at a level's cut
+            break;
+        }
+        if (rc) return rc;
+        if (n >= SFMGMS_MAX_TRAIN_ROWS) return fail(ctx, SFMGMS_ERR_TRAIN_ROWS, "image %d has %d keypoints >= 2^18", i, n);
+        off[(size_t)i + 1] = off[(size_t)i] + n;
+        sizes[2 * (size_t)i] = widths[i]; sizes[2 * (size_t)i + 1] = heights[i];
+        desc.insert(desc.end(), dbuf.begin(), dbuf.begin() + (size_t)n * 32);
+        ctx->orb_keypoints.insert(ctx->orb_keypoints.end(), kbuf.begin(), kbuf.begin() + (size_t)n * 28);
+        for (int k = 0; k < n; ++k) {
+            float p[2];
+            memcpy(p, kbuf.data() + (size_t)k * 28, 8);
+            xy.push_back(p[0]); xy.push_back(p[1]);
+        }
+    }
+    if (kp_offsets_out) memcpy(kp_offsets_out, off.data(), off.size() * sizeof(int64_t));
+    static const uint8_t dummy_desc[32] = {0};
+    static const float dummy_xy[2] = {0.f, 0.f};
+    const int rc = sfmgms_set_images(ctx, n_images, off.data(), desc.empty() ? dummy_desc : desc.data(), xy.empty() ? dummy_xy : xy.data(),
+                                     sizes.data(), SFMGMS_HOST);
+    if (rc) return rc;
+    return cudaStreamSynchronize(ctx->stream) == cudaSuccess ? SFMGMS_OK : fail(ctx, SFMGMS_ERR_CUDA, "upload of the image set failed");
+}
+
+int sfmgms_get_image_keypoints(sfmgms_ctx* ctx, int image, void* keypoints, int capacity, int* n_out) {
+    if (!ctx) return SFMGMS_ERR_ARG;
+    if (n_out) *n_out = 0;
+    if (image < 0 || image >= ctx->n_images || ctx->orb_keypoints.size() != (size_t)ctx->offsets[(size_t)ctx->n_images] * 28)
+        return fail(ctx, SFMGMS_ERR_STATE, "no ORB keypoints for image %d (call sfmgms_set_images_from_pixels first)", image);
+    const int64_t a = ctx->offsets[(size_t)image], b = ctx->offsets[(size_t)image + 1];
+    if (n_out) *n_out = (int)(b - a);
+    if (b - a > capacity) return fail(ctx, SFMGMS_ERR_ARG, "capacity %d < %lld keypoints", capacity, (long long)(b - a));
+    if (keypoints && b > a) memcpy(keypoints, ctx->orb_keypoints.data() + (size_t)a * 28, (size_t)(b - a) * 28);
+    return SFMGMS_OK;
 }
 
 int sfmgms_match_offsets(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int64_t* match_offsets) {
@@ -1068,6 +1126,7 @@ int sfmgms_match_image_set(sfmgms_ctx* ctx, int n_images, const int64_t* kp_offs
     CU(ctx->d_set_kp.ensure((size_t)total_rows * 8 + 8));
     ctx->set_desc = (const uint8_t*)ctx->d_set_desc.p; ctx->set_kp = (const float*)ctx->d_set_kp.p;
     ctx->n_images = n_images;
+    ctx->orb_keypoints.clear();
     ctx->offsets.assign(kp_offsets, kp_offsets + n_images + 1);
     ctx->sizes.assign(sizes_wh, sizes_wh + 2 * (size_t)n_images);
     ctx->set_version++;

@@ -759,3 +759,29 @@ def test_device_descriptors_must_be_16_byte_aligned(ctx):
     with pytest.raises(SfmGmsError):
         ctx.set_images_raw(off, raw.data_ptr() + 4, kp.data_ptr(), sizes, api.SFMGMS_DEVICE, keepalive=(raw, kp))
     ctx.set_images_raw(off, raw.data_ptr(), kp.data_ptr(), sizes, api.SFMGMS_DEVICE, keepalive=(raw, kp))     # aligned: accepted
+
+
+def test_pixels_to_inlier_matches_api(ctx, oracle_mod):
+    """sfmgms_set_images_from_pixels + sfmgms_match_pairs: three views of a scene in, inlier matches of all ordered
+    pairs out -- against ORB oracle -> BF oracle -> GMS oracle on the same pixels"""
+    from oracle import orb as orb_oracle
+
+    g = load_golden("orb_detect")
+    base = g["view0_bgr_img"]
+    imgs = [base, np.ascontiguousarray(base[7:, 11:]), np.ascontiguousarray(base[:-9, 5:-3])]
+    off = ctx.set_images_from_pixels(imgs, nfeatures=1200, fast_threshold=5)
+    exp = [orb_oracle.orb_detect_and_compute(im, 1200, 5) for im in imgs]
+    assert off.tolist() == np.concatenate([[0], np.cumsum([len(k) for k, _ in exp])]).tolist()
+    for i, (k, _) in enumerate(exp):
+        assert np.array_equal(ctx.get_image_keypoints(i).astype(np.float64), k)
+    pairs = np.array([[0, 1], [1, 2], [2, 0], [1, 0]], np.int32)
+    r = ctx.match_pairs(pairs, False, False)
+    for p, (a, b) in enumerate(pairs):
+        (ka, da), (kb, db) = exp[a], exp[b]
+        idx, dist = oracle_mod.bf_hamming(da, db)
+        sa, sb = (imgs[a].shape[1], imgs[a].shape[0]), (imgs[b].shape[1], imgs[b].shape[0])
+        o = oracle_mod.gms(sa, sb, ka[:, :2].astype(np.float32), kb[:, :2].astype(np.float32),
+                           np.arange(len(idx), dtype=np.int32), idx, False, False)
+        lo, hi = r["offsets"][p], r["offsets"][p + 1]
+        assert np.array_equal(r["train_idx"][lo:hi], idx) and np.array_equal(r["dist"][lo:hi], dist)
+        assert np.array_equal(r["mask"][lo:hi].astype(bool), o["mask"]) and r["n_inliers"][p] == o["n_inliers"] > 100
