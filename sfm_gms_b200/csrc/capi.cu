@@ -11,6 +11,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <algorithm>
 #include <vector>
 
@@ -79,6 +80,8 @@ struct sfmgms_ctx {
     TcState tc;   // tensor-core Hamming operand cache (hamming_tc.cu)
     OrbWorkspace* orb = nullptr;   // ORB pyramid + scratch (orb.cu), created on first use
     std::vector<uint8_t> orb_keypoints;   // cv::KeyPoint records of the last sfmgms_set_images_from_pixels
+    std::vector<OrbWorkspace*> orb_pool;  // per-worker workspaces + streams of sfmgms_set_images_from_pixels
+    std::vector<cudaStream_t> orb_streams;
 
     // image set
     int n_images = 0;
@@ -381,6 +384,8 @@ void sfmgms_destroy(sfmgms_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     tc_release(ctx->tc);
     if (ctx->orb) orb_ws_destroy(ctx->orb);
+    for (OrbWorkspace* w : ctx->orb_pool) orb_ws_destroy(w);
+    for (cudaStream_t q : ctx->orb_streams) cudaStreamDestroy(q);
     ctx->h_stage.release(); ctx->h_pairs_pinned.release(); ctx->h_results.release();
     for (int k = 0; k < 3; ++k) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
@@ -939,30 +944,79 @@ int sfmgms_set_images_from_pixels(sfmgms_ctx* ctx, int n_images, const uint8_t* 
     if (!ctx) return SFMGMS_ERR_ARG;
     if (n_images < 0 || (n_images > 0 && (!images || !widths || !heights || !channels || !prm)))
         return fail(ctx, SFMGMS_ERR_ARG, "bad image list");
+    {   // argument checks once, through the single-image entry point's rules
+        sfmgms_orb_params p = *prm;
+        if (p.nfeatures < 0 || p.fast_threshold < 0 || p.fast_threshold > 255 || !(p.scale_factor > 1.0f) || p.nlevels < 1 || p.nlevels > 16 ||
+            p.first_level != 0 || p.wta_k < 2 || p.wta_k > 4 || p.patch_size < 2 || p.patch_size > 63 || (p.score_type != 0 && p.score_type != 1) ||
+            p.edge_threshold < 0)
+            return fail(ctx, SFMGMS_ERR_ARG, "bad ORB parameters (see sfmgms_orb_params)");
+        for (int i = 0; i < n_images; ++i)
+            if (!images[i] || widths[i] <= 0 || heights[i] <= 0 || (channels[i] != 1 && channels[i] != 3) ||
+                (strides && strides[i] < widths[i] * channels[i]))
+                return fail(ctx, SFMGMS_ERR_ARG, "image %d: bad pointer / size / channels / stride", i);
+    }
+    // ORB per image is dominated by its host half (retainBest = std::nth_element over every FAST corner, as OpenCV
+    // does it), so images are spread over a few host threads, each with its own workspace and stream: one image's
+    // host work overlaps the others' kernels.
+    struct PerImage { std::vector<uint8_t> kp, desc; int n = 0; };
+    std::vector<PerImage> res((size_t)n_images);
+    const int n_workers = n_images < 4 ? (n_images > 0 ? n_images : 1) : 4;
+    std::vector<std::string> errs((size_t)n_workers);
+    std::vector<int> launches((size_t)n_workers, 0);
+    const int device = ctx->device, sm_count = ctx->sm_count;
+    while ((int)ctx->orb_pool.size() < n_workers) {            // created once per context, reused by later calls
+        cudaStream_t q = nullptr;
+        CU(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+        ctx->orb_streams.push_back(q);
+        ctx->orb_pool.push_back(orb_ws_create());
+    }
+    auto work = [&](int t) {
+        if (cudaSetDevice(device) != cudaSuccess) { errs[(size_t)t] = "cudaSetDevice failed"; return; }
+        cudaStream_t st = ctx->orb_streams[(size_t)t];
+        OrbWorkspace* ws = ctx->orb_pool[(size_t)t];
+        for (int i = t; i < n_images && errs[(size_t)t].empty(); i += n_workers) {
+            PerImage& r = res[(size_t)i];
+            int cap = 2 * prm->nfeatures + 64;
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                r.kp.resize((size_t)cap * 28); r.desc.resize((size_t)cap * 32);
+                int needed = 0;
+                const int got = orb_detect_and_compute(ws, images[i], widths[i], heights[i], channels[i],
+                                                       strides ? strides[i] : widths[i] * channels[i], prm->nfeatures, prm->fast_threshold,
+                                                       prm->nlevels, prm->scale_factor, prm->edge_threshold, prm->score_type, prm->wta_k,
+                                                       prm->patch_size, r.kp.data(), r.desc.data(), cap, &needed, sm_count, st, &launches[(size_t)t]);
+                if (got == -2 && attempt == 0) { cap = needed; continue; }       // ties at a level's cut
+                if (got < 0) { errs[(size_t)t] = std::string("image ") + std::to_string(i) + ": " + orb_ws_error(ws); break; }
+                r.n = got;
+                break;
+            }
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < n_workers; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+        cudaSetDevice(device);
+    }
+    for (int t = 0; t < n_workers; ++t) {
+        ctx->launches += launches[(size_t)t];
+        if (!errs[(size_t)t].empty()) return fail(ctx, SFMGMS_ERR_CUDA, "%s", errs[(size_t)t].c_str());
+    }
     std::vector<uint8_t> desc;
     std::vector<float> xy;
     std::vector<int64_t> off((size_t)n_images + 1, 0);
     std::vector<int32_t> sizes((size_t)n_images * 2);
     ctx->orb_keypoints.clear();
-    std::vector<uint8_t> kbuf, dbuf;
     for (int i = 0; i < n_images; ++i) {
-        int cap = 2 * prm->nfeatures + 64, n = 0, rc = SFMGMS_OK;
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            kbuf.resize((size_t)cap * 28); dbuf.resize((size_t)cap * 32);
-            rc = sfmgms_orb_detect_and_compute_ex(ctx, images[i], widths[i], heights[i], channels[i],
-                                                  strides ? strides[i] : widths[i] * channels[i], prm, kbuf.data(), dbuf.data(), cap, &n);
-            if (rc == SFMGMS_ERR_ARG && n > cap) { cap = n; continue; }      // ties at a level's cut
-            break;
-        }
-        if (rc) return rc;
-        if (n >= SFMGMS_MAX_TRAIN_ROWS) return fail(ctx, SFMGMS_ERR_TRAIN_ROWS, "image %d has %d keypoints >= 2^18", i, n);
-        off[(size_t)i + 1] = off[(size_t)i] + n;
+        const PerImage& r = res[(size_t)i];
+        if (r.n >= SFMGMS_MAX_TRAIN_ROWS) return fail(ctx, SFMGMS_ERR_TRAIN_ROWS, "image %d has %d keypoints >= 2^18", i, r.n);
+        off[(size_t)i + 1] = off[(size_t)i] + r.n;
         sizes[2 * (size_t)i] = widths[i]; sizes[2 * (size_t)i + 1] = heights[i];
-        desc.insert(desc.end(), dbuf.begin(), dbuf.begin() + (size_t)n * 32);
-        ctx->orb_keypoints.insert(ctx->orb_keypoints.end(), kbuf.begin(), kbuf.begin() + (size_t)n * 28);
-        for (int k = 0; k < n; ++k) {
+        desc.insert(desc.end(), r.desc.begin(), r.desc.begin() + (size_t)r.n * 32);
+        ctx->orb_keypoints.insert(ctx->orb_keypoints.end(), r.kp.begin(), r.kp.begin() + (size_t)r.n * 28);
+        for (int k = 0; k < r.n; ++k) {
             float p[2];
-            memcpy(p, kbuf.data() + (size_t)k * 28, 8);
+            memcpy(p, r.kp.data() + (size_t)k * 28, 8);
             xy.push_back(p[0]); xy.push_back(p[1]);
         }
     }
