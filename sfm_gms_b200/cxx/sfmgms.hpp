@@ -318,8 +318,8 @@ inline void match(const ::cv::Mat& desc1, const ::cv::Mat& desc2, std::vector<::
     CV_Assert(desc1.type() == desc2.type() && desc1.isContinuous() && desc2.isContinuous());
     std::vector<cv::DMatch> m;
     if (desc1.type() == CV_32F) {   // SIFT: BFMatcher::create() = NORM_L2, exactly the reference's FeatureMatchUtil.cpp:66-68
-        CV_Assert(desc1.cols == 128 && desc2.cols == 128);
-        cv::BFMatcher(cv::NORM_L2).match(desc1.ptr<float>(), desc1.rows, desc2.ptr<float>(), desc2.rows, m);
+        CV_Assert(desc1.cols == desc2.cols && desc1.cols >= 1 && desc1.cols <= 256);
+        cv::BFMatcher(cv::NORM_L2).match(desc1.ptr<float>(), desc1.rows, desc2.ptr<float>(), desc2.rows, m, desc1.cols);
     } else {
         CV_Assert(desc1.type() == CV_8U && desc1.cols == 32 && desc2.cols == 32);
         cv::BFMatcher().match(desc1.ptr<uint8_t>(), desc1.rows, desc2.ptr<uint8_t>(), desc2.rows, m);
