@@ -43,6 +43,12 @@ def lib():
                                                       ctypes.c_int, ctypes.c_int, ctypes.c_double, u8p, ip, ip,
                                                       ip, ip]
         L.oracle_gms.restype = ctypes.c_int
+        L.oracle_gms_ex.argtypes = L.oracle_gms.argtypes + [u8p]
+        L.oracle_gms_ex.restype = ctypes.c_int
+        L.oracle_gms_tables.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.oracle_gms_grid_left.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_void_p]
+        L.oracle_gms_grid_right.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.oracle_gms_right_grid.argtypes = [ctypes.c_int]
         L.oracle_bf_l2.argtypes = [f32p, ctypes.c_int, f32p, ctypes.c_int, ctypes.c_int, i32p, f32p, ip]
         L.oracle_bf_l2.restype = ctypes.c_int
         L.oracle_orb_blur7.argtypes = [u8p, ctypes.c_int, ctypes.c_int, u8p]
@@ -150,11 +156,38 @@ def brute_force_match(q, t, norm="l2", cross_check=True, distance_coef=4.0, max_
     return qi[:n], idx[:n].astype(np.int32), dist[:n]
 
 
+def gms_tables():
+    """-> (ROT int32[8][9], SCALE float64[5]) of the restatement (compared with the DLL's in tests/test_gms_dll.py)."""
+    rot = np.zeros(72, np.int32)
+    sc = np.zeros(5, np.float64)
+    lib().oracle_gms_tables(rot.ctypes.data, sc.ctypes.data)
+    return rot.reshape(8, 9), sc
+
+
+def gms_right_grid(s):
+    return lib().oracle_gms_right_grid(int(s))
+
+
+def gms_grid_left(norm_pts, gtype):
+    p = np.ascontiguousarray(norm_pts, np.float32).reshape(-1, 2)
+    out = np.empty(len(p), np.int32)
+    lib().oracle_gms_grid_left(p.ctypes.data, len(p), int(gtype), out.ctypes.data)
+    return out
+
+
+def gms_grid_right(norm_pts, wr, hr):
+    p = np.ascontiguousarray(norm_pts, np.float32).reshape(-1, 2)
+    out = np.empty(len(p), np.int32)
+    lib().oracle_gms_grid_right(p.ctypes.data, len(p), int(wr), int(hr), out.ctypes.data)
+    return out
+
+
 def gms(size1, size2, kp1_xy, kp2_xy, query_idx, train_idx, with_rotation=False, with_scale=False,
-        threshold_factor=6.0):
+        threshold_factor=6.0, want_all_masks=False):
     """matchGMS semantics.  size = (width, height).  Returns dict(mask, n_inliers, hyp_counts, best_hyp).
 
     mask has length n_matches, or 0 when rotation/scale search found nothing (reference quirk).
+    want_all_masks: also 'all_masks' bool[40, n] — the mask of every hypothesis that was run.
     """
     kp1 = np.ascontiguousarray(kp1_xy, dtype=np.float32).reshape(-1, 2)
     kp2 = np.ascontiguousarray(kp2_xy, dtype=np.float32).reshape(-1, 2)
@@ -164,11 +197,16 @@ def gms(size1, size2, kp1_xy, kp2_xy, query_idx, train_idx, with_rotation=False,
     mask = np.zeros(max(n, 1), np.uint8)
     mlen, ninl, bh = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(-1)
     hyp = np.full(40, -1, np.int32)
-    rc = lib().oracle_gms(int(size1[0]), int(size1[1]), int(size2[0]), int(size2[1]),
+    allm = np.zeros((40, max(n, 1)), np.uint8) if want_all_masks else None
+    rc = lib().oracle_gms_ex(int(size1[0]), int(size1[1]), int(size2[0]), int(size2[1]),
                           _p(kp1, ctypes.c_float), kp1.shape[0], 2, _p(kp2, ctypes.c_float), kp2.shape[0], 2,
                           _p(qi, ctypes.c_int32), _p(ti, ctypes.c_int32), 1, n, int(bool(with_rotation)),
                           int(bool(with_scale)), float(threshold_factor), _p(mask, ctypes.c_uint8),
-                          ctypes.byref(mlen), ctypes.byref(ninl), _p(hyp, ctypes.c_int), ctypes.byref(bh))
+                          ctypes.byref(mlen), ctypes.byref(ninl), _p(hyp, ctypes.c_int), ctypes.byref(bh),
+                          _p(allm, ctypes.c_uint8) if want_all_masks else None)
     if rc:
         raise ValueError("oracle_gms rc=%d" % rc)
-    return dict(mask=mask[: mlen.value].astype(bool), n_inliers=ninl.value, hyp_counts=hyp, best_hyp=bh.value)
+    out = dict(mask=mask[: mlen.value].astype(bool), n_inliers=ninl.value, hyp_counts=hyp, best_hyp=bh.value)
+    if want_all_masks:
+        out["all_masks"] = allm[:, :n].astype(bool)
+    return out

@@ -17,11 +17,14 @@
  *            the algorithm below follows the disassembly-verified specification in
  *            /root/repo/SURVEY.md Appendix A (virtual addresses quoted per function).
  *
- * PARITY PINNING: stage 1 is pinned by an executable reference (cv2).  Stage 2 has NO
- * executable reference and the reference ships NO tests or golden vectors for it: it is pinned
- * by (a) the constants extracted from the DLL, (b) the survey's independent numpy-restatement
- * anchors on the reference's own images and (c) hand-derivable
- * micro-cases.  => GMS parity is "unpinned by reference tests" in the sense of the task brief.
+ * PARITY PINNING: stage 1 is pinned by an executable reference (cv2).  Stage 2 is pinned by the
+ * reference's OWN MACHINE CODE: oracle/dllref/gms_dll_host.c maps the vendored DLL
+ * (SfM-GMS/bin/opencv_xfeatures2d452.dll) and calls its exported matchGMS (@VA 0x180048280), its
+ * GMSMatcher ctor/setScale/run and its grid-index leaf functions; tests/golden/make_gms_dll_golden.py
+ * records those outputs (tests/golden/gms_dll.npz) and tests/test_gms_dll.py checks this file
+ * against them — masks, all 40 per-hypothesis masks, cell indices on edge-of-cell f32 values, and
+ * the ROT / SCALE tables — plus, where the DLL is present, a live randomised comparison.  The older
+ * pins stay as regressions: the survey's numpy anchors and the micro-cases.
  *
  * Build: see oracle/Makefile (-O2 -ffp-contract=off: every f32/f64 op is separately rounded,
  * exactly like the divss/mulss/addsd/divsd/sqrtsd/mulsd sequence in the DLL).
@@ -244,11 +247,42 @@ static int run(gms_t* g, int rot) {
  * Returns 0; -2 if a referenced keypoint is outside [0,w)x[0,h) (UB in the reference);
  * -3 if a match index is out of range (UB in the reference); -1 on bad arguments.
  */
+int oracle_gms_ex(int w1, int h1, int w2, int h2, const float* kp1_xy, int n1, int kp1_stride,
+               const float* kp2_xy, int n2, int kp2_stride, const int32_t* query_idx,
+               const int32_t* train_idx, int idx_stride, int n_matches, int with_rotation,
+               int with_scale, double threshold_factor, uint8_t* mask, int* mask_len,
+               int* n_inliers, int* hyp_counts, int* best_hyp, uint8_t* all_masks);
+
 int oracle_gms(int w1, int h1, int w2, int h2, const float* kp1_xy, int n1, int kp1_stride,
                const float* kp2_xy, int n2, int kp2_stride, const int32_t* query_idx,
                const int32_t* train_idx, int idx_stride, int n_matches, int with_rotation,
                int with_scale, double threshold_factor, uint8_t* mask, int* mask_len,
                int* n_inliers, int* hyp_counts, int* best_hyp) {
+    return oracle_gms_ex(w1, h1, w2, h2, kp1_xy, n1, kp1_stride, kp2_xy, n2, kp2_stride, query_idx, train_idx,
+                         idx_stride, n_matches, with_rotation, with_scale, threshold_factor, mask, mask_len,
+                         n_inliers, hyp_counts, best_hyp, NULL);
+}
+
+/* Tables and leaf functions, exported so that tests can hold them against the DLL's own. */
+void oracle_gms_tables(int32_t rot[72], double scale[5]) {
+    for (int r = 0; r < 8; ++r) for (int k = 0; k < 9; ++k) rot[r * 9 + k] = ROT[r][k];
+    for (int s = 0; s < 5; ++s) scale[s] = scale_ratio(s);
+}
+void oracle_gms_grid_left(const float* norm_xy, long n, int type, int32_t* out) {
+    for (long i = 0; i < n; ++i) out[i] = left_idx(norm_xy + 2 * i, type);
+}
+void oracle_gms_grid_right(const float* norm_xy, long n, int wr, int hr, int32_t* out) {
+    gms_t g; g.wr = wr; g.hr = hr;
+    for (long i = 0; i < n; ++i) out[i] = right_idx(&g, norm_xy + 2 * i);
+}
+int oracle_gms_right_grid(int s) { return cv_round_d((double)GRID_L * scale_ratio(s)); }
+
+/* all_masks (optional): [40][n_matches] bytes, the mask of EVERY hypothesis that was run (scale-major). */
+int oracle_gms_ex(int w1, int h1, int w2, int h2, const float* kp1_xy, int n1, int kp1_stride,
+               const float* kp2_xy, int n2, int kp2_stride, const int32_t* query_idx,
+               const int32_t* train_idx, int idx_stride, int n_matches, int with_rotation,
+               int with_scale, double threshold_factor, uint8_t* mask, int* mask_len,
+               int* n_inliers, int* hyp_counts, int* best_hyp, uint8_t* all_masks) {
     if (n1 < 0 || n2 < 0 || n_matches < 0 || w1 <= 0 || h1 <= 0 || w2 <= 0 || h2 <= 0) return -1;
     const int GL = GRID_L * GRID_L;
     int rc = 0;
@@ -298,12 +332,14 @@ int oracle_gms(int w1, int h1, int w2, int h2, const float* kp1_xy, int n1, int 
         len = n_matches;
         bh = 0;
         if (hyp_counts) hyp_counts[0] = best;
+        if (all_masks && n_matches) memcpy(all_masks, g.mask, (size_t)n_matches);
     } else {
         for (int s = 0; s < (with_scale ? 5 : 1); ++s) {
             set_scale(&g, s);
             for (int r = 1; r <= (with_rotation ? 8 : 1); ++r) {
                 int c = run(&g, r);
                 if (hyp_counts) hyp_counts[s * 8 + r - 1] = c;
+                if (all_masks && n_matches) memcpy(all_masks + (size_t)(s * 8 + r - 1) * n_matches, g.mask, (size_t)n_matches);
                 if (c > best) { /* strict >, first wins */
                     memcpy(mask, g.mask, (size_t)n_matches);
                     best = c; len = n_matches; bh = s * 8 + r - 1;

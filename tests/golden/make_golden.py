@@ -9,8 +9,8 @@ Sources of truth, per field:
   xc_*                 cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match (FeatureMatchUtil.cpp:22).
   anchor_*             SURVEY.md Appendix C per-hypothesis inlier counts (survey's independent numpy
                        restatement of the DLL disassembly) -- typed in from SURVEY.md, NOT computed here.
-  gms_mask_*           the C oracle's masks (regression pin of the oracle itself; no executable
-                       reference exists for stage 2 -- see oracle/sfmgms_oracle.c header).
+  gms_mask_*           the C oracle's masks (regression pin of the oracle itself).  The EXECUTABLE reference for
+                       stage 2 is the vendored DLL's own code: see make_gms_dll_golden.py / gms_dll.npz.
 /root/reference is not available on the GPU box; tests only read the .npz files written here.
 """
 import os
