@@ -37,6 +37,8 @@ extern "C" {
 #define SFMGMS_ERR_INDEX 4      /* queryIdx/trainIdx out of range: undefined behaviour in OpenCV GMS */
 #define SFMGMS_ERR_CUDA 5       /* CUDA runtime error (message in sfmgms_last_error) */
 #define SFMGMS_ERR_STATE 6      /* call order violated (e.g. match_pairs before set_images) */
+#define SFMGMS_ERR_CAPACITY 7   /* a caller buffer of stated capacity is too small (needed size reported) */
+#define SFMGMS_ERR_NCCL 8       /* multi-GPU: NCCL could not be loaded or a collective failed */
 
 #define SFMGMS_MAX_TRAIN_ROWS (1 << 18)
 
@@ -55,7 +57,12 @@ extern "C" {
                                          sfmgms_match_pairs calls; 0: unpack again on every call */
 #define SFMGMS_OPT_L2_KERNEL 5        /* sfmgms_bf_l2: 0 auto, 1 DP4A CUDA-core kernel, 2 tcgen05 kind::i8 kernel (1, 2: integer-valued
                                          data, else the fp32 kernel takes over), 3 always the order-exact fp32 kernel */
-#define SFMGMS_OPT_TIMING 3          /* 1: record CUDA events around the Hamming and GMS stages of each batch */
+#define SFMGMS_OPT_TIMING 3          /* 1: record CUDA events around the Hamming and GMS stages of each batch;
+                                        2: additionally one event after every kernel (sfmgms_kernel_times) */
+#define SFMGMS_OPT_CHUNK_ROWS 6      /* sfmgms_match_pairs[_compact] walk a pair list in chunks of at most this many match
+                                        rows (default 4 Mi): per-match device scratch is O(chunk), never O(list) */
+#define SFMGMS_OPT_GMS_DENSE 7       /* 1: force the global-memory histogram path of GMS (otherwise only pairs with
+                                        >= 65536 matches take it) -- for tests and measurements */
 
 typedef struct sfmgms_ctx sfmgms_ctx;
 
@@ -70,6 +77,9 @@ int64_t sfmgms_kernel_launches(const sfmgms_ctx* ctx);
 /* With SFMGMS_OPT_TIMING on: device milliseconds (CUDA events on the context stream) of the last batch:
  * out_ms[0] = Hamming kernel(s), out_ms[1] = GMS kernels, out_ms[2] = number of Hamming kernel launches. */
 int sfmgms_last_timing(sfmgms_ctx* ctx, double* out_ms /*3*/);
+/* With SFMGMS_OPT_TIMING = 2 (measurement runs: an event after every kernel): writes "name:total_ms:launches;..." for
+ * every kernel launched by multi-pair / single-pair calls since the last read, then clears the accumulators. */
+int sfmgms_kernel_times(sfmgms_ctx* ctx, char* buf, int buf_len);
 /* the CUDA stream (cudaStream_t) the context launches on, for event timing by the caller */
 void* sfmgms_stream(sfmgms_ctx* ctx);
 
@@ -222,6 +232,22 @@ int sfmgms_match_pairs(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int w
                        int32_t* mask_len, int32_t* train_idx, int32_t* dist, uint8_t* mask);
 int sfmgms_match_offsets(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int64_t* match_offsets /*n_pairs+1*/);
 
+/* sfmgms_match_pairs_compact: the same computation, returning what the reference's caller actually keeps -- the
+ * `matchesGMS` vector of every pair (FeatureMatchUtil.cpp:69: matchGMS clears it and pushes matches1to2[i] for every set
+ * mask bit, in input order) and the coordinate lists SfMUtil.cpp:25-35 / DisparityUtil.cpp:179-185 gather from it --
+ * for the whole pair list, back to back:
+ *   n_inliers[n_pairs], best_hyp[n_pairs]      int32 per pair
+ *   inlier_offsets[n_pairs + 1]                int64: pair p owns rows [inlier_offsets[p], inlier_offsets[p+1])
+ *   matches[capacity]                          16-byte cv::DMatch records {queryIdx, trainIdx, imgIdx = 0, distance (float)}
+ *   pts1[capacity * 2], pts2[capacity * 2]     kp1[queryIdx].pt / kp2[trainIdx].pt of the same rows
+ * Any output may be NULL.  *n_total = total inliers; if it exceeds `capacity` the first `capacity` rows are valid and
+ * the call returns SFMGMS_ERR_CAPACITY.  out_location selects host or device pointers for all outputs.  A pair costs
+ * 16-32 bytes per INLIER on the way back to the host instead of 9 bytes per MATCH plus a per-pair gather call. */
+int sfmgms_match_pairs_compact(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int with_rotation, int with_scale,
+                               double threshold_factor, int out_location, int32_t* n_inliers, int32_t* best_hyp,
+                               int64_t* inlier_offsets, void* matches, float* pts1, float* pts2, int64_t capacity,
+                               int64_t* n_total);
+
 /* sfmgms_match_image_set: sfmgms_set_images(SFMGMS_HOST) + sfmgms_match_pairs(SFMGMS_HOST outputs) in ONE
  * synchronous call that pipelines internally: the image set goes to the device in chunks on a copy stream while
  * earlier pairs already compute, and finished pairs' results return on a third stream.  Pairs are processed in
@@ -239,6 +265,18 @@ int sfmgms_match_image_set(sfmgms_ctx* ctx, int n_images, const int64_t* kp_offs
  * pts1[k] = kp1[queryIdx].pt, pts2[k] = kp2[trainIdx].pt in match order (k < n_inliers), ready for
  * findEssentialMat (SfMUtil.cpp:39).  pts1/pts2: host float arrays of capacity*2; *n_out = n_inliers. */
 int sfmgms_inlier_points(sfmgms_ctx* ctx, int pair_index, float* pts1, float* pts2, int capacity, int* n_out);
+/* (a one-pair view of sfmgms_match_pairs_compact; valid after a single-pair call or a pair list that ran as ONE chunk,
+ * see SFMGMS_OPT_CHUNK_ROWS -- for whole lists use the compact call.) */
+
+/* Inlier counts of all 40 (scale, rotation) hypotheses of one pair, scale-major: what GMSMatcher::run returns for each
+ * (rotation 1..8 inside scale 0..4) and getInlierMask compares (DLL @VA 0x180047dc0).  Inputs as for sfmgms_gms. */
+int sfmgms_gms_hypotheses(sfmgms_ctx* ctx, int w1, int h1, int w2, int h2, const void* kp1, int n1, int kp1_stride_bytes,
+                          const void* kp2, int n2, int kp2_stride_bytes, const int32_t* query_idx,
+                          const int32_t* train_idx, int idx_stride_bytes, int n_matches, double threshold_factor,
+                          int32_t* counts /*40*/);
+
+/* device memory currently owned by the context (bytes) */
+int64_t sfmgms_device_bytes(const sfmgms_ctx* ctx);
 
 #ifdef __cplusplus
 }

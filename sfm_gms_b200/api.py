@@ -20,9 +20,14 @@ NORM_L2 = 4       # cv::NORM_L2
 
 SFMGMS_HOST, SFMGMS_DEVICE = 0, 1
 OPT_HAMMING_KERNEL, OPT_GMS_CHUNK_BYTES, OPT_TIMING, OPT_TC_OPERAND_CACHE, OPT_L2_KERNEL = 1, 2, 3, 4, 5
+OPT_CHUNK_ROWS, OPT_GMS_DENSE = 6, 7
 HAMMING_AUTO, HAMMING_POPC, HAMMING_TC, HAMMING_FP4 = 0, 1, 2, 3
 
-_ERR_NAMES = {1: "ERR_ARG", 2: "ERR_TRAIN_ROWS", 3: "ERR_DOMAIN", 4: "ERR_INDEX", 5: "ERR_CUDA", 6: "ERR_STATE"}
+_ERR_NAMES = {1: "ERR_ARG", 2: "ERR_TRAIN_ROWS", 3: "ERR_DOMAIN", 4: "ERR_INDEX", 5: "ERR_CUDA", 6: "ERR_STATE",
+              7: "ERR_CAPACITY", 8: "ERR_NCCL"}
+
+# cv::DMatch, 16 bytes (the record sfmgms_match_pairs_compact writes)
+DMATCH_DT = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
 
 DMatch = namedtuple("DMatch", ["queryIdx", "trainIdx", "imgIdx", "distance"])
 
@@ -93,6 +98,13 @@ def load_library():
     L.sfmgms_match_image_set.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                          c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.sfmgms_inlier_points.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, P(c_int)]
+    L.sfmgms_match_pairs_compact.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_i64, P(c_i64)]
+    L.sfmgms_gms_hypotheses.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
+                                        c_void_p, c_void_p, c_int, c_int, c_double, c_void_p]
+    L.sfmgms_kernel_times.argtypes = [c_void_p, ctypes.c_char_p, c_int]
+    L.sfmgms_device_bytes.argtypes = [c_void_p]
+    L.sfmgms_device_bytes.restype = c_i64
     _LIB = L
     return L
 
@@ -326,6 +338,33 @@ class Context:
                                          ctypes.byref(bh)))
         return dict(mask=mask[: ml.value].astype(bool), n_inliers=ni.value, best_hyp=bh.value)
 
+    def gms_hypotheses(self, size1, size2, kp1, kp2, query_idx, train_idx, threshold_factor=6.0):
+        """-> int32[40]: inlier count of every (scale, rotation) hypothesis, scale-major (GMSMatcher::run per hypothesis)."""
+        w1, h1 = _size(size1)
+        w2, h2 = _size(size2)
+        k1, k2 = _kp_xy(kp1), _kp_xy(kp2)
+        qi = np.ascontiguousarray(query_idx, dtype=np.int32)
+        ti = np.ascontiguousarray(train_idx, dtype=np.int32)
+        counts = np.zeros(40, np.int32)
+        self._check(self._lib.sfmgms_gms_hypotheses(self._h, w1, h1, w2, h2, _ptr(k1), k1.shape[0], 8, _ptr(k2), k2.shape[0], 8,
+                                                    _ptr(qi), _ptr(ti), 4, qi.shape[0], float(threshold_factor), _ptr(counts)))
+        return counts
+
+    def kernel_times(self):
+        """OPT_TIMING = 2: {kernel name: (total ms, launches)} since the last call."""
+        buf = ctypes.create_string_buffer(8192)
+        self._check(self._lib.sfmgms_kernel_times(self._h, buf, 8192))
+        out = {}
+        for item in buf.value.decode().split(";"):
+            if item:
+                name, ms, n = item.split(":")
+                out[name] = (float(ms), int(n))
+        return out
+
+    @property
+    def device_bytes(self):
+        return int(self._lib.sfmgms_device_bytes(self._h))
+
     # -- fused pair ---------------------------------------------------------------------------------
     def match_pair(self, desc1, desc2, kp1, kp2, size1, size2, with_rotation=False, with_scale=False,
                    threshold_factor=6.0):
@@ -400,6 +439,42 @@ class Context:
         if want_mask:
             out["mask"] = mk
         return out
+
+    def match_pairs_compact(self, pairs, with_rotation=False, with_scale=False, threshold_factor=6.0, capacity=None,
+                            want_matches=True, want_points=True):
+        """Host outputs: every pair's matchesGMS (cv::DMatch records) and inlier coordinates, back to back.
+        -> dict(n_inliers, best_hyp, offsets int64[n+1], n_total[, matches (DMATCH_DT)][, pts1, pts2 float32[n,2]])."""
+        pr = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        n = pr.shape[0]
+        if capacity is None:
+            capacity = int(self.match_offsets(pr)[-1])
+        ninl = np.zeros(n, np.int32)
+        bh = np.zeros(n, np.int32)
+        off = np.zeros(n + 1, np.int64)
+        m = np.zeros(max(capacity, 1), DMATCH_DT) if want_matches else None
+        p1 = np.zeros((max(capacity, 1), 2), np.float32) if want_points else None
+        p2 = np.zeros((max(capacity, 1), 2), np.float32) if want_points else None
+        tot = ctypes.c_int64(0)
+        self._check(self._lib.sfmgms_match_pairs_compact(self._h, _ptr(pr), n, int(bool(with_rotation)), int(bool(with_scale)),
+                                                         float(threshold_factor), SFMGMS_HOST, _ptr(ninl), _ptr(bh), _ptr(off),
+                                                         _ptr(m), _ptr(p1), _ptr(p2), int(capacity), ctypes.byref(tot)))
+        out = dict(n_inliers=ninl, best_hyp=bh, offsets=off, n_total=tot.value)
+        if want_matches:
+            out["matches"] = m[: tot.value]
+        if want_points:
+            out["pts1"], out["pts2"] = p1[: tot.value], p2[: tot.value]
+        return out
+
+    def match_pairs_compact_raw(self, pairs_np, with_rotation, with_scale, threshold_factor, out_location, capacity,
+                                n_inliers=0, best_hyp=0, offsets=0, matches=0, pts1=0, pts2=0):
+        """Raw-pointer form (ints are addresses; 0 = NULL).  -> n_total"""
+        p = lambda v: ctypes.c_void_p(int(v)) if v else None  # noqa: E731
+        tot = ctypes.c_int64(0)
+        self._check(self._lib.sfmgms_match_pairs_compact(self._h, _ptr(pairs_np), pairs_np.shape[0], int(with_rotation),
+                                                         int(with_scale), float(threshold_factor), int(out_location),
+                                                         p(n_inliers), p(best_hyp), p(offsets), p(matches), p(pts1), p(pts2),
+                                                         int(capacity), ctypes.byref(tot)))
+        return tot.value
 
     def match_pairs_raw(self, pairs_np, with_rotation, with_scale, threshold_factor, out_location, n_inliers=0,
                         best_hyp=0, mask_len=0, train_idx=0, dist=0, mask=0):

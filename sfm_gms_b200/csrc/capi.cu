@@ -57,6 +57,8 @@ char g_create_error[512] = "";
 
 }  // namespace
 
+namespace sfmgms { thread_local KernelMarks* tl_marks = nullptr; }
+
 struct sfmgms_ctx {
     int device = 0;
     int sm_count = 148;
@@ -67,7 +69,6 @@ struct sfmgms_ctx {
     size_t gms_chunk_bytes = 64ull << 20;
     int timing = 0;
     int l2_kernel = 0;   // 0 auto (tcgen05, fp32 fallback), 1 dp4a, 2 tcgen05, 3 fp32 order-exact
-    bool timing_mid_pending = false;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // pipelined host<->device copies (match_image_set)
     std::vector<cudaEvent_t> events;                           // pool of timing-disabled events
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -80,6 +81,7 @@ struct sfmgms_ctx {
     TcState tc;   // tensor-core Hamming operand cache (hamming_tc.cu)
     OrbWorkspace* orb = nullptr;   // ORB pyramid + scratch (orb.cu), created on first use
     std::vector<uint8_t> orb_keypoints;   // cv::KeyPoint records of the last sfmgms_set_images_from_pixels
+    bool keep_orb_keypoints = false;      // set only around that function's own sfmgms_set_images call
     std::vector<OrbWorkspace*> orb_pool;  // per-worker workspaces + streams of sfmgms_set_images_from_pixels
     std::vector<cudaStream_t> orb_streams;
 
@@ -94,6 +96,33 @@ struct sfmgms_ctx {
     // last batch (for sfmgms_inlier_points)
     std::vector<PairDesc> last_pairs;
     std::vector<PairResult> last_results;
+
+    // chunked pair-list runs (sfmgms_match_pairs / _compact): two slots of per-chunk device buffers so that a chunk
+    // computes while the previous one's results travel to the host; device scratch is O(chunk), not O(list)
+    struct KTime { std::string name; double ms = 0; long long n = 0; };
+    std::vector<KTime> kernel_times;       // SFMGMS_OPT_TIMING = 2: accumulated per-kernel device time
+    KernelMarks marks;                     // single-batch paths
+    void absorb(KernelMarks& m) {
+        for (int i = 1; i < m.used; ++i) {
+            float dt = 0.f;
+            if (cudaEventElapsedTime(&dt, m.ev[i - 1], m.ev[i]) != cudaSuccess) continue;
+            KTime* k = nullptr;
+            for (auto& e : kernel_times) if (e.name == m.name[i]) k = &e;
+            if (!k) { kernel_times.push_back(KTime{m.name[i], 0, 0}); k = &kernel_times.back(); }
+            k->ms += dt; k->n++;
+        }
+        m.used = 0;
+    }
+    struct Slot {
+        KernelMarks marks;
+        DevBuf key, mask, out_i32, cmatch, cpts, coff;
+        cudaEvent_t computed = nullptr, copied = nullptr, t0 = nullptr, t1 = nullptr, t2 = nullptr;
+        bool copy_pending = false;
+    } slot[2];
+    DevBuf d_cbase;                 // running inlier total of a compact run (int64)
+    HostBuf h_coff;
+    long long chunk_rows = 4ll << 20;   // match rows per chunk (SFMGMS_OPT_CHUNK_ROWS)
+    int gms_dense = 0;              // SFMGMS_OPT_GMS_DENSE
 };
 
 namespace {
@@ -152,38 +181,6 @@ __global__ void crosscheck_idx_kernel(const int32_t* __restrict__ fwd, const int
     keep[i] = j >= 0 && rev[j] == i;
 }
 
-// (§8f-1) ordered compaction of inlier coordinates for one pair: single CTA, chunked scan
-__global__ void __launch_bounds__(1024) inlier_points_kernel(PairDesc pd, float2* __restrict__ pts1,
-                                                              float2* __restrict__ pts2, int capacity,
-                                                              int* __restrict__ n_out) {
-    __shared__ int wsum[32];
-    __shared__ int carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < pd.n_matches; base += 1024) {
-        const int i = base + threadIdx.x;
-        const int m = (i < pd.n_matches) ? (pd.mask[i] != 0) : 0;
-        const unsigned bal = __ballot_sync(0xffffffffu, m);
-        const int within = __popc(bal & ((1u << lane) - 1u));
-        if (lane == 0) wsum[warp] = __popc(bal);
-        __syncthreads();
-        int woff = 0, tot = 0;
-        for (int k = 0; k < 32; ++k) { int v = wsum[k]; if (k < warp) woff += v; tot += v; }
-        const int pos = carry + woff + within;
-        if (m && pos < capacity) {
-            const int qi = pd.mq ? pd.mq[i] : i;
-            const int ti = pd.mt ? pd.mt[i] : (int)(pd.key[i] & kTrainIdxMask);
-            pts1[pos] = reinterpret_cast<const float2*>(pd.kp1)[qi];
-            pts2[pos] = reinterpret_cast<const float2*>(pd.kp2)[ti];
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) carry += tot;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *n_out = carry;
-}
-
 int choose_hamming(const sfmgms_ctx* c) {
     if (c->hamming_kernel == SFMGMS_HAMMING_AUTO) return SFMGMS_HAMMING_FP4;   // fastest measured (profiles/r1_notes.md)
     return c->hamming_kernel;
@@ -205,8 +202,8 @@ int upload_pairs(sfmgms_ctx* ctx, const std::vector<PairDesc>& hp) {
 // Enqueues Hamming (optional) + GMS (optional) for pairs [r0, r0+rn) of an uploaded batch.  Asynchronous: nothing
 // here waits for the device.  Scratch reuse across ranges is ordered by the stream.
 int enqueue_range(sfmgms_ctx* ctx, const std::vector<PairDesc>& hp, int r0, int rn, bool do_hamming, bool do_gms,
-                  int with_rotation, int with_scale, double factor, int* ham_launches) {
-    if (rn <= 0) return SFMGMS_OK;
+                  int with_rotation, int with_scale, double factor, int* ham_launches, cudaEvent_t mid = nullptr) {
+    if (rn <= 0) { if (mid) CU(cudaEventRecord(mid, ctx->stream)); return SFMGMS_OK; }
     cudaStream_t st = ctx->stream;
     const PairDesc* dp = static_cast<const PairDesc*>(ctx->d_pairs.p) + r0;
     const PairDesc* hpp = hp.data() + r0;
@@ -231,7 +228,7 @@ int enqueue_range(sfmgms_ctx* ctx, const std::vector<PairDesc>& hp, int r0, int 
         }
         CU(cudaGetLastError());
     }
-    if (ctx->timing && ctx->timing_mid_pending) { CU(cudaEventRecord(ctx->ev[1], st)); ctx->timing_mid_pending = false; }
+    if (mid) CU(cudaEventRecord(mid, st));   // between the Hamming and the GMS stage
     if (do_gms) {
         const int n_scales = with_scale ? kNumScales : 1;
         const size_t per_pair = gms_scratch_bytes_per_pair(n_scales);
@@ -241,7 +238,8 @@ int enqueue_range(sfmgms_ctx* ctx, const std::vector<PairDesc>& hp, int r0, int 
         CU(ctx->d_hist.ensure(budget));
         CU(ctx->d_msc.ensure(gms_match_scratch_bytes(gms_match_rows(hpp, rn), n_scales)));
         int l = launch_gms(dp, hpp, rn, with_rotation, with_scale, factor,
-                           static_cast<PairResult*>(ctx->d_results.p) + r0, ctx->d_hist.p, budget, ctx->d_msc.p, st);
+                           static_cast<PairResult*>(ctx->d_results.p) + r0, ctx->d_hist.p, budget, ctx->d_msc.p, st,
+                           ctx->gms_dense);
         if (l < 0) return fail(ctx, SFMGMS_ERR_CUDA, "GMS scratch too small");
         ctx->launches += l;
         CU(cudaGetLastError());
@@ -281,11 +279,15 @@ int run_batch(sfmgms_ctx* ctx, std::vector<PairDesc>& hp, bool do_hamming, bool 
     int rc = upload_pairs(ctx, hp);
     if (rc) return rc;
     int ham_launches = 0;
-    if (ctx->timing) { CU(cudaEventRecord(ctx->ev[0], ctx->stream)); ctx->timing_mid_pending = true; }
-    rc = enqueue_range(ctx, hp, 0, n, do_hamming, do_gms, with_rotation, with_scale, factor, &ham_launches);
+    if (ctx->timing) CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (ctx->timing >= 2) { ctx->marks.used = 0; tl_marks = &ctx->marks; kmark("begin", ctx->stream); }
+    rc = enqueue_range(ctx, hp, 0, n, do_hamming, do_gms, with_rotation, with_scale, factor, &ham_launches,
+                       ctx->timing ? ctx->ev[1] : nullptr);
+    tl_marks = nullptr;
     if (rc) { cudaStreamSynchronize(ctx->stream); tc_reset_arena(ctx->tc); return rc; }
     rc = finish_batch(ctx, n, do_gms);
     if (rc) return rc;
+    if (ctx->timing >= 2) ctx->absorb(ctx->marks);
     if (ctx->timing) {
         float a = 0.f, b = 0.f;
         CU(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
@@ -380,8 +382,17 @@ void sfmgms_destroy(sfmgms_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_pairs, &ctx->d_results, &ctx->d_key, &ctx->d_mask, &ctx->d_hist, &ctx->d_msc, &ctx->d_q,
                       &ctx->d_kp1, &ctx->d_kp2, &ctx->d_mq, &ctx->d_mt, &ctx->d_out_i32, &ctx->d_pts,
-                      &ctx->d_set_desc, &ctx->d_set_kp};
+                      &ctx->d_set_desc, &ctx->d_set_kp, &ctx->d_cbase};
     for (DevBuf* b : bufs) b->release();
+    for (auto& sl : ctx->slot) {
+        DevBuf* sb[] = {&sl.key, &sl.mask, &sl.out_i32, &sl.cmatch, &sl.cpts, &sl.coff};
+        for (DevBuf* b : sb) b->release();
+        cudaEvent_t* ev[] = {&sl.computed, &sl.copied, &sl.t0, &sl.t1, &sl.t2};
+        for (cudaEvent_t* e : ev) if (*e) cudaEventDestroy(*e);
+    }
+    ctx->h_coff.release();
+    for (int i = 0; i < ctx->marks.created; ++i) cudaEventDestroy(ctx->marks.ev[i]);
+    for (auto& sl : ctx->slot) for (int i = 0; i < sl.marks.created; ++i) cudaEventDestroy(sl.marks.ev[i]);
     tc_release(ctx->tc);
     if (ctx->orb) orb_ws_destroy(ctx->orb);
     for (OrbWorkspace* w : ctx->orb_pool) orb_ws_destroy(w);
@@ -411,6 +422,15 @@ int sfmgms_set_option(sfmgms_ctx* ctx, int key, int64_t value) {
         ctx->gms_chunk_bytes = (size_t)value;
         return SFMGMS_OK;
     }
+    if (key == SFMGMS_OPT_CHUNK_ROWS) {
+        if (value < 1) return fail(ctx, SFMGMS_ERR_ARG, "chunk rows must be positive");
+        ctx->chunk_rows = (long long)value;
+        return SFMGMS_OK;
+    }
+    if (key == SFMGMS_OPT_GMS_DENSE) {
+        ctx->gms_dense = value ? 1 : 0;
+        return SFMGMS_OK;
+    }
     if (key == SFMGMS_OPT_L2_KERNEL) {
         if (value < 0 || value > 3) return fail(ctx, SFMGMS_ERR_ARG, "bad L2 kernel %lld", (long long)value);
         ctx->l2_kernel = (int)value;
@@ -426,7 +446,8 @@ int sfmgms_set_option(sfmgms_ctx* ctx, int key, int64_t value) {
         if (value && !ctx->ev[0])
             for (int k = 0; k < 3; ++k)
                 if (cudaEventCreate(&ctx->ev[k]) != cudaSuccess) return fail(ctx, SFMGMS_ERR_CUDA, "cudaEventCreate failed");
-        ctx->timing = value ? 1 : 0;
+        ctx->timing = value >= 2 ? 2 : (value ? 1 : 0);
+        if (ctx->timing < 2) ctx->kernel_times.clear();
         return SFMGMS_OK;
     }
     return fail(ctx, SFMGMS_ERR_ARG, "unknown option %d", key);
@@ -643,7 +664,7 @@ int sfmgms_bf_l2_crosscheck(sfmgms_ctx* ctx, const float* query, int nq, const f
 int sfmgms_brute_force_match(sfmgms_ctx* ctx, int norm_type, int cross_check, const void* query, int nq,
                              const void* train, int nt, int width, double distance_coef, int max_matching_size,
                              int32_t* query_idx, int32_t* train_idx, float* dist, int capacity, int* n_out) {
-    if (!ctx) return SFMGMS_ERR_ARG;
+    GUARD_BEGIN
     if (n_out) *n_out = 0;
     if (norm_type != SFMGMS_NORM_L2 && norm_type != SFMGMS_NORM_HAMMING)
         return fail(ctx, SFMGMS_ERR_ARG, "norm_type must be SFMGMS_NORM_L2 (4) or SFMGMS_NORM_HAMMING (6), got %d", norm_type);
@@ -681,6 +702,7 @@ int sfmgms_brute_force_match(sfmgms_ctx* ctx, int norm_type, int cross_check, co
     }
     if (n_out) *n_out = (int)m.size();
     return SFMGMS_OK;
+    GUARD_END
 }
 
 // ---- (§8f-4) cv::ORB: compute on provided keypoints, detectAndCompute -----------------------------------
@@ -927,11 +949,13 @@ int sfmgms_set_images(sfmgms_ctx* ctx, int n_images, const int64_t* kp_offsets, 
         return fail(ctx, SFMGMS_ERR_ARG, "bad location %d", location);
     }
     ctx->n_images = n_images;
-    if (ctx->orb_keypoints.size() != (size_t)total * 28) ctx->orb_keypoints.clear();
+    if (!ctx->keep_orb_keypoints) ctx->orb_keypoints.clear();   // only set_images_from_pixels keeps its own keypoints
     ctx->offsets.assign(kp_offsets, kp_offsets + n_images + 1);
     ctx->sizes.assign(sizes_wh, sizes_wh + 2 * (size_t)n_images);
     ctx->set_version++;
     tc_invalidate(ctx->tc);
+    tc_pin_span(ctx->tc, ctx->set_desc, total);   // the set's +-1 operands are derived once and serve every later launch
+    ctx->last_pairs.clear();
     return SFMGMS_OK;
     GUARD_END
 }
@@ -941,8 +965,9 @@ int sfmgms_set_images(sfmgms_ctx* ctx, int n_images, const int64_t* kp_offsets, 
 int sfmgms_set_images_from_pixels(sfmgms_ctx* ctx, int n_images, const uint8_t* const* images, const int32_t* widths,
                                   const int32_t* heights, const int32_t* channels, const int32_t* strides,
                                   const sfmgms_orb_params* prm, int64_t* kp_offsets_out) {
-    if (!ctx) return SFMGMS_ERR_ARG;
-    if (n_images < 0 || (n_images > 0 && (!images || !widths || !heights || !channels || !prm)))
+    GUARD_BEGIN
+    if (!prm) return fail(ctx, SFMGMS_ERR_ARG, "null parameter block");
+    if (n_images < 0 || (n_images > 0 && (!images || !widths || !heights || !channels)))
         return fail(ctx, SFMGMS_ERR_ARG, "bad image list");
     {   // argument checks once, through the single-image entry point's rules
         sfmgms_orb_params p = *prm;
@@ -970,7 +995,8 @@ int sfmgms_set_images_from_pixels(sfmgms_ctx* ctx, int n_images, const uint8_t* 
         ctx->orb_streams.push_back(q);
         ctx->orb_pool.push_back(orb_ws_create());
     }
-    auto work = [&](int t) {
+    std::vector<int> thread_err((size_t)n_workers, 0);   // set when even the error string could not be built
+    auto work_body = [&](int t) {
         if (cudaSetDevice(device) != cudaSuccess) { errs[(size_t)t] = "cudaSetDevice failed"; return; }
         cudaStream_t st = ctx->orb_streams[(size_t)t];
         OrbWorkspace* ws = ctx->orb_pool[(size_t)t];
@@ -991,15 +1017,18 @@ int sfmgms_set_images_from_pixels(sfmgms_ctx* ctx, int n_images, const uint8_t* 
             }
         }
     };
+    auto work = [&](int t) {   // nothing may escape a worker thread (std::terminate) or the extern "C" boundary
+        try { work_body(t); } catch (...) { thread_err[(size_t)t] = 1; }
+    };
     {
         std::vector<std::thread> th;
         for (int t = 1; t < n_workers; ++t) th.emplace_back(work, t);
         work(0);
         for (auto& x : th) x.join();
-        cudaSetDevice(device);
     }
     for (int t = 0; t < n_workers; ++t) {
         ctx->launches += launches[(size_t)t];
+        if (thread_err[(size_t)t]) return fail(ctx, SFMGMS_ERR_ARG, "host allocation failed in an ORB worker");
         if (!errs[(size_t)t].empty()) return fail(ctx, SFMGMS_ERR_CUDA, "%s", errs[(size_t)t].c_str());
     }
     std::vector<uint8_t> desc;
@@ -1023,10 +1052,13 @@ int sfmgms_set_images_from_pixels(sfmgms_ctx* ctx, int n_images, const uint8_t* 
     if (kp_offsets_out) memcpy(kp_offsets_out, off.data(), off.size() * sizeof(int64_t));
     static const uint8_t dummy_desc[32] = {0};
     static const float dummy_xy[2] = {0.f, 0.f};
+    ctx->keep_orb_keypoints = true;
     const int rc = sfmgms_set_images(ctx, n_images, off.data(), desc.empty() ? dummy_desc : desc.data(), xy.empty() ? dummy_xy : xy.data(),
                                      sizes.data(), SFMGMS_HOST);
-    if (rc) return rc;
+    ctx->keep_orb_keypoints = false;
+    if (rc) { ctx->orb_keypoints.clear(); return rc; }
     return cudaStreamSynchronize(ctx->stream) == cudaSuccess ? SFMGMS_OK : fail(ctx, SFMGMS_ERR_CUDA, "upload of the image set failed");
+    GUARD_END
 }
 
 int sfmgms_get_image_keypoints(sfmgms_ctx* ctx, int image, void* keypoints, int capacity, int* n_out) {
@@ -1081,68 +1113,265 @@ static int build_pair_table(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, 
     return SFMGMS_OK;
 }
 
+// ---- chunked pair-list runner -------------------------------------------------------------------------
+// One implementation behind sfmgms_match_pairs and sfmgms_match_pairs_compact.  The pair list is walked in chunks
+// of at most ctx->chunk_rows match rows (and kMaxChunkPairs pairs); all per-match device scratch (keys, masks, GMS
+// cell indices, decoded / compacted outputs) is sized for ONE chunk and lives in two slots, so chunk c+1 computes
+// while chunk c's results are copied out.  The reference handles one pair at a time (FeatureMatchUtil.cpp:66-69),
+// i.e. has no list-size limit either.
+namespace {
+
+struct PairsJob {
+    const int32_t* pairs = nullptr; int n_pairs = 0;
+    int with_rotation = 0, with_scale = 0; double factor = 6.0;
+    int out_location = SFMGMS_HOST;
+    int32_t *n_inliers = nullptr, *best_hyp = nullptr, *mask_len = nullptr;   // per pair
+    int32_t *train_idx = nullptr, *dist = nullptr; uint8_t* mask = nullptr;   // per match row, list order
+    bool compact = false;                                                     // compacted inliers
+    int64_t* inlier_offsets = nullptr; void* matches = nullptr; float *pts1 = nullptr, *pts2 = nullptr;
+    int64_t capacity = 0; int64_t* n_total = nullptr;
+};
+
+constexpr int kMaxChunkPairs = 4096;
+
+int ensure_slot_events(sfmgms_ctx* ctx) {
+    for (auto& sl : ctx->slot) {
+        if (!sl.computed) CU(cudaEventCreateWithFlags(&sl.computed, cudaEventDisableTiming));
+        if (!sl.copied) CU(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
+        if (ctx->timing && !sl.t0) { CU(cudaEventCreate(&sl.t0)); CU(cudaEventCreate(&sl.t1)); CU(cudaEventCreate(&sl.t2)); }
+    }
+    return SFMGMS_OK;
+}
+
+int run_pairs_job(sfmgms_ctx* ctx, const PairsJob& J) {
+    const int n_pairs = J.n_pairs;
+    if (n_pairs < 0 || (n_pairs > 0 && !J.pairs)) return fail(ctx, SFMGMS_ERR_ARG, "bad pair list");
+    if (J.out_location != SFMGMS_HOST && J.out_location != SFMGMS_DEVICE) return fail(ctx, SFMGMS_ERR_ARG, "bad out_location");
+    if (n_pairs > 0 && ctx->n_images == 0) return fail(ctx, SFMGMS_ERR_STATE, "sfmgms_set_images has not been called");
+    if (J.compact && (J.capacity < 0 || (J.capacity > 0 && !J.matches && !J.pts1 && !J.pts2)))
+        return fail(ctx, SFMGMS_ERR_ARG, "compact output: capacity > 0 needs at least one of matches / pts1 / pts2");
+    if (J.n_total) *J.n_total = 0;
+    cudaStream_t st = ctx->stream;
+    const bool dev_out = (J.out_location == SFMGMS_DEVICE);
+    std::vector<PairDesc> hp;
+    int64_t total = 0;
+    int rc = build_pair_table(ctx, J.pairs, n_pairs, hp, &total);
+    if (rc) return rc;
+    ctx->last_pairs.clear();
+    ctx->last_results.assign((size_t)n_pairs, PairResult{0, -1, 0, 0});
+    if (J.inlier_offsets) J.inlier_offsets[0] = 0;   // overwritten below for device output
+    if (n_pairs == 0) {
+        if (J.inlier_offsets && dev_out) CU(cudaMemsetAsync(J.inlier_offsets, 0, 8, st));
+        CU(cudaStreamSynchronize(st));
+        return SFMGMS_OK;
+    }
+    if (!ctx->d2h_stream) CU(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    if ((rc = ensure_slot_events(ctx))) return rc;
+
+    // ---- chunk boundaries -------------------------------------------------------------------------------
+    std::vector<int> cbeg;
+    {
+        int p = 0;
+        while (p < n_pairs) {
+            cbeg.push_back(p);
+            long long rows = 0;
+            int q = p;
+            while (q < n_pairs && q - p < kMaxChunkPairs && (q == p || rows + hp[q].n1 <= ctx->chunk_rows)) rows += hp[q++].n1;
+            p = q;
+        }
+        cbeg.push_back(n_pairs);
+    }
+    const int n_chunks = (int)cbeg.size() - 1;
+    long long max_rows = 0;
+    int max_cp = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        const long long rows = (cbeg[c + 1] < n_pairs ? hp[cbeg[c + 1]].match_base : total) - hp[cbeg[c]].match_base;
+        if (rows > max_rows) max_rows = rows;
+        if (cbeg[c + 1] - cbeg[c] > max_cp) max_cp = cbeg[c + 1] - cbeg[c];
+    }
+    // ---- buffers: one pair table / result table for the list (96 + 16 B per pair), per-chunk scratch in 2 slots ----
+    const int n_slots = n_chunks > 1 ? 2 : 1;
+    const bool want_idx = J.train_idx || J.dist;
+    const bool stage_mask = !(dev_out && J.mask);                 // device output: kernels write the caller's mask directly
+    const bool stage_idx = want_idx && !dev_out;
+    const bool stage_compact = J.compact && !dev_out;
+    for (int b = 0; b < n_slots; ++b) {
+        auto& sl = ctx->slot[b];
+        CU(sl.key.ensure((size_t)max_rows * 4 + 4));
+        if (stage_mask) CU(sl.mask.ensure((size_t)max_rows + 1));
+        if (stage_idx) CU(sl.out_i32.ensure((size_t)max_rows * 8 + 8));
+        if (J.compact) CU(sl.coff.ensure((size_t)(max_cp + 1) * 8));
+        if (stage_compact && J.matches) CU(sl.cmatch.ensure((size_t)max_rows * 16 + 16));
+        if (stage_compact && (J.pts1 || J.pts2)) CU(sl.cpts.ensure((size_t)max_rows * 16 + 16));
+    }
+    if (J.compact) { CU(ctx->d_cbase.ensure(8)); CU(cudaMemsetAsync(ctx->d_cbase.p, 0, 8, st)); }
+    for (int c = 0; c < n_chunks; ++c) {
+        auto& sl = ctx->slot[c % n_slots];
+        const int64_t cb = hp[cbeg[c]].match_base;
+        for (int p = cbeg[c]; p < cbeg[c + 1]; ++p) {
+            hp[p].key = (uint32_t*)sl.key.p + (hp[p].match_base - cb);
+            hp[p].mask = stage_mask ? (uint8_t*)sl.mask.p + (hp[p].match_base - cb) : J.mask + hp[p].match_base;
+            hp[p].match_base -= cb;                               // chunk-local row offset from here on
+        }
+    }
+    std::vector<int64_t> chunk_row0((size_t)n_chunks + 1);
+    {
+        int64_t o = 0;
+        for (int c = 0; c < n_chunks; ++c) {
+            chunk_row0[c] = o;
+            for (int p = cbeg[c]; p < cbeg[c + 1]; ++p) o += hp[p].n1;
+        }
+        chunk_row0[n_chunks] = o;
+    }
+    if ((rc = upload_pairs(ctx, hp))) return rc;
+    CU(ctx->h_results.ensure(sizeof(PairResult) * (size_t)n_pairs));
+    if (J.compact) CU(ctx->h_coff.ensure((size_t)(max_cp + 1) * 8 * 2));
+    double t_ham = 0, t_gms = 0;
+    int ham_launches = 0;
+    int64_t inl_total = 0;           // inliers of finished chunks (host outputs: also the write cursor)
+    bool overflow = false;
+    int err_rc = SFMGMS_OK;
+
+    // finalize(c): wait for chunk c, read its per-pair results, start the copies of its outputs to the caller
+    auto finalize = [&](int c) -> int {
+        auto& sl = ctx->slot[c % n_slots];
+        const int p0 = cbeg[c], pn = cbeg[c + 1] - cbeg[c];
+        CU(cudaEventSynchronize(sl.computed));
+        if (ctx->timing) {
+            float a = 0.f, b = 0.f;
+            CU(cudaEventElapsedTime(&a, sl.t0, sl.t1)); CU(cudaEventElapsedTime(&b, sl.t1, sl.t2));
+            t_ham += a; t_gms += b;
+            if (ctx->timing >= 2) ctx->absorb(sl.marks);
+        }
+        const PairResult* hr = static_cast<const PairResult*>(ctx->h_results.p) + p0;
+        int64_t chunk_inl = 0;
+        for (int p = 0; p < pn; ++p) {
+            ctx->last_results[(size_t)p0 + p] = hr[p];
+            if (hr[p].status == 4 && !err_rc) err_rc = fail(ctx, SFMGMS_ERR_INDEX, "pair %d: queryIdx/trainIdx out of range", p0 + p);
+            if (hr[p].status == 3 && !err_rc) err_rc = fail(ctx, SFMGMS_ERR_DOMAIN, "pair %d: matched keypoint outside [0,w)x[0,h)", p0 + p);
+            if (!dev_out) {
+                if (J.n_inliers) J.n_inliers[p0 + p] = hr[p].n_inliers;
+                if (J.best_hyp) J.best_hyp[p0 + p] = hr[p].best_hyp;
+                if (J.mask_len) J.mask_len[p0 + p] = hr[p].mask_len;
+                if (J.inlier_offsets) J.inlier_offsets[p0 + p] = inl_total + chunk_inl;
+            }
+            chunk_inl += hr[p].mask_len > 0 ? hr[p].n_inliers : 0;
+        }
+        if (!dev_out) {
+            const int64_t r0 = chunk_row0[c], rows = chunk_row0[c + 1] - chunk_row0[c];
+            if (rows > 0) {
+                int32_t* dti = (int32_t*)sl.out_i32.p;
+                if (J.train_idx) CU(cudaMemcpyAsync(J.train_idx + r0, dti, (size_t)rows * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                if (J.dist) CU(cudaMemcpyAsync(J.dist + r0, dti + rows, (size_t)rows * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                if (J.mask) CU(cudaMemcpyAsync(J.mask + r0, sl.mask.p, (size_t)rows, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+            }
+            if (J.compact && chunk_inl > 0) {
+                int64_t n = chunk_inl;
+                if (inl_total + n > J.capacity) { overflow = true; n = J.capacity > inl_total ? J.capacity - inl_total : 0; }
+                if (n > 0) {
+                    if (J.matches) CU(cudaMemcpyAsync((char*)J.matches + inl_total * 16, sl.cmatch.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                    if (J.pts1) CU(cudaMemcpyAsync(J.pts1 + inl_total * 2, sl.cpts.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                    if (J.pts2) CU(cudaMemcpyAsync(J.pts2 + inl_total * 2, (char*)sl.cpts.p + (size_t)max_rows * 8, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                }
+            }
+            CU(cudaEventRecord(sl.copied, ctx->d2h_stream));
+            sl.copy_pending = true;
+        }
+        inl_total += chunk_inl;
+        return SFMGMS_OK;
+    };
+
+    for (int c = 0; c < n_chunks && !err_rc; ++c) {
+        auto& sl = ctx->slot[c % n_slots];
+        const int p0 = cbeg[c], pn = cbeg[c + 1] - cbeg[c];
+        const int64_t rows = chunk_row0[c + 1] - chunk_row0[c];
+        if (sl.copy_pending) { CU(cudaStreamWaitEvent(st, sl.copied, 0)); sl.copy_pending = false; }
+        if (rows > 0) {
+            CU(cudaMemsetAsync(sl.key.p, 0xFF, (size_t)rows * 4, st));
+            CU(cudaMemsetAsync(stage_mask ? (uint8_t*)sl.mask.p : J.mask + chunk_row0[c], 0, (size_t)rows, st));
+        }
+        if (ctx->timing) CU(cudaEventRecord(sl.t0, st));
+        if (ctx->timing >= 2) { sl.marks.used = 0; tl_marks = &sl.marks; kmark("begin", st); }
+        rc = enqueue_range(ctx, hp, p0, pn, true, true, J.with_rotation, J.with_scale, J.factor, &ham_launches,
+                           ctx->timing ? sl.t1 : nullptr);
+        if (rc) { tl_marks = nullptr; err_rc = rc; break; }
+        if (ctx->timing) CU(cudaEventRecord(sl.t2, st));
+        if (rows > 0 && want_idx) {
+            int32_t* dti = dev_out ? (J.train_idx ? J.train_idx + chunk_row0[c] : nullptr) : (J.train_idx ? (int32_t*)sl.out_i32.p : nullptr);
+            int32_t* ddi = dev_out ? (J.dist ? J.dist + chunk_row0[c] : nullptr) : (J.dist ? (int32_t*)sl.out_i32.p + rows : nullptr);
+            decode_keys_kernel<<<(unsigned)((rows + 255) / 256 > 8192 ? 8192 : (rows + 255) / 256), 256, 0, st>>>(
+                (const uint32_t*)sl.key.p, rows, dti, ddi);
+            ctx->launches++; kmark("decode_keys", st);
+        }
+        if (J.compact) {
+            // host output: chunk-local offsets into the slot's staging (base reset per chunk); device output: the
+            // caller's buffers and offsets array directly, one running base
+            if (!dev_out) CU(cudaMemsetAsync(ctx->d_cbase.p, 0, 8, st));
+            long long* doff = dev_out && J.inlier_offsets ? (long long*)J.inlier_offsets + p0 : (long long*)sl.coff.p;
+            DMatchRec* dm = dev_out ? (DMatchRec*)J.matches : (J.matches ? (DMatchRec*)sl.cmatch.p : nullptr);
+            float* dp1 = dev_out ? J.pts1 : (J.pts1 ? (float*)sl.cpts.p : nullptr);
+            float* dp2 = dev_out ? J.pts2 : (J.pts2 ? (float*)((char*)sl.cpts.p + (size_t)max_rows * 8) : nullptr);
+            ctx->launches += launch_gms_compact(static_cast<const PairDesc*>(ctx->d_pairs.p) + p0, static_cast<const PairResult*>(ctx->d_results.p) + p0,
+                                                pn, (long long*)ctx->d_cbase.p, doff, dev_out ? J.capacity : rows, dm, dp1, dp2, st);
+            CU(cudaGetLastError());
+        }
+        tl_marks = nullptr;
+        CU(cudaMemcpyAsync(static_cast<PairResult*>(ctx->h_results.p) + p0, static_cast<const PairResult*>(ctx->d_results.p) + p0,
+                           sizeof(PairResult) * (size_t)pn, cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(sl.computed, st));
+        if (c > 0 && (rc = finalize(c - 1))) { err_rc = rc; break; }
+    }
+    if (!err_rc && (rc = finalize(n_chunks - 1))) err_rc = rc;
+    cudaStreamSynchronize(st);
+    cudaStreamSynchronize(ctx->d2h_stream);
+    for (auto& sl : ctx->slot) sl.copy_pending = false;
+    tc_reset_arena(ctx->tc);
+    if (ctx->timing) { ctx->last_ms[0] = t_ham; ctx->last_ms[1] = t_gms; ctx->last_ms[2] = ham_launches; }
+    if (err_rc) return err_rc;
+    if (dev_out) {   // per-pair summaries for device callers (small; after the run)
+        std::vector<int32_t> tmp((size_t)n_pairs);
+        int32_t* outs[3] = {J.n_inliers, J.best_hyp, J.mask_len};
+        for (int k = 0; k < 3; ++k) {
+            if (!outs[k]) continue;
+            for (int p = 0; p < n_pairs; ++p)
+                tmp[p] = k == 0 ? ctx->last_results[p].n_inliers : k == 1 ? ctx->last_results[p].best_hyp : ctx->last_results[p].mask_len;
+            CU(cudaMemcpy(outs[k], tmp.data(), (size_t)n_pairs * 4, cudaMemcpyHostToDevice));
+        }
+    } else if (J.inlier_offsets) {
+        J.inlier_offsets[n_pairs] = inl_total;
+    }
+    if (J.n_total) *J.n_total = inl_total;
+    if (n_chunks == 1) ctx->last_pairs = hp;     // sfmgms_inlier_points: only while the chunk's buffers are intact
+    if (J.compact && (overflow || (dev_out && inl_total > J.capacity)))
+        return fail(ctx, SFMGMS_ERR_CAPACITY, "compact output needs %lld rows, capacity is %lld", (long long)inl_total, (long long)J.capacity);
+    return SFMGMS_OK;
+}
+
+}  // namespace
+
 int sfmgms_match_pairs(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int with_rotation, int with_scale,
                        double threshold_factor, int out_location, int32_t* n_inliers, int32_t* best_hyp,
                        int32_t* mask_len, int32_t* train_idx, int32_t* dist, uint8_t* mask) {
     GUARD_BEGIN
-    if (n_pairs < 0 || (n_pairs > 0 && !pairs)) return fail(ctx, SFMGMS_ERR_ARG, "bad pair list");
-    if (out_location != SFMGMS_HOST && out_location != SFMGMS_DEVICE) return fail(ctx, SFMGMS_ERR_ARG, "bad out_location");
-    if (n_pairs > 0 && ctx->n_images == 0) return fail(ctx, SFMGMS_ERR_STATE, "sfmgms_set_images has not been called");
-    cudaStream_t st = ctx->stream;
-    std::vector<PairDesc> hp;
-    int64_t total = 0;
-    int rc = build_pair_table(ctx, pairs, n_pairs, hp, &total);
-    if (rc) return rc;
-    CU(ctx->d_key.ensure((size_t)total * 4 + 4));
-    const bool dev_out = (out_location == SFMGMS_DEVICE);
-    uint8_t* dmask = (dev_out && mask) ? mask : nullptr;
-    if (!dmask) { CU(ctx->d_mask.ensure((size_t)total + 1)); dmask = (uint8_t*)ctx->d_mask.p; }
-    for (int p = 0; p < n_pairs; ++p) {
-        hp[p].key = (uint32_t*)ctx->d_key.p + hp[p].match_base;
-        hp[p].mask = dmask + hp[p].match_base;
-    }
-    if (total) {
-        CU(cudaMemsetAsync(ctx->d_key.p, 0xFF, (size_t)total * 4, st));
-        CU(cudaMemsetAsync(dmask, 0, (size_t)total, st));
-    }
-    rc = run_batch(ctx, hp, true, true, with_rotation, with_scale, threshold_factor);
-    ctx->last_pairs = hp;
-    if (rc) return rc;
-    // per-pair results
-    if (n_inliers || best_hyp || mask_len) {
-        std::vector<int32_t> tmp((size_t)n_pairs * 3);
-        for (int p = 0; p < n_pairs; ++p) {
-            tmp[p] = ctx->last_results[p].n_inliers;
-            tmp[n_pairs + p] = ctx->last_results[p].best_hyp;
-            tmp[2 * (size_t)n_pairs + p] = ctx->last_results[p].mask_len;
-        }
-        int32_t* outs[3] = {n_inliers, best_hyp, mask_len};
-        for (int k = 0; k < 3; ++k) {
-            if (!outs[k] || n_pairs == 0) continue;
-            if (dev_out) CU(cudaMemcpy(outs[k], tmp.data() + (size_t)k * n_pairs, (size_t)n_pairs * 4, cudaMemcpyHostToDevice));
-            else memcpy(outs[k], tmp.data() + (size_t)k * n_pairs, (size_t)n_pairs * 4);
-        }
-    }
-    if (total && (train_idx || dist)) {
-        int32_t *dti = nullptr, *ddi = nullptr;
-        if (dev_out) { dti = train_idx; ddi = dist; }
-        else {
-            CU(ctx->d_out_i32.ensure((size_t)total * 8));
-            dti = (int32_t*)ctx->d_out_i32.p; ddi = dti + total;
-            if (!train_idx) dti = nullptr;
-            if (!dist) ddi = nullptr;
-        }
-        decode_keys_kernel<<<(unsigned)((total + 255) / 256 > 8192 ? 8192 : (total + 255) / 256), 256, 0, st>>>(
-            (const uint32_t*)ctx->d_key.p, total, dti, ddi);
-        ctx->launches++;
-        if (!dev_out) {
-            if (train_idx) CU(cudaMemcpyAsync(train_idx, dti, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
-            if (dist) CU(cudaMemcpyAsync(dist, ddi, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
-        }
-    }
-    if (total && mask && !dev_out) CU(cudaMemcpyAsync(mask, dmask, (size_t)total, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    return SFMGMS_OK;
+    PairsJob J;
+    J.pairs = pairs; J.n_pairs = n_pairs; J.with_rotation = with_rotation; J.with_scale = with_scale; J.factor = threshold_factor;
+    J.out_location = out_location; J.n_inliers = n_inliers; J.best_hyp = best_hyp; J.mask_len = mask_len;
+    J.train_idx = train_idx; J.dist = dist; J.mask = mask;
+    return run_pairs_job(ctx, J);
+    GUARD_END
+}
+
+int sfmgms_match_pairs_compact(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int with_rotation, int with_scale,
+                               double threshold_factor, int out_location, int32_t* n_inliers, int32_t* best_hyp,
+                               int64_t* inlier_offsets, void* matches, float* pts1, float* pts2, int64_t capacity,
+                               int64_t* n_total) {
+    GUARD_BEGIN
+    PairsJob J;
+    J.pairs = pairs; J.n_pairs = n_pairs; J.with_rotation = with_rotation; J.with_scale = with_scale; J.factor = threshold_factor;
+    J.out_location = out_location; J.n_inliers = n_inliers; J.best_hyp = best_hyp;
+    J.compact = true; J.inlier_offsets = inlier_offsets; J.matches = matches; J.pts1 = pts1; J.pts2 = pts2;
+    J.capacity = capacity; J.n_total = n_total;
+    return run_pairs_job(ctx, J);
     GUARD_END
 }
 
@@ -1185,6 +1414,10 @@ int sfmgms_match_image_set(sfmgms_ctx* ctx, int n_images, const int64_t* kp_offs
     ctx->sizes.assign(sizes_wh, sizes_wh + 2 * (size_t)n_images);
     ctx->set_version++;
     tc_invalidate(ctx->tc);
+    tc_pin_span(ctx->tc, nullptr, 0);   // the set arrives chunk by chunk here: operands are derived per sub-batch span
+    ctx->last_pairs.clear();
+    // every early return below must leave no copy in flight into the caller's buffers
+    auto drain = [&]() { cudaStreamSynchronize(ctx->h2d_stream); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->d2h_stream); tc_reset_arena(ctx->tc); };
 
     static const bool trace = getenv("SFMGMS_TRACE") != nullptr;   // developer aid: print the stream timeline
     auto now_ms = []() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
@@ -1255,7 +1488,7 @@ int sfmgms_match_image_set(sfmgms_ctx* ctx, int n_images, const int64_t* kp_offs
     rc = upload_pairs(ctx, hp);
     if (rc) { cudaStreamSynchronize(ctx->h2d_stream); return rc; }
     mark("pairs-uploaded");
-    if (ctx->timing) { CU(cudaEventRecord(ctx->ev[0], st)); CU(cudaEventRecord(ctx->ev[1], st)); ctx->timing_mid_pending = false; }
+    if (ctx->timing) { CU(cudaEventRecord(ctx->ev[0], st)); CU(cudaEventRecord(ctx->ev[1], st)); }
     // ---- sub-batches in list order: wait for the chunk(s) they need, compute, hand results to the D2H stream ----
     // Sub-batch sizes DECREASE along the list: compute is faster than the H2D transfer, so every sub-batch ends up
     // waiting for its images and the time after the last byte has arrived is one sub-batch of compute — keep that
@@ -1287,12 +1520,12 @@ int sfmgms_match_image_set(sfmgms_ctx* ctx, int n_images, const int64_t* kp_offs
             if (c > need) need = c;
         }
         if (trace) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); fprintf(stderr, "[sfmgms trace] host t=%.3f ms: range at pair %d needs chunk %d\n", ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6, r0, need); }
-        if ((rc = issue_chunks_upto(need + kLookahead))) return rc;
+        if ((rc = issue_chunks_upto(need + kLookahead))) { drain(); return rc; }
         mark("before-wait");
         CU(cudaStreamWaitEvent(st, ctx->events[(size_t)need], 0));
         mark("after-wait");
         rc = enqueue_range(ctx, hp, r0, rn, true, true, with_rotation, with_scale, threshold_factor, &ham_launches);
-        if (rc) { cudaStreamSynchronize(ctx->h2d_stream); cudaStreamSynchronize(st); tc_reset_arena(ctx->tc); return rc; }
+        if (rc) { drain(); return rc; }
         const int64_t m0 = hp[r0].match_base;
         const int64_t m1 = (r0 + rn < n_pairs) ? hp[r0 + rn].match_base : total;
         if (m1 > m0) {
@@ -1303,7 +1536,7 @@ int sfmgms_match_image_set(sfmgms_ctx* ctx, int n_images, const int64_t* kp_offs
             }
             cudaEvent_t e;
             rc = get_event(ctx, ev_k++, &e);
-            if (rc) return rc;
+            if (rc) { drain(); return rc; }
             CU(cudaEventRecord(e, st));
             if (trace) { cudaEvent_t t; cudaEventCreate(&t); cudaEventRecord(t, st); tr_cmp.push_back(t); }
             CU(cudaStreamWaitEvent(ctx->d2h_stream, e, 0));
@@ -1314,13 +1547,12 @@ int sfmgms_match_image_set(sfmgms_ctx* ctx, int n_images, const int64_t* kp_offs
     }
     {
         const int rc2 = issue_chunks_upto(n_chunks - 1);   // images no pair referenced still belong to the registered set
-        if (rc2) return rc2;
+        if (rc2) { drain(); return rc2; }
     }
     t_enq = now_ms();
     rc = finish_batch(ctx, n_pairs, true);
     t_fin = now_ms();
-    CU(cudaStreamSynchronize(ctx->h2d_stream));
-    CU(cudaStreamSynchronize(ctx->d2h_stream));
+    drain();
     ctx->last_pairs = hp;
     if (trace) {
         cudaEvent_t tend; cudaEventCreate(&tend); cudaEventRecord(tend, ctx->d2h_stream); cudaEventSynchronize(tend);
@@ -1350,29 +1582,77 @@ int sfmgms_match_image_set(sfmgms_ctx* ctx, int n_images, const int64_t* kp_offs
 
 int sfmgms_inlier_points(sfmgms_ctx* ctx, int pair_index, float* pts1, float* pts2, int capacity, int* n_out) {
     GUARD_BEGIN
-    if (pair_index < 0 || pair_index >= (int)ctx->last_pairs.size()) return fail(ctx, SFMGMS_ERR_STATE, "no such pair in the last batch");
     if (capacity < 0 || !n_out || (capacity > 0 && (!pts1 || !pts2))) return fail(ctx, SFMGMS_ERR_ARG, "bad arguments");
+    if (ctx->last_pairs.empty() && !ctx->last_results.empty())
+        return fail(ctx, SFMGMS_ERR_STATE, "the last pair list ran in several chunks; use sfmgms_match_pairs_compact for its coordinates");
+    if (pair_index < 0 || pair_index >= (int)ctx->last_pairs.size()) return fail(ctx, SFMGMS_ERR_STATE, "no such pair in the last batch");
     const PairDesc& pd = ctx->last_pairs[pair_index];
     const PairResult& r = ctx->last_results[pair_index];
-    if (r.mask_len == 0 || pd.n_matches == 0) { *n_out = 0; return SFMGMS_OK; }
+    if (r.mask_len == 0 || pd.n_matches == 0 || r.n_inliers == 0) { *n_out = 0; return SFMGMS_OK; }
+    // a one-pair view of the batched compaction (same kernels as sfmgms_match_pairs_compact)
     cudaStream_t st = ctx->stream;
-    CU(ctx->d_pts.ensure((size_t)capacity * 16 + 16));
-    float2* d1 = (float2*)ctx->d_pts.p;
-    float2* d2 = d1 + capacity;
-    int* dn = (int*)(d2 + capacity);
-    inlier_points_kernel<<<1, 1024, 0, st>>>(pd, d1, d2, capacity, dn);
-    ctx->launches++;
-    int n = 0;
-    CU(cudaMemcpyAsync(&n, dn, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    const int m = n < capacity ? n : capacity;
+    CU(ctx->d_pts.ensure((size_t)capacity * 16 + 64));
+    float* d1 = (float*)ctx->d_pts.p;
+    float* d2 = d1 + 2 * (size_t)capacity;
+    long long* dbase = (long long*)(d2 + 2 * (size_t)capacity);
+    CU(cudaMemsetAsync(dbase, 0, 8, st));
+    ctx->launches += launch_gms_compact(static_cast<const PairDesc*>(ctx->d_pairs.p) + pair_index,
+                                        static_cast<const PairResult*>(ctx->d_results.p) + pair_index, 1, dbase, dbase + 1,
+                                        capacity, nullptr, d1, d2, st);
+    const int m = r.n_inliers < capacity ? r.n_inliers : capacity;
     if (m > 0) {
-        CU(cudaMemcpy(pts1, d1, (size_t)m * 8, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(pts2, d2, (size_t)m * 8, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpyAsync(pts1, d1, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(pts2, d2, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
     }
-    *n_out = n;
+    CU(cudaStreamSynchronize(st));
+    *n_out = r.n_inliers;
     return SFMGMS_OK;
     GUARD_END
+}
+
+// All 40 hypotheses of one pair (diagnostic / parity entry point): the inlier count GMSMatcher::run returns for
+// every (scale, rotation), scale-major — what getInlierMask compares (DLL @VA 0x180047dc0).
+int sfmgms_gms_hypotheses(sfmgms_ctx* ctx, int w1, int h1, int w2, int h2, const void* kp1, int n1, int kp1_stride_bytes,
+                          const void* kp2, int n2, int kp2_stride_bytes, const int32_t* query_idx, const int32_t* train_idx,
+                          int idx_stride_bytes, int n_matches, double threshold_factor, int32_t* counts) {
+    GUARD_BEGIN
+    if (!counts) return fail(ctx, SFMGMS_ERR_ARG, "counts is null");
+    int rc = sfmgms_gms(ctx, w1, h1, w2, h2, kp1, n1, kp1_stride_bytes, kp2, n2, kp2_stride_bytes, query_idx, train_idx,
+                        idx_stride_bytes, n_matches, 1, 1, threshold_factor, nullptr, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    const size_t off = gms_counts_offset_words(kNumScales, kNumRot, n_matches, ctx->gms_dense);
+    CU(cudaMemcpy(counts, static_cast<const int32_t*>(ctx->d_hist.p) + off, kMaxHyp * 4, cudaMemcpyDeviceToHost));
+    return SFMGMS_OK;
+    GUARD_END
+}
+
+// "name:total_ms:launches;..." of every kernel timed since SFMGMS_OPT_TIMING was set to 2 (resets the accumulators)
+int sfmgms_kernel_times(sfmgms_ctx* ctx, char* buf, int buf_len) {
+    GUARD_BEGIN
+    if (!buf || buf_len <= 0) return fail(ctx, SFMGMS_ERR_ARG, "bad buffer");
+    std::string o;
+    for (const auto& k : ctx->kernel_times) {
+        char tmp[160];
+        snprintf(tmp, sizeof tmp, "%s:%.6f:%lld;", k.name.c_str(), k.ms, k.n);
+        o += tmp;
+    }
+    if ((int)o.size() + 1 > buf_len) return fail(ctx, SFMGMS_ERR_CAPACITY, "buffer of %d bytes too small (%zu needed)", buf_len, o.size() + 1);
+    memcpy(buf, o.c_str(), o.size() + 1);
+    ctx->kernel_times.clear();
+    return SFMGMS_OK;
+    GUARD_END
+}
+
+int64_t sfmgms_device_bytes(const sfmgms_ctx* ctx) {
+    if (!ctx) return 0;
+    size_t t = 0;
+    const DevBuf* bufs[] = {&ctx->d_pairs, &ctx->d_results, &ctx->d_key, &ctx->d_mask, &ctx->d_hist, &ctx->d_msc, &ctx->d_q,
+                            &ctx->d_kp1, &ctx->d_kp2, &ctx->d_mq, &ctx->d_mt, &ctx->d_out_i32, &ctx->d_pts,
+                            &ctx->d_set_desc, &ctx->d_set_kp, &ctx->d_cbase};
+    for (const DevBuf* b : bufs) t += b->cap;
+    for (const auto& sl : ctx->slot) t += sl.key.cap + sl.mask.cap + sl.out_i32.cap + sl.cmatch.cap + sl.cpts.cap + sl.coff.cap;
+    t += ctx->tc.ops_cap + ctx->tc.work_cap;
+    return (int64_t)t;
 }
 
 }  // extern "C"

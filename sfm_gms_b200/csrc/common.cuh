@@ -48,6 +48,22 @@ struct PairResult {
     int status;     // 0 ok, SFMGMS_ERR_DOMAIN, SFMGMS_ERR_INDEX
 };
 
+// Per-kernel timing (SFMGMS_OPT_TIMING = 2, measurement runs only): launchers drop a named CUDA event after each
+// kernel; the C ABI layer turns consecutive events into per-kernel milliseconds (sfmgms_kernel_times).
+struct KernelMarks {
+    cudaEvent_t ev[64];
+    const char* name[64];
+    int created = 0, used = 0;
+    void mark(const char* nm, cudaStream_t st) {
+        if (used >= 64) return;
+        if (used >= created) { if (cudaEventCreate(&ev[created]) != cudaSuccess) return; ++created; }
+        cudaEventRecord(ev[used], st);
+        name[used++] = nm;
+    }
+};
+extern thread_local KernelMarks* tl_marks;   // set by the C ABI layer around a batch (one context per host thread)
+inline void kmark(const char* nm, cudaStream_t st) { if (tl_marks) tl_marks->mark(nm, st); }
+
 // launchers (each returns the number of kernel launches it issued; errors via cudaGetLastError)
 int launch_hamming_popc(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, int sm_count,
                         cudaStream_t st);
@@ -62,7 +78,20 @@ long long gms_match_rows(const PairDesc* h_pairs, int n);   // rows of the per-m
 size_t gms_match_scratch_bytes(long long n_matches_total, int n_scales);
 int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, int with_rotation, int with_scale,
                double factor, PairResult* d_results, void* d_hist_scratch, size_t hist_scratch_bytes,
-               void* d_match_scratch, cudaStream_t st);
+               void* d_match_scratch, cudaStream_t st, int force_dense = 0);
+
+// Number of int32 words from a pair's scratch base to its 40 per-hypothesis inlier counters, for the layout
+// launch_gms picks for (n_scales, n_rot, max matches per pair) — sfmgms_gms_hypotheses reads them back.
+size_t gms_counts_offset_words(int n_scales, int n_rot, int max_matches, int force_dense);
+
+// (§8f-1 fused) compacted output of a batch: the reference's matchesGMS vectors (cv::DMatch records of the inliers,
+// in match order) of all pairs back to back, plus the gathered coordinates SfMUtil.cpp:25-35 builds from them.
+// offsets[p] = *base + sum of n_inliers of earlier pairs (exclusive scan, written by the offsets kernel, n_pairs + 1
+// entries); *base += total afterwards.  Rows at or beyond `capacity` are not written.  2 launches.
+struct DMatchRec { int32_t queryIdx, trainIdx, imgIdx; float distance; };
+int launch_gms_compact(const PairDesc* d_pairs, const PairResult* d_results, int n_pairs, long long* d_base,
+                       long long* d_offsets, long long capacity, DMatchRec* d_matches, float* d_pts1, float* d_pts2,
+                       cudaStream_t st);
 
 // L2 brute force for integer-valued float descriptors (OpenCV SIFT), l2_dp4a.cu
 size_t l2_scratch_bytes(int nq, int nt);

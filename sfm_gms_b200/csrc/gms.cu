@@ -158,15 +158,20 @@ __global__ void __launch_bounds__(256) gms_verify_kernel(int32_t* scratch, Layou
     int cp = -1;
     if (ccount > 0) {
         // argmax with strict '>' from maxv = 0 => lowest j among the maxima, count > 0
+        // 64-bit key: the dense path serves pairs with >= 65536 matches, so a count may exceed 21 bits
         const int32_t* row = hist + (size_t)cell * gr;
-        uint32_t bestk = 0;
+        unsigned long long bestk = 0;
         for (int j = lane; j < gr; j += 32) {
-            uint32_t c = (uint32_t)row[j];
-            uint32_t k = (c << 11) | (uint32_t)(2047 - j);
+            const unsigned long long c = (unsigned long long)(uint32_t)row[j];
+            const unsigned long long k = (c << 11) | (unsigned long long)(2047 - j);
             bestk = (c > 0 && k > bestk) ? k : bestk;
         }
-        bestk = __reduce_max_sync(0xffffffffu, bestk);
-        cp = 2047 - (int)(bestk & 2047u);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, bestk, o);
+            bestk = other > bestk ? other : bestk;
+        }
+        cp = 2047 - (int)(bestk & 2047ull);
     }
     for (int r = 0; r < L.n_rot; ++r) {
         int out = cp;
@@ -362,7 +367,97 @@ __global__ void __launch_bounds__(256) gms_mask_kernel(const PairDesc* __restric
     }
 }
 
+// ---- compacted outputs (§8f-1): offsets = exclusive scan of the inlier counts, then an ORDERED per-pair compaction
+__global__ void __launch_bounds__(1024) gms_compact_offsets_kernel(const PairResult* __restrict__ results, int n_pairs,
+                                                                    long long* base_io, long long* __restrict__ offsets) {
+    __shared__ long long wsum[32];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = *base_io;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int p0 = 0; p0 < n_pairs; p0 += 1024) {
+        const int p = p0 + threadIdx.x;
+        const long long v = (p < n_pairs && results[p].mask_len > 0) ? results[p].n_inliers : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        long long woff = 0, tot = 0;
+        for (int k = 0; k < 32; ++k) { const long long w = wsum[k]; if (k < warp) woff += w; tot += w; }
+        if (p < n_pairs) offsets[p] = carry + woff + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { offsets[n_pairs] = carry; *base_io = carry; }
+}
+
+__global__ void __launch_bounds__(1024) gms_compact_kernel(const PairDesc* __restrict__ pairs, const PairResult* __restrict__ results,
+                                                            const long long* __restrict__ offsets, long long capacity,
+                                                            DMatchRec* __restrict__ matches, float2* __restrict__ pts1,
+                                                            float2* __restrict__ pts2) {
+    const PairDesc pd = pairs[blockIdx.x];
+    if (results[blockIdx.x].mask_len <= 0 || results[blockIdx.x].n_inliers <= 0) return;
+    const long long out0 = offsets[blockIdx.x];
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < pd.n_matches; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int m = (i < pd.n_matches) ? (pd.mask[i] != 0) : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, m);
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { const int v = wsum[k]; if (k < warp) woff += v; tot += v; }
+        const long long pos = out0 + carry + woff + __popc(bal & ((1u << lane) - 1u));
+        if (m && pos < capacity) {
+            const uint32_t key = pd.key ? pd.key[i] : 0u;
+            const int qi = pd.mq ? pd.mq[i] : i;
+            const int ti = pd.mt ? pd.mt[i] : (int)(key & kTrainIdxMask);
+            if (matches) {
+                DMatchRec r;
+                r.queryIdx = qi; r.trainIdx = ti; r.imgIdx = 0; r.distance = pd.key ? (float)(key >> kTrainIdxBits) : 0.f;
+                *reinterpret_cast<int4*>(matches + pos) = *reinterpret_cast<const int4*>(&r);
+            }
+            if (pts1) pts1[pos] = reinterpret_cast<const float2*>(pd.kp1)[qi];
+            if (pts2) pts2[pos] = reinterpret_cast<const float2*>(pd.kp2)[ti];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+}
+
 }  // namespace
+
+int launch_gms_compact(const PairDesc* d_pairs, const PairResult* d_results, int n_pairs, long long* d_base,
+                       long long* d_offsets, long long capacity, DMatchRec* d_matches, float* d_pts1, float* d_pts2,
+                       cudaStream_t st) {
+    if (n_pairs <= 0) return 0;
+    gms_compact_offsets_kernel<<<1, 1024, 0, st>>>(d_results, n_pairs, d_base, d_offsets);
+    kmark("gms_compact_offsets", st);
+    gms_compact_kernel<<<n_pairs, 1024, 0, st>>>(d_pairs, d_results, d_offsets, capacity, d_matches,
+                                                 reinterpret_cast<float2*>(d_pts1), reinterpret_cast<float2*>(d_pts2));
+    kmark("gms_compact", st);
+    return 2;
+}
+
+static bool gms_dense_path(int max_matches, int force_dense) {
+    static const bool env_dense = getenv("SFMGMS_GMS_DENSE") != nullptr;
+    return force_dense || env_dense || max_matches >= 65536;
+}
+
+size_t gms_counts_offset_words(int n_scales, int n_rot, int max_matches, int force_dense) {
+    return make_layout(n_scales, n_rot, gms_dense_path(max_matches, force_dense)).counts_off;
+}
 
 long long gms_match_rows(const PairDesc* h_pairs, int n) {
     if (n <= 0) return 0;
@@ -377,7 +472,10 @@ size_t gms_match_scratch_bytes(long long n_matches_total, int n_scales) {
 
 // Left-grid rows per shared-memory band for scale s: (rows + 2 halo) * 20 cells * (G_r u16 + one int) must fit.
 static int smem_band_rows(int s) {
-    static const int b0 = getenv("SFMGMS_GMS_BAND0") ? atoi(getenv("SFMGMS_GMS_BAND0")) : 5;   // tuning experiments only
+    static const int b0 = [] {   // tuning experiments only; clamped to a valid band height
+        const int v = getenv("SFMGMS_GMS_BAND0") ? atoi(getenv("SFMGMS_GMS_BAND0")) : 5;
+        return v < 1 ? 1 : (v > 10 ? 10 : v);
+    }();
     return s == 0 ? b0 : s == 1 ? 20 : s == 2 ? 10 : s == 3 ? 4 : 1;
 }
 static size_t smem_band_bytes(int s) {
@@ -391,15 +489,14 @@ static size_t smem_band_bytes(int s) {
 // sized so that a chunk's histograms fit the scratch budget (kept L2-resident by the caller's choice).
 int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, int with_rotation, int with_scale,
                double factor, PairResult* d_results, void* d_hist_scratch, size_t hist_scratch_bytes,
-               void* d_match_scratch, cudaStream_t st) {
+               void* d_match_scratch, cudaStream_t st, int force_dense) {
     if (n_pairs <= 0) return 0;
     const int n_scales = with_scale ? kNumScales : 1;
     const int n_rot = with_rotation ? kNumRot : 1;
     const int flags_on = (with_rotation || with_scale) ? 1 : 0;
     int max_all = 0;
     for (int p = 0; p < n_pairs; ++p) if (h_pairs[p].n_matches > max_all) max_all = h_pairs[p].n_matches;
-    static const bool force_dense = getenv("SFMGMS_GMS_DENSE") != nullptr;
-    const bool dense = force_dense || max_all >= 65536;
+    const bool dense = gms_dense_path(max_all, force_dense);
     const Layout L = make_layout(n_scales, n_rot, dense);
     const size_t per_pair = L.total_words * 4;
     int chunk_cap = (int)(hist_scratch_bytes / per_pair);
@@ -423,40 +520,41 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
         uint16_t* ridx = lidx + (size_t)4 * cm;
         // zero cnt/counts/hist of every pair in the chunk (cp is fully rewritten by verify)
         cudaMemsetAsync(scratch, 0, (size_t)cn * per_pair, st);
+        kmark("gms_memset", st);
         const int bx = max_m > 0 ? (max_m + 255) / 256 : 1;
         if (dense) {
             if (max_m > 0) {
                 gms_assign_kernel<true><<<dim3(bx, 1, cn), 256, 0, st>>>(d_pairs + c0, d_results + c0, scratch, L, lidx, ridx,
                                                                        cbase, cm);
-                ++launches;
+                ++launches; kmark("gms_assign_dense", st);
             }
             const long long warps = (long long)cn * n_scales * 4 * kCellsL;
             gms_verify_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(scratch, L, factor, cn);
-            ++launches;
+            ++launches; kmark("gms_verify_dense", st);
         } else {
             if (max_m > 0) {
                 gms_assign_kernel<false><<<dim3(bx, 1, cn), 256, 0, st>>>(d_pairs + c0, d_results + c0, scratch, L, lidx, ridx,
                                                                         cbase, cm);
-                ++launches;
+                ++launches; kmark("gms_assign", st);
             }
             for (int s = 0; s < n_scales; ++s) {
                 const int b = smem_band_rows(s);
                 const int bands = (kGridL + b - 1) / b;
                 gms_vote_smem_kernel<<<dim3(bands, 4, cn), 512, smem_band_bytes(s), st>>>(d_pairs + c0, scratch, L, factor, lidx,
                                                                                         ridx, cbase, cm, s, b);
-                ++launches;
+                ++launches; kmark("gms_vote_smem", st);
             }
         }
         if (max_m > 0) {
             gms_count_kernel<<<dim3(bx, n_scales * n_rot, cn), 256, 0, st>>>(d_pairs + c0, scratch, L, lidx, ridx, cbase,
                                                                          cm, flags_on ? 0 : 1);
-            ++launches;
+            ++launches; kmark("gms_count", st);
         }
         gms_select_kernel<<<(cn + 127) / 128, 128, 0, st>>>(d_pairs + c0, d_results + c0, scratch, L, cn, flags_on);
-        ++launches;
+        ++launches; kmark("gms_select", st);
         if (flags_on && max_m > 0) {
             gms_mask_kernel<<<dim3(bx, 1, cn), 256, 0, st>>>(d_pairs + c0, d_results + c0, scratch, L, lidx, ridx, cbase, cm);
-            ++launches;
+            ++launches; kmark("gms_mask", st);
         }
     }
     return launches;

@@ -496,8 +496,10 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
         }
     }
     if (!lo) return 0;
+    const bool pinned = s.cache_enabled && s.span_lo && lo >= s.span_lo && hi <= s.span_lo + (size_t)s.span_rows * 32;
+    tc_apply_span(s, lo, hi);
     const long long n_rows = (hi - lo) / 32;
-    if (n_rows >= (1ll << 31) || n_rows > 64 * ref_rows + 4096) {
+    if (n_rows >= (1ll << 31) || (!pinned && n_rows > 64 * ref_rows + 4096)) {
         snprintf(g_err, sizeof g_err, "descriptor operands are not in one contiguous array");
         return -1;
     }
@@ -508,7 +510,7 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
         if (blocks > 148 * 32) blocks = 148 * 32;
         unpack_fp4_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(lo), n_words,
                                                             static_cast<uint4*>(s.d_ops));
-        ++launches;
+        ++launches; kmark("unpack_fp4", st);
         s.ops_src = lo; s.ops_rows = n_rows; s.ops_row_bytes = ROWB;
         s.set_valid = s.cache_enabled;
     }
@@ -574,6 +576,7 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
     }
     const int grid = n_units < sm_count ? n_units : sm_count;
     kern<<<grid, kThreads, SMEM_BYTES, st>>>(tmap, tmapB, lm, d_pairs);
+    kmark("hamming_fp4", st);
     if (dbg) return launches + 1;
     int max_n1 = 0;
     for (int p = 0; p < n_pairs; ++p)
@@ -582,6 +585,7 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
     const dim3 rgrid((unsigned)((max_n1 + rows_per_block - 1) / rows_per_block), (unsigned)n_pairs);
     if (aligned16) hamming_resolve_kernel<true><<<rgrid, 256, 0, st>>>(d_pairs);
     else hamming_resolve_kernel<false><<<rgrid, 256, 0, st>>>(d_pairs);
+    kmark("hamming_resolve", st);
     return launches + 2;
 }
 

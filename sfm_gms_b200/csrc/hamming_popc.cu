@@ -131,6 +131,7 @@ int launch_hamming_popc(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_
     }
     dim3 grid(qtiles, tsplit, n_pairs);
     hamming_popc_kernel<<<grid, kThreads, 0, st>>>(d_pairs, tsplit);
+    kmark("hamming_popc", st);
     return 1;
 }
 

@@ -398,6 +398,7 @@ int tc_unpack(TcState& s, const uint8_t* desc, long long n_rows, cudaStream_t st
     if (blocks > 148 * 32) blocks = 148 * 32;
     unpack_pm1_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(desc), n_words,
                                                         static_cast<uint4*>(s.d_ops));
+    kmark("unpack_pm1", st);
     s.ops_rows = n_rows;
     return 1;
 }
@@ -424,10 +425,12 @@ int launch_hamming_tc(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pai
         }
     }
     if (!lo) return 0;
+    const bool pinned = s.cache_enabled && s.span_lo && lo >= s.span_lo && hi <= s.span_lo + (size_t)s.span_rows * 32;
+    tc_apply_span(s, lo, hi);
     const long long n_rows = (hi - lo) / 32;
     long long ref_rows = 0;
     for (int p = 0; p < n_pairs; ++p) ref_rows += (long long)h_pairs[p].n1 + h_pairs[p].n2;
-    if (n_rows > 64 * ref_rows + 4096) {   // the span must be one descriptor array, not two unrelated allocations
+    if (!pinned && n_rows > 64 * ref_rows + 4096) {   // the span must be one descriptor array, not two unrelated allocations
         snprintf(g_tc_err, sizeof g_tc_err, "descriptor operands are not in one contiguous array");
         return -1;
     }
@@ -521,6 +524,7 @@ int launch_hamming_tc(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pai
     }
     const int grid = (int)(n_units < (size_t)sm_count ? n_units : (size_t)sm_count);
     kern<<<grid, kThreads, SMEM_BYTES, st>>>(tmap, d_wu, (int)n_units);
+    kmark("hamming_tc", st);
     s.work_used += wbytes;
     return launches + 1;
 }

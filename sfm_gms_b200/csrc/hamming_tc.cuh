@@ -17,7 +17,20 @@ struct TcState {
     const uint8_t* ops_src = nullptr;
     long long ops_rows = 0;
     int ops_row_bytes = 0;      // 256 (int8 kernel) or 128 (fp4 kernel)
+    // A registered image set pins the operand span to the WHOLE set, so every launch over it (any chunk of any pair
+    // list) finds the same unpacked array: each image is unpacked once per set, not once per launch.
+    const uint8_t* span_lo = nullptr;
+    long long span_rows = 0;
 };
+
+inline void tc_pin_span(TcState& s, const uint8_t* lo, long long rows) { s.span_lo = lo; s.span_rows = rows; }
+// widen [lo, hi) to the pinned span when it lies inside it
+inline void tc_apply_span(const TcState& s, const uint8_t*& lo, const uint8_t*& hi) {
+    if (s.cache_enabled && s.span_lo && lo >= s.span_lo && hi <= s.span_lo + (size_t)s.span_rows * 32) {
+        lo = s.span_lo;
+        hi = s.span_lo + (size_t)s.span_rows * 32;
+    }
+}
 
 bool tc_available();
 const char* tc_last_error();
