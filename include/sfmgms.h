@@ -278,6 +278,35 @@ int sfmgms_gms_hypotheses(sfmgms_ctx* ctx, int w1, int h1, int w2, int h2, const
 /* device memory currently owned by the context (bytes) */
 int64_t sfmgms_device_bytes(const sfmgms_ctx* ctx);
 
+/* ---- multi-GPU: one process, one host thread per GPU, pairs sharded, ONE broadcast of the set ----
+ * The reference matches one pair per call (FeatureMatchUtil.cpp:66-69) inside loops over an image sequence
+ * (main.cpp:32,39,47; SfMUtil.cpp:16-18).  A sfmgms_multi owns one sfmgms_ctx per GPU.  sfmgms_multi_set_images sends the
+ * HOST image set to the first GPU once and from there to all others with one ncclBroadcast per array (ncclCommInitAll over
+ * the listed GPUs; NCCL is bound with dlopen("libnccl.so.2") when n_devices > 1 -> SFMGMS_ERR_NCCL if absent).  The match
+ * calls cut the pair list into contiguous shards of equal work (one per GPU, in list order), run them on one host thread
+ * per GPU and write every GPU's results straight into the caller's HOST buffers; there is no collective on the result
+ * path.  Results are bit-identical to the single-GPU calls.
+ *   devices == NULL: GPUs 0 .. n_devices-1 (n_devices <= 0: all visible GPUs).
+ *   sfmgms_multi_match_pairs          outputs exactly as sfmgms_match_pairs(SFMGMS_HOST).
+ *   sfmgms_multi_match_pairs_compact  as sfmgms_match_pairs_compact(SFMGMS_HOST), except that the GPUs append to the one
+ *       matches / pts1 / pts2 buffer as their chunks finish: rows of a pair are contiguous and in match order, pairs are
+ *       NOT in list order; inlier_begin[p] (n_pairs entries) is the first row of pair p, n_inliers[p] its row count. */
+typedef struct sfmgms_multi sfmgms_multi;
+int sfmgms_multi_create(sfmgms_multi** out, const int* devices, int n_devices);
+void sfmgms_multi_destroy(sfmgms_multi* m);
+const char* sfmgms_multi_last_error(const sfmgms_multi* m); /* m may be NULL: message of the failed create */
+int sfmgms_multi_device_count(const sfmgms_multi* m);
+sfmgms_ctx* sfmgms_multi_context(sfmgms_multi* m, int i);  /* the i-th GPU's context (options, timing, launches) */
+double sfmgms_multi_last_broadcast_ms(const sfmgms_multi* m); /* device time of the last set's broadcast on GPU 0 */
+int sfmgms_multi_set_images(sfmgms_multi* m, int n_images, const int64_t* kp_offsets, const uint8_t* desc,
+                            const float* kp_xy, const int32_t* sizes_wh);
+int sfmgms_multi_match_pairs(sfmgms_multi* m, const int32_t* pairs, int n_pairs, int with_rotation, int with_scale,
+                             double threshold_factor, int32_t* n_inliers, int32_t* best_hyp, int32_t* mask_len,
+                             int32_t* train_idx, int32_t* dist, uint8_t* mask);
+int sfmgms_multi_match_pairs_compact(sfmgms_multi* m, const int32_t* pairs, int n_pairs, int with_rotation, int with_scale,
+                                     double threshold_factor, int32_t* n_inliers, int32_t* best_hyp, int64_t* inlier_begin,
+                                     void* matches, float* pts1, float* pts2, int64_t capacity, int64_t* n_total);
+
 #ifdef __cplusplus
 }
 #endif

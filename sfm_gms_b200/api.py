@@ -102,6 +102,21 @@ def load_library():
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_i64, P(c_i64)]
     L.sfmgms_gms_hypotheses.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
                                         c_void_p, c_void_p, c_int, c_int, c_double, c_void_p]
+    L.sfmgms_multi_create.argtypes = [P(c_void_p), c_void_p, c_int]
+    L.sfmgms_multi_destroy.argtypes = [c_void_p]
+    L.sfmgms_multi_destroy.restype = None
+    L.sfmgms_multi_last_error.argtypes = [c_void_p]
+    L.sfmgms_multi_last_error.restype = ctypes.c_char_p
+    L.sfmgms_multi_device_count.argtypes = [c_void_p]
+    L.sfmgms_multi_context.argtypes = [c_void_p, c_int]
+    L.sfmgms_multi_context.restype = c_void_p
+    L.sfmgms_multi_last_broadcast_ms.argtypes = [c_void_p]
+    L.sfmgms_multi_last_broadcast_ms.restype = c_double
+    L.sfmgms_multi_set_images.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.sfmgms_multi_match_pairs.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_void_p]
+    L.sfmgms_multi_match_pairs_compact.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p,
+                                                   c_void_p, c_void_p, c_void_p, c_i64, P(c_i64)]
     L.sfmgms_kernel_times.argtypes = [c_void_p, ctypes.c_char_p, c_int]
     L.sfmgms_device_bytes.argtypes = [c_void_p]
     L.sfmgms_device_bytes.restype = c_i64
@@ -578,6 +593,87 @@ class Context:
 
 
 _default = threading.local()
+
+
+class MultiContext:
+    """One process, several GPUs (sfmgms_multi_*): the set is broadcast once, the pair list is sharded."""
+
+    def __init__(self, devices=None, n_devices=0):
+        self._lib = load_library()
+        h = ctypes.c_void_p()
+        dv = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+        rc = self._lib.sfmgms_multi_create(ctypes.byref(h), _ptr(dv), len(dv) if dv is not None else int(n_devices))
+        if rc:
+            raise SfmGmsError(rc, self._lib.sfmgms_multi_last_error(None).decode())
+        self._h = h
+        self.n_devices = self._lib.sfmgms_multi_device_count(h)
+        self._offsets = None
+
+    def close(self):
+        if self._h:
+            self._lib.sfmgms_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise SfmGmsError(rc, self._lib.sfmgms_multi_last_error(self._h).decode())
+
+    def set_option(self, key, value):
+        for i in range(self.n_devices):
+            c = ctypes.c_void_p(self._lib.sfmgms_multi_context(self._h, i))
+            rc = self._lib.sfmgms_set_option(c, int(key), int(value))
+            if rc:
+                raise SfmGmsError(rc, self._lib.sfmgms_last_error(c).decode())
+
+    @property
+    def last_broadcast_ms(self):
+        return float(self._lib.sfmgms_multi_last_broadcast_ms(self._h))
+
+    def set_images(self, kp_offsets, desc, kp_xy, sizes_wh):
+        off = np.ascontiguousarray(kp_offsets, dtype=np.int64)
+        d = Context._desc(desc)
+        k = np.ascontiguousarray(kp_xy, dtype=np.float32).reshape(-1, 2)
+        s = np.ascontiguousarray(sizes_wh, dtype=np.int32).reshape(-1, 2)
+        self._check(self._lib.sfmgms_multi_set_images(self._h, off.shape[0] - 1, _ptr(off), _ptr(d), _ptr(k), _ptr(s)))
+        self._offsets = off
+
+    def match_pairs(self, pairs, with_rotation=False, with_scale=False, threshold_factor=6.0):
+        pr = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        n = pr.shape[0]
+        rows = (self._offsets[pr[:, 0] + 1] - self._offsets[pr[:, 0]]) if n else np.zeros(0, np.int64)
+        off = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
+        total = int(off[-1])
+        ninl, bh, ml = (np.zeros(n, np.int32) for _ in range(3))
+        ti, di = np.empty(total, np.int32), np.empty(total, np.int32)
+        mk = np.zeros(total, np.uint8)
+        self._check(self._lib.sfmgms_multi_match_pairs(self._h, _ptr(pr), n, int(bool(with_rotation)), int(bool(with_scale)),
+                                                       float(threshold_factor), _ptr(ninl), _ptr(bh), _ptr(ml), _ptr(ti), _ptr(di),
+                                                       _ptr(mk)))
+        return dict(n_inliers=ninl, best_hyp=bh, mask_len=ml, offsets=off, train_idx=ti, dist=di, mask=mk)
+
+    def match_pairs_compact(self, pairs, with_rotation=False, with_scale=False, threshold_factor=6.0, capacity=None):
+        """-> dict(n_inliers, best_hyp, begin int64[n], n_total, matches (DMATCH_DT), pts1, pts2); pair p owns rows
+        [begin[p], begin[p] + n_inliers[p])."""
+        pr = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        n = pr.shape[0]
+        if capacity is None:
+            capacity = int((self._offsets[pr[:, 0] + 1] - self._offsets[pr[:, 0]]).sum()) if n else 0
+        ninl, bh = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        beg = np.zeros(n, np.int64)
+        m = np.zeros(max(capacity, 1), DMATCH_DT)
+        p1, p2 = np.zeros((max(capacity, 1), 2), np.float32), np.zeros((max(capacity, 1), 2), np.float32)
+        tot = ctypes.c_int64(0)
+        self._check(self._lib.sfmgms_multi_match_pairs_compact(self._h, _ptr(pr), n, int(bool(with_rotation)), int(bool(with_scale)),
+                                                               float(threshold_factor), _ptr(ninl), _ptr(bh), _ptr(beg), _ptr(m),
+                                                               _ptr(p1), _ptr(p2), int(capacity), ctypes.byref(tot)))
+        return dict(n_inliers=ninl, best_hyp=bh, begin=beg, n_total=tot.value, matches=m[: tot.value], pts1=p1[: tot.value],
+                    pts2=p2[: tot.value])
 
 
 def default_context(device=0):

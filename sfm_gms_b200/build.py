@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["capi.cu", "hamming_popc.cu", "hamming_tc.cu", "hamming_fp4.cu", "gms.cu", "l2_dp4a.cu", "l2_tc.cu", "l2_f32.cu", "orb.cu"]
+SOURCES = ["capi.cu", "multi.cu", "hamming_popc.cu", "hamming_tc.cu", "hamming_fp4.cu", "gms.cu", "l2_dp4a.cu", "l2_tc.cu", "l2_f32.cu", "orb.cu"]
 HEADERS = ["common.cuh", "hamming_tc.cuh", "tc_ptx.cuh", "orb_pattern.inc", os.path.join("..", "..", "include", "sfmgms.h")]
 LIB = os.path.join(HERE, "libsfmgms.so")
 
@@ -65,7 +65,7 @@ def _build(force, verbose, defines, bdir):
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -1113,6 +1113,8 @@ static int build_pair_table(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, 
     return SFMGMS_OK;
 }
 
+}  // extern "C" (the runner below is C++; the entry points after it re-open the block)
+
 // ---- chunked pair-list runner -------------------------------------------------------------------------
 // One implementation behind sfmgms_match_pairs and sfmgms_match_pairs_compact.  The pair list is walked in chunks
 // of at most ctx->chunk_rows match rows (and kMaxChunkPairs pairs); all per-match device scratch (keys, masks, GMS
@@ -1130,6 +1132,9 @@ struct PairsJob {
     bool compact = false;                                                     // compacted inliers
     int64_t* inlier_offsets = nullptr; void* matches = nullptr; float *pts1 = nullptr, *pts2 = nullptr;
     int64_t capacity = 0; int64_t* n_total = nullptr;
+    // multi-GPU (host outputs only): several contexts append their chunks to ONE caller buffer through a shared
+    // cursor (atomic reservation per chunk); inlier_offsets[p] then is the absolute first row of pair p (n entries)
+    int64_t* shared_cursor = nullptr;
 };
 
 constexpr int kMaxChunkPairs = 4096;
@@ -1159,7 +1164,7 @@ int run_pairs_job(sfmgms_ctx* ctx, const PairsJob& J) {
     if (rc) return rc;
     ctx->last_pairs.clear();
     ctx->last_results.assign((size_t)n_pairs, PairResult{0, -1, 0, 0});
-    if (J.inlier_offsets) J.inlier_offsets[0] = 0;   // overwritten below for device output
+    if (J.inlier_offsets && !dev_out) J.inlier_offsets[0] = 0;
     if (n_pairs == 0) {
         if (J.inlier_offsets && dev_out) CU(cudaMemsetAsync(J.inlier_offsets, 0, 8, st));
         CU(cudaStreamSynchronize(st));
@@ -1229,6 +1234,7 @@ int run_pairs_job(sfmgms_ctx* ctx, const PairsJob& J) {
     double t_ham = 0, t_gms = 0;
     int ham_launches = 0;
     int64_t inl_total = 0;           // inliers of finished chunks (host outputs: also the write cursor)
+    int64_t produced = 0;            // inliers this call produced (== inl_total unless a shared cursor places the chunks)
     bool overflow = false;
     int err_rc = SFMGMS_OK;
 
@@ -1245,6 +1251,11 @@ int run_pairs_job(sfmgms_ctx* ctx, const PairsJob& J) {
         }
         const PairResult* hr = static_cast<const PairResult*>(ctx->h_results.p) + p0;
         int64_t chunk_inl = 0;
+        if (J.shared_cursor) {     // reserve this chunk's rows in the shared output
+            int64_t need = 0;
+            for (int p = 0; p < pn; ++p) need += hr[p].mask_len > 0 ? hr[p].n_inliers : 0;
+            inl_total = __atomic_fetch_add(J.shared_cursor, need, __ATOMIC_RELAXED);
+        }
         for (int p = 0; p < pn; ++p) {
             ctx->last_results[(size_t)p0 + p] = hr[p];
             if (hr[p].status == 4 && !err_rc) err_rc = fail(ctx, SFMGMS_ERR_INDEX, "pair %d: queryIdx/trainIdx out of range", p0 + p);
@@ -1278,6 +1289,7 @@ int run_pairs_job(sfmgms_ctx* ctx, const PairsJob& J) {
             sl.copy_pending = true;
         }
         inl_total += chunk_inl;
+        produced += chunk_inl;
         return SFMGMS_OK;
     };
 
@@ -1337,17 +1349,37 @@ int run_pairs_job(sfmgms_ctx* ctx, const PairsJob& J) {
                 tmp[p] = k == 0 ? ctx->last_results[p].n_inliers : k == 1 ? ctx->last_results[p].best_hyp : ctx->last_results[p].mask_len;
             CU(cudaMemcpy(outs[k], tmp.data(), (size_t)n_pairs * 4, cudaMemcpyHostToDevice));
         }
-    } else if (J.inlier_offsets) {
+    } else if (J.inlier_offsets && !J.shared_cursor) {
         J.inlier_offsets[n_pairs] = inl_total;
     }
-    if (J.n_total) *J.n_total = inl_total;
+    if (J.n_total) *J.n_total = produced;
     if (n_chunks == 1) ctx->last_pairs = hp;     // sfmgms_inlier_points: only while the chunk's buffers are intact
     if (J.compact && (overflow || (dev_out && inl_total > J.capacity)))
-        return fail(ctx, SFMGMS_ERR_CAPACITY, "compact output needs %lld rows, capacity is %lld", (long long)inl_total, (long long)J.capacity);
+        return fail(ctx, SFMGMS_ERR_CAPACITY, "compact output needs %lld rows, capacity is %lld",
+                    (long long)(J.shared_cursor ? __atomic_load_n(J.shared_cursor, __ATOMIC_RELAXED) : inl_total), (long long)J.capacity);
     return SFMGMS_OK;
 }
 
 }  // namespace
+
+// used by multi.cu: one shard of a multi-GPU compact run (host outputs appended through the shared cursor)
+namespace sfmgms {
+int match_pairs_compact_shared(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int with_rotation, int with_scale,
+                               double threshold_factor, int32_t* n_inliers, int32_t* best_hyp, int64_t* inlier_begin,
+                               void* matches, float* pts1, float* pts2, int64_t capacity, int64_t* shared_cursor) {
+    GUARD_BEGIN
+    PairsJob J;
+    J.pairs = pairs; J.n_pairs = n_pairs; J.with_rotation = with_rotation; J.with_scale = with_scale; J.factor = threshold_factor;
+    J.out_location = SFMGMS_HOST; J.n_inliers = n_inliers; J.best_hyp = best_hyp;
+    J.compact = true; J.inlier_offsets = inlier_begin; J.matches = matches; J.pts1 = pts1; J.pts2 = pts2;
+    J.capacity = capacity; J.shared_cursor = shared_cursor;
+    return run_pairs_job(ctx, J);
+    GUARD_END
+}
+const char* ctx_error(const sfmgms_ctx* ctx) { return ctx->err; }
+}  // namespace sfmgms
+
+extern "C" {
 
 int sfmgms_match_pairs(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int with_rotation, int with_scale,
                        double threshold_factor, int out_location, int32_t* n_inliers, int32_t* best_hyp,

@@ -18,7 +18,9 @@
 #pragma once
 #include <cstdint>
 #include <stdexcept>
+#include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/sfmgms.h"
@@ -306,6 +308,117 @@ inline void matchBFHammingGMS(const uint8_t* desc1, const uint8_t* desc2, const 
     for (int i = 0; i < mask_len; ++i)
         if (mask[i]) matchesGMS.push_back(matches[i]);
 }
+
+// ---- image sequences: the FeatureMatchUtil.cpp:66-69 block applied to a list of image pairs (all-pairs / sliding window
+// SfM matching; the reference drives it pair by pair from main.cpp:32,39,47 and SfMUtil.cpp:16-18) ---------------------------
+struct ImageSet {
+    std::vector<int64_t> offsets{0};
+    std::vector<uint8_t> desc;      // 32 bytes per keypoint
+    std::vector<float> kp_xy;       // pt.x, pt.y per keypoint
+    std::vector<int32_t> sizes_wh;  // width, height per image
+    int size() const { return (int)offsets.size() - 1; }
+    // one image: its keypoints, its ORB descriptors (keypoints.size() rows of 32 bytes), its size
+    void add(const std::vector<cv::KeyPoint>& keypoints, const uint8_t* descriptors, cv::Size size) {
+        for (const cv::KeyPoint& k : keypoints) { kp_xy.push_back(k.pt.x); kp_xy.push_back(k.pt.y); }
+        desc.insert(desc.end(), descriptors, descriptors + keypoints.size() * 32);
+        offsets.push_back(offsets.back() + (int64_t)keypoints.size());
+        sizes_wh.push_back(size.width); sizes_wh.push_back(size.height);
+    }
+};
+
+// Every pair's `matchesGMS` (what matchGMS leaves in its output vector) and the coordinate lists SfMUtil.cpp:25-35 builds
+// from it, for a whole pair list: pair p owns rows [begin[p], begin[p] + n_inliers[p]) of matches / pts1 / pts2.
+struct PairMatches {
+    std::vector<int32_t> n_inliers, best_hyp;
+    std::vector<int64_t> begin;
+    std::vector<cv::DMatch> matches;
+    std::vector<cv::Point2f> pts1, pts2;
+    std::vector<cv::DMatch> matchesGMS(int p) const {
+        return std::vector<cv::DMatch>(matches.begin() + begin[(size_t)p], matches.begin() + begin[(size_t)p] + n_inliers[(size_t)p]);
+    }
+};
+
+namespace detail {
+inline std::vector<int32_t> flat_pairs(const std::vector<std::pair<int, int>>& pairs) {
+    std::vector<int32_t> f;
+    f.reserve(pairs.size() * 2);
+    for (const auto& p : pairs) { f.push_back(p.first); f.push_back(p.second); }
+    return f;
+}
+inline int64_t pair_rows(const ImageSet& s, const std::vector<std::pair<int, int>>& pairs) {
+    int64_t rows = 0;
+    for (const auto& p : pairs)
+        if (p.first >= 0 && p.first < s.size()) rows += s.offsets[(size_t)p.first + 1] - s.offsets[(size_t)p.first];
+    return rows;
+}
+}  // namespace detail
+
+// one GPU: Context + image set + pair list
+inline void matchPairs(Context& c, const ImageSet& set, const std::vector<std::pair<int, int>>& pairs, PairMatches& out,
+                       bool withRotation = false, bool withScale = false, double thresholdFactor = 6.0, bool wantPoints = true) {
+    static const uint8_t zero_d[32] = {0};
+    static const float zero_k[2] = {0.f, 0.f};
+    c.check(sfmgms_set_images(c.get(), set.size(), set.offsets.data(), set.desc.empty() ? zero_d : set.desc.data(),
+                              set.kp_xy.empty() ? zero_k : set.kp_xy.data(), set.sizes_wh.data(), SFMGMS_HOST));
+    const std::vector<int32_t> fp = detail::flat_pairs(pairs);
+    const int n = (int)pairs.size();
+    const int64_t cap = detail::pair_rows(set, pairs);
+    out.n_inliers.assign((size_t)n, 0); out.best_hyp.assign((size_t)n, -1);
+    std::vector<int64_t> off((size_t)n + 1, 0);
+    out.matches.resize((size_t)cap);
+    out.pts1.resize(wantPoints ? (size_t)cap : 0); out.pts2.resize(wantPoints ? (size_t)cap : 0);
+    int64_t total = 0;
+    c.check(sfmgms_match_pairs_compact(c.get(), fp.data(), n, withRotation ? 1 : 0, withScale ? 1 : 0, thresholdFactor, SFMGMS_HOST,
+                                       out.n_inliers.data(), out.best_hyp.data(), off.data(), out.matches.data(),
+                                       wantPoints && cap ? &out.pts1[0].x : nullptr, wantPoints && cap ? &out.pts2[0].x : nullptr, cap,
+                                       &total));
+    out.begin.assign(off.begin(), off.begin() + n);
+    out.matches.resize((size_t)total);
+    if (wantPoints) { out.pts1.resize((size_t)total); out.pts2.resize((size_t)total); }
+}
+
+// several GPUs of one box: one host thread per GPU inside the library, the set is broadcast once (NCCL), pairs are sharded
+class MultiGpuMatcher {
+   public:
+    explicit MultiGpuMatcher(const std::vector<int>& devices = {}) {   // empty: all visible GPUs
+        if (int rc = sfmgms_multi_create(&m_, devices.empty() ? nullptr : devices.data(), (int)devices.size()))
+            throw Error(rc, sfmgms_multi_last_error(nullptr));
+    }
+    ~MultiGpuMatcher() { sfmgms_multi_destroy(m_); }
+    MultiGpuMatcher(const MultiGpuMatcher&) = delete;
+    MultiGpuMatcher& operator=(const MultiGpuMatcher&) = delete;
+    int deviceCount() const { return sfmgms_multi_device_count(m_); }
+    double lastBroadcastMs() const { return sfmgms_multi_last_broadcast_ms(m_); }
+    void setImages(const ImageSet& set) {
+        static const uint8_t zero_d[32] = {0};
+        static const float zero_k[2] = {0.f, 0.f};
+        check(sfmgms_multi_set_images(m_, set.size(), set.offsets.data(), set.desc.empty() ? zero_d : set.desc.data(),
+                                      set.kp_xy.empty() ? zero_k : set.kp_xy.data(), set.sizes_wh.data()));
+        set_ = &set;
+    }
+    void matchPairs(const std::vector<std::pair<int, int>>& pairs, PairMatches& out, bool withRotation = false, bool withScale = false,
+                    double thresholdFactor = 6.0, bool wantPoints = true) {
+        if (!set_) throw Error(SFMGMS_ERR_STATE, "setImages has not been called");
+        const std::vector<int32_t> fp = detail::flat_pairs(pairs);
+        const int n = (int)pairs.size();
+        const int64_t cap = detail::pair_rows(*set_, pairs);
+        out.n_inliers.assign((size_t)n, 0); out.best_hyp.assign((size_t)n, -1); out.begin.assign((size_t)n, 0);
+        out.matches.resize((size_t)cap);
+        out.pts1.resize(wantPoints ? (size_t)cap : 0); out.pts2.resize(wantPoints ? (size_t)cap : 0);
+        int64_t total = 0;
+        check(sfmgms_multi_match_pairs_compact(m_, fp.data(), n, withRotation ? 1 : 0, withScale ? 1 : 0, thresholdFactor,
+                                               out.n_inliers.data(), out.best_hyp.data(), out.begin.data(), out.matches.data(),
+                                               wantPoints && cap ? &out.pts1[0].x : nullptr, wantPoints && cap ? &out.pts2[0].x : nullptr,
+                                               cap, &total));
+        out.matches.resize((size_t)total);
+        if (wantPoints) { out.pts1.resize((size_t)total); out.pts2.resize((size_t)total); }
+    }
+
+   private:
+    void check(int rc) const { if (rc) throw Error(rc, sfmgms_multi_last_error(m_)); }
+    sfmgms_multi* m_ = nullptr;
+    const ImageSet* set_ = nullptr;
+};
 
 }  // namespace sfmgms
 

@@ -220,18 +220,16 @@ def test_gpu_equals_dll_stress_and_microcases(G, ctx):
 
 
 @pytest.mark.gpu
-def test_gpu_dense_path_equals_dll(G):
-    """the global-memory histogram fallback (>= 65536 matches per pair) forced on: same answers"""
-    import os
+def test_gpu_dense_path_equals_dll(G, ctx):
+    """the global-memory histogram path (what pairs with >= 65536 matches take) forced on: same answers"""
+    from sfm_gms_b200 import api
 
-    import sfm_gms_b200 as sg
-
-    os.environ["SFMGMS_GMS_DENSE"] = "1"
+    ctx.set_option(api.OPT_GMS_DENSE, 1)
     try:
-        c2 = sg.Context(0)
         for name in ("view01_2k", "bun12_rot180_3k"):
-            _check_case(G, name, C.real_case(name), c2.gms)
-        _check_case(G, "edge_pixels", C.edge_pixels_case(), c2.gms)
-        c2.close()
+            c = C.real_case(name)
+            _check_case(G, name, c, ctx.gms)
+            assert ctx.gms_hypotheses(c["size1"], c["size2"], c["kp1"], c["kp2"], c["q"], c["t"]).tolist() == G[name + "/hyp_counts"].tolist()
+        _check_case(G, "edge_pixels", C.edge_pixels_case(), ctx.gms)
     finally:
-        del os.environ["SFMGMS_GMS_DENSE"]
+        ctx.set_option(api.OPT_GMS_DENSE, 0)

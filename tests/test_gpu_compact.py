@@ -142,20 +142,22 @@ def test_inlier_points_is_a_view_of_the_compact_output(ctx):
         assert np.array_equal(p1, res["pts1"][co[p]:co[p + 1]]) and np.array_equal(p2, res["pts2"][co[p]:co[p + 1]])
 
 
-def test_all_pairs_sequence_bounded_memory(ctx, oracle_mod):
+def test_all_pairs_sequence_bounded_memory(oracle_mod):
     """BASELINE config 5 in miniature: all pairs over a 24-image sequence (10k keypoints each, 276 pairs) walked in
     chunks of 2^20 rows.  Sampled pairs equal the oracle; library-owned device memory stays far below the list size."""
+    import sfm_gms_b200 as sg
     from sfm_gms_b200 import api, synth
 
     s = synth.make_sequence(24)
     pairs = synth.all_pairs(24)
+    ctx = sg.Context(0)                            # a fresh context: its device memory is this test's alone
     ctx.set_images(s["offsets"], s["desc"], s["kp"], s["sizes"])
-    ctx.set_option(api.OPT_CHUNK_ROWS, 1 << 20)
-    try:
-        res = ctx.match_pairs_compact(pairs, capacity=len(pairs) * 10_000)
-    finally:
-        ctx.set_option(api.OPT_CHUNK_ROWS, 4 << 20)
-    assert ctx.device_bytes < 600 << 20            # 276 pairs x 10k rows would need ~40 B x 2.76 M rows per array set
+    ctx.set_option(api.OPT_CHUNK_ROWS, 1 << 19)
+    res = ctx.match_pairs_compact(pairs, capacity=len(pairs) * 10_000)
+    used = ctx.device_bytes
+    ctx.close()
+    # 276 pairs x 10k rows: per-list buffers would hold 2.76 M rows (x ~70 B); chunks of 2^19 rows keep it ~5x smaller
+    assert used < 300 << 20, used
     rng = np.random.default_rng(9)
     pick = rng.choice(len(pairs), 6, replace=False)
     exp = _oracle_compact(oracle_mod, s["offsets"], s["desc"], s["kp"], s["sizes"], pairs[pick], 0, 0)
