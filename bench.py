@@ -308,6 +308,7 @@ def kernel_rooflines(kt, steps, kind, n_pairs, n_kp, n_hyp_scales):
         "unpack_pm1": ("hbm", 2 * rows * (32 + 256)),
         "hamming_resolve": ("hbm", rows * (4 + 32 + 8 * 32 + 4)),
         "gms_assign": ("hbm", rows * (4 + 8 + 8 + 2 * (4 + S))),
+        "gms_assign_cnt": ("hbm", rows * (4 + 8 + 8 + 2 * (4 + S))),
         "gms_count": ("hbm", rows * (2 * (4 + S) + 1)),
         "gms_mask": ("hbm", rows * (2 * 5 + 1)),
         "gms_compact": ("hbm", rows * (1 + 4) + 0.5 * rows * (16 + 32)),
@@ -325,9 +326,11 @@ def kernel_rooflines(kt, steps, kind, n_pairs, n_kp, n_hyp_scales):
             # shared-memory histogram build: 4 shifts x S scales x rows votes (plus halo duplicates, not counted)
             ops = rows * 4 * S
             e.update(bound="smem_atomic", achieved=ops / (per_step_ms * 1e-3) / 1e9, unit="Gvotes/s", algorithmic_votes_per_step=ops)
-            pk = unit.get("smem_atomic_gops")
+            pk = unit.get("smem_vote_gvotes") if name == "gms_vote2" else (unit.get("smem_atomic_gops", 0) / 2 or None)
             if pk:
-                e.update(peak=pk, frac=e["achieved"] / pk, peak_source="profiles/r2_unit_peaks.json: random-address shared atomicAdd loop, all SMs")
+                e.update(peak=pk, frac=e["achieved"] / pk,
+                         peak_source="profiles/r2_unit_peaks.json: shared-memory vote microbenchmark (returning atomicAdd on a random "
+                                     "histogram word + atomicMax on a row slot per vote, 2 CTAs x 512 threads per SM)")
         out.append(e)
     return out
 

@@ -643,7 +643,12 @@ class MultiContext:
         self._check(self._lib.sfmgms_multi_set_images(self._h, off.shape[0] - 1, _ptr(off), _ptr(d), _ptr(k), _ptr(s)))
         self._offsets = off
 
+    def _need_set(self):
+        if self._offsets is None:
+            raise SfmGmsError(6, "set_images has not been called")
+
     def match_pairs(self, pairs, with_rotation=False, with_scale=False, threshold_factor=6.0):
+        self._need_set()
         pr = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
         n = pr.shape[0]
         rows = (self._offsets[pr[:, 0] + 1] - self._offsets[pr[:, 0]]) if n else np.zeros(0, np.int64)
@@ -660,6 +665,7 @@ class MultiContext:
     def match_pairs_compact(self, pairs, with_rotation=False, with_scale=False, threshold_factor=6.0, capacity=None):
         """-> dict(n_inliers, best_hyp, begin int64[n], n_total, matches (DMATCH_DT), pts1, pts2); pair p owns rows
         [begin[p], begin[p] + n_inliers[p])."""
+        self._need_set()
         pr = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
         n = pr.shape[0]
         if capacity is None:

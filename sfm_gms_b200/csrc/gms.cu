@@ -59,7 +59,7 @@ __host__ __device__ inline Layout make_layout(int n_scales, int n_rot, bool dens
     Layout L;
     L.n_scales = n_scales; L.n_rot = n_rot;
     size_t o = 0;
-    L.cnt_off = o; o += dense ? 4 * kCellsL : 0;
+    L.cnt_off = o; o += 4 * kCellsL;   // both paths: cell totals per shift
     L.counts_off = o; o += 64;
     for (int s = 0; s < kNumScales; ++s) {
         L.hist_off[s] = o;
@@ -272,6 +272,160 @@ __global__ void __launch_bounds__(512) gms_vote_smem_kernel(const PairDesc* __re
                 }
                 const int score = __reduce_add_sync(0xffffffffu, v);
                 const int tsum = __reduce_add_sync(0xffffffffu, c);
+                const int num = __popc(__ballot_sync(0xffffffffu, valid));
+                const double thresh = __dmul_rn(factor, __dsqrt_rn(__ddiv_rn((double)tsum, (double)num)));
+                if ((double)score < thresh) out = -2;
+            }
+            if (lane == 0) cpv[(((size_t)s * L.n_rot + r) * 4 + t) * kCellsL + cell] = (int16_t)out;
+        }
+    }
+}
+
+// ---- a4 + a5 (+ the cell totals of a7) for the shared-memory path: one CTA per (pair, slice of <= kAssignSlice matches).
+// Per match: normalise, 4 left cells, S right cells -> lidx / ridx (as gms_assign_kernel<false>); the number of matches per
+// (shift, left cell) is accumulated with shared-memory atomics and flushed once per CTA (non-zero cells only), so the
+// vote kernels need neither a second atomic per match nor a row-sum scan.
+constexpr int kAssignSlice = 16384;
+__global__ void __launch_bounds__(1024) gms_assign_cnt_kernel(const PairDesc* __restrict__ pairs, PairResult* results,
+                                                               int32_t* scratch, Layout L, uint16_t* lidx, uint16_t* ridx,
+                                                               long long chunk_match_base, long long chunk_matches) {
+    __shared__ int cnt_s[4 * kCellsL];
+    const PairDesc pd = pairs[blockIdx.z];
+    const int i_begin = blockIdx.x * kAssignSlice;
+    if (i_begin >= pd.n_matches) return;                        // whole CTA leaves together
+    const int i_end = min(pd.n_matches, i_begin + kAssignSlice);
+    for (int k = threadIdx.x; k < 4 * kCellsL; k += blockDim.x) cnt_s[k] = 0;
+    __syncthreads();
+    int bad = 0;
+    for (int i = i_begin + threadIdx.x; i < i_end; i += blockDim.x) {
+        const long long mi = pd.match_base - chunk_match_base + i;
+        const int qi = pd.mq ? pd.mq[i] : i;
+        const int ti = pd.mt ? pd.mt[i] : (int)(pd.key[i] & kTrainIdxMask);
+        bool ok = true;
+        if (qi < 0 || qi >= pd.n1 || ti < 0 || ti >= pd.n2) { bad = max(bad, 4); ok = false; }
+        float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
+        if (ok) {
+            const float2 a = reinterpret_cast<const float2*>(pd.kp1)[qi];
+            const float2 b = reinterpret_cast<const float2*>(pd.kp2)[ti];
+            x1 = a.x; y1 = a.y; x2 = b.x; y2 = b.y;
+            if (!(x1 >= 0.f && x1 < (float)pd.w1 && y1 >= 0.f && y1 < (float)pd.h1 && x2 >= 0.f && x2 < (float)pd.w2 &&
+                  y2 >= 0.f && y2 < (float)pd.h2)) {
+                bad = max(bad, 3);
+                ok = false;
+            }
+        }
+        if (!ok) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) lidx[(size_t)t * chunk_matches + mi] = kNoCell;
+            for (int s = 0; s < L.n_scales; ++s) ridx[(size_t)s * chunk_matches + mi] = kNoCell;
+            continue;
+        }
+        const float nx1 = __fdiv_rn(x1, (float)pd.w1), ny1 = __fdiv_rn(y1, (float)pd.h1);     // normalizePoints @VA 0x180048420
+        const float nx2 = __fdiv_rn(x2, (float)pd.w2), ny2 = __fdiv_rn(y2, (float)pd.h2);
+        const float fx = __fmul_rn((float)kGridL, nx1), fy = __fmul_rn((float)kGridL, ny1);   // getGridIndexLeft @VA 0x180047bc0
+        const int xa = cv_floor_f(fx), ya = cv_floor_f(fy);
+        const int xb = cv_floor_d(__dadd_rn((double)fx, 0.5)), yb = cv_floor_d(__dadd_rn((double)fy, 0.5));
+        int l[4];
+        l[0] = (xa >= kGridL || ya >= kGridL) ? -1 : xa + ya * kGridL;
+        l[1] = (xb >= kGridL || ya >= kGridL) ? -1 : xb + ya * kGridL;
+        l[2] = (xa >= kGridL || yb >= kGridL) ? -1 : xa + yb * kGridL;
+        l[3] = (xb >= kGridL || yb >= kGridL) ? -1 : xb + yb * kGridL;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            lidx[(size_t)t * chunk_matches + mi] = l[t] < 0 ? kNoCell : (uint16_t)l[t];
+            if (l[t] >= 0) atomicAdd(&cnt_s[t * kCellsL + l[t]], 1);
+        }
+        for (int s = 0; s < L.n_scales; ++s) {                                                // getGridIndexRight @VA 0x180047d60
+            const int w = right_grid_w(s);
+            const int rx = cv_floor_f(__fmul_rn((float)w, nx2)), ry = cv_floor_f(__fmul_rn((float)w, ny2));
+            ridx[(size_t)s * chunk_matches + mi] = (uint16_t)(rx + ry * w);
+        }
+    }
+    if (bad) atomicMax(&results[blockIdx.z].status, bad);
+    __syncthreads();
+    int32_t* cnt_g = scratch + (size_t)blockIdx.z * L.total_words + L.cnt_off;
+    const bool single = pd.n_matches <= kAssignSlice;          // one CTA owns the pair: plain stores into the zeroed scratch
+    for (int k = threadIdx.x; k < 4 * kCellsL; k += blockDim.x) {
+        const int c = cnt_s[k];
+        if (c) { if (single) cnt_g[k] = c; else atomicAdd(&cnt_g[k], c); }
+    }
+}
+
+// ---- a7 + a8 in shared memory, second generation.  One CTA per (pair, shift, band of left-grid rows + 1 halo row each
+// side) for scale s.  The band's left-cell x right-cell histogram lives in shared memory as 16-bit counters (two per word;
+// a pair has < 65536 matches on this path).  ONE atomic builds it and, from the value the atomic returns, a second one
+// maintains the row arg-max directly: key = (new count << 11 | 2047 - r) only grows while a counter grows, so after the last
+// vote best[l] holds (max count, lowest right cell attaining it) -- verifyCellPairs' strict-'>' scan (DLL @VA 0x180048d10)
+// without scanning any row.  Cell totals come from gms_assign_cnt_kernel.  Then one warp per left cell: 9-slot support
+// gather, the three separately rounded f64 operations, all rotations from the same histogram.
+__global__ void __launch_bounds__(512) gms_vote2_kernel(const PairDesc* __restrict__ pairs, int32_t* scratch, Layout L,
+                                                        double factor, const uint16_t* __restrict__ lidx,
+                                                        const uint16_t* __restrict__ ridx, long long chunk_match_base,
+                                                        long long chunk_matches, int s, int band_rows) {
+    extern __shared__ uint32_t sm_u32[];
+    const PairDesc pd = pairs[blockIdx.z];
+    const int t = blockIdx.y;
+    const int w = right_grid_w(s), gr = w * w;
+    const int y0 = blockIdx.x * band_rows, y1 = min(kGridL, y0 + band_rows);
+    const int ys0 = max(0, y0 - 1), ys1 = min(kGridL, y1 + 1);
+    const int cells_sm = (ys1 - ys0) * kGridL;
+    const int hist_words = cells_sm * gr / 2;                   // gr is even for every scale
+    uint32_t* h32 = sm_u32;
+    uint32_t* best = sm_u32 + hist_words;
+    {
+        uint4* z = reinterpret_cast<uint4*>(sm_u32);            // (hist_words + cells_sm) is a multiple of 4
+        for (int i = threadIdx.x; i < (hist_words + cells_sm) / 4; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    const uint16_t* lt = lidx + (size_t)t * chunk_matches + (pd.match_base - chunk_match_base);
+    const uint16_t* rs = ridx + (size_t)s * chunk_matches + (pd.match_base - chunk_match_base);
+    const int lo = ys0 * kGridL, hi = ys1 * kGridL;
+    constexpr int U = 8;                                        // loads in flight per thread
+    for (int i0 = threadIdx.x; i0 < pd.n_matches; i0 += U * blockDim.x) {
+        int l[U], r[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int i = i0 + k * blockDim.x;
+            l[k] = i < pd.n_matches ? (int)__ldg(lt + i) : 0xFFFF;
+            r[k] = i < pd.n_matches ? (int)__ldg(rs + i) : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            if (l[k] >= lo && l[k] < hi) {                      // kNoCell (0xFFFF) fails this test too
+                const int idx = (l[k] - lo) * gr + r[k];
+                const int sh = (idx & 1) * 16;
+                const uint32_t old = atomicAdd(&h32[idx >> 1], 1u << sh);
+                const uint32_t c = ((old >> sh) & 0xFFFFu) + 1u;
+                atomicMax(&best[l[k] - lo], (c << 11) | (uint32_t)(2047 - r[k]));
+            }
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    int32_t* sp = scratch + (size_t)blockIdx.z * L.total_words;
+    const int32_t* cnt = sp + L.cnt_off + t * kCellsL;
+    int16_t* cpv = reinterpret_cast<int16_t*>(sp + L.cp_off);
+    const uint16_t* h16 = reinterpret_cast<const uint16_t*>(h32);
+    for (int cell = y0 * kGridL + warp; cell < y1 * kGridL; cell += nwarps) {
+        const uint32_t bk = best[cell - lo];
+        const int cp = bk ? 2047 - (int)(bk & 2047u) : -1;      // no vote in the row <=> its total is 0
+        int ll = -1, c = 0;
+        if (lane < 9) {
+            ll = nb9(cell, lane, kGridL, kGridL);
+            if (ll != -1) c = __ldg(cnt + ll);
+        }
+        for (int r = 0; r < L.n_rot; ++r) {
+            int out = cp;
+            if (cp >= 0) {
+                int v = 0;
+                bool valid = false;
+                if (lane < 9) {
+                    const int rr = nb9(cp, c_rot[r][lane] - 1, w, w);
+                    valid = (ll != -1 && rr != -1);
+                    if (valid) v = h16[(size_t)(ll - lo) * gr + rr];
+                }
+                const int score = __reduce_add_sync(0xffffffffu, v);
+                const int tsum = __reduce_add_sync(0xffffffffu, valid ? c : 0);
                 const int num = __popc(__ballot_sync(0xffffffffu, valid));
                 const double thresh = __dmul_rn(factor, __dsqrt_rn(__ddiv_rn((double)tsum, (double)num)));
                 if ((double)score < thresh) out = -2;
@@ -504,8 +658,10 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
     if (chunk_cap > 32768) chunk_cap = 32768;
     int launches = 0;
     int32_t* scratch = static_cast<int32_t*>(d_hist_scratch);
+    static const bool use_v1 = getenv("SFMGMS_GMS_V1") != nullptr;   // previous-generation vote kernel (A/B measurements only)
     if (!dense) {
         if (cudaFuncSetAttribute(gms_vote_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(gms_vote2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
     }
     for (int c0 = 0; c0 < n_pairs; c0 += chunk_cap) {
         const int cn = (n_pairs - c0 < chunk_cap) ? n_pairs - c0 : chunk_cap;
@@ -531,7 +687,7 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
             const long long warps = (long long)cn * n_scales * 4 * kCellsL;
             gms_verify_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(scratch, L, factor, cn);
             ++launches; kmark("gms_verify_dense", st);
-        } else {
+        } else if (use_v1) {
             if (max_m > 0) {
                 gms_assign_kernel<false><<<dim3(bx, 1, cn), 256, 0, st>>>(d_pairs + c0, d_results + c0, scratch, L, lidx, ridx,
                                                                         cbase, cm);
@@ -543,6 +699,20 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
                 gms_vote_smem_kernel<<<dim3(bands, 4, cn), 512, smem_band_bytes(s), st>>>(d_pairs + c0, scratch, L, factor, lidx,
                                                                                         ridx, cbase, cm, s, b);
                 ++launches; kmark("gms_vote_smem", st);
+            }
+        } else {
+            if (max_m > 0) {
+                const int nsplit = (max_m + kAssignSlice - 1) / kAssignSlice;
+                gms_assign_cnt_kernel<<<dim3(nsplit, 1, cn), 1024, 0, st>>>(d_pairs + c0, d_results + c0, scratch, L, lidx, ridx,
+                                                                          cbase, cm);
+                ++launches; kmark("gms_assign_cnt", st);
+            }
+            for (int s = 0; s < n_scales; ++s) {
+                const int b = smem_band_rows(s);
+                const int bands = (kGridL + b - 1) / b;
+                gms_vote2_kernel<<<dim3(bands, 4, cn), 512, smem_band_bytes(s), st>>>(d_pairs + c0, scratch, L, factor, lidx, ridx,
+                                                                                    cbase, cm, s, b);
+                ++launches; kmark("gms_vote2", st);
             }
         }
         if (max_m > 0) {
