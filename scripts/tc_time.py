@@ -7,12 +7,13 @@ from sfm_gms_b200 import api
 import bench
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 dev = torch.device("cuda", 0)
-desc, kp = bench.gen_pairs_torch(P, 2, dev)
+_s = bench.make_batch("cfg2", P)
+desc, kp = torch.from_numpy(_s["desc"]).to(dev), torch.from_numpy(_s["kp"]).to(dev)
 ctx = sg.Context(0)
 ctx.set_option(api.OPT_TIMING, 1)
 KERN = os.environ.get("SFMGMS_KERNEL", "tc")
 ctx.set_option(api.OPT_HAMMING_KERNEL, {"tc": api.HAMMING_TC, "fp4": api.HAMMING_FP4, "popc": api.HAMMING_POPC}[KERN])
-off = np.arange(2 * P + 1, dtype=np.int64) * bench.N_KP
+off = np.arange(2 * P + 1, dtype=np.int64) * 10_000
 sizes = np.tile(np.array([[640, 480]], np.int32), (2 * P, 1))
 pairs = np.ascontiguousarray(np.arange(2 * P, dtype=np.int32).reshape(-1, 2))
 ctx.set_images_raw(off, desc.data_ptr(), kp.data_ptr(), sizes, api.SFMGMS_DEVICE, keepalive=(desc, kp))

@@ -333,6 +333,7 @@ size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 #define GUARD_BEGIN                  \
     if (!ctx) return SFMGMS_ERR_ARG; \
     DeviceGuard guard__(ctx->device); \
+    cudaGetLastError(); /* a stale non-sticky error of someone else's call must not be blamed on ours */ \
     try {
 #define GUARD_END                                                        \
     }                                                                    \

@@ -352,86 +352,109 @@ __global__ void __launch_bounds__(1024) gms_assign_cnt_kernel(const PairDesc* __
 }
 
 // ---- a7 + a8 in shared memory, second generation.  One CTA per (pair, shift, band of left-grid rows + 1 halo row each
-// side) for scale s.  The band's left-cell x right-cell histogram lives in shared memory as 16-bit counters (two per word;
+// side) for scale S.  The band's left-cell x right-cell histogram lives in shared memory as 16-bit counters (two per word;
 // a pair has < 65536 matches on this path).  ONE atomic builds it and, from the value the atomic returns, a second one
 // maintains the row arg-max directly: key = (new count << 11 | 2047 - r) only grows while a counter grows, so after the last
 // vote best[l] holds (max count, lowest right cell attaining it) -- verifyCellPairs' strict-'>' scan (DLL @VA 0x180048d10)
-// without scanning any row.  Cell totals come from gms_assign_cnt_kernel.  Then one warp per left cell: 9-slot support
-// gather, the three separately rounded f64 operations, all rotations from the same histogram.
+// without scanning any row.  Cell totals come from gms_assign_cnt_kernel.  The kernel is instruction-issue bound (ncu:
+// profiles/r2_notes.md), so: cell indices arrive as 128-bit loads of 8 matches, the right-grid width is a template constant,
+// and verification runs one THREAD per (left cell, rotation) -- 9-slot support gather, the three separately rounded f64
+// operations -- instead of one warp per cell.
+__constant__ int8_t c_rdx[kNumRot][9], c_rdy[kNumRot][9];   // ROT[r][k]-1 as (dx, dy) in the 3x3 neighbourhood; filled at first launch
+
+template <int S>
 __global__ void __launch_bounds__(512) gms_vote2_kernel(const PairDesc* __restrict__ pairs, int32_t* scratch, Layout L,
                                                         double factor, const uint16_t* __restrict__ lidx,
                                                         const uint16_t* __restrict__ ridx, long long chunk_match_base,
-                                                        long long chunk_matches, int s, int band_rows) {
+                                                        long long chunk_matches, int band_rows) {
     extern __shared__ uint32_t sm_u32[];
+    constexpr int w = S == 0 ? 20 : S == 1 ? 10 : S == 2 ? 14 : S == 3 ? 28 : 40, gr = w * w;
     const PairDesc pd = pairs[blockIdx.z];
     const int t = blockIdx.y;
-    const int w = right_grid_w(s), gr = w * w;
     const int y0 = blockIdx.x * band_rows, y1 = min(kGridL, y0 + band_rows);
     const int ys0 = max(0, y0 - 1), ys1 = min(kGridL, y1 + 1);
     const int cells_sm = (ys1 - ys0) * kGridL;
     const int hist_words = cells_sm * gr / 2;                   // gr is even for every scale
     uint32_t* h32 = sm_u32;
     uint32_t* best = sm_u32 + hist_words;
+    int* cnt_s = reinterpret_cast<int*>(best + cells_sm);
+    const int lo = ys0 * kGridL, hi = ys1 * kGridL;
+    int32_t* sp = scratch + (size_t)blockIdx.z * L.total_words;
     {
         uint4* z = reinterpret_cast<uint4*>(sm_u32);            // (hist_words + cells_sm) is a multiple of 4
         for (int i = threadIdx.x; i < (hist_words + cells_sm) / 4; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        const int32_t* cnt_g = sp + L.cnt_off + t * kCellsL + lo;
+        for (int i = threadIdx.x; i < cells_sm; i += blockDim.x) cnt_s[i] = __ldg(cnt_g + i);
     }
     __syncthreads();
-    const uint16_t* lt = lidx + (size_t)t * chunk_matches + (pd.match_base - chunk_match_base);
-    const uint16_t* rs = ridx + (size_t)s * chunk_matches + (pd.match_base - chunk_match_base);
-    const int lo = ys0 * kGridL, hi = ys1 * kGridL;
-    constexpr int U = 8;                                        // loads in flight per thread
-    for (int i0 = threadIdx.x; i0 < pd.n_matches; i0 += U * blockDim.x) {
-        int l[U], r[U];
+    // 8 matches per 128-bit load; the pair's rows start `shift` elements into an aligned group (rows of other pairs in the
+    // first / last group are masked out)
+    const long long e0 = pd.match_base - chunk_match_base;
+    const int shift = (int)(e0 & 7);
+    const uint4* l4 = reinterpret_cast<const uint4*>(lidx + (size_t)t * chunk_matches + (e0 - shift));
+    const uint4* r4 = reinterpret_cast<const uint4*>(ridx + (size_t)S * chunk_matches + (e0 - shift));
+    const int n = pd.n_matches;
+    const int ngroups = n > 0 ? (shift + n + 7) >> 3 : 0;
+    const unsigned span = (unsigned)(hi - lo);
+    auto vote8 = [&](uint4 lv, uint4 rv, int g) {
+        uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w}, rw[4] = {rv.x, rv.y, rv.z, rv.w};
+        if (g == 0 || g == ngroups - 1) {                       // edge groups: drop elements outside [0, n)
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-            const int i = i0 + k * blockDim.x;
-            l[k] = i < pd.n_matches ? (int)__ldg(lt + i) : 0xFFFF;
-            r[k] = i < pd.n_matches ? (int)__ldg(rs + i) : 0;
+            for (int j = 0; j < 8; ++j) {
+                const int i = g * 8 + j - shift;
+                if (i < 0 || i >= n) lw[j >> 1] |= 0xFFFFu << (16 * (j & 1));   // kNoCell fails the band test
+            }
         }
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-            if (l[k] >= lo && l[k] < hi) {                      // kNoCell (0xFFFF) fails this test too
-                const int idx = (l[k] - lo) * gr + r[k];
-                const int sh = (idx & 1) * 16;
+        for (int j = 0; j < 8; ++j) {
+            const unsigned rel = ((lw[j >> 1] >> (16 * (j & 1))) & 0xFFFFu) - (unsigned)lo;
+            if (rel < span) {
+                const unsigned r = (rw[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+                const unsigned idx = rel * gr + r;
+                const unsigned sh = (idx & 1u) * 16u;
                 const uint32_t old = atomicAdd(&h32[idx >> 1], 1u << sh);
                 const uint32_t c = ((old >> sh) & 0xFFFFu) + 1u;
-                atomicMax(&best[l[k] - lo], (c << 11) | (uint32_t)(2047 - r[k]));
+                atomicMax(&best[rel], (c << 11) | (2047u - r));
             }
         }
+    };
+    for (int g = threadIdx.x; g < ngroups; g += 2 * blockDim.x) {   // two groups (16 matches) in flight per thread
+        const int g2 = g + blockDim.x;
+        const uint4 la = __ldg(l4 + g), ra = __ldg(r4 + g);
+        uint4 lb = make_uint4(0, 0, 0, 0), rb = lb;
+        if (g2 < ngroups) { lb = __ldg(l4 + g2); rb = __ldg(r4 + g2); }
+        vote8(la, ra, g);
+        if (g2 < ngroups) vote8(lb, rb, g2);
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    int32_t* sp = scratch + (size_t)blockIdx.z * L.total_words;
-    const int32_t* cnt = sp + L.cnt_off + t * kCellsL;
     int16_t* cpv = reinterpret_cast<int16_t*>(sp + L.cp_off);
     const uint16_t* h16 = reinterpret_cast<const uint16_t*>(h32);
-    for (int cell = y0 * kGridL + warp; cell < y1 * kGridL; cell += nwarps) {
+    const int n_own = (y1 - y0) * kGridL;
+    for (int task = threadIdx.x; task < n_own * L.n_rot; task += blockDim.x) {
+        const int r = task / n_own, cell = y0 * kGridL + (task - r * n_own);
         const uint32_t bk = best[cell - lo];
-        const int cp = bk ? 2047 - (int)(bk & 2047u) : -1;      // no vote in the row <=> its total is 0
-        int ll = -1, c = 0;
-        if (lane < 9) {
-            ll = nb9(cell, lane, kGridL, kGridL);
-            if (ll != -1) c = __ldg(cnt + ll);
-        }
-        for (int r = 0; r < L.n_rot; ++r) {
-            int out = cp;
-            if (cp >= 0) {
-                int v = 0;
-                bool valid = false;
-                if (lane < 9) {
-                    const int rr = nb9(cp, c_rot[r][lane] - 1, w, w);
-                    valid = (ll != -1 && rr != -1);
-                    if (valid) v = h16[(size_t)(ll - lo) * gr + rr];
+        int out = -1;                                           // no vote in the row <=> its total is 0
+        if (bk) {
+            const int cp = 2047 - (int)(bk & 2047u);
+            const int x = cell % kGridL, y = cell / kGridL, cx = cp % w, cy = cp / w;
+            int score = 0, tsum = 0, num = 0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const int xx = x + (k % 3) - 1, yy = y + (k / 3) - 1;
+                const int rx = cx + c_rdx[r][k], ry = cy + c_rdy[r][k];
+                if ((unsigned)xx < (unsigned)kGridL && (unsigned)yy < (unsigned)kGridL && (unsigned)rx < (unsigned)w &&
+                    (unsigned)ry < (unsigned)w) {
+                    const int ll = xx + yy * kGridL - lo;
+                    score += h16[ll * gr + rx + ry * w];
+                    tsum += cnt_s[ll];
+                    ++num;
                 }
-                const int score = __reduce_add_sync(0xffffffffu, v);
-                const int tsum = __reduce_add_sync(0xffffffffu, valid ? c : 0);
-                const int num = __popc(__ballot_sync(0xffffffffu, valid));
-                const double thresh = __dmul_rn(factor, __dsqrt_rn(__ddiv_rn((double)tsum, (double)num)));
-                if ((double)score < thresh) out = -2;
             }
-            if (lane == 0) cpv[(((size_t)s * L.n_rot + r) * 4 + t) * kCellsL + cell] = (int16_t)out;
+            // thresh = factor * sqrt(T / n): divsd, sqrtsd, mulsd -- three separately rounded f64 operations
+            const double thresh = __dmul_rn(factor, __dsqrt_rn(__ddiv_rn((double)tsum, (double)num)));
+            out = ((double)score < thresh) ? -2 : cp;
         }
+        cpv[(((size_t)S * L.n_rot + r) * 4 + t) * kCellsL + cell] = (int16_t)out;
     }
 }
 
@@ -621,7 +644,7 @@ long long gms_match_rows(const PairDesc* h_pairs, int n) {
 }
 size_t gms_scratch_bytes_per_pair(int n_scales) { return make_layout(n_scales, kNumRot, true).total_words * 4; }
 size_t gms_match_scratch_bytes(long long n_matches_total, int n_scales) {
-    return (size_t)n_matches_total * 2 * (4 + n_scales) + 256;
+    return (size_t)(n_matches_total + 8) * 2 * (4 + n_scales) + 1024;
 }
 
 // Left-grid rows per shared-memory band for scale s: (rows + 2 halo) * 20 cells * (G_r u16 + one int) must fit.
@@ -632,10 +655,10 @@ static int smem_band_rows(int s) {
     }();
     return s == 0 ? b0 : s == 1 ? 20 : s == 2 ? 10 : s == 3 ? 4 : 1;
 }
-static size_t smem_band_bytes(int s) {
+static size_t smem_band_bytes(int s, int extra_per_cell = 0) {
     const int w = right_grid_w(s), gr = w * w, b = smem_band_rows(s);
     const int rows = b >= kGridL ? kGridL : b + 2;
-    return (size_t)rows * kGridL * ((size_t)gr * 2 + 4);
+    return (size_t)rows * kGridL * ((size_t)gr * 2 + 4 + extra_per_cell);
 }
 
 // Runs GMS for n_pairs pairs.  Default: histograms in shared memory (one launch per scale for the whole batch).
@@ -661,7 +684,21 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
     static const bool use_v1 = getenv("SFMGMS_GMS_V1") != nullptr;   // previous-generation vote kernel (A/B measurements only)
     if (!dense) {
         if (cudaFuncSetAttribute(gms_vote_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
-        if (cudaFuncSetAttribute(gms_vote2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
+        static bool v2_ready = false;
+        if (!v2_ready) {
+            const void* fns[5] = {(const void*)gms_vote2_kernel<0>, (const void*)gms_vote2_kernel<1>, (const void*)gms_vote2_kernel<2>,
+                                  (const void*)gms_vote2_kernel<3>, (const void*)gms_vote2_kernel<4>};
+            for (const void* f : fns)
+                if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
+            static const int8_t rot[kNumRot][9] = {{1, 2, 3, 4, 5, 6, 7, 8, 9}, {4, 1, 2, 7, 5, 3, 8, 9, 6}, {7, 4, 1, 8, 5, 2, 9, 6, 3},
+                                                   {8, 7, 4, 9, 5, 1, 6, 3, 2}, {9, 8, 7, 6, 5, 4, 3, 2, 1}, {6, 9, 8, 3, 5, 7, 2, 1, 4},
+                                                   {3, 6, 9, 2, 5, 8, 1, 4, 7}, {2, 3, 6, 1, 5, 9, 4, 7, 8}};
+            int8_t dx[kNumRot][9], dy[kNumRot][9];
+            for (int r = 0; r < kNumRot; ++r)
+                for (int k = 0; k < 9; ++k) { dx[r][k] = (int8_t)((rot[r][k] - 1) % 3 - 1); dy[r][k] = (int8_t)((rot[r][k] - 1) / 3 - 1); }
+            if (cudaMemcpyToSymbol(c_rdx, dx, sizeof dx) != cudaSuccess || cudaMemcpyToSymbol(c_rdy, dy, sizeof dy) != cudaSuccess) return -1;
+            v2_ready = true;
+        }
     }
     for (int c0 = 0; c0 < n_pairs; c0 += chunk_cap) {
         const int cn = (n_pairs - c0 < chunk_cap) ? n_pairs - c0 : chunk_cap;
@@ -670,7 +707,7 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
         // rows of the per-match arrays spanned by this chunk: match_base advances by a pair's ROW count (n1 for
         // fused pairs, even when an empty train image leaves it with 0 matches), not by n_matches
         const long long cbase = h_pairs[c0].match_base;
-        const long long cm = gms_match_rows(h_pairs + c0, cn);
+        const long long cm = (gms_match_rows(h_pairs + c0, cn) + 7) & ~7LL;   // rows of lidx/ridx stay 16-byte aligned
         // per-match cell indices for this chunk: lidx[4][cm], ridx[n_scales][cm] (uint16)
         uint16_t* lidx = static_cast<uint16_t*>(d_match_scratch);
         uint16_t* ridx = lidx + (size_t)4 * cm;
@@ -710,8 +747,12 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
             for (int s = 0; s < n_scales; ++s) {
                 const int b = smem_band_rows(s);
                 const int bands = (kGridL + b - 1) / b;
-                gms_vote2_kernel<<<dim3(bands, 4, cn), 512, smem_band_bytes(s), st>>>(d_pairs + c0, scratch, L, factor, lidx, ridx,
-                                                                                    cbase, cm, s, b);
+                const dim3 grid(bands, 4, cn);
+                const size_t sm = smem_band_bytes(s, 4);
+#define SFMGMS_VOTE2(S) gms_vote2_kernel<S><<<grid, 512, sm, st>>>(d_pairs + c0, scratch, L, factor, lidx, ridx, cbase, cm, b)
+                if (s == 0) SFMGMS_VOTE2(0); else if (s == 1) SFMGMS_VOTE2(1); else if (s == 2) SFMGMS_VOTE2(2);
+                else if (s == 3) SFMGMS_VOTE2(3); else SFMGMS_VOTE2(4);
+#undef SFMGMS_VOTE2
                 ++launches; kmark("gms_vote2", st);
             }
         }

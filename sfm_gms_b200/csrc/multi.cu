@@ -155,6 +155,7 @@ int sfmgms_multi_create(sfmgms_multi** out, const int* devices, int n_devices) {
         m->n = n_devices;
         for (int i = 0; i < n_devices; ++i) {
             const int d = devices ? devices[i] : i;
+            if (d < 0 || d >= count) { delete m; return mfail(nullptr, SFMGMS_ERR_ARG, "device %d out of range [0,%d)", d, count); }
             for (int j = 0; j < i; ++j)
                 if (m->devices[(size_t)j] == d) { delete m; return mfail(nullptr, SFMGMS_ERR_ARG, "device %d listed twice", d); }
             m->devices.push_back(d);
@@ -202,12 +203,14 @@ void sfmgms_multi_destroy(sfmgms_multi* m) {
     for (size_t i = 0; i < m->comms.size(); ++i)
         if (m->comms[i]) m->nccl.CommDestroy(m->comms[i]);
     for (size_t i = 0; i < m->ctx.size(); ++i) {
-        if (m->ctx[i]) sfmgms_destroy(m->ctx[i]);      // before the buffers it adopted are freed
-        cudaSetDevice(m->devices[i]);
+        if (!m->ctx[i]) continue;                      // never created: nothing of this device to release
+        sfmgms_destroy(m->ctx[i]);                     // before the buffers it adopted are freed
+        if (cudaSetDevice(m->devices[i]) != cudaSuccess) continue;
         if (m->d_desc[i]) cudaFree(m->d_desc[i]);
         if (m->d_kp[i]) cudaFree(m->d_kp[i]);
         if (m->streams[i]) cudaStreamDestroy(m->streams[i]);
     }
+    cudaGetLastError();                                // leave no stale (non-sticky) error behind for the next launch check
     delete m;
 }
 
