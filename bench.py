@@ -310,6 +310,7 @@ def kernel_rooflines(kt, steps, kind, n_pairs, n_kp, n_hyp_scales):
         "gms_assign": ("hbm", rows * (4 + 8 + 8 + 2 * (4 + S))),
         "gms_assign_cnt": ("hbm", rows * (4 + 8 + 8 + 2 * (4 + S))),
         "gms_count": ("hbm", rows * (2 * (4 + S) + 1)),
+        "gms_count_scale": ("hbm", rows * (2 * (4 + S))),
         "gms_mask": ("hbm", rows * (2 * 5 + 1)),
         "gms_compact": ("hbm", rows * (1 + 4) + 0.5 * rows * (16 + 32)),
         "decode_keys": ("hbm", rows * 12),

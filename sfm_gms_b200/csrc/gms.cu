@@ -360,10 +360,12 @@ __global__ void __launch_bounds__(1024) gms_assign_cnt_kernel(const PairDesc* __
 // profiles/r2_notes.md), so: cell indices arrive as 128-bit loads of 8 matches, the right-grid width is a template constant,
 // and verification runs one THREAD per (left cell, rotation) -- 9-slot support gather, the three separately rounded f64
 // operations -- instead of one warp per cell.
-__constant__ int8_t c_rdx[kNumRot][9], c_rdy[kNumRot][9];   // ROT[r][k]-1 as (dx, dy) in the 3x3 neighbourhood; filled at first launch
+// (ROT[r][k] - 1) = v as (dx, dy) = (v mod 3 - 1, v div 3 - 1) in the 3x3 neighbourhood of the right cell
+__constant__ int8_t c_rdx[kNumRot][9] = {{-1, 0, 1, -1, 0, 1, -1, 0, 1}, {-1, -1, 0, -1, 0, 1, 0, 1, 1}, {-1, -1, -1, 0, 0, 0, 1, 1, 1}, {0, -1, -1, 1, 0, -1, 1, 1, 0}, {1, 0, -1, 1, 0, -1, 1, 0, -1}, {1, 1, 0, 1, 0, -1, 0, -1, -1}, {1, 1, 1, 0, 0, 0, -1, -1, -1}, {0, 1, 1, -1, 0, 1, -1, -1, 0}};
+__constant__ int8_t c_rdy[kNumRot][9] = {{-1, -1, -1, 0, 0, 0, 1, 1, 1}, {0, -1, -1, 1, 0, -1, 1, 1, 0}, {1, 0, -1, 1, 0, -1, 1, 0, -1}, {1, 1, 0, 1, 0, -1, 0, -1, -1}, {1, 1, 1, 0, 0, 0, -1, -1, -1}, {0, 1, 1, -1, 0, 1, -1, -1, 0}, {-1, 0, 1, -1, 0, 1, -1, 0, 1}, {-1, -1, 0, -1, 0, 1, 0, 1, 1}};
 
 template <int S>
-__global__ void __launch_bounds__(512) gms_vote2_kernel(const PairDesc* __restrict__ pairs, int32_t* scratch, Layout L,
+__global__ void __launch_bounds__(1024) gms_vote2_kernel(const PairDesc* __restrict__ pairs, int32_t* scratch, Layout L,
                                                         double factor, const uint16_t* __restrict__ lidx,
                                                         const uint16_t* __restrict__ ridx, long long chunk_match_base,
                                                         long long chunk_matches, int band_rows) {
@@ -497,6 +499,53 @@ __global__ void __launch_bounds__(256) gms_count_kernel(const PairDesc* __restri
         for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += wsum[k];
         if (tot) atomicAdd(&sp[L.counts_off + hyp], tot);
     }
+}
+
+// ---- a9 for the rotation / scale search: one CTA per (pair, scale, slice of matches) counts the inliers of ALL rotations
+// of that scale at once.  The scale's cell-pair tables (n_rot x 4 shifts x 400 cells, int16) sit in shared memory; a match
+// reads its 4 left cells and its right cell once and does n_rot x 4 table look-ups there (the per-hypothesis kernel above
+// re-read the indices and gathered from global memory 8 times).
+__global__ void __launch_bounds__(256) gms_count_scale_kernel(const PairDesc* __restrict__ pairs, int32_t* scratch, Layout L,
+                                                              const uint16_t* __restrict__ lidx, const uint16_t* __restrict__ ridx,
+                                                              long long chunk_match_base, long long chunk_matches) {
+    extern __shared__ uint32_t cs_u32[];
+    __shared__ int cnt_s[kNumRot];
+    const PairDesc pd = pairs[blockIdx.z];
+    const int s = blockIdx.y;
+    int32_t* sp = scratch + (size_t)blockIdx.z * L.total_words;
+    const int words = L.n_rot * 4 * kCellsL / 2;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const int16_t*>(sp + L.cp_off) + (size_t)s * L.n_rot * 4 * kCellsL);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) cs_u32[i] = src[i];
+    if (threadIdx.x < kNumRot) cnt_s[threadIdx.x] = 0;
+    __syncthreads();
+    const int16_t* cp_s = reinterpret_cast<const int16_t*>(cs_u32);
+    const long long mb = pd.match_base - chunk_match_base;
+    const int lane = threadIdx.x & 31;
+    for (int base = blockIdx.x * blockDim.x; base < pd.n_matches; base += gridDim.x * blockDim.x) {   // warp-uniform trip count
+        const int i = base + threadIdx.x;
+        unsigned m = 0;
+        if (i < pd.n_matches) {
+            const uint16_t r = ridx[(size_t)s * chunk_matches + mb + i];
+            if (r != kNoCell) {
+                uint16_t l[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) l[t] = lidx[(size_t)t * chunk_matches + mb + i];
+                for (int rot = 0; rot < L.n_rot; ++rot) {
+                    bool inl = false;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (l[t] != kNoCell) inl |= (cp_s[(rot * 4 + t) * kCellsL + l[t]] == (int16_t)r);
+                    m |= (unsigned)inl << rot;
+                }
+            }
+        }
+        for (int rot = 0; rot < L.n_rot; ++rot) {
+            const int c = __popc(__ballot_sync(0xffffffffu, (m >> rot) & 1u));
+            if (lane == 0 && c) atomicAdd(&cnt_s[rot], c);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < L.n_rot && cnt_s[threadIdx.x]) atomicAdd(&sp[L.counts_off + s * L.n_rot + threadIdx.x], cnt_s[threadIdx.x]);
 }
 
 // ---- a10: getInlierMask — best hypothesis, scale-major / rotation-minor, strict '>' (first wins) -----
@@ -650,7 +699,7 @@ size_t gms_match_scratch_bytes(long long n_matches_total, int n_scales) {
 // Left-grid rows per shared-memory band for scale s: (rows + 2 halo) * 20 cells * (G_r u16 + one int) must fit.
 static int smem_band_rows(int s) {
     static const int b0 = [] {   // tuning experiments only; clamped to a valid band height
-        const int v = getenv("SFMGMS_GMS_BAND0") ? atoi(getenv("SFMGMS_GMS_BAND0")) : 5;
+        const int v = getenv("SFMGMS_GMS_BAND0") ? atoi(getenv("SFMGMS_GMS_BAND0")) : 10;
         return v < 1 ? 1 : (v > 10 ? 10 : v);
     }();
     return s == 0 ? b0 : s == 1 ? 20 : s == 2 ? 10 : s == 3 ? 4 : 1;
@@ -684,19 +733,15 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
     static const bool use_v1 = getenv("SFMGMS_GMS_V1") != nullptr;   // previous-generation vote kernel (A/B measurements only)
     if (!dense) {
         if (cudaFuncSetAttribute(gms_vote_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
-        static bool v2_ready = false;
+        static bool ready_dev[64] = {false};     // function attributes and __constant__ copies are PER DEVICE
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+        bool& v2_ready = ready_dev[dev];
         if (!v2_ready) {
             const void* fns[5] = {(const void*)gms_vote2_kernel<0>, (const void*)gms_vote2_kernel<1>, (const void*)gms_vote2_kernel<2>,
                                   (const void*)gms_vote2_kernel<3>, (const void*)gms_vote2_kernel<4>};
             for (const void* f : fns)
                 if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
-            static const int8_t rot[kNumRot][9] = {{1, 2, 3, 4, 5, 6, 7, 8, 9}, {4, 1, 2, 7, 5, 3, 8, 9, 6}, {7, 4, 1, 8, 5, 2, 9, 6, 3},
-                                                   {8, 7, 4, 9, 5, 1, 6, 3, 2}, {9, 8, 7, 6, 5, 4, 3, 2, 1}, {6, 9, 8, 3, 5, 7, 2, 1, 4},
-                                                   {3, 6, 9, 2, 5, 8, 1, 4, 7}, {2, 3, 6, 1, 5, 9, 4, 7, 8}};
-            int8_t dx[kNumRot][9], dy[kNumRot][9];
-            for (int r = 0; r < kNumRot; ++r)
-                for (int k = 0; k < 9; ++k) { dx[r][k] = (int8_t)((rot[r][k] - 1) % 3 - 1); dy[r][k] = (int8_t)((rot[r][k] - 1) / 3 - 1); }
-            if (cudaMemcpyToSymbol(c_rdx, dx, sizeof dx) != cudaSuccess || cudaMemcpyToSymbol(c_rdy, dy, sizeof dy) != cudaSuccess) return -1;
             v2_ready = true;
         }
     }
@@ -749,16 +794,22 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
                 const int bands = (kGridL + b - 1) / b;
                 const dim3 grid(bands, 4, cn);
                 const size_t sm = smem_band_bytes(s, 4);
-#define SFMGMS_VOTE2(S) gms_vote2_kernel<S><<<grid, 512, sm, st>>>(d_pairs + c0, scratch, L, factor, lidx, ridx, cbase, cm, b)
+                static const int vthreads = getenv("SFMGMS_GMS_THREADS") ? atoi(getenv("SFMGMS_GMS_THREADS")) : 512;   // tuning only
+#define SFMGMS_VOTE2(S) gms_vote2_kernel<S><<<grid, vthreads == 1024 ? 1024 : 512, sm, st>>>(d_pairs + c0, scratch, L, factor, lidx, ridx, cbase, cm, b)
                 if (s == 0) SFMGMS_VOTE2(0); else if (s == 1) SFMGMS_VOTE2(1); else if (s == 2) SFMGMS_VOTE2(2);
                 else if (s == 3) SFMGMS_VOTE2(3); else SFMGMS_VOTE2(4);
 #undef SFMGMS_VOTE2
                 ++launches; kmark("gms_vote2", st);
             }
         }
-        if (max_m > 0) {
-            gms_count_kernel<<<dim3(bx, n_scales * n_rot, cn), 256, 0, st>>>(d_pairs + c0, scratch, L, lidx, ridx, cbase,
-                                                                         cm, flags_on ? 0 : 1);
+        if (max_m > 0 && flags_on) {
+            int cbx = (max_m + 2047) / 2048;
+            cbx = cbx > 32 ? 32 : cbx;
+            gms_count_scale_kernel<<<dim3(cbx, n_scales, cn), 256, (size_t)n_rot * 4 * kCellsL * 2, st>>>(d_pairs + c0, scratch, L, lidx,
+                                                                                                      ridx, cbase, cm);
+            ++launches; kmark("gms_count_scale", st);
+        } else if (max_m > 0) {
+            gms_count_kernel<<<dim3(bx, 1, cn), 256, 0, st>>>(d_pairs + c0, scratch, L, lidx, ridx, cbase, cm, 1);
             ++launches; kmark("gms_count", st);
         }
         gms_select_kernel<<<(cn + 127) / 128, 128, 0, st>>>(d_pairs + c0, d_results + c0, scratch, L, cn, flags_on);
