@@ -86,6 +86,13 @@ __constant__ float2 c_grouptag[kGroups / 2] = {{31.f / 32.f, 30.f / 32.f}, {29.f
                                                {13.f / 32.f, 12.f / 32.f}};
 #endif
 
+// one lane of the (converged) warp: elect.sync
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 // (lo, hi) + (c.x, c.y) with one packed fp32x2 add (sm_100: add.rn.f32x2 -> FADD2)
 __device__ __forceinline__ void add2(float lo, float hi, float2 c, float& out_lo, float& out_hi) {
     unsigned long long x, cc, r;
@@ -252,66 +259,74 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     __syncthreads();
     tc_fence_after();
 
+    // The two single-issuer roles run with the WHOLE warp converged and elect one lane per issue (elect.sync): every
+    // operand of the TMA / MMA instructions is then warp-uniform and ptxas keeps it in uniform registers.  (With the role
+    // loop inside `if (lane == 0)` it had to wrap every UTCOMMA / UTMALDG in an R2UR + ELECT + BRA.U.ANY serialisation loop;
+    // ncu showed the MMA thread spending ~75 % of its samples in that issue sequence and only ~12 % waiting on barriers.)
     if (warp == kProdWarp) {
-        if (lane == 0) {
+        if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
-            uint32_t stage = 0, phase = 0, abuf = 0, a_phase = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const WorkUnit wu = make_unit(lm, pairs, u);
-                const int nsub = (wu.n_rows + BM - 1) / BM;
-                mbar_wait(a_empty_bar + 8 * abuf, a_phase ^ 1);
+        }
+        uint32_t stage = 0, phase = 0, abuf = 0, a_phase = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const WorkUnit wu = make_unit(lm, pairs, u);
+            const int nsub = (wu.n_rows + BM - 1) / BM;
+            mbar_wait(a_empty_bar + 8 * abuf, a_phase ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(a_full_bar + 8 * abuf, (uint32_t)(nsub * TILE_BYTES));
                 for (int s = 0; s < nsub; ++s)
                     tma_load_2d(a_smem + abuf * A_BUF_BYTES + s * TILE_BYTES, &tmap, 0, (int)(wu.a_row0 + s * BM),
                                 a_full_bar + 8 * abuf);
-                if (++abuf == A_BUFS) { abuf = 0; a_phase ^= 1; }
-                for (int t = wu.t_begin; t < wu.t_end; t += BN) {
-                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+            }
+            if (++abuf == A_BUFS) { abuf = 0; a_phase ^= 1; }
+            for (int t = wu.t_begin; t < wu.t_end; t += BN) {
+                mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx(full_bar + 8 * stage, (uint32_t)BTILE_BYTES);
                     tma_load_2d(b_smem + stage * BTILE_BYTES, &tmapB, 0, (int)(wu.b_row0 + t), full_bar + 8 * stage);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == kMmaWarp) {
-        if (lane == 0) {
-            // accumulator slot = sub-tile index & 1 (compile-time in the epilogue's unrolled loop); one phase bit per slot
-            uint32_t stage = 0, phase = 0, abuf = 0, a_phase = 0, slot_phase[ACC_SLOTS] = {0, 0};
-            const uint32_t a_lo0 = sdesc_lo(a_smem), b_lo0 = sdesc_lo(b_smem);
-            const uint32_t sf = tmem_base + SF_COL;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const WorkUnit wu = make_unit(lm, pairs, u);
-                const int nsub = (wu.n_rows + BM - 1) / BM;
-                const int ntiles = (wu.t_end - wu.t_begin + BN - 1) / BN;
-                mbar_wait(a_full_bar + 8 * abuf, a_phase);
-                const uint32_t a_lo_buf = a_lo0 + abuf * (A_BUF_BYTES >> 4);
-                for (int ti = 0; ti < ntiles; ++ti) {
-                    mbar_wait(full_bar + 8 * stage, phase);
-                    const uint32_t b_lo = b_lo0 + stage * (BTILE_BYTES >> 4);
+        // accumulator slot = sub-tile index & 1 (compile-time in the epilogue's unrolled loop); one phase bit per slot
+        uint32_t stage = 0, phase = 0, abuf = 0, a_phase = 0, slot_phase[ACC_SLOTS] = {0, 0};
+        const uint32_t a_lo0 = sdesc_lo(a_smem), b_lo0 = sdesc_lo(b_smem);
+        const uint32_t sf = tmem_base + SF_COL;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const WorkUnit wu = make_unit(lm, pairs, u);
+            const int nsub = (wu.n_rows + BM - 1) / BM;
+            const int ntiles = (wu.t_end - wu.t_begin + BN - 1) / BN;
+            mbar_wait(a_full_bar + 8 * abuf, a_phase);
+            const uint32_t a_lo_buf = a_lo0 + abuf * (A_BUF_BYTES >> 4);
+            for (int ti = 0; ti < ntiles; ++ti) {
+                mbar_wait(full_bar + 8 * stage, phase);
+                const uint32_t b_lo = b_lo0 + stage * (BTILE_BYTES >> 4);
 #pragma unroll
-                    for (int s = 0; s < MSUB; ++s) {
-                        if (s >= nsub) break;
-                        const int slot = s & 1;
-                        mbar_wait(tempty_bar + 8 * slot, slot_phase[slot] ^ 1);
-                        slot_phase[slot] ^= 1;
-                        tc_fence_after();
-                        const uint32_t d = tmem_base + slot * BN;
-                        const uint32_t a_lo = a_lo_buf + s * (TILE_BYTES >> 4);
+                for (int s = 0; s < MSUB; ++s) {
+                    if (s >= nsub) break;
+                    const int slot = s & 1;
+                    mbar_wait(tempty_bar + 8 * slot, slot_phase[slot] ^ 1);
+                    slot_phase[slot] ^= 1;
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + slot * BN;
+                    const uint32_t a_lo = a_lo_buf + s * (TILE_BYTES >> 4);
+                    if (elect_one()) {
                         if (dbg != 3) {   // DEBUG 3: no tensor work
-                        tc_mma_mxf4<0>(d, a_lo + 0, b_lo + 0, kDescHi, kIdesc, sf, sf);
-                        tc_mma_mxf4<1>(d, a_lo + 2, b_lo + 2, kDescHi, kIdesc, sf, sf);
-                        tc_mma_mxf4<1>(d, a_lo + 4, b_lo + 4, kDescHi, kIdesc, sf, sf);
-                        tc_mma_mxf4<1>(d, a_lo + 6, b_lo + 6, kDescHi, kIdesc, sf, sf);
+                            tc_mma_mxf4<0>(d, a_lo + 0, b_lo + 0, kDescHi, kIdesc, sf, sf);
+                            tc_mma_mxf4<1>(d, a_lo + 2, b_lo + 2, kDescHi, kIdesc, sf, sf);
+                            tc_mma_mxf4<1>(d, a_lo + 4, b_lo + 4, kDescHi, kIdesc, sf, sf);
+                            tc_mma_mxf4<1>(d, a_lo + 6, b_lo + 6, kDescHi, kIdesc, sf, sf);
                         }
                         tc_commit(tfull_bar + 8 * slot);
                     }
-                    tc_commit(empty_bar + 8 * stage);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(a_empty_bar + 8 * abuf);
-                if (++abuf == A_BUFS) { abuf = 0; a_phase ^= 1; }
+                if (elect_one()) tc_commit(empty_bar + 8 * stage);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (elect_one()) tc_commit(a_empty_bar + 8 * abuf);
+            if (++abuf == A_BUFS) { abuf = 0; a_phase ^= 1; }
         }
     } else if (warp < kEpiWarps) {
         // ================= epilogue: 12 warps; warp = (lane quadrant, 80-column part) of every accumulator ==========
