@@ -1,5 +1,7 @@
 """Randomised stress: many ragged shapes, all Hamming kernels must agree bit-for-bit with the POPC kernel (itself
-oracle-checked in tests); multi-pair batches through both host paths; repeated to shake out rare synchronisation bugs."""
+oracle-checked in tests); multi-pair batches through both host paths, random chunk sizes of the pair-list runner, the
+compacted outputs against the per-match outputs, every 7th batch against the CPU oracle; repeated to shake out rare
+synchronisation bugs."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -38,6 +40,7 @@ while time.time() < t_end:
         n_pairs = int(rng.integers(1, 40))
         pairs = rng.integers(0, n_img, (n_pairs, 2)).astype(np.int32)
         rot, sc = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+        ctx.set_option(api.OPT_CHUNK_ROWS, int(rng.choice([1, 2000, 7000, 1 << 22])))
         ref = None
         for k in (api.HAMMING_POPC, api.HAMMING_FP4, api.HAMMING_TC):
             ctx.set_option(api.OPT_HAMMING_KERNEL, k)
@@ -51,4 +54,25 @@ while time.time() < t_end:
             else:
                 for key in ("train_idx", "dist", "mask", "n_inliers", "best_hyp", "mask_len"):
                     assert np.array_equal(out[key], ref[key]), (it, k, key)
+        # compacted outputs == the inliers of the per-match outputs
+        ctx.set_images(off, desc, kp, wh)
+        c = ctx.match_pairs_compact(pairs, rot, sc)
+        mo = ref["offsets"]
+        for p in range(n_pairs):
+            m = ref["mask"][mo[p]:mo[p + 1]].astype(bool)
+            rows = c["matches"][c["offsets"][p]:c["offsets"][p + 1]]
+            assert np.array_equal(rows["queryIdx"], np.nonzero(m)[0]) and np.array_equal(rows["trainIdx"], ref["train_idx"][mo[p]:mo[p + 1]][m]), (it, p)
+            assert np.array_equal(c["pts1"][c["offsets"][p]:c["offsets"][p + 1]], kp[off[pairs[p, 0]]:off[pairs[p, 0] + 1]][m]), (it, p)
+        if it % 7 == 1:
+            import oracle
+            for p in range(min(n_pairs, 6)):
+                a, b = pairs[p]
+                if sizes_n[a] == 0 or sizes_n[b] == 0:
+                    continue
+                oi, od = oracle.bf_hamming(descs[a], descs[b])
+                o = oracle.gms((w, 480), (w, 480), kps[a], kps[b], np.arange(len(oi), dtype=np.int32), oi, rot, sc)
+                sl = slice(mo[p], mo[p + 1])
+                assert np.array_equal(ref["train_idx"][sl], oi) and np.array_equal(ref["dist"][sl], od), (it, p, "bf vs oracle")
+                full = o["mask"] if len(o["mask"]) == len(oi) else np.zeros(len(oi), bool)
+                assert np.array_equal(ref["mask"][sl].astype(bool), full) and ref["n_inliers"][p] == o["n_inliers"], (it, p, "gms vs oracle")
 print("stress ok: %d iterations in %.0f s" % (it, budget))
