@@ -794,8 +794,11 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
                 const int bands = (kGridL + b - 1) / b;
                 const dim3 grid(bands, 4, cn);
                 const size_t sm = smem_band_bytes(s, 4);
-                static const int vthreads = getenv("SFMGMS_GMS_THREADS") ? atoi(getenv("SFMGMS_GMS_THREADS")) : 512;   // tuning only
-#define SFMGMS_VOTE2(S) gms_vote2_kernel<S><<<grid, vthreads == 1024 ? 1024 : 512, sm, st>>>(d_pairs + c0, scratch, L, factor, lidx, ridx, cbase, cm, b)
+                // one CTA per SM (band needs > half of the shared memory): 1024 threads hide the index-load latency better;
+                // two CTAs per SM: 512 threads each
+                static const int vthreads = getenv("SFMGMS_GMS_THREADS") ? atoi(getenv("SFMGMS_GMS_THREADS")) : 0;   // tuning only
+                const int nthreads = vthreads ? (vthreads == 1024 ? 1024 : 512) : (sm > 113 * 1024 ? 1024 : 512);
+#define SFMGMS_VOTE2(S) gms_vote2_kernel<S><<<grid, nthreads, sm, st>>>(d_pairs + c0, scratch, L, factor, lidx, ridx, cbase, cm, b)
                 if (s == 0) SFMGMS_VOTE2(0); else if (s == 1) SFMGMS_VOTE2(1); else if (s == 2) SFMGMS_VOTE2(2);
                 else if (s == 3) SFMGMS_VOTE2(3); else SFMGMS_VOTE2(4);
 #undef SFMGMS_VOTE2

@@ -86,13 +86,6 @@ __constant__ float2 c_grouptag[kGroups / 2] = {{31.f / 32.f, 30.f / 32.f}, {29.f
                                                {13.f / 32.f, 12.f / 32.f}};
 #endif
 
-// one lane of the (converged) warp: elect.sync
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
-    return pred != 0;
-}
-
 // (lo, hi) + (c.x, c.y) with one packed fp32x2 add (sm_100: add.rn.f32x2 -> FADD2)
 __device__ __forceinline__ void add2(float lo, float hi, float2 c, float& out_lo, float& out_hi) {
     unsigned long long x, cc, r;

@@ -171,25 +171,27 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkUnit* __re
     const uint32_t tmem_acc = tmem_base + A_COLS;             // accumulator slots follow the query operand
 
     if (warp == 0) {
-        // ================= TMA producer: train tiles =================
-        if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+        // ================= TMA producer: train tiles (warp converged, one elected lane issues) =================
+        {
+            if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
             uint32_t stage = 0, phase = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const WorkUnit wu = units[u];
                 for (int t = wu.t_begin; t < wu.t_end; t += BN) {
                     mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-                    mbar_expect_tx(full_bar + 8 * stage, (uint32_t)B_STAGE_BYTES);
-                    for (int kc = 0; kc < NKCH; ++kc)
-                        tma_load_2d(b_smem + stage * B_STAGE_BYTES + kc * TILE_BYTES, &tmap, kc * KCH,
-                                    (int)(wu.b_row0 + t), full_bar + 8 * stage);
+                    if (elect_one()) {
+                        mbar_expect_tx(full_bar + 8 * stage, (uint32_t)B_STAGE_BYTES);
+                        for (int kc = 0; kc < NKCH; ++kc)
+                            tma_load_2d(b_smem + stage * B_STAGE_BYTES + kc * TILE_BYTES, &tmap, kc * KCH,
+                                        (int)(wu.b_row0 + t), full_bar + 8 * stage);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer (warp converged, one elected lane issues) =================
+        {
             uint32_t stage = 0, phase = 0, a_phase = 0, slot = 0, slot_phase = 0;
             const uint32_t b_lo0 = sdesc_lo(b_smem);
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -208,6 +210,7 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkUnit* __re
                         const uint32_t d = tmem_acc + slot * BN;
                         const uint32_t a = tmem_base + s * (KBYTES / 4);    // 8 TMEM columns per K step of 32 bytes
                         // K = 256 = 2 swizzle chunks x 4 steps of 32 (one 128x128x32 int8 MMA each)
+                        if (elect_one()) {
                         if (dbg != 3) {   // DEBUG 3: no tensor work
                         tc_mma_i8_ts<0>(d, a + 0, b_lo + 0, kDescHi, kIdesc);
                         tc_mma_i8_ts<1>(d, a + 8, b_lo + 2, kDescHi, kIdesc);
@@ -219,12 +222,13 @@ hamming_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkUnit* __re
                         tc_mma_i8_ts<1>(d, a + 56, b_lo + (TILE_BYTES >> 4) + 6, kDescHi, kIdesc);
                         }
                         tc_commit(tfull_bar + 8 * slot);                   // accumulator ready for the epilogue
+                        }
                         if (++slot == ACC_SLOTS) { slot = 0; slot_phase ^= 1; }
                     }
-                    tc_commit(empty_bar + 8 * stage);                      // B stage reusable once these MMAs retire
+                    if (elect_one()) tc_commit(empty_bar + 8 * stage);     // B stage reusable once these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(a_empty_bar);                                     // query operand may be overwritten
+                if (elect_one()) tc_commit(a_empty_bar);                    // query operand may be overwritten
             }
         }
     } else if (warp >= kLoadWarp0) {

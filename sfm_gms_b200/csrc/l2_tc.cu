@@ -130,30 +130,37 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_ptr_generic;
     const int n_units = P.n_units;
 
+    // single-issuer roles: the whole warp runs the loop converged and elects one lane per issue (see hamming_fp4.cu)
     if (warp == kProdWarp) {
-        if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
+        {
+            if (elect_one()) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
+            }
             uint32_t stage = 0, phase = 0, abuf = 0, a_phase = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const Unit wu = make_unit(P, u);
                 const int nsub = (wu.n_rows + BM - 1) / BM;
                 mbar_wait(a_empty_bar + 8 * abuf, a_phase ^ 1);
-                mbar_expect_tx(a_full_bar + 8 * abuf, (uint32_t)(nsub * TILE_BYTES));
-                for (int s = 0; s < nsub; ++s)
-                    tma_load_2d(a_smem + abuf * A_BUF_BYTES + s * TILE_BYTES, &tmapA, 0, (int)(P.a_row0 + wu.q0 + s * BM),
-                                a_full_bar + 8 * abuf);
+                if (elect_one()) {
+                    mbar_expect_tx(a_full_bar + 8 * abuf, (uint32_t)(nsub * TILE_BYTES));
+                    for (int s = 0; s < nsub; ++s)
+                        tma_load_2d(a_smem + abuf * A_BUF_BYTES + s * TILE_BYTES, &tmapA, 0, (int)(P.a_row0 + wu.q0 + s * BM),
+                                    a_full_bar + 8 * abuf);
+                }
                 if (++abuf == A_BUFS) { abuf = 0; a_phase ^= 1; }
                 for (int t = wu.t_begin; t < wu.t_end; t += BN) {
                     mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-                    mbar_expect_tx(full_bar + 8 * stage, (uint32_t)BTILE_BYTES);
-                    tma_load_2d(b_smem + stage * BTILE_BYTES, &tmapB, 0, (int)(P.b_row0 + t), full_bar + 8 * stage);
+                    if (elect_one()) {
+                        mbar_expect_tx(full_bar + 8 * stage, (uint32_t)BTILE_BYTES);
+                        tma_load_2d(b_smem + stage * BTILE_BYTES, &tmapB, 0, (int)(P.b_row0 + t), full_bar + 8 * stage);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == kMmaWarp) {
-        if (lane == 0) {
+        {
             uint32_t stage = 0, phase = 0, abuf = 0, a_phase = 0, slot = 0, slot_phase = 0;
             const uint32_t a_lo0 = sdesc_lo(a_smem), b_lo0 = sdesc_lo(b_smem);
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -170,17 +177,19 @@ l2_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
                         tc_fence_after();
                         const uint32_t d = tmem_base + slot * BN;
                         const uint32_t a_lo = a_lo_buf + s * (TILE_BYTES >> 4);
-                        tc_mma_u8<0>(d, a_lo + 0, b_lo + 0);      // K = 128 = 4 steps of 32 bytes inside the swizzle row
-                        tc_mma_u8<1>(d, a_lo + 2, b_lo + 2);
-                        tc_mma_u8<1>(d, a_lo + 4, b_lo + 4);
-                        tc_mma_u8<1>(d, a_lo + 6, b_lo + 6);
-                        tc_commit(tfull_bar + 8 * slot);
+                        if (elect_one()) {
+                            tc_mma_u8<0>(d, a_lo + 0, b_lo + 0);      // K = 128 = 4 steps of 32 bytes inside the swizzle row
+                            tc_mma_u8<1>(d, a_lo + 2, b_lo + 2);
+                            tc_mma_u8<1>(d, a_lo + 4, b_lo + 4);
+                            tc_mma_u8<1>(d, a_lo + 6, b_lo + 6);
+                            tc_commit(tfull_bar + 8 * slot);
+                        }
                         if (++slot == ACC_SLOTS) { slot = 0; slot_phase ^= 1; }
                     }
-                    tc_commit(empty_bar + 8 * stage);
+                    if (elect_one()) tc_commit(empty_bar + 8 * stage);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(a_empty_bar + 8 * abuf);
+                if (elect_one()) tc_commit(a_empty_bar + 8 * abuf);
                 if (++abuf == A_BUFS) { abuf = 0; a_phase ^= 1; }
             }
         }
