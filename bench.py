@@ -743,7 +743,7 @@ def main():
                 # the CPU reference path on a bounded sample of the very pairs the GPU just matched -- its results are
                 # the parity check of the GPU arm
                 cpu = CpuPath(threads)
-                n_s = args.cpu_pairs or {"cfg2": 128, "cfg3": 2, "cfg4": 1}[kind]
+                n_s = args.cpu_pairs or {"cfg2": 256, "cfg3": 4, "cfg4": 1}[kind]
                 n_s = min(n_s, P)
                 res = cpu_pairs(cpu, b["set"], b["set"]["pairs"][:n_s], b["rot"], b["sc"])
                 line["parity_checked_pairs"] = check_batch_parity(res, b["res"], n_kp)

@@ -248,6 +248,19 @@ int sfmgms_match_pairs_compact(sfmgms_ctx* ctx, const int32_t* pairs, int n_pair
                                int64_t* inlier_offsets, void* matches, float* pts1, float* pts2, int64_t capacity,
                                int64_t* n_total);
 
+/* Asynchronous variants (SURVEY §8b "synchronous by default with an async stream variant"): DEVICE outputs only.  The whole
+ * pair list is enqueued on the context's stream (sfmgms_stream) and the call returns; outputs are valid after sfmgms_wait
+ * (or after the caller's own event / stream synchronisation on that stream).  Conditions the device detects (keypoint
+ * outside the image, index out of range, compact capacity exceeded) are reported by sfmgms_wait, which also returns the total
+ * number of inliers.  No other call on the context between the two.  pairs must stay valid until the call returns only. */
+int sfmgms_match_pairs_async(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int with_rotation, int with_scale,
+                             double threshold_factor, int32_t* n_inliers, int32_t* best_hyp, int32_t* mask_len,
+                             int32_t* train_idx, int32_t* dist, uint8_t* mask);
+int sfmgms_match_pairs_compact_async(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int with_rotation, int with_scale,
+                                     double threshold_factor, int32_t* n_inliers, int32_t* best_hyp, int64_t* inlier_offsets,
+                                     void* matches, float* pts1, float* pts2, int64_t capacity);
+int sfmgms_wait(sfmgms_ctx* ctx, int64_t* n_total /* may be NULL */);
+
 /* sfmgms_match_image_set: sfmgms_set_images(SFMGMS_HOST) + sfmgms_match_pairs(SFMGMS_HOST outputs) in ONE
  * synchronous call that pipelines internally: the image set goes to the device in chunks on a copy stream while
  * earlier pairs already compute, and finished pairs' results return on a third stream.  Pairs are processed in

@@ -100,6 +100,11 @@ def load_library():
     L.sfmgms_inlier_points.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, P(c_int)]
     L.sfmgms_match_pairs_compact.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_i64, P(c_i64)]
+    L.sfmgms_match_pairs_async.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_void_p]
+    L.sfmgms_match_pairs_compact_async.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p,
+                                                   c_void_p, c_void_p, c_void_p, c_i64]
+    L.sfmgms_wait.argtypes = [c_void_p, P(c_i64)]
     L.sfmgms_gms_hypotheses.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
                                         c_void_p, c_void_p, c_int, c_int, c_double, c_void_p]
     L.sfmgms_multi_create.argtypes = [P(c_void_p), c_void_p, c_int]
@@ -489,6 +494,27 @@ class Context:
                                                          int(with_scale), float(threshold_factor), int(out_location),
                                                          p(n_inliers), p(best_hyp), p(offsets), p(matches), p(pts1), p(pts2),
                                                          int(capacity), ctypes.byref(tot)))
+        return tot.value
+
+    def match_pairs_compact_async_raw(self, pairs_np, with_rotation, with_scale, threshold_factor, capacity, n_inliers=0, best_hyp=0,
+                                      offsets=0, matches=0, pts1=0, pts2=0):
+        """Device pointers only; returns at once.  Finish with wait()."""
+        p = lambda v: ctypes.c_void_p(int(v)) if v else None  # noqa: E731
+        self._check(self._lib.sfmgms_match_pairs_compact_async(self._h, _ptr(pairs_np), pairs_np.shape[0], int(with_rotation),
+                                                               int(with_scale), float(threshold_factor), p(n_inliers), p(best_hyp),
+                                                               p(offsets), p(matches), p(pts1), p(pts2), int(capacity)))
+
+    def match_pairs_async_raw(self, pairs_np, with_rotation, with_scale, threshold_factor, n_inliers=0, best_hyp=0, mask_len=0,
+                              train_idx=0, dist=0, mask=0):
+        p = lambda v: ctypes.c_void_p(int(v)) if v else None  # noqa: E731
+        self._check(self._lib.sfmgms_match_pairs_async(self._h, _ptr(pairs_np), pairs_np.shape[0], int(with_rotation), int(with_scale),
+                                                       float(threshold_factor), p(n_inliers), p(best_hyp), p(mask_len), p(train_idx),
+                                                       p(dist), p(mask)))
+
+    def wait(self):
+        """Completes an asynchronous pair list -> total number of inliers."""
+        tot = ctypes.c_int64(0)
+        self._check(self._lib.sfmgms_wait(self._h, ctypes.byref(tot)))
         return tot.value
 
     def match_pairs_raw(self, pairs_np, with_rotation, with_scale, threshold_factor, out_location, n_inliers=0,

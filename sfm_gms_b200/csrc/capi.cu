@@ -121,6 +121,7 @@ struct sfmgms_ctx {
     } slot[2];
     DevBuf d_cbase;                 // running inlier total of a compact run (int64)
     HostBuf h_coff;
+    struct Pending { bool active = false; int n_pairs = 0; bool compact = false; long long capacity = 0; } pending;   // *_async
     long long chunk_rows = 4ll << 20;   // match rows per chunk (SFMGMS_OPT_CHUNK_ROWS)
     int gms_dense = 0;              // SFMGMS_OPT_GMS_DENSE
 };
@@ -160,6 +161,17 @@ __global__ void decode_keys_kernel(const uint32_t* __restrict__ key, long long n
         if (train_idx) train_idx[i] = none ? -1 : (int32_t)(k & kTrainIdxMask);
         if (dist) dist[i] = none ? -1 : (int32_t)(k >> kTrainIdxBits);
     }
+}
+
+// per-pair summaries of a batch for device callers (the asynchronous pair-list calls cannot pass through the host)
+__global__ void export_results_kernel(const PairResult* __restrict__ res, int n, int32_t* __restrict__ n_inliers,
+                                      int32_t* __restrict__ best_hyp, int32_t* __restrict__ mask_len) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const PairResult r = res[p];
+    if (n_inliers) n_inliers[p] = r.n_inliers;
+    if (best_hyp) best_hyp[p] = r.best_hyp;
+    if (mask_len) mask_len[p] = r.mask_len;
 }
 
 // cross-check: for each train row j the nearest query (lowest query index on ties) is rkey[j];
@@ -1136,6 +1148,7 @@ struct PairsJob {
     // multi-GPU (host outputs only): several contexts append their chunks to ONE caller buffer through a shared
     // cursor (atomic reservation per chunk); inlier_offsets[p] then is the absolute first row of pair p (n entries)
     int64_t* shared_cursor = nullptr;
+    bool async = false;   // device outputs only: enqueue everything on the context stream and return (sfmgms_wait finishes)
 };
 
 constexpr int kMaxChunkPairs = 4096;
@@ -1157,8 +1170,10 @@ int run_pairs_job(sfmgms_ctx* ctx, const PairsJob& J) {
     if (J.compact && (J.capacity < 0 || (J.capacity > 0 && !J.matches && !J.pts1 && !J.pts2)))
         return fail(ctx, SFMGMS_ERR_ARG, "compact output: capacity > 0 needs at least one of matches / pts1 / pts2");
     if (J.n_total) *J.n_total = 0;
+    if (ctx->pending.active) return fail(ctx, SFMGMS_ERR_STATE, "an asynchronous pair list is in flight: call sfmgms_wait first");
     cudaStream_t st = ctx->stream;
     const bool dev_out = (J.out_location == SFMGMS_DEVICE);
+    if (J.async && !dev_out) return fail(ctx, SFMGMS_ERR_ARG, "asynchronous calls take device outputs only");
     std::vector<PairDesc> hp;
     int64_t total = 0;
     int rc = build_pair_table(ctx, J.pairs, n_pairs, hp, &total);
@@ -1234,6 +1249,7 @@ int run_pairs_job(sfmgms_ctx* ctx, const PairsJob& J) {
     if (J.compact) CU(ctx->h_coff.ensure((size_t)(max_cp + 1) * 8 * 2));
     double t_ham = 0, t_gms = 0;
     int ham_launches = 0;
+    const int timing = J.async ? 0 : ctx->timing;      // per-chunk events are read back by the host: not in async mode
     int64_t inl_total = 0;           // inliers of finished chunks (host outputs: also the write cursor)
     int64_t produced = 0;            // inliers this call produced (== inl_total unless a shared cursor places the chunks)
     bool overflow = false;
@@ -1244,11 +1260,11 @@ int run_pairs_job(sfmgms_ctx* ctx, const PairsJob& J) {
         auto& sl = ctx->slot[c % n_slots];
         const int p0 = cbeg[c], pn = cbeg[c + 1] - cbeg[c];
         CU(cudaEventSynchronize(sl.computed));
-        if (ctx->timing) {
+        if (timing) {
             float a = 0.f, b = 0.f;
             CU(cudaEventElapsedTime(&a, sl.t0, sl.t1)); CU(cudaEventElapsedTime(&b, sl.t1, sl.t2));
             t_ham += a; t_gms += b;
-            if (ctx->timing >= 2) ctx->absorb(sl.marks);
+            if (timing >= 2) ctx->absorb(sl.marks);
         }
         const PairResult* hr = static_cast<const PairResult*>(ctx->h_results.p) + p0;
         int64_t chunk_inl = 0;
@@ -1303,12 +1319,12 @@ int run_pairs_job(sfmgms_ctx* ctx, const PairsJob& J) {
             CU(cudaMemsetAsync(sl.key.p, 0xFF, (size_t)rows * 4, st));
             CU(cudaMemsetAsync(stage_mask ? (uint8_t*)sl.mask.p : J.mask + chunk_row0[c], 0, (size_t)rows, st));
         }
-        if (ctx->timing) CU(cudaEventRecord(sl.t0, st));
-        if (ctx->timing >= 2) { sl.marks.used = 0; tl_marks = &sl.marks; kmark("begin", st); }
+        if (timing) CU(cudaEventRecord(sl.t0, st));
+        if (timing >= 2) { sl.marks.used = 0; tl_marks = &sl.marks; kmark("begin", st); }
         rc = enqueue_range(ctx, hp, p0, pn, true, true, J.with_rotation, J.with_scale, J.factor, &ham_launches,
-                           ctx->timing ? sl.t1 : nullptr);
+                           timing ? sl.t1 : nullptr);
         if (rc) { tl_marks = nullptr; err_rc = rc; break; }
-        if (ctx->timing) CU(cudaEventRecord(sl.t2, st));
+        if (timing) CU(cudaEventRecord(sl.t2, st));
         if (rows > 0 && want_idx) {
             int32_t* dti = dev_out ? (J.train_idx ? J.train_idx + chunk_row0[c] : nullptr) : (J.train_idx ? (int32_t*)sl.out_i32.p : nullptr);
             int32_t* ddi = dev_out ? (J.dist ? J.dist + chunk_row0[c] : nullptr) : (J.dist ? (int32_t*)sl.out_i32.p + rows : nullptr);
@@ -1332,7 +1348,18 @@ int run_pairs_job(sfmgms_ctx* ctx, const PairsJob& J) {
         CU(cudaMemcpyAsync(static_cast<PairResult*>(ctx->h_results.p) + p0, static_cast<const PairResult*>(ctx->d_results.p) + p0,
                            sizeof(PairResult) * (size_t)pn, cudaMemcpyDeviceToHost, st));
         CU(cudaEventRecord(sl.computed, st));
-        if (c > 0 && (rc = finalize(c - 1))) { err_rc = rc; break; }
+        if (!J.async && c > 0 && (rc = finalize(c - 1))) { err_rc = rc; break; }
+    }
+    if (J.async) {
+        if (err_rc) { cudaStreamSynchronize(st); tc_reset_arena(ctx->tc); return err_rc; }
+        export_results_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(static_cast<const PairResult*>(ctx->d_results.p), n_pairs, J.n_inliers,
+                                                                    J.best_hyp, J.mask_len);
+        ctx->launches++;
+        CU(cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, sizeof(PairResult) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+        CU(cudaGetLastError());
+        ctx->pending.active = true; ctx->pending.n_pairs = n_pairs; ctx->pending.compact = J.compact; ctx->pending.capacity = J.capacity;
+        if (n_chunks == 1) ctx->last_pairs = hp;
+        return SFMGMS_OK;
     }
     if (!err_rc && (rc = finalize(n_chunks - 1))) err_rc = rc;
     cudaStreamSynchronize(st);
@@ -1391,6 +1418,55 @@ int sfmgms_match_pairs(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int w
     J.out_location = out_location; J.n_inliers = n_inliers; J.best_hyp = best_hyp; J.mask_len = mask_len;
     J.train_idx = train_idx; J.dist = dist; J.mask = mask;
     return run_pairs_job(ctx, J);
+    GUARD_END
+}
+
+int sfmgms_match_pairs_async(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int with_rotation, int with_scale,
+                             double threshold_factor, int32_t* n_inliers, int32_t* best_hyp, int32_t* mask_len, int32_t* train_idx,
+                             int32_t* dist, uint8_t* mask) {
+    GUARD_BEGIN
+    PairsJob J;
+    J.pairs = pairs; J.n_pairs = n_pairs; J.with_rotation = with_rotation; J.with_scale = with_scale; J.factor = threshold_factor;
+    J.out_location = SFMGMS_DEVICE; J.n_inliers = n_inliers; J.best_hyp = best_hyp; J.mask_len = mask_len;
+    J.train_idx = train_idx; J.dist = dist; J.mask = mask; J.async = true;
+    return run_pairs_job(ctx, J);
+    GUARD_END
+}
+
+int sfmgms_match_pairs_compact_async(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int with_rotation, int with_scale,
+                                     double threshold_factor, int32_t* n_inliers, int32_t* best_hyp, int64_t* inlier_offsets,
+                                     void* matches, float* pts1, float* pts2, int64_t capacity) {
+    GUARD_BEGIN
+    PairsJob J;
+    J.pairs = pairs; J.n_pairs = n_pairs; J.with_rotation = with_rotation; J.with_scale = with_scale; J.factor = threshold_factor;
+    J.out_location = SFMGMS_DEVICE; J.n_inliers = n_inliers; J.best_hyp = best_hyp;
+    J.compact = true; J.inlier_offsets = inlier_offsets; J.matches = matches; J.pts1 = pts1; J.pts2 = pts2; J.capacity = capacity;
+    J.async = true;
+    return run_pairs_job(ctx, J);
+    GUARD_END
+}
+
+// Completes an asynchronous pair list: waits for the context stream, turns device-side status flags into error codes.
+int sfmgms_wait(sfmgms_ctx* ctx, int64_t* n_total) {
+    GUARD_BEGIN
+    if (n_total) *n_total = 0;
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->pending.active) return SFMGMS_OK;
+    ctx->pending.active = false;
+    tc_reset_arena(ctx->tc);
+    const int n = ctx->pending.n_pairs;
+    const PairResult* hr = static_cast<const PairResult*>(ctx->h_results.p);
+    ctx->last_results.assign(hr, hr + n);
+    long long total = 0;
+    for (int p = 0; p < n; ++p) {
+        if (hr[p].status == 4) return fail(ctx, SFMGMS_ERR_INDEX, "pair %d: queryIdx/trainIdx out of range", p);
+        if (hr[p].status == 3) return fail(ctx, SFMGMS_ERR_DOMAIN, "pair %d: matched keypoint outside [0,w)x[0,h)", p);
+        total += hr[p].mask_len > 0 ? hr[p].n_inliers : 0;
+    }
+    if (n_total) *n_total = total;
+    if (ctx->pending.compact && total > ctx->pending.capacity)
+        return fail(ctx, SFMGMS_ERR_CAPACITY, "compact output needs %lld rows, capacity is %lld", total, ctx->pending.capacity);
+    return SFMGMS_OK;
     GUARD_END
 }
 

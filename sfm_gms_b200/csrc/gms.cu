@@ -297,48 +297,71 @@ __global__ void __launch_bounds__(1024) gms_assign_cnt_kernel(const PairDesc* __
     for (int k = threadIdx.x; k < 4 * kCellsL; k += blockDim.x) cnt_s[k] = 0;
     __syncthreads();
     int bad = 0;
-    for (int i = i_begin + threadIdx.x; i < i_end; i += blockDim.x) {
-        const long long mi = pd.match_base - chunk_match_base + i;
-        const int qi = pd.mq ? pd.mq[i] : i;
-        const int ti = pd.mt ? pd.mt[i] : (int)(pd.key[i] & kTrainIdxMask);
-        bool ok = true;
-        if (qi < 0 || qi >= pd.n1 || ti < 0 || ti >= pd.n2) { bad = max(bad, 4); ok = false; }
-        float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
-        if (ok) {
-            const float2 a = reinterpret_cast<const float2*>(pd.kp1)[qi];
-            const float2 b = reinterpret_cast<const float2*>(pd.kp2)[ti];
-            x1 = a.x; y1 = a.y; x2 = b.x; y2 = b.y;
-            if (!(x1 >= 0.f && x1 < (float)pd.w1 && y1 >= 0.f && y1 < (float)pd.h1 && x2 >= 0.f && x2 < (float)pd.w2 &&
-                  y2 >= 0.f && y2 < (float)pd.h2)) {
+    // the per-match chain is two dependent gathers (match index -> keypoint) in front of a little arithmetic: four matches
+    // per thread are kept in flight through both of them
+    constexpr int U = 4;
+    for (int i0 = i_begin + threadIdx.x; i0 < i_end; i0 += U * blockDim.x) {
+        int qi[U], ti[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int i = i0 + k * blockDim.x;
+            qi[k] = ti[k] = -1;
+            if (i < i_end) {
+                qi[k] = pd.mq ? pd.mq[i] : i;
+                ti[k] = pd.mt ? pd.mt[i] : (int)(pd.key[i] & kTrainIdxMask);
+            }
+        }
+        float2 pa[U], pb[U];
+        bool inr[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            inr[k] = qi[k] >= 0 && qi[k] < pd.n1 && ti[k] >= 0 && ti[k] < pd.n2;
+            pa[k] = pb[k] = make_float2(0.f, 0.f);
+            if (inr[k]) {
+                pa[k] = reinterpret_cast<const float2*>(pd.kp1)[qi[k]];
+                pb[k] = reinterpret_cast<const float2*>(pd.kp2)[ti[k]];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int i = i0 + k * blockDim.x;
+            if (i >= i_end) continue;
+            const long long mi = pd.match_base - chunk_match_base + i;
+            bool ok = inr[k];
+            if (!ok) bad = max(bad, 4);
+            const float x1 = pa[k].x, y1 = pa[k].y, x2 = pb[k].x, y2 = pb[k].y;
+            // supported domain 0 <= x < w, 0 <= y < h (outside is UB in the reference; NaN fails too)
+            if (ok && !(x1 >= 0.f && x1 < (float)pd.w1 && y1 >= 0.f && y1 < (float)pd.h1 && x2 >= 0.f && x2 < (float)pd.w2 &&
+                        y2 >= 0.f && y2 < (float)pd.h2)) {
                 bad = max(bad, 3);
                 ok = false;
             }
-        }
-        if (!ok) {
+            if (!ok) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) lidx[(size_t)t * chunk_matches + mi] = kNoCell;
-            for (int s = 0; s < L.n_scales; ++s) ridx[(size_t)s * chunk_matches + mi] = kNoCell;
-            continue;
-        }
-        const float nx1 = __fdiv_rn(x1, (float)pd.w1), ny1 = __fdiv_rn(y1, (float)pd.h1);     // normalizePoints @VA 0x180048420
-        const float nx2 = __fdiv_rn(x2, (float)pd.w2), ny2 = __fdiv_rn(y2, (float)pd.h2);
-        const float fx = __fmul_rn((float)kGridL, nx1), fy = __fmul_rn((float)kGridL, ny1);   // getGridIndexLeft @VA 0x180047bc0
-        const int xa = cv_floor_f(fx), ya = cv_floor_f(fy);
-        const int xb = cv_floor_d(__dadd_rn((double)fx, 0.5)), yb = cv_floor_d(__dadd_rn((double)fy, 0.5));
-        int l[4];
-        l[0] = (xa >= kGridL || ya >= kGridL) ? -1 : xa + ya * kGridL;
-        l[1] = (xb >= kGridL || ya >= kGridL) ? -1 : xb + ya * kGridL;
-        l[2] = (xa >= kGridL || yb >= kGridL) ? -1 : xa + yb * kGridL;
-        l[3] = (xb >= kGridL || yb >= kGridL) ? -1 : xb + yb * kGridL;
+                for (int t = 0; t < 4; ++t) lidx[(size_t)t * chunk_matches + mi] = kNoCell;
+                for (int s = 0; s < L.n_scales; ++s) ridx[(size_t)s * chunk_matches + mi] = kNoCell;
+                continue;
+            }
+            const float nx1 = __fdiv_rn(x1, (float)pd.w1), ny1 = __fdiv_rn(y1, (float)pd.h1);     // normalizePoints @VA 0x180048420
+            const float nx2 = __fdiv_rn(x2, (float)pd.w2), ny2 = __fdiv_rn(y2, (float)pd.h2);
+            const float fx = __fmul_rn((float)kGridL, nx1), fy = __fmul_rn((float)kGridL, ny1);   // getGridIndexLeft @VA 0x180047bc0
+            const int xa = cv_floor_f(fx), ya = cv_floor_f(fy);
+            const int xb = cv_floor_d(__dadd_rn((double)fx, 0.5)), yb = cv_floor_d(__dadd_rn((double)fy, 0.5));
+            int l[4];
+            l[0] = (xa >= kGridL || ya >= kGridL) ? -1 : xa + ya * kGridL;
+            l[1] = (xb >= kGridL || ya >= kGridL) ? -1 : xb + ya * kGridL;
+            l[2] = (xa >= kGridL || yb >= kGridL) ? -1 : xa + yb * kGridL;
+            l[3] = (xb >= kGridL || yb >= kGridL) ? -1 : xb + yb * kGridL;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            lidx[(size_t)t * chunk_matches + mi] = l[t] < 0 ? kNoCell : (uint16_t)l[t];
-            if (l[t] >= 0) atomicAdd(&cnt_s[t * kCellsL + l[t]], 1);
-        }
-        for (int s = 0; s < L.n_scales; ++s) {                                                // getGridIndexRight @VA 0x180047d60
-            const int w = right_grid_w(s);
-            const int rx = cv_floor_f(__fmul_rn((float)w, nx2)), ry = cv_floor_f(__fmul_rn((float)w, ny2));
-            ridx[(size_t)s * chunk_matches + mi] = (uint16_t)(rx + ry * w);
+            for (int t = 0; t < 4; ++t) {
+                lidx[(size_t)t * chunk_matches + mi] = l[t] < 0 ? kNoCell : (uint16_t)l[t];
+                if (l[t] >= 0) atomicAdd(&cnt_s[t * kCellsL + l[t]], 1);
+            }
+            for (int s = 0; s < L.n_scales; ++s) {                                                // getGridIndexRight @VA 0x180047d60
+                const int w = right_grid_w(s);
+                const int rx = cv_floor_f(__fmul_rn((float)w, nx2)), ry = cv_floor_f(__fmul_rn((float)w, ny2));
+                ridx[(size_t)s * chunk_matches + mi] = (uint16_t)(rx + ry * w);
+            }
         }
     }
     if (bad) atomicMax(&results[blockIdx.z].status, bad);
@@ -502,41 +525,49 @@ __global__ void __launch_bounds__(256) gms_count_kernel(const PairDesc* __restri
 }
 
 // ---- a9 for the rotation / scale search: one CTA per (pair, scale, slice of matches) counts the inliers of ALL rotations
-// of that scale at once.  The scale's cell-pair tables (n_rot x 4 shifts x 400 cells, int16) sit in shared memory; a match
-// reads its 4 left cells and its right cell once and does n_rot x 4 table look-ups there (the per-hypothesis kernel above
-// re-read the indices and gathered from global memory 8 times).
+// of that scale at once.  The scale's cell-pair tables sit in shared memory TRANSPOSED to [shift][left cell][rotation]
+// (8 x int16 = one 128-bit word per (shift, cell)): a match reads its 4 left cells and its right cell once and does 4
+// shared-memory loads, each compared against the right cell for all rotations with packed 16-bit compares (the
+// per-hypothesis kernel re-read the indices and gathered from global memory once per hypothesis).
 __global__ void __launch_bounds__(256) gms_count_scale_kernel(const PairDesc* __restrict__ pairs, int32_t* scratch, Layout L,
                                                               const uint16_t* __restrict__ lidx, const uint16_t* __restrict__ ridx,
                                                               long long chunk_match_base, long long chunk_matches) {
-    extern __shared__ uint32_t cs_u32[];
+    extern __shared__ uint32_t cs_u32[];                        // [4][400][8] int16
     __shared__ int cnt_s[kNumRot];
     const PairDesc pd = pairs[blockIdx.z];
     const int s = blockIdx.y;
     int32_t* sp = scratch + (size_t)blockIdx.z * L.total_words;
-    const int words = L.n_rot * 4 * kCellsL / 2;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const int16_t*>(sp + L.cp_off) + (size_t)s * L.n_rot * 4 * kCellsL);
-    for (int i = threadIdx.x; i < words; i += blockDim.x) cs_u32[i] = src[i];
+    const int16_t* src = reinterpret_cast<const int16_t*>(sp + L.cp_off) + (size_t)s * L.n_rot * 4 * kCellsL;   // [rot][shift][cell]
+    int16_t* cp_t = reinterpret_cast<int16_t*>(cs_u32);
+    for (int i = threadIdx.x; i < 4 * kCellsL * kNumRot; i += blockDim.x) {
+        const int rot = i & 7, tc = i >> 3;                     // tc = shift * 400 + cell
+        cp_t[i] = rot < L.n_rot ? src[(size_t)rot * 4 * kCellsL + tc] : (int16_t)-3;   // -3 never equals a right cell
+    }
     if (threadIdx.x < kNumRot) cnt_s[threadIdx.x] = 0;
     __syncthreads();
-    const int16_t* cp_s = reinterpret_cast<const int16_t*>(cs_u32);
+    const uint4* cp4 = reinterpret_cast<const uint4*>(cs_u32);
     const long long mb = pd.match_base - chunk_match_base;
     const int lane = threadIdx.x & 31;
     for (int base = blockIdx.x * blockDim.x; base < pd.n_matches; base += gridDim.x * blockDim.x) {   // warp-uniform trip count
         const int i = base + threadIdx.x;
-        unsigned m = 0;
+        unsigned m = 0;                                         // bit rot: inlier under rotation rot
         if (i < pd.n_matches) {
-            const uint16_t r = ridx[(size_t)s * chunk_matches + mb + i];
+            const uint32_t r = ridx[(size_t)s * chunk_matches + mb + i];
             if (r != kNoCell) {
-                uint16_t l[4];
+                const uint32_t rr = r | (r << 16);
+                uint4 acc = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                for (int t = 0; t < 4; ++t) l[t] = lidx[(size_t)t * chunk_matches + mb + i];
-                for (int rot = 0; rot < L.n_rot; ++rot) {
-                    bool inl = false;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t)
-                        if (l[t] != kNoCell) inl |= (cp_s[(rot * 4 + t) * kCellsL + l[t]] == (int16_t)r);
-                    m |= (unsigned)inl << rot;
+                for (int t = 0; t < 4; ++t) {
+                    const uint32_t l = lidx[(size_t)t * chunk_matches + mb + i];
+                    if (l != kNoCell) {
+                        const uint4 c = cp4[t * kCellsL + l];
+                        acc.x |= __vcmpeq2(c.x, rr); acc.y |= __vcmpeq2(c.y, rr);
+                        acc.z |= __vcmpeq2(c.z, rr); acc.w |= __vcmpeq2(c.w, rr);
+                    }
                 }
+                // halves are 0xFFFF / 0x0000: bit 0 and bit 16 of each word -> rotation bits 0..7
+                m = (acc.x & 1u) | ((acc.x >> 15) & 2u) | ((acc.y & 1u) << 2) | ((acc.y >> 13) & 8u) | ((acc.z & 1u) << 4) |
+                    ((acc.z >> 11) & 32u) | ((acc.w & 1u) << 6) | ((acc.w >> 9) & 128u);
             }
         }
         for (int rot = 0; rot < L.n_rot; ++rot) {
@@ -808,7 +839,7 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
         if (max_m > 0 && flags_on) {
             int cbx = (max_m + 2047) / 2048;
             cbx = cbx > 32 ? 32 : cbx;
-            gms_count_scale_kernel<<<dim3(cbx, n_scales, cn), 256, (size_t)n_rot * 4 * kCellsL * 2, st>>>(d_pairs + c0, scratch, L, lidx,
+            gms_count_scale_kernel<<<dim3(cbx, n_scales, cn), 256, (size_t)kNumRot * 4 * kCellsL * 2, st>>>(d_pairs + c0, scratch, L, lidx,
                                                                                                       ridx, cbase, cm);
             ++launches; kmark("gms_count_scale", st);
         } else if (max_m > 0) {

@@ -169,3 +169,48 @@ def test_all_pairs_sequence_bounded_memory(oracle_mod):
     # neighbours in the sequence share most landmarks, distant images share none
     near = res["n_inliers"][(pairs[:, 1] - pairs[:, 0]) == 1]
     assert near.min() > 2000
+
+
+@pytest.mark.parametrize("chunk_rows", [6000, 1 << 22])
+def test_async_variants_equal_sync(ctx, chunk_rows):
+    """sfmgms_match_pairs_async / _compact_async + sfmgms_wait: device outputs, the call returns before the work is done;
+    results equal the synchronous calls (single- and multi-chunk lists)"""
+    torch = pytest.importorskip("torch")
+    from sfm_gms_b200 import api
+
+    rng = np.random.default_rng(11)
+    off, desc, kp, wh = _ragged_set(rng, SIZES)
+    ctx.set_images(off, desc, kp, wh)
+    ref = ctx.match_pairs(PAIRS, 1, 1)
+    refc = ctx.match_pairs_compact(PAIRS, 1, 1)
+    dev = torch.device("cuda", 0)
+    n, rows, total = len(PAIRS), int(ref["offsets"][-1]), int(refc["n_total"])
+    i32 = lambda k: torch.zeros(k, dtype=torch.int32, device=dev)  # noqa: E731
+    ninl, bh, ml, ti, di = i32(n), i32(n), i32(n), i32(rows), i32(rows)
+    mk = torch.zeros(rows, dtype=torch.uint8, device=dev)
+    pr = np.ascontiguousarray(PAIRS)
+    ctx.set_option(api.OPT_CHUNK_ROWS, chunk_rows)
+    try:
+        ctx.match_pairs_async_raw(pr, 1, 1, 6.0, ninl.data_ptr(), bh.data_ptr(), ml.data_ptr(), ti.data_ptr(), di.data_ptr(), mk.data_ptr())
+        with pytest.raises(api.SfmGmsError):           # the context is busy until wait()
+            ctx.match_pairs(PAIRS)
+        assert ctx.wait() == total
+        for a, b in ((ninl, "n_inliers"), (bh, "best_hyp"), (ml, "mask_len"), (ti, "train_idx"), (di, "dist"), (mk, "mask")):
+            assert np.array_equal(a.cpu().numpy(), ref[b]), b
+        offs = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        m = i32(total * 4 + 4)
+        p1 = torch.zeros(total * 2 + 2, dtype=torch.float32, device=dev)
+        ninl.zero_()
+        ctx.match_pairs_compact_async_raw(pr, 1, 1, 6.0, total, ninl.data_ptr(), bh.data_ptr(), offs.data_ptr(), m.data_ptr(), p1.data_ptr())
+        assert ctx.wait() == total
+        assert np.array_equal(offs.cpu().numpy(), refc["offsets"]) and np.array_equal(ninl.cpu().numpy(), refc["n_inliers"])
+        assert np.array_equal(m.cpu().numpy()[: total * 4].view(api.DMATCH_DT), refc["matches"])
+        assert np.array_equal(p1.cpu().numpy()[: total * 2].reshape(-1, 2), refc["pts1"])
+        # too small a buffer is reported by wait()
+        ctx.match_pairs_compact_async_raw(pr, 1, 1, 6.0, total - 1, ninl.data_ptr(), bh.data_ptr(), offs.data_ptr(), m.data_ptr())
+        with pytest.raises(api.SfmGmsError) as e:
+            ctx.wait()
+        assert e.value.code == 7
+        assert ctx.wait() == 0                           # nothing pending any more
+    finally:
+        ctx.set_option(api.OPT_CHUNK_ROWS, 4 << 20)
