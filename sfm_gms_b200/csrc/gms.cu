@@ -837,7 +837,7 @@ int launch_gms(const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, in
             }
         }
         if (max_m > 0 && flags_on) {
-            int cbx = (max_m + 2047) / 2048;
+            int cbx = (max_m + 8191) / 8192;             // a CTA first stages 25.6 KB of tables: give it >= 8192 matches
             cbx = cbx > 32 ? 32 : cbx;
             gms_count_scale_kernel<<<dim3(cbx, n_scales, cn), 256, (size_t)kNumRot * 4 * kCellsL * 2, st>>>(d_pairs + c0, scratch, L, lidx,
                                                                                                       ridx, cbase, cm);
