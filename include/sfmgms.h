@@ -61,6 +61,8 @@ extern "C" {
                                         2: additionally one event after every kernel (sfmgms_kernel_times) */
 #define SFMGMS_OPT_CHUNK_ROWS 6      /* sfmgms_match_pairs[_compact] walk a pair list in chunks of at most this many match
                                         rows (default 4 Mi): per-match device scratch is O(chunk), never O(list) */
+#define SFMGMS_OPT_OVERLAP 8         /* 1 (default): a batch's tensor-core work is split into up to three launches and the small
+                                        tie-resolution kernel of each runs on a second stream beside the next launch; 0: one stream */
 #define SFMGMS_OPT_GMS_DENSE 7       /* 1: force the global-memory histogram path of GMS (otherwise only pairs with
                                         >= 65536 matches take it) -- for tests and measurements */
 

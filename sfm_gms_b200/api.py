@@ -20,7 +20,7 @@ NORM_L2 = 4       # cv::NORM_L2
 
 SFMGMS_HOST, SFMGMS_DEVICE = 0, 1
 OPT_HAMMING_KERNEL, OPT_GMS_CHUNK_BYTES, OPT_TIMING, OPT_TC_OPERAND_CACHE, OPT_L2_KERNEL = 1, 2, 3, 4, 5
-OPT_CHUNK_ROWS, OPT_GMS_DENSE = 6, 7
+OPT_CHUNK_ROWS, OPT_GMS_DENSE, OPT_OVERLAP = 6, 7, 8
 HAMMING_AUTO, HAMMING_POPC, HAMMING_TC, HAMMING_FP4 = 0, 1, 2, 3
 
 _ERR_NAMES = {1: "ERR_ARG", 2: "ERR_TRAIN_ROWS", 3: "ERR_DOMAIN", 4: "ERR_INDEX", 5: "ERR_CUDA", 6: "ERR_STATE",

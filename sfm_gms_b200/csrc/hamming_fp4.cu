@@ -417,10 +417,11 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 // After the tensor-core pass every key holds (distance << 18 | first train row of the winning group of 8).
 // Eight lanes per query row recompute the 8 candidates' Hamming distances on the original 256-bit descriptors
 // and the key becomes (distance << 18 | lowest train row attaining it) -- BFMatcher's tie rule.
+constexpr int kResolveThreads = 128;
 template <bool kVec>   // kVec: every descriptor row is 16-byte aligned (two 128-bit loads per row)
-__global__ void __launch_bounds__(256) hamming_resolve_kernel(const PairDesc* __restrict__ pairs) {
+__global__ void __launch_bounds__(kResolveThreads) hamming_resolve_kernel(const PairDesc* __restrict__ pairs) {
     const PairDesc& pd = pairs[blockIdx.y];
-    const int row = blockIdx.x * (256 / kGroup) + (threadIdx.x >> kGroupShift);
+    const int row = blockIdx.x * (kResolveThreads / kGroup) + (threadIdx.x >> kGroupShift);
     const int l = threadIdx.x & (kGroup - 1);
     if (pd.n1 <= 0 || pd.n2 <= 0 || row >= pd.n1) return;      // whole 8-lane groups leave together
     const uint32_t key = pd.key[row];
@@ -484,7 +485,7 @@ bool ensure_dev(void*& p, size_t& cap, size_t bytes) {
 const char* fp4_last_error() { return g_err; }
 
 int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, int sm_count,
-                       cudaStream_t st) {
+                       cudaStream_t st, cudaStream_t resolve_st, cudaEvent_t resolve_ev) {
     if (n_pairs <= 0) return 0;
     if (!load_encode()) return -1;
     int launches = 0;
@@ -589,10 +590,20 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
     int max_n1 = 0;
     for (int p = 0; p < n_pairs; ++p)
         if (h_pairs[p].n2 > 0 && h_pairs[p].n1 > max_n1) max_n1 = h_pairs[p].n1;
-    const int rows_per_block = 256 / kGroup;
+    // The exact tie resolution is a small L2-bound kernel.  Given a second stream it runs BESIDE the next tensor-core launch
+    // (its 128-thread, 32-register CTAs fit into the registers the persistent kernel leaves free on every SM).
+    cudaStream_t rst = st;
+    if (resolve_st && resolve_ev && !tl_marks) {
+        if (cudaEventRecord(resolve_ev, st) != cudaSuccess || cudaStreamWaitEvent(resolve_st, resolve_ev, 0) != cudaSuccess) {
+            snprintf(g_err, sizeof g_err, "event hand-over to the resolve stream failed");
+            return -1;
+        }
+        rst = resolve_st;
+    }
+    const int rows_per_block = kResolveThreads / kGroup;
     const dim3 rgrid((unsigned)((max_n1 + rows_per_block - 1) / rows_per_block), (unsigned)n_pairs);
-    if (aligned16) hamming_resolve_kernel<true><<<rgrid, 256, 0, st>>>(d_pairs);
-    else hamming_resolve_kernel<false><<<rgrid, 256, 0, st>>>(d_pairs);
+    if (aligned16) hamming_resolve_kernel<true><<<rgrid, kResolveThreads, 0, rst>>>(d_pairs);
+    else hamming_resolve_kernel<false><<<rgrid, kResolveThreads, 0, rst>>>(d_pairs);
     kmark("hamming_resolve", st);
     return launches + 2;
 }

@@ -45,7 +45,9 @@ int launch_hamming_tc(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pai
 
 // FP4 (tcgen05 kind::mxf4 block-scaled) variant, hamming_fp4.cu — same contract as launch_hamming_tc
 const char* fp4_last_error();
+// resolve_st / resolve_ev (optional): run the tie-resolution kernel on a second stream, ordered after the tensor-core kernel
+// through the event; the caller joins that stream before anything reads the keys.
 int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, int sm_count,
-                       cudaStream_t st);
+                       cudaStream_t st, cudaStream_t resolve_st = nullptr, cudaEvent_t resolve_ev = nullptr);
 
 }  // namespace sfmgms
