@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["capi.cu", "multi.cu", "hamming_popc.cu", "hamming_tc.cu", "hamming_fp4.cu", "gms.cu", "l2_dp4a.cu", "l2_tc.cu", "l2_f32.cu", "orb.cu"]
-HEADERS = ["common.cuh", "hamming_tc.cuh", "tc_ptx.cuh", "orb_pattern.inc", os.path.join("..", "..", "include", "sfmgms.h")]
+HEADERS = ["common.cuh", "capi_internal.h", "hamming_tc.cuh", "tc_ptx.cuh", "orb_pattern.inc", os.path.join("..", "..", "include", "sfmgms.h")]
 LIB = os.path.join(HERE, "libsfmgms.so")
 
 NVCC_FLAGS = [

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/sfmgms.h"
+#include "capi_internal.h"
 #include "common.cuh"
 #include "hamming_tc.cuh"
 
@@ -1445,7 +1446,6 @@ int match_pairs_compact_shared(sfmgms_ctx* ctx, const int32_t* pairs, int n_pair
     return run_pairs_job(ctx, J);
     GUARD_END
 }
-const char* ctx_error(const sfmgms_ctx* ctx) { return ctx->err; }
 }  // namespace sfmgms
 
 extern "C" {

@@ -354,7 +354,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-char g_tc_err[256] = "";
+thread_local char g_tc_err[256] = "";   // one context per host thread: messages never interleave
 EncodeTiledFn g_encode = nullptr;
 
 bool load_encode() {

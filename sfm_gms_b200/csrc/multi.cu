@@ -21,13 +21,7 @@
 #include <vector>
 
 #include "../../include/sfmgms.h"
-
-struct sfmgms_ctx;
-namespace sfmgms {
-int match_pairs_compact_shared(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int with_rotation, int with_scale,
-                               double threshold_factor, int32_t* n_inliers, int32_t* best_hyp, int64_t* inlier_begin,
-                               void* matches, float* pts1, float* pts2, int64_t capacity, int64_t* shared_cursor);
-}
+#include "capi_internal.h"
 
 namespace {
 
