@@ -406,6 +406,19 @@ def timed_host_calls(D, fn, steps):
     return D.max_ms(e0.elapsed_time(e1)), D.max_ms(1e3 * wall)
 
 
+def _pinned(a):
+    """Host tensor in page-locked memory from the library's own allocator (sfmgms_host_alloc), holding a copy of `a`."""
+    import torch
+    from sfm_gms_b200 import api
+    return torch.from_numpy(api.host_array(a))
+
+
+def _pinned_zeros(n, dtype):
+    import torch
+    from sfm_gms_b200 import api
+    return torch.from_numpy(api.host_zeros(int(n), dtype))
+
+
 def make_ctx(args, local_rank):
     import sfm_gms_b200 as sg
     from sfm_gms_b200 import api
@@ -428,8 +441,8 @@ def run_batch_workload(args, D, kind, local_rank):
     s = make_batch(kind, P, first_pair=rank * P)
     total_pairs = P * world
     tot_m = P * n_kp
-    h_desc = torch.from_numpy(s["desc"]).pin_memory()
-    h_kp = torch.from_numpy(s["kp"]).pin_memory()
+    h_desc = _pinned(s["desc"])
+    h_kp = _pinned(s["kp"])
     d_desc, d_kp = h_desc.to(dev), h_kp.to(dev)
     ctx = make_ctx(args, local_rank)
     ctx.set_option(api.OPT_TIMING, 1)
@@ -473,8 +486,8 @@ def run_batch_workload(args, D, kind, local_rank):
     ctx.set_option(api.OPT_TIMING, 1)
 
     # ---- e2e: host (pinned) buffers through the C ABI, H2D + D2H inside the timed region, every step ------------
-    h_out = [torch.zeros(P, dtype=torch.int32).pin_memory() for _ in range(3)] + \
-            [torch.zeros(tot_m, dtype=torch.int32).pin_memory() for _ in range(2)] + [torch.zeros(tot_m, dtype=torch.uint8).pin_memory()]
+    h_out = [_pinned_zeros(P, np.int32) for _ in range(3)] + \
+            [_pinned_zeros(tot_m, np.int32) for _ in range(2)] + [_pinned_zeros(tot_m, np.uint8)]
     h2d = h_desc.numel() + h_kp.numel() * 4
     d2h = 3 * P * 4 + tot_m * 9
 
@@ -490,7 +503,7 @@ def run_batch_workload(args, D, kind, local_rank):
     # the other's compute tail and D2H.  Every step still moves its inputs and results across PCIe inside the region.
     ctx2 = make_ctx(args, local_rank)
     ctx2.set_option(api.OPT_TC_OPERAND_CACHE, 0)
-    h_out2 = [torch.zeros_like(o).pin_memory() for o in h_out]
+    h_out2 = [_pinned_zeros(o.numel(), o.numpy().dtype) for o in h_out]
 
     def streaming(steps):
         n1 = (steps + 1) // 2
@@ -550,8 +563,8 @@ def run_allpairs(args, D, local_rank, steps, warmup, n_images=SEQ_IMAGES):
     n_total_pairs = len(pairs_all)
     my_idx, my_pairs = sd.shard_pairs(pairs_all, rank, world, "contiguous")
     n_my = len(my_pairs)
-    h_desc = torch.from_numpy(s["desc"]).pin_memory()
-    h_kp = torch.from_numpy(s["kp"]).pin_memory()
+    h_desc = _pinned(s["desc"])
+    h_kp = _pinned(s["kp"])
     d_desc = torch.empty_like(h_desc, device=dev)
     d_kp = torch.empty_like(h_kp, device=dev)
     ctx = make_ctx(args, local_rank)
@@ -562,8 +575,8 @@ def run_allpairs(args, D, local_rank, steps, warmup, n_images=SEQ_IMAGES):
     d_m = torch.empty(cap * 4, dtype=torch.int32, device=dev)
     d_ninl, d_bh = (torch.zeros(n_my, dtype=torch.int32, device=dev) for _ in range(2))
     d_off = torch.zeros(n_my + 1, dtype=torch.int64, device=dev)
-    h_ninl, h_bh = (torch.zeros(n_my, dtype=torch.int32).pin_memory() for _ in range(2))
-    h_off = torch.zeros(n_my + 1, dtype=torch.int64).pin_memory()
+    h_ninl, h_bh = (_pinned_zeros(n_my, np.int32) for _ in range(2))
+    h_off = _pinned_zeros(n_my + 1, np.int64)
 
     def upload_and_broadcast():
         if rank == 0:
@@ -587,7 +600,7 @@ def run_allpairs(args, D, local_rank, steps, warmup, n_images=SEQ_IMAGES):
         step_resident()
     # the host result buffer holds exactly what this shard produces (known from the warm-up; the data is deterministic);
     # the device buffer above is sized for the worst case
-    h_m = torch.empty(max(1, totals[-1]) * 4, dtype=torch.int32).pin_memory()
+    h_m = _pinned_zeros(max(1, totals[-1]) * 4, np.int32)
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
     l0 = ctx.kernel_launches
     ham_ms, gms_ms = [], []

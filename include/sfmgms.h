@@ -24,6 +24,7 @@
 #ifndef SFMGMS_H_
 #define SFMGMS_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -292,6 +293,14 @@ int sfmgms_gms_hypotheses(sfmgms_ctx* ctx, int w1, int h1, int w2, int h2, const
 
 /* device memory currently owned by the context (bytes) */
 int64_t sfmgms_device_bytes(const sfmgms_ctx* ctx);
+
+/* Page-locked host memory for image sets and result tables handed to the calls above with SFMGMS_HOST (the reference
+ * keeps descriptors / key points in cv::Mat / std::vector storage, FeatureMatchUtil.cpp:49-56; pageable memory works
+ * too but is staged through a bounce buffer).  cudaHostAlloc(portable): visible to every GPU of a sfmgms_multi.
+ * Measured on this pool: 55 GB/s H2D from these buffers (profiles/r2_h2d_probe.txt).  No context needed; returns
+ * SFMGMS_ERR_CUDA when the allocation fails, SFMGMS_ERR_ARG on NULL. */
+int sfmgms_host_alloc(size_t bytes, void** out);
+int sfmgms_host_free(void* p);
 
 /* ---- multi-GPU: one process, one host thread per GPU, pairs sharded, ONE broadcast of the set ----
  * The reference matches one pair per call (FeatureMatchUtil.cpp:66-69) inside loops over an image sequence

@@ -125,12 +125,56 @@ def load_library():
     L.sfmgms_kernel_times.argtypes = [c_void_p, ctypes.c_char_p, c_int]
     L.sfmgms_device_bytes.argtypes = [c_void_p]
     L.sfmgms_device_bytes.restype = c_i64
+    L.sfmgms_host_alloc.argtypes = [ctypes.c_size_t, P(c_void_p)]
+    L.sfmgms_host_free.argtypes = [c_void_p]
     _LIB = L
     return L
 
 
 def _ptr(a):
     return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+class _HostBlock:
+    """One sfmgms_host_alloc allocation; freed when the last array viewing it goes away."""
+
+    def __init__(self, nbytes):
+        self._lib = load_library()
+        p = ctypes.c_void_p()
+        rc = self._lib.sfmgms_host_alloc(nbytes, ctypes.byref(p))
+        if rc != 0:
+            raise SfmGmsError(rc, "sfmgms_host_alloc(%d bytes) failed" % nbytes)
+        self.ptr = p.value or 0
+        self.buf = (ctypes.c_uint8 * nbytes).from_address(self.ptr) if nbytes else (ctypes.c_uint8 * 0)()
+        self.buf._owner = self     # the ctypes view keeps the block alive for as long as numpy holds it
+
+    def __del__(self):
+        if getattr(self, "ptr", 0):
+            self._lib.sfmgms_host_free(ctypes.c_void_p(self.ptr))
+            self.ptr = 0
+
+
+def host_empty(shape, dtype):
+    """numpy array in page-locked host memory from sfmgms_host_alloc (contents undefined)."""
+    dt = np.dtype(dtype)
+    shape = (shape,) if np.isscalar(shape) else tuple(shape)
+    n = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+    blk = _HostBlock(n)
+    return np.frombuffer(blk.buf, dtype=dt, count=n // dt.itemsize).reshape(shape)
+
+
+def host_zeros(shape, dtype):
+    a = host_empty(shape, dtype)
+    a[...] = 0
+    return a
+
+
+def host_array(a):
+    """Copy of `a` (C order) in page-locked host memory."""
+    a = np.asarray(a)
+    out = host_empty(a.shape, a.dtype)
+    out[...] = a
+    return out
 
 
 def _kp_xy(kps):

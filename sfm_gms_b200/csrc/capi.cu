@@ -1805,4 +1805,20 @@ int64_t sfmgms_device_bytes(const sfmgms_ctx* ctx) {
     return (int64_t)t;
 }
 
+int sfmgms_host_alloc(size_t bytes, void** out) {
+    if (!out) return SFMGMS_ERR_ARG;
+    *out = nullptr;
+    if (bytes == 0) return SFMGMS_OK;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); *out = nullptr; return SFMGMS_ERR_CUDA; }
+    return SFMGMS_OK;
+}
+
+int sfmgms_host_free(void* p) {
+    if (!p) return SFMGMS_OK;
+    cudaError_t e = cudaFreeHost(p);
+    if (e != cudaSuccess) { cudaGetLastError(); return SFMGMS_ERR_CUDA; }
+    return SFMGMS_OK;
+}
+
 }  // extern "C"

@@ -63,3 +63,21 @@ def test_product_never_imports_the_oracle():
                     if re.search(r"\bimport oracle\b|from oracle\b|oracle/|libsfmgms_oracle", txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_host_alloc_fails_loudly_without_gpu():
+    """sfmgms_host_alloc hands out page-locked memory: without a CUDA device it reports an error, never a malloc."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import sfm_gms_b200 as sg
+    from sfm_gms_b200 import api
+
+    lib = sg.load_library()
+    p = ctypes.c_void_p(1)
+    assert lib.sfmgms_host_alloc(1024, ctypes.byref(p)) == 5 and not p.value   # SFMGMS_ERR_CUDA
+    assert lib.sfmgms_host_alloc(1024, None) == 1                                # SFMGMS_ERR_ARG
+    assert lib.sfmgms_host_free(None) == 0
+    with pytest.raises(sg.SfmGmsError):
+        api.host_empty(16, "u1")

@@ -214,3 +214,33 @@ def test_async_variants_equal_sync(ctx, chunk_rows):
         assert ctx.wait() == 0                           # nothing pending any more
     finally:
         ctx.set_option(api.OPT_CHUNK_ROWS, 4 << 20)
+
+
+@pytest.mark.gpu
+def test_host_alloc_buffers_round_trip(ctx):
+    """sfmgms_host_alloc memory as the image set and the result tables: same results as ordinary numpy arrays, and the
+    block is page-locked (cudaHostAlloc) -- torch reports it as pinned."""
+    torch = pytest.importorskip("torch")
+    from sfm_gms_b200 import api
+
+    rng = np.random.default_rng(5)
+    off, desc, kp, wh = _ragged_set(rng, SIZES)
+    ctx.set_images(off, desc, kp, wh)
+    ref = ctx.match_pairs(PAIRS, 1, 0)
+    h_desc, h_kp = api.host_array(desc), api.host_array(kp)
+    assert h_desc.flags.c_contiguous and np.array_equal(h_desc, desc)
+    assert torch.from_numpy(h_desc).is_pinned() and torch.from_numpy(h_kp).is_pinned()
+    ctx.set_images(off, h_desc, h_kp, wh)
+    got = ctx.match_pairs(PAIRS, 1, 0)
+    for k in ("n_inliers", "best_hyp", "train_idx", "dist", "mask"):
+        assert np.array_equal(got[k], ref[k]), k
+    n, rows = len(PAIRS), int(ref["offsets"][-1])
+    outs = [api.host_zeros(n, np.int32) for _ in range(3)] + [api.host_zeros(rows, np.int32) for _ in range(2)] + \
+           [api.host_zeros(rows, np.uint8)]
+    ctx.match_image_set_raw(off, h_desc.ctypes.data, h_kp.ctypes.data, wh, np.ascontiguousarray(PAIRS), 1, 0, 6.0,
+                            *[o.ctypes.data for o in outs])
+    for o, k in zip(outs, ("n_inliers", "best_hyp", "mask_len", "train_idx", "dist", "mask")):
+        assert np.array_equal(o, ref[k]), k
+    z = api.host_empty((0, 32), np.uint8)
+    assert z.shape == (0, 32)
+    del h_desc, h_kp, outs                                 # blocks are released with their last view
