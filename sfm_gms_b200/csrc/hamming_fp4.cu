@@ -18,6 +18,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
+#include <vector>
 
 #include "hamming_tc.cuh"
 #include "tc_ptx.cuh"
@@ -53,37 +55,44 @@ constexpr int kEpiWarp0 = 0;            // epilogue warps first: the scheduler f
 #endif
 constexpr int kEpiWarps = SFMGMS_FP4_EPIW;        // 12: 3 per TMEM lane quadrant x 80 columns; 16: 4 x 60 columns
 constexpr int kEpiCols = BN / (kEpiWarps / 4);    // 80 = x64 + x16 tcgen05.ld; 60 = x32 + x16 + x8 + x4
-constexpr int kProdWarp = kEpiWarps;     // latency-critical single-lane roles (TMA producer, MMA issuer)
-constexpr int kMmaWarp = kEpiWarps + 1;
-constexpr int kAllocWarp = kEpiWarps + 2;
+#ifndef SFMGMS_FP4_PRODW
+#define SFMGMS_FP4_PRODW 0
+#define SFMGMS_FP4_MMAW 1
+#define SFMGMS_FP4_ALLOCW 2
+#endif
+constexpr int kProdWarp = kEpiWarps + SFMGMS_FP4_PRODW;     // latency-critical single-lane roles (TMA producer, MMA issuer)
+constexpr int kMmaWarp = kEpiWarps + SFMGMS_FP4_MMAW;
+constexpr int kAllocWarp = kEpiWarps + SFMGMS_FP4_ALLOCW;
 constexpr int kThreads = 32 * (kEpiWarps + 4);   // 512
 static_assert(STAGES >= 3, "B ring too shallow");
 static_assert(BTILE_BYTES % 1024 == 0 && (kEpiCols == 80 || kEpiCols == 60) && SF_COL + SF_COLS <= 512, "layout");
 
 // Epilogue reduction.  A warp's 80 accumulator columns are 10 GROUPS of 8 consecutive columns.  Per group the
-// plain maximum of the 8 dot products (FMNMX3, ALU pipe), then key_g = groupmax_g + (15 - g)/16 (one packed FADD2
+// plain maximum of the 8 dot products (FMNMX3, ALU pipe), then key_g = groupmax_g + (31 - g)/32 (one packed FADD2
 // per two groups, FMA pipe) and the maximum of the 10 keys: its integer part is the best dot product of the part,
-// its fraction names the FIRST group that attains it.  |dot| <= 256 and the fraction has 4 bits: keys are exact
-// in fp32.  Which of the group's 8 train rows is the lowest-index minimum is settled afterwards by
-// hamming_resolve_kernel on the original descriptors (8 candidates per query row instead of n2).  Group size 4
-// (-DSFMGMS_FP4_GROUP=4: 20 tags, half the resolve traffic) measured 3 % slower overall, 16 would double the resolve.
-// This halves the epilogue's instruction count against tagging every column (80 adds -> 10).
+// its fraction names the FIRST group that attains it.  |dot| <= 256 and the fraction has 5 bits: keys are exact
+// in fp32.  All fractions lie in [22/32, 31/32], a span below 1/2, so "this key's dot product is larger than the
+// best so far" is simply key > best + 1/2 (no floor in the loop).  Which of the group's 8 train rows is the
+// lowest-index minimum is settled afterwards by hamming_resolve_kernel on the original descriptors (8 candidates
+// per query row instead of n2).  Group size 4 (-DSFMGMS_FP4_GROUP=4: 20 tags, half the resolve traffic) measured
+// 3 % slower overall, 16 would double the resolve.  This halves the epilogue's instruction count against tagging
+// every column (80 adds -> 10).
 #ifndef SFMGMS_FP4_GROUP
 #define SFMGMS_FP4_GROUP 8
 #endif
 constexpr int kGroup = SFMGMS_FP4_GROUP;                 // 8 (default) or 4 columns per tagged group
 constexpr int kGroupShift = kGroup == 8 ? 3 : 2;
 constexpr int kGroups = kEpiCols / kGroup;
-constexpr int kTagDen = kGroups <= 16 ? 16 : 32;         // tag of group g = (kTagDen - 1 - g) / kTagDen
+constexpr int kTagDen = kGroups <= 16 ? 32 : 64;         // tag of group g = (kTagDen - 1 - g) / kTagDen: all tags within a span < 1/2
 static_assert(kEpiCols == 80 && (kGroup == 8 || kGroup == 4), "group tags below are written for 10 groups of 8 / 20 of 4");
 #if SFMGMS_FP4_GROUP == 8
-__constant__ float2 c_grouptag[kGroups / 2] = {{15.f / 16.f, 14.f / 16.f}, {13.f / 16.f, 12.f / 16.f}, {11.f / 16.f, 10.f / 16.f},
-                                               {9.f / 16.f, 8.f / 16.f}, {7.f / 16.f, 6.f / 16.f}};
-#else
 __constant__ float2 c_grouptag[kGroups / 2] = {{31.f / 32.f, 30.f / 32.f}, {29.f / 32.f, 28.f / 32.f}, {27.f / 32.f, 26.f / 32.f},
-                                               {25.f / 32.f, 24.f / 32.f}, {23.f / 32.f, 22.f / 32.f}, {21.f / 32.f, 20.f / 32.f},
-                                               {19.f / 32.f, 18.f / 32.f}, {17.f / 32.f, 16.f / 32.f}, {15.f / 32.f, 14.f / 32.f},
-                                               {13.f / 32.f, 12.f / 32.f}};
+                                               {25.f / 32.f, 24.f / 32.f}, {23.f / 32.f, 22.f / 32.f}};
+#else
+__constant__ float2 c_grouptag[kGroups / 2] = {{63.f / 64.f, 62.f / 64.f}, {61.f / 64.f, 60.f / 64.f}, {59.f / 64.f, 58.f / 64.f},
+                                               {57.f / 64.f, 56.f / 64.f}, {55.f / 64.f, 54.f / 64.f}, {53.f / 64.f, 52.f / 64.f},
+                                               {51.f / 64.f, 50.f / 64.f}, {49.f / 64.f, 48.f / 64.f}, {47.f / 64.f, 46.f / 64.f},
+                                               {45.f / 64.f, 44.f / 64.f}};
 #endif
 
 // (lo, hi) + (c.x, c.y) with one packed fp32x2 add (sm_100: add.rn.f32x2 -> FADD2)
@@ -121,8 +130,14 @@ constexpr int kMaxPairsPerLaunch = 768;
 struct LaunchMap {
     const uint8_t* lo;         // first descriptor row of the operand span (row index = (ptr - lo) / 32)
     int n_pairs, tsplit, n_units, pad;
+    long long* trace;          // DEBUG 7 only: per-accumulator clock64() stamps of CTA 0 (see kTraceAccs), else NULL
     int prefix[kMaxPairsPerLaunch + 1];
 };
+
+constexpr int kTraceAccs = 512;      // DEBUG 7: stamps[acc][warp 0..15][4]
+__device__ __forceinline__ void trace_stamp(const LaunchMap& lm, int acc, int warp, int k) {
+    if (blockIdx.x == 0 && acc < kTraceAccs && (threadIdx.x & 31) == 0) lm.trace[(acc * 16 + warp) * 4 + k] = clock64();
+}
 
 __host__ __device__ inline int units_of_pair(int n1, int n2, int tsplit, int* nts_out) {
     if (n1 <= 0 || n2 <= 0) { if (nts_out) *nts_out = 0; return 0; }
@@ -230,6 +245,7 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    if (threadIdx.x == 32) tmem_ptr_generic[1] = tfull_bar;   // read back below as an opaque value (see the epilogue)
     if (warp == kAllocWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_smem), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -276,8 +292,12 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             for (int t = wu.t_begin; t < wu.t_end; t += BN) {
                 mbar_wait(empty_bar + 8 * stage, phase ^ 1);
                 if (elect_one()) {
-                    mbar_expect_tx(full_bar + 8 * stage, (uint32_t)BTILE_BYTES);
-                    tma_load_2d(b_smem + stage * BTILE_BYTES, &tmapB, 0, (int)(wu.b_row0 + t), full_bar + 8 * stage);
+                    if (dbg >= 5) {   // DEBUG 5/6: train tiles are not re-read (whatever the stage holds is multiplied)
+                        mbar_arrive(full_bar + 8 * stage);
+                    } else {
+                        mbar_expect_tx(full_bar + 8 * stage, (uint32_t)BTILE_BYTES);
+                        tma_load_2d(b_smem + stage * BTILE_BYTES, &tmapB, 0, (int)(wu.b_row0 + t), full_bar + 8 * stage);
+                    }
                 }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
@@ -285,6 +305,7 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     } else if (warp == kMmaWarp) {
         // accumulator slot = sub-tile index & 1 (compile-time in the epilogue's unrolled loop); one phase bit per slot
         uint32_t stage = 0, phase = 0, abuf = 0, a_phase = 0, slot_phase[ACC_SLOTS] = {0, 0};
+        int tr_acc = 0;
         const uint32_t a_lo0 = sdesc_lo(a_smem), b_lo0 = sdesc_lo(b_smem);
         const uint32_t sf = tmem_base + SF_COL;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -300,9 +321,11 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 for (int s = 0; s < MSUB; ++s) {
                     if (s >= nsub) break;
                     const int slot = s & 1;
+                    if (dbg == 7) trace_stamp(lm, tr_acc, warp, 0);
                     mbar_wait(tempty_bar + 8 * slot, slot_phase[slot] ^ 1);
                     slot_phase[slot] ^= 1;
                     tc_fence_after();
+                    if (dbg == 7) trace_stamp(lm, tr_acc, warp, 1);
                     const uint32_t d = tmem_base + slot * BN;
                     const uint32_t a_lo = a_lo_buf + s * (TILE_BYTES >> 4);
                     if (elect_one()) {
@@ -314,6 +337,7 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         }
                         tc_commit(tfull_bar + 8 * slot);
                     }
+                    if (dbg == 7) trace_stamp(lm, tr_acc++, warp, 2);
                 }
                 if (elect_one()) tc_commit(empty_bar + 8 * stage);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -326,80 +350,118 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const int quad = warp & 3;                        // TMEM lanes [32*quad, 32*quad+32)
         const int c0 = ((warp - kEpiWarp0) >> 2) * kEpiCols; // accumulator columns [c0, c0+80)
         const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + c0;
+        // the accumulator barriers' address as a LOADED value: at the 128-register cap ptxas otherwise re-derives the
+        // shared-memory base (6 instructions) in front of every wait of the loop
+        const uint32_t tfull_e = tmem_ptr_generic[1], tempty_e = tfull_e + 8 * ACC_SLOTS;
         uint32_t slot_phase[ACC_SLOTS] = {0, 0};
+        int tr_acc = 0;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             const WorkUnit wu = make_unit(lm, pairs, u);
             const int nsub = (wu.n_rows + BM - 1) / BM;
-            // per row: best key so far (dot + index fraction), the smallest key that would beat it (integer part + 1:
+            // per row: best key so far (dot + index fraction), the threshold a key must exceed to beat it (best + 1/2:
             // strict '>' on the dot product keeps the earliest tile / part) and the column base it came from
             float best_key[MSUB], beat[MSUB];
             int best_base[MSUB];
 #pragma unroll
             for (int s = 0; s < MSUB; ++s) { best_key[s] = -1.0e30f; beat[s] = -1.0e29f; best_base[s] = -1; }
-            for (int t = wu.t_begin; t < wu.t_end; t += BN) {
+            // one accumulator (sub-tile S of the tile at train row t): wait, TMEM -> registers, hand the slot back, reduce.
+            // kTail: the tile may reach past the image (columns >= valid are masked).
+            auto pass = [&](auto s_c, auto tail_c, uint32_t parity, int t, int valid) {
+                constexpr int S = decltype(s_c)::value;
+                constexpr bool kTail = decltype(tail_c)::value;
+                constexpr int slot = S & 1;
+                if (dbg == 7) trace_stamp(lm, tr_acc, warp, 0);
+                mbar_wait(tfull_e + 8 * slot, parity);
+                tc_fence_after();
+                if (dbg == 7) trace_stamp(lm, tr_acc, warp, 1);
+                int r[kEpiCols];
+                if (dbg == 4 || dbg == 6) {    // DEBUG 4/6: no TMEM read, no ALU
+#pragma unroll
+                    for (int j = 0; j < kEpiCols; ++j) r[j] = 0;
+                } else {
+                    ld_part(tbase + slot * BN, r);
+                    tc_wait_ld();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_e + 8 * slot);   // values are in registers now
+                if (dbg == 7) trace_stamp(lm, tr_acc, warp, 2);
+                if (dbg == 4 || dbg == 6) return;
+                float v[kEpiCols];
+#pragma unroll
+                for (int j = 0; j < kEpiCols; ++j) v[j] = __int_as_float(r[j]);
+                if (dbg == 1) { best_key[S] = fmaxf(best_key[S], v[0] + v[kEpiCols - 1]); return; }   // DEBUG 1: no max tree
+                if (kTail && c0 + kEpiCols > valid) {                // tail tile: mask columns outside the image
+#pragma unroll
+                    for (int j = 0; j < kEpiCols; ++j)
+                        if (c0 + j >= valid) v[j] = -1.0e30f;
+                }
+                float gm[kGroups];
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) {
+                    const float* x = v + kGroup * g;
+                    if constexpr (kGroup == 8) {
+                        const float a = fmaxf(fmaxf(x[0], x[1]), x[2]);
+                        const float b = fmaxf(fmaxf(x[3], x[4]), x[5]);
+                        gm[g] = fmaxf(fmaxf(fmaxf(x[6], x[7]), a), b);
+                    } else {
+                        gm[g] = fmaxf(fmaxf(fmaxf(x[0], x[1]), x[2]), x[3]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < kGroups / 2; ++k) add2(gm[2 * k], gm[2 * k + 1], c_grouptag[k], gm[2 * k], gm[2 * k + 1]);
+                float m = gm[0];
+#pragma unroll
+                for (int g = 1; g < kGroups; ++g) m = fmaxf(m, gm[g]);
+                if (m > beat[S]) {                                   // integer part exceeds the best so far (see kTagDen)
+                    best_key[S] = m;
+                    beat[S] = m + 0.5f;
+                    best_base[S] = t + c0;
+                }
+                if (dbg == 7) { if (best_key[S] == 12345.f) tr_acc += 1 << 20; trace_stamp(lm, tr_acc++, warp, 3); }
+            };
+            using std::integral_constant;
+            int t = wu.t_begin;
+            if (MSUB == 4 && nsub == MSUB) {
+                // full unit, whole tiles: each slot is used twice per tile, so the barrier parities repeat tile after tile
+                // (no phase bookkeeping, no sub-tile or tail tests in the loop)
+                const uint32_t p0 = slot_phase[0], p1 = slot_phase[1];
+                // (the always-true row tests keep every pass in its own basic block: in straight-line code ptxas hoists
+                // the next pass's try_wait above the current max tree, the warp is then SUSPENDED with that ALU work
+                // undone, and the slot comes back late -- measured 3 % slower)
+                for (; t + BN <= wu.t_end; t += BN) {
+                    pass(integral_constant<int, 0>{}, integral_constant<bool, false>{}, p0, t, BN);
+                    if (wu.n_rows > 1 * BM) pass(integral_constant<int, 1>{}, integral_constant<bool, false>{}, p1, t, BN);
+                    if (wu.n_rows > 2 * BM) pass(integral_constant<int, 2 % MSUB>{}, integral_constant<bool, false>{}, p0 ^ 1, t, BN);
+                    if (wu.n_rows > 3 * BM) pass(integral_constant<int, 3 % MSUB>{}, integral_constant<bool, false>{}, p1 ^ 1, t, BN);
+                }
+            }
+            for (; t < wu.t_end; t += BN) {
                 const int valid = wu.t_end - t;
 #pragma unroll
                 for (int s = 0; s < MSUB; ++s) {
                     if (s < nsub) {
                         const int slot = s & 1;                              // compile-time after unrolling
-                        mbar_wait(tfull_bar + 8 * slot, slot_phase[slot]);
+                        const uint32_t parity = slot_phase[slot];
                         slot_phase[slot] ^= 1;
-                        tc_fence_after();
-                        int r[kEpiCols];
-                        if (dbg == 4) {    // DEBUG 4: no TMEM read, no ALU
-#pragma unroll
-                            for (int j = 0; j < kEpiCols; ++j) r[j] = 0;
-                        } else {
-                            ld_part(tbase + slot * BN, r);
-                            tc_wait_ld();
-                        }
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty_bar + 8 * slot);   // values are in registers now
-                        if (dbg == 4) continue;
-                        float v[kEpiCols];
-#pragma unroll
-                        for (int j = 0; j < kEpiCols; ++j) v[j] = __int_as_float(r[j]);
-                        if (dbg == 1) { best_key[s] = fmaxf(best_key[s], v[0] + v[kEpiCols - 1]); continue; }   // DEBUG 1: no max tree
-                        if (c0 + kEpiCols > valid) {                         // tail tile: mask columns outside the image
-#pragma unroll
-                            for (int j = 0; j < kEpiCols; ++j)
-                                if (c0 + j >= valid) v[j] = -1.0e30f;
-                        }
-                        float gm[kGroups];
-#pragma unroll
-                        for (int g = 0; g < kGroups; ++g) {
-                            const float* x = v + kGroup * g;
-                            if constexpr (kGroup == 8) {
-                                const float a = fmaxf(fmaxf(x[0], x[1]), x[2]);
-                                const float b = fmaxf(fmaxf(x[3], x[4]), x[5]);
-                                gm[g] = fmaxf(fmaxf(fmaxf(x[6], x[7]), a), b);
-                            } else {
-                                gm[g] = fmaxf(fmaxf(fmaxf(x[0], x[1]), x[2]), x[3]);
-                            }
-                        }
-#pragma unroll
-                        for (int k = 0; k < kGroups / 2; ++k) add2(gm[2 * k], gm[2 * k + 1], c_grouptag[k], gm[2 * k], gm[2 * k + 1]);
-                        float m = gm[0];
-#pragma unroll
-                        for (int g = 1; g < kGroups; ++g) m = fmaxf(m, gm[g]);
-                        if (m >= beat[s]) {                                  // integer part exceeds the best so far
-                            best_key[s] = m;
-                            beat[s] = floorf(m) + 1.0f;
-                            best_base[s] = t + c0;
-                        }
+                        if (s == 0) pass(integral_constant<int, 0>{}, integral_constant<bool, true>{}, parity, t, valid);
+                        if (s == 1) pass(integral_constant<int, 1 % MSUB>{}, integral_constant<bool, true>{}, parity, t, valid);
+                        if (s == 2) pass(integral_constant<int, 2 % MSUB>{}, integral_constant<bool, true>{}, parity, t, valid);
+                        if (s == 3) pass(integral_constant<int, 3 % MSUB>{}, integral_constant<bool, true>{}, parity, t, valid);
                     }
                 }
             }
 #pragma unroll
             for (int s = 0; s < MSUB; ++s) {
                 const int row = s * BM + quad * 32 + lane;
-                if (s < nsub && row < wu.n_rows && (best_base[s] >= 0 || dbg)) {
+                if (s < nsub && row < wu.n_rows && (best_base[s] >= 0 || (dbg != 0 && dbg != 7))) {   // (dbg: the values are junk, the work is real)
                     // key = dot + (15 - g)/16 : <a,b> = 256 - 2*hamming; idx = first train row of the winning group
                     const float fl = floorf(best_key[s]);
                     const int g = kTagDen - 1 - (int)((best_key[s] - fl) * (float)kTagDen);
-                    const uint32_t dist = dbg ? 7u : (uint32_t)(256 - (int)fl) >> 1;
-                    const uint32_t idx = dbg ? 0u : (uint32_t)(best_base[s] + kGroup * g);
+                    constexpr bool kTiming = dbg != 0 && dbg != 7;   // timing builds: keep the work alive, keep the key in range
+                    constexpr bool kNoData = dbg == 4 || dbg == 6;
+                    const uint32_t dist = kNoData ? 7u : kTiming ? ((uint32_t)(256 - (int)fl) >> 1) & 7u : (uint32_t)(256 - (int)fl) >> 1;
+                    const uint32_t idx = kNoData ? 0u : kTiming ? (uint32_t)(best_base[s] + kGroup * g) & 7u : (uint32_t)(best_base[s] + kGroup * g);
                     atomicMin(wu.key + row, (dist << kTrainIdxBits) | idx);
                 }
             }
@@ -567,7 +629,7 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
     }
     if (n_pairs > kMaxPairsPerLaunch) { snprintf(g_err, sizeof g_err, "too many pairs per launch"); return -1; }
     LaunchMap lm;
-    lm.lo = lo; lm.n_pairs = n_pairs; lm.tsplit = tsplit; lm.pad = 0;
+    lm.lo = lo; lm.n_pairs = n_pairs; lm.tsplit = tsplit; lm.pad = 0; lm.trace = nullptr;
     int n_units = 0;
     for (int p = 0; p < n_pairs; ++p) {
         lm.prefix[p] = n_units;
@@ -578,7 +640,15 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
     if (n_units == 0) return launches;
     static const int dbg = getenv("SFMGMS_TC_DEBUG") ? atoi(getenv("SFMGMS_TC_DEBUG")) : 0;   // timing experiments only
     auto kern = dbg == 1 ? hamming_fp4_kernel<1> : dbg == 3 ? hamming_fp4_kernel<3> : dbg == 4 ? hamming_fp4_kernel<4>
-                                                                                                   : hamming_fp4_kernel<0>;
+              : dbg == 5 ? hamming_fp4_kernel<5> : dbg == 6 ? hamming_fp4_kernel<6> : dbg == 7 ? hamming_fp4_kernel<7>
+                                                                                         : hamming_fp4_kernel<0>;
+    if (dbg == 7) {   // DEBUG 7: clock stamps of CTA 0's first kTraceAccs accumulators -> $SFMGMS_TC_TRACE (raw int64)
+        static long long* d_trace = nullptr;
+        const size_t tb = sizeof(long long) * kTraceAccs * 16 * 4;
+        if (!d_trace) cudaMalloc(&d_trace, tb);
+        cudaMemsetAsync(d_trace, 0, tb, st);
+        lm.trace = d_trace;
+    }
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
         snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute(smem=%d) failed", SMEM_BYTES);
         return -1;
@@ -586,7 +656,14 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
     const int grid = n_units < sm_count ? n_units : sm_count;
     kern<<<grid, kThreads, SMEM_BYTES, st>>>(tmap, tmapB, lm, d_pairs);
     kmark("hamming_fp4", st);
-    if (dbg) return launches + 1;
+    if (dbg == 7 && getenv("SFMGMS_TC_TRACE")) {
+        const size_t tb = sizeof(long long) * kTraceAccs * 16 * 4;
+        std::vector<long long> h(tb / sizeof(long long));
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h.data(), lm.trace, tb, cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(getenv("SFMGMS_TC_TRACE"), "wb")) { fwrite(h.data(), 1, tb, f); fclose(f); }
+    }
+    if (dbg && dbg != 7) return launches + 1;
     int max_n1 = 0;
     for (int p = 0; p < n_pairs; ++p)
         if (h_pairs[p].n2 > 0 && h_pairs[p].n1 > max_n1) max_n1 = h_pairs[p].n1;

@@ -24,6 +24,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "WAIT_%=:\n\t"
 #ifdef SFMGMS_MBAR_HINT_NS
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+#elif defined(SFMGMS_MBAR_TEST_WAIT)
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"   // non-blocking poll (experiment)
 #else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
 #endif
