@@ -3,7 +3,6 @@
 //              accumulator slots) keep the tensor rate, or does the shared-memory operand read rate cap it?
 //   ldtm W     W warps per SM (W/4 per TMEM lane quadrant) reading 80 fp32 columns per lane per iteration
 //              (tcgen05.ld 32x32b x64 + x16, the kernel's epilogue load): TMEM read bytes per clock per SM.
-//   max W      W warps running the epilogue's max tree on registers (40 x 3-input + 5 x 2-input max per 80 values).
 //   mma+ldtm, mma+max, mma+ldtm+max: the MMA loop with 12 reader / ALU warps beside it (no barriers between them): the
 //              tensor rate each mix leaves, and the reader / ALU rate.
 // Built and run by scripts/epi_probe.py; output -> profiles/r2_epi_probe.txt.
@@ -37,10 +36,10 @@ template <int N, int mode>
 __global__ void __launch_bounds__(512, 1) probe_kernel(int nw, int mma_iters, int epi_iters, float* sink, long long* clk_out) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t a_smem = base, b_smem = base + 16384, bar = base + 16384 + 32768, tptr = bar + 16;   // bar+32, bar+40: dummy barriers
+    const uint32_t a_smem = base, b_smem = base + 65536, bar = base + 65536 + 3 * 30720, tptr = bar + 16;   // bar+32, bar+40: dummy barriers
     volatile uint32_t* tptr_g = reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr - smem_u32(smem_raw)));
     uint32_t* data = reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)));
-    for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) data[i] = 0x2A2A2A2Au;
+    for (int i = threadIdx.x; i < (65536 + 3 * 30720) / 4; i += blockDim.x) data[i] = 0x2A2A2A2Au;
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
@@ -78,12 +77,15 @@ __global__ void __launch_bounds__(512, 1) probe_kernel(int nw, int mma_iters, in
         if (mode & 1) {
             constexpr uint32_t idesc = (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (1u << 23) | ((uint32_t)(128 >> 4) << 24);
             constexpr int kSlots = N >= 120 ? 480 / N : 4;
-            const uint32_t a_lo = sdesc_lo(a_smem), b_lo = sdesc_lo(b_smem);
+            const uint32_t a_lo0 = sdesc_lo(a_smem), b_lo0 = sdesc_lo(b_smem);
             const uint32_t sf = tmem + 480;
             int slot = 0;
             uint32_t ph = 0;          // bit k: phase of slot k
             for (int it = 0; it < mma_iters; ++it) {
                 const uint32_t d = tmem + slot * N;
+                // mode 64: operands rotate like the kernel's (4 query sub-tiles per train tile, 3 train-tile stages)
+                const uint32_t a_lo = (mode & 64) ? a_lo0 + (uint32_t)(it & 3) * (16384 >> 4) : a_lo0;
+                const uint32_t b_lo = (mode & 64) ? b_lo0 + (uint32_t)((it >> 2) % 3) * (30720 >> 4) : b_lo0;
                 if (mode & 32) {
                     mbar_wait(bar + 96 + 8 * slot, ((ph >> slot) & 1) ^ 1);
                     ph ^= 1u << slot;
@@ -210,6 +212,9 @@ int main() {
     run<240, 9>("mma N=240, commit per accumulator", 0, MI, 0, sms, sink, d_clk);
     run<240, 25>("mma N=240, 2 commits per accumulator", 0, MI, 0, sms, sink, d_clk);
     run<120, 9>("mma N=120, commit per accumulator", 0, MI, 0, sms, sink, d_clk);
+    run<240, 65>("mma N=240, rotating operands", 0, MI, 0, sms, sink, d_clk);
+    run<240, 97>("handshake N=240x2, null epilogue, rotating operands", 12, MI, MI, sms, sink, d_clk);
+    run<240, 103>("handshake N=240x2, ldtm + max tree, rotating operands", 12, MI, MI, sms, sink, d_clk);
     run<240, 33>("handshake N=240x2, null epilogue", 12, MI, MI, sms, sink, d_clk);
     run<240, 35>("handshake N=240x2, ldtm", 12, MI, MI, sms, sink, d_clk);
     run<240, 39>("handshake N=240x2, ldtm + max tree", 12, MI, MI, sms, sink, d_clk);
@@ -220,10 +225,8 @@ int main() {
     run<16, 1>("mma N=16 (issue cost)", 0, MI, 0, sms, sink, d_clk);
     run<8, 1>("mma N=8 (issue cost)", 0, MI, 0, sms, sink, d_clk);
     for (int nw : {4, 8, 12}) run<240, 2>("ldtm", nw, 0, EI, sms, sink, d_clk);
-    for (int nw : {4, 8, 12}) run<240, 4>("max tree", nw, 0, EI, sms, sink, d_clk);
     for (int nw : {4, 8, 12}) run<240, 6>("ldtm + max tree", nw, 0, EI, sms, sink, d_clk);
     run<240, 3>("mma N=240 + ldtm", 12, MI, EI * 2, sms, sink, d_clk);
-    run<240, 5>("mma N=240 + max tree", 12, MI, EI * 2, sms, sink, d_clk);
     run<240, 7>("mma N=240 + ldtm + max tree", 12, MI, EI, sms, sink, d_clk);
     run<160, 7>("mma N=160 + ldtm + max tree", 12, MI * 3 / 2, EI, sms, sink, d_clk);
     return 0;
