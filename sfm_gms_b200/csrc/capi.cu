@@ -232,8 +232,10 @@ int enqueue_range(sfmgms_ctx* ctx, const std::vector<PairDesc>& hp, int r0, int 
         // the last one stays exposed): +4.4 % on the all-pairs run.  Not when the operands are re-derived per launch (three
         // smaller unpack + tensor launches cost more than the hidden resolve: measured -3 % on 256-pair batches).
         bool side = false;
-        if (kind == SFMGMS_HAMMING_FP4 && rn >= 24 && !tl_marks && ctx->overlap_resolve && ctx->tc.cache_enabled && ctx->tc.span_lo &&
-            hpp[0].img1 >= 0) {
+        // (Only with the separate tie-resolution kernel, SFMGMS_FP4_FUSED_RESOLVE=0: by default the tensor-core kernel resolves
+        // its own ties and a batch is one launch.)
+        if (kind == SFMGMS_HAMMING_FP4 && !fp4_fused_resolve() && rn >= 24 && !tl_marks && ctx->overlap_resolve && ctx->tc.cache_enabled &&
+            ctx->tc.span_lo && hpp[0].img1 >= 0) {
             const int nsub = rn >= 96 ? 3 : 2;
             const int per = (rn + nsub - 1) / nsub;
             if (per < kMaxPerLaunch) kMaxPerLaunch = per;

@@ -11,7 +11,9 @@
 // Kernel structure (persistent, warp-specialised, 1 CTA/SM, 512 threads): warps 0-11 epilogue (warp = TMEM lane
 // quadrant x 80-column part: tcgen05.ld -> index-packed keys -> max tree -> atomicMin(dist<<18|trainIdx)),
 // warp 12 TMA producer (query sub-tiles double-buffered per work unit, 240-row train tiles through a ring),
-// warp 13 MMA issuer (4 x M128 N240 K64 per accumulator, 2 accumulator slots in TMEM), warp 14 TMEM allocator.
+// warp 13 MMA issuer (4 x M128 N240 K64 per accumulator, 2 accumulator slots in TMEM), warp 14 TMEM allocator;
+// warps 14-15 then settle the tie rule of every finished unit on the packed descriptors (fused tie resolution, below)
+// while the other warps are already on the next unit.
 // The single-lane roles sit in the highest warp ids because the warp scheduler favours those.
 #include <cuda.h>
 
@@ -45,7 +47,7 @@ constexpr int BTILE_BYTES = BN * ROWB;   // 30 KB: one train tile (multiple of 1
 constexpr int A_BUF_BYTES = MSUB * TILE_BYTES;
 constexpr int STAGES = (222 * 1024 - A_BUFS * A_BUF_BYTES) / BTILE_BYTES;   // 3 (MSUB=4) / 5 (MSUB=2)
 constexpr int SMEM_DATA = A_BUFS * A_BUF_BYTES + STAGES * BTILE_BYTES;
-constexpr int SMEM_BYTES = SMEM_DATA + 1024 + 256;
+
 constexpr int ACC_SLOTS = 2;
 constexpr int SF_COL = ACC_SLOTS * BN;   // TMEM columns [480, 512): block scales (all 1.0)
 constexpr int SF_COLS = 32;
@@ -64,6 +66,12 @@ constexpr int kProdWarp = kEpiWarps + SFMGMS_FP4_PRODW;     // latency-critical 
 constexpr int kMmaWarp = kEpiWarps + SFMGMS_FP4_MMAW;
 constexpr int kAllocWarp = kEpiWarps + SFMGMS_FP4_ALLOCW;
 constexpr int kThreads = 32 * (kEpiWarps + 4);   // 512
+constexpr int kResWarp0 = kAllocWarp;            // fused tie resolution: the allocator warp and the spare one behind it
+constexpr int kResThreads = 64;
+constexpr int kKeyParts = kEpiWarps / 4;         // epilogue warps per TMEM lane quadrant (column parts)
+constexpr int SMEM_KEYS = kKeyParts * MSUB * BM * 4;   // one candidate key per (part, row) of a unit
+constexpr int SMEM_BYTES = SMEM_DATA + 1024 + 256 + SMEM_KEYS;
+static_assert(SMEM_BYTES <= 227 * 1024 && kAllocWarp == kEpiWarps + 2, "shared memory / warp roles");
 static_assert(STAGES >= 3, "B ring too shallow");
 static_assert(BTILE_BYTES % 1024 == 0 && (kEpiCols == 80 || kEpiCols == 60) && SF_COL + SF_COLS <= 512, "layout");
 
@@ -121,6 +129,9 @@ struct WorkUnit {
     uint32_t a_row0, b_row0;   // operand rows (in the unpacked array) of the unit's first query / the train image's row 0
     int32_t n_rows, t_begin, t_end;
     uint32_t* key;
+    // fused tie resolution: the packed descriptors behind the operands, and the units that share this unit's query rows
+    const uint8_t *q_desc, *t_desc;   // first query row of the unit / train row 0
+    int32_t n2, nts, group;           // train rows; train-range splits of the pair; index of the group's first unit
 };
 
 // Work decomposition travels as a kernel PARAMETER (no table upload: the copy engine may be busy with a queued
@@ -129,7 +140,9 @@ struct WorkUnit {
 constexpr int kMaxPairsPerLaunch = 768;
 struct LaunchMap {
     const uint8_t* lo;         // first descriptor row of the operand span (row index = (ptr - lo) / 32)
-    int n_pairs, tsplit, n_units, pad;
+    int n_pairs, tsplit, n_units;
+    int fused;                 // 0: keys leave as (dist, group base), hamming_resolve_kernel follows; 1: warps 14-15 resolve; 3: and rows are 16-byte aligned
+    int* group_cnt;            // fused, tsplit > 1: arrival counter per group of units sharing query rows (zero before and after the launch)
     long long* trace;          // DEBUG 7 only: per-accumulator clock64() stamps of CTA 0 (see kTraceAccs), else NULL
     int prefix[kMaxPairsPerLaunch + 1];
 };
@@ -170,6 +183,9 @@ __device__ __forceinline__ WorkUnit make_unit(const LaunchMap& lm, const PairDes
     w.t_begin = ts * tper * BN;
     w.t_end = min((ts + 1) * tper * BN, n2);
     w.key = pd->key + q0;
+    w.q_desc = pd->desc1 + (size_t)q0 * 32;
+    w.t_desc = pd->desc2;
+    w.n2 = n2; w.nts = nts; w.group = u - ts;
     return w;
 }
 
@@ -232,6 +248,9 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     const uint32_t tfull_bar = a_empty_bar + 8 * A_BUFS;
     const uint32_t tempty_bar = tfull_bar + 8 * ACC_SLOTS;
     const uint32_t tmem_ptr_smem = tempty_bar + 8 * ACC_SLOTS;
+    const uint32_t done_bar = tmem_ptr_smem + 8;      // fused tie resolution: epilogue warps -> resolver warps, a unit's candidates are in skeys
+    const uint32_t free_bar = done_bar + 8;           // resolver warps -> epilogue warps: skeys may be overwritten
+    uint32_t* const skeys = reinterpret_cast<uint32_t*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));   // [part][row of the unit]
     volatile uint32_t* tmem_ptr_generic =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_smem - smem_u32(smem_raw)));
 
@@ -242,6 +261,7 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
         for (int s = 0; s < A_BUFS; ++s) { mbar_init(a_full_bar + 8 * s, 1); mbar_init(a_empty_bar + 8 * s, 1); }
         for (int s = 0; s < ACC_SLOTS; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, kEpiWarps); }
+        mbar_init(done_bar, kEpiWarps); mbar_init(free_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -354,6 +374,7 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         // shared-memory base (6 instructions) in front of every wait of the loop
         const uint32_t tfull_e = tmem_ptr_generic[1], tempty_e = tfull_e + 8 * ACC_SLOTS;
         uint32_t slot_phase[ACC_SLOTS] = {0, 0};
+        uint32_t free_phase = 0;
         int tr_acc = 0;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             const WorkUnit wu = make_unit(lm, pairs, u);
@@ -451,19 +472,142 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     }
                 }
             }
+            // the unit's result per row: key = dot + (kTagDen - 1 - g)/kTagDen : <a,b> = 256 - 2*hamming; idx = first train row of
+            // the winning group.  Fused: the three column parts leave their candidates in shared memory for the resolver
+            // warps (no atomics, no fence on this path); otherwise atomicMin into the global key array.
+            const bool fused = dbg == 0 && lm.fused != 0;
+            if (fused) {
+                mbar_wait(free_bar, free_phase ^ 1);            // the resolver warps have taken the previous unit's candidates
+                free_phase ^= 1;
+            }
 #pragma unroll
             for (int s = 0; s < MSUB; ++s) {
                 const int row = s * BM + quad * 32 + lane;
-                if (s < nsub && row < wu.n_rows && (best_base[s] >= 0 || (dbg != 0 && dbg != 7))) {   // (dbg: the values are junk, the work is real)
-                    // key = dot + (15 - g)/16 : <a,b> = 256 - 2*hamming; idx = first train row of the winning group
+                const bool have = s < nsub && row < wu.n_rows && (best_base[s] >= 0 || (dbg != 0 && dbg != 7));   // (dbg: the values are junk, the work is real)
+                uint32_t packed = kKeyInit;
+                if (have) {
                     const float fl = floorf(best_key[s]);
                     const int g = kTagDen - 1 - (int)((best_key[s] - fl) * (float)kTagDen);
                     constexpr bool kTiming = dbg != 0 && dbg != 7;   // timing builds: keep the work alive, keep the key in range
                     constexpr bool kNoData = dbg == 4 || dbg == 6;
                     const uint32_t dist = kNoData ? 7u : kTiming ? ((uint32_t)(256 - (int)fl) >> 1) & 7u : (uint32_t)(256 - (int)fl) >> 1;
                     const uint32_t idx = kNoData ? 0u : kTiming ? (uint32_t)(best_base[s] + kGroup * g) & 7u : (uint32_t)(best_base[s] + kGroup * g);
-                    atomicMin(wu.key + row, (dist << kTrainIdxBits) | idx);
+                    packed = (dist << kTrainIdxBits) | idx;
                 }
+                if (fused) skeys[((warp - kEpiWarp0) >> 2) * (MSUB * BM) + row] = packed;
+                else if (have) atomicMin(wu.key + row, packed);
+            }
+            if (fused) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(done_bar);
+            }
+        }
+    } else if (dbg == 0 && lm.fused != 0) {
+        // ================= fused tie resolution: warps 14-15, one unit behind the epilogue ==========================
+        // Per unit: merge the column parts' candidates (min of dist << 18 | group base) into the global key array -- a plain
+        // store when the unit covers the whole train image, atomicMin + an arrival counter when several units (train-range
+        // splits, other CTAs) share the query rows: the LAST unit of the group to arrive resolves.  Resolving = BFMatcher's
+        // tie rule on the packed 256-bit descriptors: kGroup lanes per query row re-score the kGroup train rows of the winning
+        // group (XOR / POPC) and the key becomes (distance << 18 | lowest train row attaining it).
+        // One lane per query row (8 rows per lane and unit).  The candidates' cache lines are PREFETCHED to L2 for all of a
+        // lane's rows before the first one is scored: with one row in flight per lane the two warps could not keep up with the
+        // epilogue whenever the descriptors come from DRAM (every image new, as in the streaming batches) -- measured 20 %
+        // slower than the separate kernel; the unit is then bound by 64 x 8 dependent DRAM round trips.
+        const int rt = (int)threadIdx.x - kResWarp0 * 32;
+        const bool vec = (lm.fused & 2) != 0;
+        volatile uint32_t* s_last = tmem_ptr_generic + 8;
+        constexpr int kRowsPerLane = MSUB * BM / kResThreads;   // 8
+        uint32_t done_phase = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const WorkUnit wu = make_unit(lm, pairs, u);
+            mbar_wait(done_bar, done_phase);
+            done_phase ^= 1;
+            uint32_t mk[kRowsPerLane];
+#pragma unroll
+            for (int i = 0; i < kRowsPerLane; ++i) {
+                const int row = rt + i * kResThreads;
+                uint32_t k = kKeyInit;
+                if (row < wu.n_rows) {
+                    k = skeys[row];
+#pragma unroll
+                    for (int part = 1; part < kKeyParts; ++part) k = min(k, skeys[part * (MSUB * BM) + row]);
+                    if (wu.nts > 1 && k != kKeyInit) atomicMin(wu.key + row, k);
+                }
+                mk[i] = k;
+            }
+            if (wu.nts > 1) __threadfence();
+            asm volatile("bar.sync 1, %0;" ::"n"(kResThreads) : "memory");
+            if (rt == 0) mbar_arrive(free_bar);
+            if (wu.nts > 1) {
+                if (rt == 0) {
+                    const bool last = atomicAdd(lm.group_cnt + wu.group, 1) == wu.nts - 1;
+                    if (last) lm.group_cnt[wu.group] = 0;       // leave the counters as they were found
+                    *s_last = last ? 1u : 0u;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kResThreads) : "memory");
+                if (*s_last == 0u) continue;                    // (the next write of s_last comes after the next bar.sync)
+                __threadfence();
+#pragma unroll
+                for (int i = 0; i < kRowsPerLane; ++i) {
+                    const int row = rt + i * kResThreads;
+                    mk[i] = row < wu.n_rows ? __ldcg(wu.key + row) : kKeyInit;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kRowsPerLane; ++i) {
+                if (mk[i] == kKeyInit) continue;
+                const int row = rt + i * kResThreads;
+                const uint32_t c0 = mk[i] & kTrainIdxMask;
+                const uint8_t* t = wu.t_desc + (size_t)c0 * 32;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(wu.q_desc + (size_t)row * 32));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(t));
+                if ((int)c0 + 4 < wu.n2) asm volatile("prefetch.global.L2 [%0];" ::"l"(t + 128));
+                if (kGroup == 8 && (int)c0 + 7 < wu.n2) asm volatile("prefetch.global.L2 [%0];" ::"l"(t + 7 * 32));   // (unaligned groups span 3 lines)
+            }
+#pragma unroll
+            for (int i = 0; i < kRowsPerLane; ++i) {
+                const uint32_t key = mk[i];
+                if (key == kKeyInit) continue;
+                const int row = rt + i * kResThreads;
+                const int c0 = (int)(key & kTrainIdxMask);
+                const uint8_t* q = wu.q_desc + (size_t)row * 32;
+                const uint8_t* t = wu.t_desc + (size_t)c0 * 32;
+                uint32_t a[8];
+                uint32_t best = 0xFFFFFFFFu;
+                if (vec) {
+                    const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(q)), a1 = __ldg(reinterpret_cast<const uint4*>(q) + 1);
+                    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+                    uint4 b0[kGroup], b1[kGroup];
+#pragma unroll
+                    for (int c = 0; c < kGroup; ++c) {
+                        b0[c] = b1[c] = make_uint4(0u, 0u, 0u, 0u);
+                        if (c0 + c < wu.n2) {
+                            b0[c] = __ldg(reinterpret_cast<const uint4*>(t) + 2 * c);
+                            b1[c] = __ldg(reinterpret_cast<const uint4*>(t) + 2 * c + 1);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < kGroup; ++c) {
+                        const uint32_t d = __popc(a[0] ^ b0[c].x) + __popc(a[1] ^ b0[c].y) + __popc(a[2] ^ b0[c].z) + __popc(a[3] ^ b0[c].w) +
+                                           __popc(a[4] ^ b1[c].x) + __popc(a[5] ^ b1[c].y) + __popc(a[6] ^ b1[c].z) + __popc(a[7] ^ b1[c].w);
+                        if (c0 + c < wu.n2) best = min(best, (d << kGroupShift) | (uint32_t)c);
+                    }
+                } else {
+                    const uint32_t* qw = reinterpret_cast<const uint32_t*>(q);
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) a[w] = __ldg(qw + w);
+#pragma unroll
+                    for (int c = 0; c < kGroup; ++c) {
+                        if (c0 + c < wu.n2) {
+                            const uint32_t* tw = reinterpret_cast<const uint32_t*>(t) + 8 * c;
+                            uint32_t d = 0;
+#pragma unroll
+                            for (int w = 0; w < 8; ++w) d += __popc(a[w] ^ __ldg(tw + w));
+                            best = min(best, (d << kGroupShift) | (uint32_t)c);
+                        }
+                    }
+                }
+                wu.key[row] = ((best >> kGroupShift) << kTrainIdxBits) | ((uint32_t)c0 + (best & (uint32_t)(kGroup - 1)));
             }
         }
     }
@@ -545,6 +689,11 @@ bool ensure_dev(void*& p, size_t& cap, size_t bytes) {
 }  // namespace
 
 const char* fp4_last_error() { return g_err; }
+
+bool fp4_fused_resolve() {
+    static const bool on = !(getenv("SFMGMS_FP4_FUSED_RESOLVE") && atoi(getenv("SFMGMS_FP4_FUSED_RESOLVE")) == 0);
+    return on;
+}
 
 int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, int sm_count,
                        cudaStream_t st, cudaStream_t resolve_st, cudaEvent_t resolve_ev) {
@@ -629,7 +778,7 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
     }
     if (n_pairs > kMaxPairsPerLaunch) { snprintf(g_err, sizeof g_err, "too many pairs per launch"); return -1; }
     LaunchMap lm;
-    lm.lo = lo; lm.n_pairs = n_pairs; lm.tsplit = tsplit; lm.pad = 0; lm.trace = nullptr;
+    lm.lo = lo; lm.n_pairs = n_pairs; lm.tsplit = tsplit; lm.fused = 0; lm.group_cnt = nullptr; lm.trace = nullptr;
     int n_units = 0;
     for (int p = 0; p < n_pairs; ++p) {
         lm.prefix[p] = n_units;
@@ -653,6 +802,18 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
         snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute(smem=%d) failed", SMEM_BYTES);
         return -1;
     }
+    const bool fused = dbg == 0 && fp4_fused_resolve();
+    if (fused) {
+        lm.fused = aligned16 ? 3 : 1;
+        if (tsplit > 1) {   // units that share query rows count their arrivals; the last one resolves and re-zeroes its counter
+            const size_t need = (size_t)n_units * sizeof(int);
+            if (need > s.cnt_cap) {
+                if (!ensure_dev(s.d_cnt, s.cnt_cap, need)) return -1;
+                if (cudaMemsetAsync(s.d_cnt, 0, s.cnt_cap, st) != cudaSuccess) { snprintf(g_err, sizeof g_err, "cudaMemsetAsync(counters) failed"); return -1; }
+            }
+            lm.group_cnt = static_cast<int*>(s.d_cnt);
+        }
+    }
     const int grid = n_units < sm_count ? n_units : sm_count;
     kern<<<grid, kThreads, SMEM_BYTES, st>>>(tmap, tmapB, lm, d_pairs);
     kmark("hamming_fp4", st);
@@ -663,7 +824,7 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
         cudaMemcpy(h.data(), lm.trace, tb, cudaMemcpyDeviceToHost);
         if (FILE* f = fopen(getenv("SFMGMS_TC_TRACE"), "wb")) { fwrite(h.data(), 1, tb, f); fclose(f); }
     }
-    if (dbg && dbg != 7) return launches + 1;
+    if ((dbg && dbg != 7) || fused) return launches + 1;
     int max_n1 = 0;
     for (int p = 0; p < n_pairs; ++p)
         if (h_pairs[p].n2 > 0 && h_pairs[p].n1 > max_n1) max_n1 = h_pairs[p].n1;

@@ -389,6 +389,7 @@ void tc_reset_arena(TcState& s) { s.work_used = 0; }
 void tc_release(TcState& s) {
     if (s.d_ops) cudaFree(s.d_ops);
     if (s.d_work) cudaFree(s.d_work);
+    if (s.d_cnt) cudaFree(s.d_cnt);
     if (s.h_work) cudaFreeHost(s.h_work);
     s = TcState();
 }

@@ -11,6 +11,8 @@ struct TcState {
     size_t work_cap = 0;
     void* h_work = nullptr;     // pinned
     size_t h_work_cap = 0;
+    void* d_cnt = nullptr;      // fp4 kernel, fused tie resolution: arrival counters of split units (all zero between launches)
+    size_t cnt_cap = 0;
     size_t work_used = 0;       // arena cursor (bytes) into h_work/d_work; reset by tc_reset_arena() after a sync
     bool set_valid = false;     // d_ops holds the unpacked form of [ops_src, ops_src + 32*ops_rows)
     bool cache_enabled = true;  // keep the unpacked operands across calls until tc_invalidate()
@@ -45,8 +47,11 @@ int launch_hamming_tc(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pai
 
 // FP4 (tcgen05 kind::mxf4 block-scaled) variant, hamming_fp4.cu — same contract as launch_hamming_tc
 const char* fp4_last_error();
-// resolve_st / resolve_ev (optional): run the tie-resolution kernel on a second stream, ordered after the tensor-core kernel
+// By default the kernel settles the tie rule itself (two otherwise idle warps per CTA, one unit behind the epilogue);
+// SFMGMS_FP4_FUSED_RESOLVE=0 brings back the separate hamming_resolve_kernel (fp4_fused_resolve() tells which).
+// resolve_st / resolve_ev (optional, separate kernel only): run it on a second stream, ordered after the tensor-core kernel
 // through the event; the caller joins that stream before anything reads the keys.
+bool fp4_fused_resolve();
 int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pairs, int n_pairs, int sm_count,
                        cudaStream_t st, cudaStream_t resolve_st = nullptr, cudaEvent_t resolve_ev = nullptr);
 
