@@ -20,7 +20,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "hamming_tc.cuh"
@@ -70,7 +72,8 @@ constexpr int kResWarp0 = kAllocWarp;            // fused tie resolution: the al
 constexpr int kResThreads = 64;
 constexpr int kKeyParts = kEpiWarps / 4;         // epilogue warps per TMEM lane quadrant (column parts)
 constexpr int SMEM_KEYS = kKeyParts * MSUB * BM * 4;   // one candidate key per (part, row) of a unit
-constexpr int SMEM_BYTES = SMEM_DATA + 1024 + 256 + SMEM_KEYS;
+constexpr int SMEM_LUT = 256 * 4;                      // packed query tiles: descriptor byte -> 8 e2m1 values
+constexpr int SMEM_BYTES = SMEM_DATA + 1024 + 256 + SMEM_KEYS + SMEM_LUT;
 static_assert(SMEM_BYTES <= 227 * 1024 && kAllocWarp == kEpiWarps + 2, "shared memory / warp roles");
 static_assert(STAGES >= 3, "B ring too shallow");
 static_assert(BTILE_BYTES % 1024 == 0 && (kEpiCols == 80 || kEpiCols == 60) && SF_COL + SF_COLS <= 512, "layout");
@@ -141,7 +144,9 @@ constexpr int kMaxPairsPerLaunch = 768;
 struct LaunchMap {
     const uint8_t* lo;         // first descriptor row of the operand span (row index = (ptr - lo) / 32)
     int n_pairs, tsplit, n_units;
-    int fused;                 // 0: keys leave as (dist, group base), hamming_resolve_kernel follows; 1: warps 14-15 resolve; 3: and rows are 16-byte aligned
+    int fused;                 // 0: keys leave as (dist, group base), hamming_resolve_kernel follows; 1: warps 14-15 resolve
+    int a_packed;              // 1: query tiles are expanded from the packed descriptors by warps 14-15 (no unpacked copy of query images)
+    int vec16;                 // every descriptor row is 16-byte aligned (128-bit loads in warps 14-15)
     int* group_cnt;            // fused, tsplit > 1: arrival counter per group of units sharing query rows (zero before and after the launch)
     long long* trace;          // DEBUG 7 only: per-accumulator clock64() stamps of CTA 0 (see kTraceAccs), else NULL
     int prefix[kMaxPairsPerLaunch + 1];
@@ -231,6 +236,29 @@ __global__ void __launch_bounds__(256) unpack_fp4_kernel(const uint32_t* __restr
     for (; i < n_words; i += step) out[i] = fp4_from_word(__ldg(desc + i));
 }
 
+// Operands derived per launch: only TRAIN images need the unpacked copy in global memory (the kernel expands its query tiles
+// itself).  One grid row per pair; `first` masks pairs whose train image an earlier pair of the launch already covers.
+struct FirstUse { uint32_t bits[kMaxPairsPerLaunch / 32]; };
+__global__ void __launch_bounds__(256) unpack_fp4_train_kernel(const PairDesc* __restrict__ pairs, const uint8_t* lo,
+                                                               const __grid_constant__ FirstUse first, uint4* __restrict__ out) {
+    const int p = blockIdx.y;
+    if (!((first.bits[p >> 5] >> (p & 31)) & 1u)) return;
+    const PairDesc& pd = pairs[p];
+    if (pd.n1 <= 0 || pd.n2 <= 0) return;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(pd.desc2);
+    uint4* dst = out + ((size_t)(pd.desc2 - lo) >> 5) * kDescWords;
+    const int n_words = pd.n2 * kDescWords;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += 4 * stride) {   // four words in flight per thread
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] = i + k * stride < n_words ? __ldg(src + i + k * stride) : 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i + k * stride < n_words) dst[i + k * stride] = fp4_from_word(w[k]);
+    }
+}
+
 template <int dbg>   // dbg != 0: timing experiments only (results invalid); production is dbg = 0
 __global__ void __launch_bounds__(kThreads, 1)
 hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmapB,
@@ -301,14 +329,16 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             const WorkUnit wu = make_unit(lm, pairs, u);
             const int nsub = (wu.n_rows + BM - 1) / BM;
-            mbar_wait(a_empty_bar + 8 * abuf, a_phase ^ 1);
-            if (elect_one()) {
-                mbar_expect_tx(a_full_bar + 8 * abuf, (uint32_t)(nsub * TILE_BYTES));
-                for (int s = 0; s < nsub; ++s)
-                    tma_load_2d(a_smem + abuf * A_BUF_BYTES + s * TILE_BYTES, &tmap, 0, (int)(wu.a_row0 + s * BM),
-                                a_full_bar + 8 * abuf);
+            if (!lm.a_packed) {   // (packed: warps 14-15 fill the query tiles)
+                mbar_wait(a_empty_bar + 8 * abuf, a_phase ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(a_full_bar + 8 * abuf, (uint32_t)(nsub * TILE_BYTES));
+                    for (int s = 0; s < nsub; ++s)
+                        tma_load_2d(a_smem + abuf * A_BUF_BYTES + s * TILE_BYTES, &tmap, 0, (int)(wu.a_row0 + s * BM),
+                                    a_full_bar + 8 * abuf);
+                }
+                if (++abuf == A_BUFS) { abuf = 0; a_phase ^= 1; }
             }
-            if (++abuf == A_BUFS) { abuf = 0; a_phase ^= 1; }
             for (int t = wu.t_begin; t < wu.t_end; t += BN) {
                 mbar_wait(empty_bar + 8 * stage, phase ^ 1);
                 if (elect_one()) {
@@ -502,7 +532,7 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 if (lane == 0) mbar_arrive(done_bar);
             }
         }
-    } else if (dbg == 0 && lm.fused != 0) {
+    } else if (dbg == 0 && (lm.fused != 0 || lm.a_packed != 0)) {
         // ================= fused tie resolution: warps 14-15, one unit behind the epilogue ==========================
         // Per unit: merge the column parts' candidates (min of dist << 18 | group base) into the global key array -- a plain
         // store when the unit covers the whole train image, atomicMin + an arrival counter when several units (train-range
@@ -514,12 +544,11 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         // epilogue whenever the descriptors come from DRAM (every image new, as in the streaming batches) -- measured 20 %
         // slower than the separate kernel; the unit is then bound by 64 x 8 dependent DRAM round trips.
         const int rt = (int)threadIdx.x - kResWarp0 * 32;
-        const bool vec = (lm.fused & 2) != 0;
+        const bool vec = lm.vec16 != 0;
         volatile uint32_t* s_last = tmem_ptr_generic + 8;
         constexpr int kRowsPerLane = MSUB * BM / kResThreads;   // 8
         uint32_t done_phase = 0;
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const WorkUnit wu = make_unit(lm, pairs, u);
+        auto resolve_unit = [&](const WorkUnit& wu) {
             mbar_wait(done_bar, done_phase);
             done_phase ^= 1;
             uint32_t mk[kRowsPerLane];
@@ -545,7 +574,7 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     *s_last = last ? 1u : 0u;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kResThreads) : "memory");
-                if (*s_last == 0u) continue;                    // (the next write of s_last comes after the next bar.sync)
+                if (*s_last == 0u) return;                     // (the next write of s_last comes after the next bar.sync)
                 __threadfence();
 #pragma unroll
                 for (int i = 0; i < kRowsPerLane; ++i) {
@@ -609,6 +638,57 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 }
                 wu.key[row] = ((best >> kGroupShift) << kTrainIdxBits) | ((uint32_t)c0 + (best & (uint32_t)(kGroup - 1)));
             }
+        };
+        // ---- query tiles from the packed descriptors (a_packed): the four 128-row sub-tiles of a unit, written in the layout a
+        // 128B-swizzled TMA box load would leave (row r of a tile at r * 128, its 16-byte chunk c at (c ^ (r & 7)) * 16; one
+        // chunk = one descriptor word = 32 e2m1 values), then handed to the MMA warp through the same a_full barrier.  Double
+        // buffered like the TMA path: the tiles of unit k+2 are written while unit k+1 runs.
+        uint32_t abuf = 0, a_phase = 0;
+        uint8_t* const a_generic = smem_raw + (a_smem - smem_u32(smem_raw));
+        // byte -> 8 e2m1 values through a 1 KB table (4 shared-memory loads per descriptor word instead of ~24 ALU instructions:
+        // these two warps share their schedulers' issue slots with six epilogue warps)
+        const uint32_t* const lut = skeys + SMEM_KEYS / 4;
+        if (lm.a_packed) {
+            for (int b = rt; b < 256; b += kResThreads) const_cast<uint32_t*>(lut)[b] = fp4_from_word((uint32_t)b).x;
+            asm volatile("bar.sync 1, %0;" ::"n"(kResThreads) : "memory");
+        }
+        auto expand = [&](uint32_t w) {
+            return make_uint4(lut[w & 0xFFu], lut[(w >> 8) & 0xFFu], lut[(w >> 16) & 0xFFu], lut[w >> 24]);
+        };
+        auto fill_unit = [&](const WorkUnit& wu) {
+            mbar_wait(a_empty_bar + 8 * abuf, a_phase ^ 1);
+            uint8_t* const dst = a_generic + abuf * A_BUF_BYTES;
+            if (vec) {
+                for (int i = rt; i < wu.n_rows * 2; i += kResThreads) {        // i = (row, half): 16 packed bytes -> 64 unpacked
+                    const int row = i >> 1, h = i & 1;
+                    const uint4 w = __ldg(reinterpret_cast<const uint4*>(wu.q_desc) + i);
+                    uint8_t* const rp = dst + row * ROWB;
+                    const int sw = row & 7;
+                    *reinterpret_cast<uint4*>(rp + (((4 * h + 0) ^ sw) << 4)) = expand(w.x);
+                    *reinterpret_cast<uint4*>(rp + (((4 * h + 1) ^ sw) << 4)) = expand(w.y);
+                    *reinterpret_cast<uint4*>(rp + (((4 * h + 2) ^ sw) << 4)) = expand(w.z);
+                    *reinterpret_cast<uint4*>(rp + (((4 * h + 3) ^ sw) << 4)) = expand(w.w);
+                }
+            } else {
+                for (int i = rt; i < wu.n_rows * kDescWords; i += kResThreads) {
+                    const int row = i >> 3, c = i & 7;
+                    *reinterpret_cast<uint4*>(dst + row * ROWB + ((c ^ (row & 7)) << 4)) =
+                        expand(__ldg(reinterpret_cast<const uint32_t*>(wu.q_desc) + i));
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's reads
+            asm volatile("bar.sync 1, %0;" ::"n"(kResThreads) : "memory");
+            if (rt == 0) mbar_arrive(a_full_bar + 8 * abuf);
+            if (++abuf == A_BUFS) { abuf = 0; a_phase ^= 1; }
+        };
+        const int ustep = (int)gridDim.x;
+        if (lm.a_packed) {
+            for (int k = 0; k < A_BUFS; ++k)
+                if ((int)blockIdx.x + k * ustep < n_units) fill_unit(make_unit(lm, pairs, (int)blockIdx.x + k * ustep));
+        }
+        for (int u = blockIdx.x; u < n_units; u += ustep) {
+            if (lm.fused) resolve_unit(make_unit(lm, pairs, u));
+            if (lm.a_packed && u + A_BUFS * ustep < n_units) fill_unit(make_unit(lm, pairs, u + A_BUFS * ustep));
         }
     }
 
@@ -690,6 +770,12 @@ bool ensure_dev(void*& p, size_t& cap, size_t bytes) {
 
 const char* fp4_last_error() { return g_err; }
 
+// SFMGMS_FP4_PACKED_QUERIES=0: launches that derive their operands unpack query images too and load them with TMA
+static bool fp4_packed_queries() {
+    static const bool on = !(getenv("SFMGMS_FP4_PACKED_QUERIES") && atoi(getenv("SFMGMS_FP4_PACKED_QUERIES")) == 0);
+    return on;
+}
+
 bool fp4_fused_resolve() {
     static const bool on = !(getenv("SFMGMS_FP4_FUSED_RESOLVE") && atoi(getenv("SFMGMS_FP4_FUSED_RESOLVE")) == 0);
     return on;
@@ -723,16 +809,60 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
         snprintf(g_err, sizeof g_err, "descriptor operands are not in one contiguous array");
         return -1;
     }
+    // work decomposition: pick the train-range split that minimises the static-schedule makespan
+    // ceil(units / #SM) / tsplit (small sub-batches of the pipelined host path otherwise lose a whole round)
+    long long qblocks = 0;
+    int min_tiles = 1 << 30;
+    for (int p = 0; p < n_pairs; ++p) {
+        if (h_pairs[p].n1 <= 0 || h_pairs[p].n2 <= 0) continue;
+        qblocks += (h_pairs[p].n1 + BM * MSUB - 1) / (BM * MSUB);
+        const int tiles = (h_pairs[p].n2 + BN - 1) / BN;
+        if (tiles < min_tiles) min_tiles = tiles;
+    }
+    // Small launches (a pair or two: every CTA gets about one short unit) keep the separate unpack / resolve kernels -- there the
+    // helper warps' work would sit on the critical path of a 20-us kernel; batches let warps 14-15 do both jobs in the shadow
+    // of the tensor work.
+    const bool batch = qblocks >= 2LL * sm_count;
+    static const int dbg = getenv("SFMGMS_TC_DEBUG") ? atoi(getenv("SFMGMS_TC_DEBUG")) : 0;   // timing experiments only
+    bool a_packed = false;
     if (!(s.set_valid && s.ops_src == lo && s.ops_rows == n_rows && s.ops_row_bytes == ROWB)) {
         if (!ensure_dev(s.d_ops, s.ops_cap, (size_t)(n_rows + 256) * ROWB)) return -1;
-        const long long n_words = n_rows * kDescWords;
-        long long blocks = (n_words + 255) / 256;
-        if (blocks > 148 * 32) blocks = 148 * 32;
-        unpack_fp4_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(lo), n_words,
-                                                            static_cast<uint4*>(s.d_ops));
-        ++launches; kmark("unpack_fp4", st);
-        s.ops_src = lo; s.ops_rows = n_rows; s.ops_row_bytes = ROWB;
-        s.set_valid = s.cache_enabled;
+        if (pinned || !batch || dbg != 0 || !fp4_packed_queries() || n_pairs > kMaxPairsPerLaunch) {
+            // a registered image set with the operand cache on: every image once, valid for all later launches
+            const long long n_words = n_rows * kDescWords;
+            long long blocks = (n_words + 255) / 256;
+            if (blocks > 148 * 32) blocks = 148 * 32;
+            unpack_fp4_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(lo), n_words,
+                                                                static_cast<uint4*>(s.d_ops));
+            ++launches; kmark("unpack_fp4", st);
+            s.ops_src = lo; s.ops_rows = n_rows; s.ops_row_bytes = ROWB;
+            s.set_valid = s.cache_enabled;
+        } else {
+            // operands derived for this launch only: the train images (each once), the kernel expands its query tiles itself
+            FirstUse fu;
+            memset(&fu, 0, sizeof fu);
+            std::vector<std::pair<const uint8_t*, int>> seen;
+            seen.reserve((size_t)n_pairs);
+            for (int p = 0; p < n_pairs; ++p)
+                if (h_pairs[p].n1 > 0 && h_pairs[p].n2 > 0) seen.push_back({h_pairs[p].desc2, p});
+            std::sort(seen.begin(), seen.end());
+            int max_n2 = 0;
+            for (size_t k = 0; k < seen.size(); ++k) {
+                if (k > 0 && seen[k].first == seen[k - 1].first && h_pairs[seen[k].second].n2 <= h_pairs[seen[k - 1].second].n2) {
+                    seen[k].second = seen[k - 1].second;   // same image (rows of the earlier entry cover it)
+                    continue;
+                }
+                const int p = seen[k].second;
+                fu.bits[p >> 5] |= 1u << (p & 31);
+                if (h_pairs[p].n2 > max_n2) max_n2 = h_pairs[p].n2;
+            }
+            int bx = (max_n2 * kDescWords + 256 * 16 - 1) / (256 * 16);   // ~16 words per thread
+            if (bx < 1) bx = 1;
+            unpack_fp4_train_kernel<<<dim3((unsigned)bx, (unsigned)n_pairs), 256, 0, st>>>(d_pairs, lo, fu, static_cast<uint4*>(s.d_ops));
+            ++launches; kmark("unpack_fp4", st);
+            s.set_valid = false;
+            a_packed = true;
+        }
     }
     CUtensorMap tmap;
     {
@@ -756,16 +886,6 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled(B) failed (%d)", (int)r); return -1; }
     }
-    // work decomposition: pick the train-range split that minimises the static-schedule makespan
-    // ceil(units / #SM) / tsplit (small sub-batches of the pipelined host path otherwise lose a whole round)
-    long long qblocks = 0;
-    int min_tiles = 1 << 30;
-    for (int p = 0; p < n_pairs; ++p) {
-        if (h_pairs[p].n1 <= 0 || h_pairs[p].n2 <= 0) continue;
-        qblocks += (h_pairs[p].n1 + BM * MSUB - 1) / (BM * MSUB);
-        const int tiles = (h_pairs[p].n2 + BN - 1) / BN;
-        if (tiles < min_tiles) min_tiles = tiles;
-    }
     int tsplit = 1;
     {
         double best = 1e30;
@@ -778,7 +898,7 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
     }
     if (n_pairs > kMaxPairsPerLaunch) { snprintf(g_err, sizeof g_err, "too many pairs per launch"); return -1; }
     LaunchMap lm;
-    lm.lo = lo; lm.n_pairs = n_pairs; lm.tsplit = tsplit; lm.fused = 0; lm.group_cnt = nullptr; lm.trace = nullptr;
+    lm.lo = lo; lm.n_pairs = n_pairs; lm.tsplit = tsplit; lm.fused = 0; lm.a_packed = 0; lm.vec16 = aligned16 ? 1 : 0; lm.group_cnt = nullptr; lm.trace = nullptr;
     int n_units = 0;
     for (int p = 0; p < n_pairs; ++p) {
         lm.prefix[p] = n_units;
@@ -787,7 +907,7 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
     lm.prefix[n_pairs] = n_units;
     lm.n_units = n_units;
     if (n_units == 0) return launches;
-    static const int dbg = getenv("SFMGMS_TC_DEBUG") ? atoi(getenv("SFMGMS_TC_DEBUG")) : 0;   // timing experiments only
+    lm.a_packed = a_packed ? 1 : 0;
     auto kern = dbg == 1 ? hamming_fp4_kernel<1> : dbg == 3 ? hamming_fp4_kernel<3> : dbg == 4 ? hamming_fp4_kernel<4>
               : dbg == 5 ? hamming_fp4_kernel<5> : dbg == 6 ? hamming_fp4_kernel<6> : dbg == 7 ? hamming_fp4_kernel<7>
                                                                                          : hamming_fp4_kernel<0>;
@@ -802,9 +922,9 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
         snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute(smem=%d) failed", SMEM_BYTES);
         return -1;
     }
-    const bool fused = dbg == 0 && fp4_fused_resolve();
+    const bool fused = dbg == 0 && batch && fp4_fused_resolve();
     if (fused) {
-        lm.fused = aligned16 ? 3 : 1;
+        lm.fused = 1;
         if (tsplit > 1) {   // units that share query rows count their arrivals; the last one resolves and re-zeroes its counter
             const size_t need = (size_t)n_units * sizeof(int);
             if (need > s.cnt_cap) {
