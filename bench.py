@@ -294,6 +294,25 @@ def hamming_roofline(kind, dists_per_step, ham_ms_per_step, clocks):
     return roof
 
 
+def gms_stage_roofline(gms_ms_per_step, n_pairs, n_kp, n_scales, n_rot):
+    """SURVEY §8d asks for two HBM figures for the GMS passes, both over the CUDA-event duration of the whole GMS stage:
+    (i) compulsory bytes per pair = 8(N1+N2) keypoints + 8N match indices + N mask bytes; (ii) the bytes the reference
+    algorithm moves when its histograms live in global memory = per (scale, shift) histogram [zero + scan 4*400*G_r(s) each +
+    12N assign/RMW] + 8*N*H mark reads + N.  The kernels keep the histograms in shared memory, so (ii) / time may exceed the
+    HBM peak: it says how far the stage is from a global-memory implementation, (i) how far from its own floor."""
+    hbm = load_json("MEASURED_PEAKS.json").get("hbm_gbs", 6532.9)
+    N = float(n_kp)
+    g_r = [400, 100, 196, 784, 1600][:n_scales]
+    H = n_scales * n_rot
+    b1 = 8 * (2 * N) + 8 * N + N
+    b2 = sum(4 * (2 * 4 * 400 * g + 12 * N) for g in g_r) + 8 * N * H + N
+    per_s = gms_ms_per_step * 1e-3
+    return {"bound": "hbm", "stage": "gms (assign + vote + count + select)", "ms_per_step": gms_ms_per_step, "peak": hbm, "unit": "GB/s",
+            "compulsory_bytes_per_pair": b1, "achieved_compulsory": n_pairs * b1 / per_s / 1e9, "frac_compulsory": n_pairs * b1 / per_s / 1e9 / hbm,
+            "reference_algorithm_bytes_per_pair": b2, "achieved_reference_algorithm": n_pairs * b2 / per_s / 1e9,
+            "frac_reference_algorithm": n_pairs * b2 / per_s / 1e9 / hbm, "hypotheses": H}
+
+
 def kernel_rooflines(kt, steps, kind, n_pairs, n_kp, n_hyp_scales):
     """per-kernel roofline entries from the per-kernel event pass (kt: name -> (total ms, launches) over `steps` steps).
     HBM-bound kernels: algorithmic bytes / time vs the measured copy bandwidth; the shared-memory histogram kernel:
@@ -304,7 +323,8 @@ def kernel_rooflines(kt, steps, kind, n_pairs, n_kp, n_hyp_scales):
     rows = float(n_pairs) * n_kp
     S = n_hyp_scales
     model = {   # algorithmic bytes per step: reads + writes each kernel cannot avoid
-        "unpack_fp4": ("hbm", 2 * rows * (32 + 128)),
+        # batches derive operands for the TRAIN images only (the kernel expands its query tiles from the packed rows)
+        "unpack_fp4": ("hbm", (1 if os.environ.get("SFMGMS_FP4_PACKED_QUERIES", "1") != "0" else 2) * rows * (32 + 128)),
         "unpack_pm1": ("hbm", 2 * rows * (32 + 256)),
         "hamming_resolve": ("hbm", rows * (4 + 32 + 8 * 32 + 4)),
         "gms_assign": ("hbm", rows * (4 + 8 + 8 + 2 * (4 + S))),
@@ -736,10 +756,21 @@ def main():
             dists = float(P) * n_kp * n_kp
             roof = hamming_roofline(hkind, dists, b["ham_ms"], b["clocks"])
             tr = load_json("profiles", "r2_traffic.json") or load_json("profiles", "r1_traffic.json")
+            kname = "hamming_%s" % hkind
+            if kname in b["kt"] and b["kt"][kname][0] > 0:
+                k_ms = b["kt"][kname][0] / 3.0          # the per-kernel event pass runs 3 steps
+                roof["kernel_ms"] = k_ms
+                roof["frac_kernel"] = roof["achieved"] * b["ham_ms"] / k_ms / roof["peak"]
+                roof["note"] = ("frac = OPs / duration of the whole Hamming STAGE in the timed region (operand unpack + the kernel; the "
+                                "kernel settles its own ties); frac_kernel = the same OPs / the kernel's own duration (separate event pass)")
             if kind == "cfg2" and tr.get("kernel") == roof["kernel"]:
                 roof["traffic"] = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * P / tr["pairs_per_launch"]
                 roof["traffic_source"] = "profiles/%s (ncu dram__bytes_read.sum + dram__bytes_write.sum)" % tr.get("file", "r1_traffic.json")
-                roof["algorithmic_bytes_per_launch"] = P * (2 * n_kp * (128 if hkind == "fp4" else 256) + 4 * n_kp)
+                # fp4: unpacked train rows (128 B) + packed query rows (32 B, expanded in the kernel) + packed train rows (32 B, the
+                # tie resolution's candidates) + keys (4 B); int8: both images unpacked (256 B rows) + keys
+                packed_q = hkind == "fp4" and os.environ.get("SFMGMS_FP4_PACKED_QUERIES", "1") != "0"
+                roof["algorithmic_bytes_per_launch"] = P * n_kp * (128 + 32 + 32 + 4) if packed_q else \
+                    P * (2 * n_kp * (128 if hkind == "fp4" else 256) + 4 * n_kp)
             n_scales = 5 if b["sc"] else 1
             line = {"metric": METRIC, "value": b["value"], "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                     "ms_per_step": b["ms_per_step"], "us_per_pair": 1e3 * b["ms_per_step"] / P, "higher_is_better": True,
@@ -751,6 +782,7 @@ def main():
                                 "parallelism": "x%d independent batches, no collective" % world, "inliers_total": b["inliers"]},
                     "e2e": b["e2e"], "gpu_launches": int(b["launches"]), "roofline": roof,
                     "roofline_kernels": kernel_rooflines(b["kt"], 3, hkind, P, n_kp, n_scales),
+                    "roofline_gms_stage": gms_stage_roofline(b["gms_ms"], P, n_kp, n_scales, 8 if b["rot"] else 1),
                     "stage_ms_per_step": {"hamming": b["ham_ms"], "gms": b["gms_ms"]}, "clocks": b["clocks"]}
             if world == 1 and not args.no_cpu_baseline:
                 # the CPU reference path on a bounded sample of the very pairs the GPU just matched -- its results are
