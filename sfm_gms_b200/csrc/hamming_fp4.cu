@@ -78,33 +78,40 @@ static_assert(SMEM_BYTES <= 227 * 1024 && kAllocWarp == kEpiWarps + 2, "shared m
 static_assert(STAGES >= 3, "B ring too shallow");
 static_assert(BTILE_BYTES % 1024 == 0 && (kEpiCols == 80 || kEpiCols == 60) && SF_COL + SF_COLS <= 512, "layout");
 
-// Epilogue reduction.  A warp's 80 accumulator columns are 10 GROUPS of 8 consecutive columns.  Per group the
-// plain maximum of the 8 dot products (FMNMX3, ALU pipe), then key_g = groupmax_g + (31 - g)/32 (one packed FADD2
-// per two groups, FMA pipe) and the maximum of the 10 keys: its integer part is the best dot product of the part,
-// its fraction names the FIRST group that attains it.  |dot| <= 256 and the fraction has 5 bits: keys are exact
-// in fp32.  All fractions lie in [22/32, 31/32], a span below 1/2, so "this key's dot product is larger than the
-// best so far" is simply key > best + 1/2 (no floor in the loop).  Which of the group's 8 train rows is the
-// lowest-index minimum is settled afterwards by hamming_resolve_kernel on the original descriptors (8 candidates
-// per query row instead of n2).  Group size 4 (-DSFMGMS_FP4_GROUP=4: 20 tags, half the resolve traffic) measured
-// 3 % slower overall, 16 would double the resolve.  This halves the epilogue's instruction count against tagging
-// every column (80 adds -> 10).
+// Epilogue reduction.  A warp's 80 accumulator columns are 9 GROUPS of 9 consecutive columns (the last one has 8).  Per
+// group the plain maximum of its dot products, then key_g = groupmax_g + (31 - g)/32 (one packed FADD2 per two groups, FMA
+// pipe) and the maximum of the 9 keys: its integer part is the best dot product of the part, its fraction names the FIRST
+// group that attains it.  |dot| <= 256 and the fraction has 5 bits: keys are exact in fp32.  All fractions lie within a span
+// below 1/2, so "this key's dot product is larger than the best so far" is simply key > best + 1/2 (no floor in the loop).
+// Which of the group's train rows is the lowest-index minimum is settled afterwards on the original descriptors (9
+// candidates per query row instead of n2: warps 14-15, or hamming_resolve_kernel for small launches).
+// Why 9: a 3-input maximum (FMNMX3) folds 2 values per instruction, so groups of ODD size cost exactly (size - 1) / 2
+// instructions -- 9 values = 4, and the 9 keys = 4 more: 36 + 5 (tags) + 4 = 45 ALU instructions per 80 columns.  Groups of 8
+// (round 2 until here) need 4 per group as well (3 FMNMX3 + 1 FMNMX) but 10 of them: 40 + 5 + 5 = 50.  The epilogue is what
+// the kernel waits for (profiles/r2_notes.md), so its instruction count is the kernel's time.  -DSFMGMS_FP4_GROUP=8 builds
+// the old grouping.
 #ifndef SFMGMS_FP4_GROUP
-#define SFMGMS_FP4_GROUP 8
+#define SFMGMS_FP4_GROUP 9
 #endif
-constexpr int kGroup = SFMGMS_FP4_GROUP;                 // 8 (default) or 4 columns per tagged group
-constexpr int kGroupShift = kGroup == 8 ? 3 : 2;
-constexpr int kGroups = kEpiCols / kGroup;
-constexpr int kTagDen = kGroups <= 16 ? 32 : 64;         // tag of group g = (kTagDen - 1 - g) / kTagDen: all tags within a span < 1/2
-static_assert(kEpiCols == 80 && (kGroup == 8 || kGroup == 4), "group tags below are written for 10 groups of 8 / 20 of 4");
-#if SFMGMS_FP4_GROUP == 8
-__constant__ float2 c_grouptag[kGroups / 2] = {{31.f / 32.f, 30.f / 32.f}, {29.f / 32.f, 28.f / 32.f}, {27.f / 32.f, 26.f / 32.f},
-                                               {25.f / 32.f, 24.f / 32.f}, {23.f / 32.f, 22.f / 32.f}};
-#else
-__constant__ float2 c_grouptag[kGroups / 2] = {{63.f / 64.f, 62.f / 64.f}, {61.f / 64.f, 60.f / 64.f}, {59.f / 64.f, 58.f / 64.f},
-                                               {57.f / 64.f, 56.f / 64.f}, {55.f / 64.f, 54.f / 64.f}, {53.f / 64.f, 52.f / 64.f},
-                                               {51.f / 64.f, 50.f / 64.f}, {49.f / 64.f, 48.f / 64.f}, {47.f / 64.f, 46.f / 64.f},
-                                               {45.f / 64.f, 44.f / 64.f}};
-#endif
+constexpr int kGroup = SFMGMS_FP4_GROUP;                           // columns per tagged group (the last group may be shorter)
+constexpr int kGroups = (kEpiCols + kGroup - 1) / kGroup;          // 9 (10 with groups of 8)
+constexpr int kLastGroup = kEpiCols - (kGroups - 1) * kGroup;      // 8
+constexpr int kCandBits = 4;                                       // candidate number within a group: 4 bits
+constexpr int kTagDen = 32;                                        // tag of group g = (kTagDen - 1 - g) / kTagDen: all tags within a span < 1/2
+static_assert(kEpiCols == 80 && kGroup >= 5 && kGroup <= 16 && kGroups <= 16 && kLastGroup >= 1, "group tags: at most 16 groups, candidates in 4 bits");
+__constant__ float2 c_grouptag[8] = {{31.f / 32.f, 30.f / 32.f}, {29.f / 32.f, 28.f / 32.f}, {27.f / 32.f, 26.f / 32.f}, {25.f / 32.f, 24.f / 32.f},
+                                     {23.f / 32.f, 22.f / 32.f}, {21.f / 32.f, 20.f / 32.f}, {19.f / 32.f, 18.f / 32.f}, {17.f / 32.f, 16.f / 32.f}};
+
+// maximum of N values as a tree of 3-input maxima (ptxas: FMNMX3)
+template <int N>
+__device__ __forceinline__ float max_tree(const float* x) {
+    if constexpr (N == 1) return x[0];
+    else if constexpr (N == 2) return fmaxf(x[0], x[1]);
+    else {
+        constexpr int n0 = (N + 2) / 3, n1 = (N + 1) / 3, n2 = N / 3;
+        return fmaxf(fmaxf(max_tree<n0>(x), max_tree<n1>(x + n0)), max_tree<n2>(x + n0 + n1));
+    }
+}
 
 // (lo, hi) + (c.x, c.y) with one packed fp32x2 add (sm_100: add.rn.f32x2 -> FADD2)
 __device__ __forceinline__ void add2(float lo, float hi, float2 c, float& out_lo, float& out_hi) {
@@ -447,23 +454,15 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     for (int j = 0; j < kEpiCols; ++j)
                         if (c0 + j >= valid) v[j] = -1.0e30f;
                 }
-                float gm[kGroups];
+                float gm[kGroups + 1];
 #pragma unroll
-                for (int g = 0; g < kGroups; ++g) {
-                    const float* x = v + kGroup * g;
-                    if constexpr (kGroup == 8) {
-                        const float a = fmaxf(fmaxf(x[0], x[1]), x[2]);
-                        const float b = fmaxf(fmaxf(x[3], x[4]), x[5]);
-                        gm[g] = fmaxf(fmaxf(fmaxf(x[6], x[7]), a), b);
-                    } else {
-                        gm[g] = fmaxf(fmaxf(fmaxf(x[0], x[1]), x[2]), x[3]);
-                    }
-                }
+                for (int g = 0; g + 1 < kGroups; ++g) gm[g] = max_tree<kGroup>(v + kGroup * g);
+                gm[kGroups - 1] = max_tree<kLastGroup>(v + kGroup * (kGroups - 1));
+                gm[kGroups] = 0.f;
 #pragma unroll
                 for (int k = 0; k < kGroups / 2; ++k) add2(gm[2 * k], gm[2 * k + 1], c_grouptag[k], gm[2 * k], gm[2 * k + 1]);
-                float m = gm[0];
-#pragma unroll
-                for (int g = 1; g < kGroups; ++g) m = fmaxf(m, gm[g]);
+                if constexpr (kGroups & 1) gm[kGroups - 1] += c_grouptag[kGroups / 2].x;
+                const float m = max_tree<kGroups>(gm);
                 if (m > beat[S]) {                                   // integer part exceeds the best so far (see kTagDen)
                     best_key[S] = m;
                     beat[S] = m + 0.5f;
@@ -591,7 +590,8 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(wu.q_desc + (size_t)row * 32));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(t));
                 if ((int)c0 + 4 < wu.n2) asm volatile("prefetch.global.L2 [%0];" ::"l"(t + 128));
-                if (kGroup == 8 && (int)c0 + 7 < wu.n2) asm volatile("prefetch.global.L2 [%0];" ::"l"(t + 7 * 32));   // (unaligned groups span 3 lines)
+                if ((int)c0 + kGroup - 1 < wu.n2) asm volatile("prefetch.global.L2 [%0];" ::"l"(t + (kGroup - 1) * 32));   // (unaligned groups span 3 lines)
+                if (kGroup > 9 && (int)c0 + 8 < wu.n2) asm volatile("prefetch.global.L2 [%0];" ::"l"(t + 256));
             }
 #pragma unroll
             for (int i = 0; i < kRowsPerLane; ++i) {
@@ -606,20 +606,25 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 if (vec) {
                     const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(q)), a1 = __ldg(reinterpret_cast<const uint4*>(q) + 1);
                     a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-                    uint4 b0[kGroup], b1[kGroup];
+                    // candidates in two batches of loads (the lane keeps at most 5 rows = 40 registers in flight)
+                    constexpr int kHalf = (kGroup + 1) / 2;
 #pragma unroll
-                    for (int c = 0; c < kGroup; ++c) {
-                        b0[c] = b1[c] = make_uint4(0u, 0u, 0u, 0u);
-                        if (c0 + c < wu.n2) {
-                            b0[c] = __ldg(reinterpret_cast<const uint4*>(t) + 2 * c);
-                            b1[c] = __ldg(reinterpret_cast<const uint4*>(t) + 2 * c + 1);
+                    for (int cb = 0; cb < kGroup; cb += kHalf) {
+                        uint4 b0[kHalf], b1[kHalf];
+#pragma unroll
+                        for (int c = 0; c < kHalf; ++c) {
+                            b0[c] = b1[c] = make_uint4(0u, 0u, 0u, 0u);
+                            if (cb + c < kGroup && c0 + cb + c < wu.n2) {
+                                b0[c] = __ldg(reinterpret_cast<const uint4*>(t) + 2 * (cb + c));
+                                b1[c] = __ldg(reinterpret_cast<const uint4*>(t) + 2 * (cb + c) + 1);
+                            }
                         }
-                    }
 #pragma unroll
-                    for (int c = 0; c < kGroup; ++c) {
-                        const uint32_t d = __popc(a[0] ^ b0[c].x) + __popc(a[1] ^ b0[c].y) + __popc(a[2] ^ b0[c].z) + __popc(a[3] ^ b0[c].w) +
-                                           __popc(a[4] ^ b1[c].x) + __popc(a[5] ^ b1[c].y) + __popc(a[6] ^ b1[c].z) + __popc(a[7] ^ b1[c].w);
-                        if (c0 + c < wu.n2) best = min(best, (d << kGroupShift) | (uint32_t)c);
+                        for (int c = 0; c < kHalf; ++c) {
+                            const uint32_t d = __popc(a[0] ^ b0[c].x) + __popc(a[1] ^ b0[c].y) + __popc(a[2] ^ b0[c].z) + __popc(a[3] ^ b0[c].w) +
+                                               __popc(a[4] ^ b1[c].x) + __popc(a[5] ^ b1[c].y) + __popc(a[6] ^ b1[c].z) + __popc(a[7] ^ b1[c].w);
+                            if (cb + c < kGroup && c0 + cb + c < wu.n2) best = min(best, (d << kCandBits) | (uint32_t)(cb + c));
+                        }
                     }
                 } else {
                     const uint32_t* qw = reinterpret_cast<const uint32_t*>(q);
@@ -632,11 +637,11 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                             uint32_t d = 0;
 #pragma unroll
                             for (int w = 0; w < 8; ++w) d += __popc(a[w] ^ __ldg(tw + w));
-                            best = min(best, (d << kGroupShift) | (uint32_t)c);
+                            best = min(best, (d << kCandBits) | (uint32_t)c);
                         }
                     }
                 }
-                wu.key[row] = ((best >> kGroupShift) << kTrainIdxBits) | ((uint32_t)c0 + (best & (uint32_t)(kGroup - 1)));
+                wu.key[row] = ((best >> kCandBits) << kTrainIdxBits) | ((uint32_t)c0 + (best & ((1u << kCandBits) - 1u)));
             }
         };
         // ---- query tiles from the packed descriptors (a_packed): the four 128-row sub-tiles of a unit, written in the layout a
@@ -700,20 +705,22 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     }
 }
 
-// After the tensor-core pass every key holds (distance << 18 | first train row of the winning group of 8).
-// Eight lanes per query row recompute the 8 candidates' Hamming distances on the original 256-bit descriptors
-// and the key becomes (distance << 18 | lowest train row attaining it) -- BFMatcher's tie rule.
+// Small launches (a pair or two) keep the tie resolution as a kernel of its own: after the tensor-core pass every key holds
+// (distance << 18 | first train row of the winning group).  Sixteen lanes per query row (kGroup of them busy) recompute the
+// candidates' Hamming distances on the original 256-bit descriptors and the key becomes (distance << 18 | lowest train row
+// attaining it) -- BFMatcher's tie rule.
 constexpr int kResolveThreads = 128;
+constexpr int kResolveLanes = 16;
 template <bool kVec>   // kVec: every descriptor row is 16-byte aligned (two 128-bit loads per row)
 __global__ void __launch_bounds__(kResolveThreads) hamming_resolve_kernel(const PairDesc* __restrict__ pairs) {
     const PairDesc& pd = pairs[blockIdx.y];
-    const int row = blockIdx.x * (kResolveThreads / kGroup) + (threadIdx.x >> kGroupShift);
-    const int l = threadIdx.x & (kGroup - 1);
-    if (pd.n1 <= 0 || pd.n2 <= 0 || row >= pd.n1) return;      // whole 8-lane groups leave together
+    const int row = blockIdx.x * (kResolveThreads / kResolveLanes) + (threadIdx.x / kResolveLanes);
+    const int l = threadIdx.x & (kResolveLanes - 1);
+    if (pd.n1 <= 0 || pd.n2 <= 0 || row >= pd.n1) return;      // whole 16-lane groups leave together
     const uint32_t key = pd.key[row];
     const int cand = (int)(key & kTrainIdxMask) + l;
     uint32_t d = 0x1FFFu;
-    if (cand < pd.n2) {
+    if (l < kGroup && cand < pd.n2) {
         d = 0;
         if constexpr (kVec) {
             const uint4* q = reinterpret_cast<const uint4*>(pd.desc1) + (size_t)row * 2;
@@ -730,11 +737,11 @@ __global__ void __launch_bounds__(kResolveThreads) hamming_resolve_kernel(const 
             for (int w = 0; w < kDescWords; ++w) d += __popc(__ldg(q + w) ^ __ldg(t + w));
         }
     }
-    uint32_t k = (d << kGroupShift) | (uint32_t)l;
-    const uint32_t mask = ((1u << kGroup) - 1u) << (threadIdx.x & 31 & ~(kGroup - 1));
+    uint32_t k = (d << kCandBits) | (uint32_t)l;
+    const uint32_t mask = 0xFFFFu << (threadIdx.x & 16);
 #pragma unroll
-    for (int o = 1; o < kGroup; o <<= 1) k = min(k, __shfl_xor_sync(mask, k, o, kGroup));
-    if (l == 0) pd.key[row] = ((k >> kGroupShift) << kTrainIdxBits) | ((key & kTrainIdxMask) + (k & (uint32_t)(kGroup - 1)));
+    for (int o = 1; o < kResolveLanes; o <<= 1) k = min(k, __shfl_xor_sync(mask, k, o, kResolveLanes));
+    if (l == 0) pd.key[row] = ((k >> kCandBits) << kTrainIdxBits) | ((key & kTrainIdxMask) + (k & ((1u << kCandBits) - 1u)));
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -958,7 +965,7 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
         }
         rst = resolve_st;
     }
-    const int rows_per_block = kResolveThreads / kGroup;
+    const int rows_per_block = kResolveThreads / kResolveLanes;
     const dim3 rgrid((unsigned)((max_n1 + rows_per_block - 1) / rows_per_block), (unsigned)n_pairs);
     if (aligned16) hamming_resolve_kernel<true><<<rgrid, kResolveThreads, 0, rst>>>(d_pairs);
     else hamming_resolve_kernel<false><<<rgrid, kResolveThreads, 0, rst>>>(d_pairs);
