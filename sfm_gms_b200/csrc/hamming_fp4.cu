@@ -221,6 +221,18 @@ __device__ __forceinline__ void tc_mma_mxf4(uint32_t d_tmem, uint32_t a_lo, uint
         "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(sfa), "r"(sfb), "n"(kAccumulate) : "memory");
 }
 
+// Operand encodings.  QUERY rows: bit -> +1 / -1.  TRAIN rows: bit -> +1 / 0 (SFMGMS_FP4_TRAIN01, default) -- then
+// <a,b> = 2 pop(a & b) - pop(b) = pop(a) - hamming(a,b): for a fixed query row still "nearest = arg-max of the dot product", and
+// the tensor pipe multiplies by zero half of the time: the MMA loop draws ~10 % less power than with +-1 x +-1 operands
+// (scripts/power_probe.cu, profiles/r2_power_probe.txt), and sustained runs of this kernel sit AT the 1,000 W cap, where power
+// is clock.  The exact distance of the winner is recomputed on the packed descriptors by the tie resolution either way, so
+// the epilogue's value only has to order the candidates.  Query tiles are then always expanded in the kernel (the unpacked
+// array in global memory holds the train encoding of every image).
+#ifndef SFMGMS_FP4_TRAIN01
+#define SFMGMS_FP4_TRAIN01 1
+#endif
+constexpr bool kTrain01 = SFMGMS_FP4_TRAIN01 != 0;
+
 // 32 descriptor bits -> 32 e2m1 values (+1.0 = 0x2, -1.0 = 0xA), element k in nibble k (low nibble first)
 __device__ __forceinline__ uint4 fp4_from_word(uint32_t w) {
     uint32_t o[4];
@@ -236,11 +248,26 @@ __device__ __forceinline__ uint4 fp4_from_word(uint32_t w) {
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// train rows: set bit -> +1.0 (0x2), clear bit -> 0 (0x0) with SFMGMS_FP4_TRAIN01, else the +-1 encoding
+__device__ __forceinline__ uint4 fp4_train_from_word(uint32_t w) {
+    if constexpr (!kTrain01) return fp4_from_word(w);
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t b = (w >> (8 * q)) & 0xFFu;
+        uint32_t s = (b | (b << 12)) & 0x000F000Fu;
+        s = (s | (s << 6)) & 0x03030303u;
+        s = (s | (s << 3)) & 0x11111111u;                 // one bit per nibble (at nibble bit 0)
+        o[q] = s << 1;                                    // 0x2 where the bit is set
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 __global__ void __launch_bounds__(256) unpack_fp4_kernel(const uint32_t* __restrict__ desc, long long n_words,
                                                          uint4* __restrict__ out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long step = (long long)gridDim.x * blockDim.x;
-    for (; i < n_words; i += step) out[i] = fp4_from_word(__ldg(desc + i));
+    for (; i < n_words; i += step) out[i] = fp4_train_from_word(__ldg(desc + i));
 }
 
 // Operands derived per launch: only TRAIN images need the unpacked copy in global memory (the kernel expands its query tiles
@@ -262,7 +289,7 @@ __global__ void __launch_bounds__(256) unpack_fp4_train_kernel(const PairDesc* _
         for (int k = 0; k < 4; ++k) w[k] = i + k * stride < n_words ? __ldg(src + i + k * stride) : 0u;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (i + k * stride < n_words) dst[i + k * stride] = fp4_from_word(w[k]);
+            if (i + k * stride < n_words) dst[i + k * stride] = fp4_train_from_word(w[k]);
     }
 }
 
@@ -519,7 +546,10 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     const int g = kTagDen - 1 - (int)((best_key[s] - fl) * (float)kTagDen);
                     constexpr bool kTiming = dbg != 0 && dbg != 7;   // timing builds: keep the work alive, keep the key in range
                     constexpr bool kNoData = dbg == 4 || dbg == 6;
-                    const uint32_t dist = kNoData ? 7u : kTiming ? ((uint32_t)(256 - (int)fl) >> 1) & 7u : (uint32_t)(256 - (int)fl) >> 1;
+                    // (+-1 x +-1: dot = 256 - 2 d; +-1 x {0,1}: dot = pop(a) - d, and 256 - dot orders the candidates of a row like d does --
+                    // the resolution pass replaces it by the recomputed distance)
+                    const uint32_t dist = kNoData ? 7u : kTiming ? ((uint32_t)(256 - (int)fl) >> 1) & 7u
+                                        : kTrain01 ? (uint32_t)(256 - (int)fl) : (uint32_t)(256 - (int)fl) >> 1;
                     const uint32_t idx = kNoData ? 0u : kTiming ? (uint32_t)(best_base[s] + kGroup * g) & 7u : (uint32_t)(best_base[s] + kGroup * g);
                     packed = (dist << kTrainIdxBits) | idx;
                 }
@@ -831,10 +861,12 @@ int launch_hamming_fp4(TcState& s, const PairDesc* d_pairs, const PairDesc* h_pa
     // of the tensor work.
     const bool batch = qblocks >= 2LL * sm_count;
     static const int dbg = getenv("SFMGMS_TC_DEBUG") ? atoi(getenv("SFMGMS_TC_DEBUG")) : 0;   // timing experiments only
-    bool a_packed = false;
+    if (n_pairs > kMaxPairsPerLaunch) { snprintf(g_err, sizeof g_err, "too many pairs per launch"); return -1; }
+    // train encoding {0,1}: the unpacked array never holds query operands, every production launch expands its query tiles
+    bool a_packed = kTrain01 && dbg == 0;
     if (!(s.set_valid && s.ops_src == lo && s.ops_rows == n_rows && s.ops_row_bytes == ROWB)) {
         if (!ensure_dev(s.d_ops, s.ops_cap, (size_t)(n_rows + 256) * ROWB)) return -1;
-        if (pinned || !batch || dbg != 0 || !fp4_packed_queries() || n_pairs > kMaxPairsPerLaunch) {
+        if (pinned || dbg != 0 || (!kTrain01 && (!batch || !fp4_packed_queries()))) {
             // a registered image set with the operand cache on: every image once, valid for all later launches
             const long long n_words = n_rows * kDescWords;
             long long blocks = (n_words + 255) / 256;
