@@ -659,11 +659,25 @@ def run_allpairs(args, D, local_rank, steps, warmup, n_images=SEQ_IMAGES):
     d2h = my_inl * 16 + n_my * 8 + (n_my + 1) * 8
     h2d = (h_desc.numel() + h_kp.numel() * 4) if rank == 0 else 0
 
+    # ---- secondary e2e: the same step with 8-byte {queryIdx, trainIdx} records (SFMGMS_OPT_COMPACT_RECORD = 1) -- what the
+    # reference's consumer of matchesGMS reads; at 8 GPUs the 16-byte records are bound by the host's ingest rate -----------
+    hm_dmatch = h_m.numpy().view(api.DMATCH_DT).copy()
+    ctx.set_option(api.OPT_COMPACT_RECORD, 1)
+    step_e2e()
+    ms_e2e8, wall_e2e8 = timed_host_calls(D, step_e2e, max(1, min(steps, 3)))
+    ctx.set_option(api.OPT_COMPACT_RECORD, 0)
+    ip = h_m.numpy()[: 2 * my_inl].reshape(-1, 2)
+    assert np.array_equal(ip[:, 0], hm_dmatch["queryIdx"][:my_inl]) and np.array_equal(ip[:, 1], hm_dmatch["trainIdx"][:my_inl]), \
+        "index-pair records differ from the DMatch records"
+    e2e8 = dict(value=n_total_pairs * max(1, min(steps, 3)) / (ms_e2e8 * 1e-3), unit="pairs/s", ms_per_step=ms_e2e8 / max(1, min(steps, 3)),
+                d2h_bytes_per_step=int(D.sum_i(my_inl * 8 + n_my * 8 + (n_my + 1) * 8)),
+                records="8-byte {queryIdx, trainIdx} (SFMGMS_OPT_COMPACT_RECORD = 1); checked equal to the DMatch records' index fields")
+
     # ---- parity: a seeded sample of THIS rank's pairs against the CPU reference path (after the timed regions) -------
     n_chk = args.check_pairs
     chk = np.sort(np.random.default_rng(777 + rank).choice(n_my, min(n_chk, n_my), replace=False))
     cpu = CpuPath(max(1, (os.cpu_count() or 1) // world))
-    hm = h_m.numpy().view(api.DMATCH_DT)
+    hm = hm_dmatch
     ho = h_off.numpy()
     ok = 1
     for p, (idx, dist, g) in zip(chk, cpu_pairs(cpu, s, my_pairs[chk], 0, 0)):
@@ -676,7 +690,7 @@ def run_allpairs(args, D, local_rank, steps, warmup, n_images=SEQ_IMAGES):
         raise AssertionError("bench parity: an all-pairs result differs from the CPU reference path")
     out = dict(value=value, ms_per_step=ms_total / steps, launches=launches, clocks=clocks, ham_ms=float(np.mean(ham_ms)),
                gms_ms=float(np.mean(gms_ms)), n_pairs=n_total_pairs, pairs_per_rank=n_my, inliers=D.sum_i(my_inl),
-               parity_checked_pairs=D.sum_i(len(chk)), device_bytes=int(dev_bytes), seq=s, cpu=cpu,
+               parity_checked_pairs=D.sum_i(len(chk)), device_bytes=int(dev_bytes), seq=s, cpu=cpu, e2e_index_pairs=e2e8,
                e2e=dict(value=n_total_pairs * steps / (ms_e2e * 1e-3), unit="pairs/s", h2d_bytes_per_step=int(D.sum_i(h2d)),
                         d2h_bytes_per_step=int(D.sum_i(d2h)), ms_per_step=ms_e2e / steps, wall_ms_per_step=wall_e2e / steps,
                         upload_plus_broadcast_ms=float(np.mean(bc_ms)),
@@ -737,7 +751,7 @@ def main():
                                 "parallelism": "pair-sharded x%d (contiguous blocks of the i-major list), one NCCL broadcast of the "
                                                "shared set per step in the e2e arm, no collective on the result path" % world,
                                 "library_device_bytes": a["device_bytes"], "inliers_total": a["inliers"]},
-                    "e2e": a["e2e"], "gpu_launches": int(a["launches"]), "roofline": roof,
+                    "e2e": a["e2e"], "e2e_index_pairs": a["e2e_index_pairs"], "gpu_launches": int(a["launches"]), "roofline": roof,
                     "stage_ms_per_step": {"hamming": a["ham_ms"], "gms": a["gms_ms"]}, "clocks": a["clocks"],
                     "parity_checked_pairs": a["parity_checked_pairs"]}
             line.update(extra)
@@ -797,7 +811,7 @@ def main():
             if ap_res is not None:
                 line["allpairs"] = {"workload": WORKLOADS["allpairs"], "value": ap_res["value"], "unit": "pairs/s", "scaling": "strong",
                                     "steps": max(1, min(args.steps, args.allpairs_steps)), "ms_per_step": ap_res["ms_per_step"],
-                                    "e2e": ap_res["e2e"], "stage_ms_per_step": {"hamming": ap_res["ham_ms"], "gms": ap_res["gms_ms"]},
+                                    "e2e": ap_res["e2e"], "e2e_index_pairs": ap_res["e2e_index_pairs"], "stage_ms_per_step": {"hamming": ap_res["ham_ms"], "gms": ap_res["gms_ms"]},
                                     "parity_checked_pairs": ap_res["parity_checked_pairs"], "library_device_bytes": ap_res["device_bytes"],
                                     "gpu_launches": int(ap_res["launches"]), "inliers_total": ap_res["inliers"]}
             print(json.dumps(line), flush=True)

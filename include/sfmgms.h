@@ -64,6 +64,11 @@ extern "C" {
                                         rows (default 4 Mi): per-match device scratch is O(chunk), never O(list) */
 #define SFMGMS_OPT_OVERLAP 8         /* 1 (default): a batch's tensor-core work is split into up to three launches and the small
                                         tie-resolution kernel of each runs on a second stream beside the next launch; 0: one stream */
+#define SFMGMS_OPT_COMPACT_RECORD 9  /* records sfmgms_match_pairs_compact writes to `matches`: 0 (default) cv::DMatch, 16 bytes
+                                        {queryIdx, trainIdx, imgIdx = 0, float distance}; 1: index pairs, 8 bytes {int32 queryIdx,
+                                        int32 trainIdx} -- all that the reference's consumer of matchesGMS reads (SfMUtil.cpp:25-35
+                                        gathers kpts1[queryIdx].pt / kpts2[trainIdx].pt); halves the result volume of long pair lists
+                                        (the 8-GPU all-pairs run is bound by the host's ingest of the 16-byte records) */
 #define SFMGMS_OPT_GMS_DENSE 7       /* 1: force the global-memory histogram path of GMS (otherwise only pairs with
                                         >= 65536 matches take it) -- for tests and measurements */
 

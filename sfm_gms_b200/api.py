@@ -20,7 +20,7 @@ NORM_L2 = 4       # cv::NORM_L2
 
 SFMGMS_HOST, SFMGMS_DEVICE = 0, 1
 OPT_HAMMING_KERNEL, OPT_GMS_CHUNK_BYTES, OPT_TIMING, OPT_TC_OPERAND_CACHE, OPT_L2_KERNEL = 1, 2, 3, 4, 5
-OPT_CHUNK_ROWS, OPT_GMS_DENSE, OPT_OVERLAP = 6, 7, 8
+OPT_CHUNK_ROWS, OPT_GMS_DENSE, OPT_OVERLAP, OPT_COMPACT_RECORD = 6, 7, 8, 9
 HAMMING_AUTO, HAMMING_POPC, HAMMING_TC, HAMMING_FP4 = 0, 1, 2, 3
 
 _ERR_NAMES = {1: "ERR_ARG", 2: "ERR_TRAIN_ROWS", 3: "ERR_DOMAIN", 4: "ERR_INDEX", 5: "ERR_CUDA", 6: "ERR_STATE",
@@ -505,9 +505,10 @@ class Context:
         return out
 
     def match_pairs_compact(self, pairs, with_rotation=False, with_scale=False, threshold_factor=6.0, capacity=None,
-                            want_matches=True, want_points=True):
+                            want_matches=True, want_points=True, index_pairs=False):
         """Host outputs: every pair's matchesGMS (cv::DMatch records) and inlier coordinates, back to back.
-        -> dict(n_inliers, best_hyp, offsets int64[n+1], n_total[, matches (DMATCH_DT)][, pts1, pts2 float32[n,2]])."""
+        -> dict(n_inliers, best_hyp, offsets int64[n+1], n_total[, matches (DMATCH_DT)][, pts1, pts2 float32[n,2]]).
+        index_pairs: `matches` holds int32 (queryIdx, trainIdx) rows instead (SFMGMS_OPT_COMPACT_RECORD = 1)."""
         pr = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
         n = pr.shape[0]
         if capacity is None:
@@ -515,13 +516,17 @@ class Context:
         ninl = np.zeros(n, np.int32)
         bh = np.zeros(n, np.int32)
         off = np.zeros(n + 1, np.int64)
-        m = np.zeros(max(capacity, 1), DMATCH_DT) if want_matches else None
+        m = (np.zeros((max(capacity, 1), 2), np.int32) if index_pairs else np.zeros(max(capacity, 1), DMATCH_DT)) if want_matches else None
         p1 = np.zeros((max(capacity, 1), 2), np.float32) if want_points else None
         p2 = np.zeros((max(capacity, 1), 2), np.float32) if want_points else None
         tot = ctypes.c_int64(0)
-        self._check(self._lib.sfmgms_match_pairs_compact(self._h, _ptr(pr), n, int(bool(with_rotation)), int(bool(with_scale)),
-                                                         float(threshold_factor), SFMGMS_HOST, _ptr(ninl), _ptr(bh), _ptr(off),
-                                                         _ptr(m), _ptr(p1), _ptr(p2), int(capacity), ctypes.byref(tot)))
+        self.set_option(OPT_COMPACT_RECORD, 1 if index_pairs else 0)
+        try:
+            self._check(self._lib.sfmgms_match_pairs_compact(self._h, _ptr(pr), n, int(bool(with_rotation)), int(bool(with_scale)),
+                                                             float(threshold_factor), SFMGMS_HOST, _ptr(ninl), _ptr(bh), _ptr(off),
+                                                             _ptr(m), _ptr(p1), _ptr(p2), int(capacity), ctypes.byref(tot)))
+        finally:
+            self.set_option(OPT_COMPACT_RECORD, 0)
         out = dict(n_inliers=ninl, best_hyp=bh, offsets=off, n_total=tot.value)
         if want_matches:
             out["matches"] = m[: tot.value]

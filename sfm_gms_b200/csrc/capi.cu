@@ -128,6 +128,7 @@ struct sfmgms_ctx {
     long long chunk_rows = 4ll << 20;   // match rows per chunk (SFMGMS_OPT_CHUNK_ROWS)
     int gms_dense = 0;              // SFMGMS_OPT_GMS_DENSE
     int overlap_resolve = 1;        // SFMGMS_OPT_OVERLAP (0: everything on one stream)
+    int compact_rec_bytes = 16;     // SFMGMS_OPT_COMPACT_RECORD: 16 = cv::DMatch records, 8 = {queryIdx, trainIdx}
 };
 
 namespace {
@@ -482,6 +483,11 @@ int sfmgms_set_option(sfmgms_ctx* ctx, int key, int64_t value) {
     }
     if (key == SFMGMS_OPT_GMS_DENSE) {
         ctx->gms_dense = value ? 1 : 0;
+        return SFMGMS_OK;
+    }
+    if (key == SFMGMS_OPT_COMPACT_RECORD) {
+        if (value != 0 && value != 1) return fail(ctx, SFMGMS_ERR_ARG, "bad compact record type %lld", (long long)value);
+        ctx->compact_rec_bytes = value ? 8 : 16;
         return SFMGMS_OK;
     }
     if (key == SFMGMS_OPT_OVERLAP) {
@@ -1341,7 +1347,7 @@ int run_pairs_job(sfmgms_ctx* ctx, const PairsJob& J) {
                 int64_t n = chunk_inl;
                 if (inl_total + n > J.capacity) { overflow = true; n = J.capacity > inl_total ? J.capacity - inl_total : 0; }
                 if (n > 0) {
-                    if (J.matches) CU(cudaMemcpyAsync((char*)J.matches + inl_total * 16, sl.cmatch.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                    if (J.matches) CU(cudaMemcpyAsync((char*)J.matches + inl_total * ctx->compact_rec_bytes, sl.cmatch.p, (size_t)n * ctx->compact_rec_bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
                     if (J.pts1) CU(cudaMemcpyAsync(J.pts1 + inl_total * 2, sl.cpts.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->d2h_stream));
                     if (J.pts2) CU(cudaMemcpyAsync(J.pts2 + inl_total * 2, (char*)sl.cpts.p + (size_t)max_rows * 8, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->d2h_stream));
                 }
@@ -1385,7 +1391,8 @@ int run_pairs_job(sfmgms_ctx* ctx, const PairsJob& J) {
             float* dp1 = dev_out ? J.pts1 : (J.pts1 ? (float*)sl.cpts.p : nullptr);
             float* dp2 = dev_out ? J.pts2 : (J.pts2 ? (float*)((char*)sl.cpts.p + (size_t)max_rows * 8) : nullptr);
             ctx->launches += launch_gms_compact(static_cast<const PairDesc*>(ctx->d_pairs.p) + p0, static_cast<const PairResult*>(ctx->d_results.p) + p0,
-                                                pn, (long long*)ctx->d_cbase.p, doff, dev_out ? J.capacity : rows, dm, dp1, dp2, st);
+                                                pn, (long long*)ctx->d_cbase.p, doff, dev_out ? J.capacity : rows, dm, dp1, dp2, st,
+                                                ctx->compact_rec_bytes == 8);
             CU(cudaGetLastError());
         }
         tl_marks = nullptr;

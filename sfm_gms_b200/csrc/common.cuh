@@ -89,9 +89,10 @@ size_t gms_counts_offset_words(int n_scales, int n_rot, int max_matches, int for
 // offsets[p] = *base + sum of n_inliers of earlier pairs (exclusive scan, written by the offsets kernel, n_pairs + 1
 // entries); *base += total afterwards.  Rows at or beyond `capacity` are not written.  2 launches.
 struct DMatchRec { int32_t queryIdx, trainIdx, imgIdx; float distance; };
+// index_pairs: d_matches receives 8-byte {queryIdx, trainIdx} records instead of DMatchRec (SFMGMS_OPT_COMPACT_RECORD)
 int launch_gms_compact(const PairDesc* d_pairs, const PairResult* d_results, int n_pairs, long long* d_base,
                        long long* d_offsets, long long capacity, DMatchRec* d_matches, float* d_pts1, float* d_pts2,
-                       cudaStream_t st);
+                       cudaStream_t st, bool index_pairs = false);
 
 // L2 brute force for integer-valued float descriptors (OpenCV SIFT), l2_dp4a.cu
 size_t l2_scratch_bytes(int nq, int nt);

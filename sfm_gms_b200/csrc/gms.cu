@@ -656,7 +656,7 @@ __global__ void __launch_bounds__(1024) gms_compact_offsets_kernel(const PairRes
 __global__ void __launch_bounds__(1024) gms_compact_kernel(const PairDesc* __restrict__ pairs, const PairResult* __restrict__ results,
                                                             const long long* __restrict__ offsets, long long capacity,
                                                             DMatchRec* __restrict__ matches, float2* __restrict__ pts1,
-                                                            float2* __restrict__ pts2) {
+                                                            float2* __restrict__ pts2, int index_pairs) {
     const PairDesc pd = pairs[blockIdx.x];
     if (results[blockIdx.x].mask_len <= 0 || results[blockIdx.x].n_inliers <= 0) return;
     const long long out0 = offsets[blockIdx.x];
@@ -679,7 +679,9 @@ __global__ void __launch_bounds__(1024) gms_compact_kernel(const PairDesc* __res
             const uint32_t key = pd.key ? pd.key[i] : 0u;
             const int qi = pd.mq ? pd.mq[i] : i;
             const int ti = pd.mt ? pd.mt[i] : (int)(key & kTrainIdxMask);
-            if (matches) {
+            if (matches && index_pairs) {
+                reinterpret_cast<int2*>(matches)[pos] = make_int2(qi, ti);
+            } else if (matches) {
                 DMatchRec r;
                 r.queryIdx = qi; r.trainIdx = ti; r.imgIdx = 0; r.distance = pd.key ? (float)(key >> kTrainIdxBits) : 0.f;
                 *reinterpret_cast<int4*>(matches + pos) = *reinterpret_cast<const int4*>(&r);
@@ -697,12 +699,12 @@ __global__ void __launch_bounds__(1024) gms_compact_kernel(const PairDesc* __res
 
 int launch_gms_compact(const PairDesc* d_pairs, const PairResult* d_results, int n_pairs, long long* d_base,
                        long long* d_offsets, long long capacity, DMatchRec* d_matches, float* d_pts1, float* d_pts2,
-                       cudaStream_t st) {
+                       cudaStream_t st, bool index_pairs) {
     if (n_pairs <= 0) return 0;
     gms_compact_offsets_kernel<<<1, 1024, 0, st>>>(d_results, n_pairs, d_base, d_offsets);
     kmark("gms_compact_offsets", st);
     gms_compact_kernel<<<n_pairs, 1024, 0, st>>>(d_pairs, d_results, d_offsets, capacity, d_matches,
-                                                 reinterpret_cast<float2*>(d_pts1), reinterpret_cast<float2*>(d_pts2));
+                                                 reinterpret_cast<float2*>(d_pts1), reinterpret_cast<float2*>(d_pts2), index_pairs ? 1 : 0);
     kmark("gms_compact", st);
     return 2;
 }

@@ -694,15 +694,25 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             mbar_wait(a_empty_bar + 8 * abuf, a_phase ^ 1);
             uint8_t* const dst = a_generic + abuf * A_BUF_BYTES;
             if (vec) {
-                for (int i = rt; i < wu.n_rows * 2; i += kResThreads) {        // i = (row, half): 16 packed bytes -> 64 unpacked
-                    const int row = i >> 1, h = i & 1;
-                    const uint4 w = __ldg(reinterpret_cast<const uint4*>(wu.q_desc) + i);
-                    uint8_t* const rp = dst + row * ROWB;
-                    const int sw = row & 7;
-                    *reinterpret_cast<uint4*>(rp + (((4 * h + 0) ^ sw) << 4)) = expand(w.x);
-                    *reinterpret_cast<uint4*>(rp + (((4 * h + 1) ^ sw) << 4)) = expand(w.y);
-                    *reinterpret_cast<uint4*>(rp + (((4 * h + 2) ^ sw) << 4)) = expand(w.z);
-                    *reinterpret_cast<uint4*>(rp + (((4 * h + 3) ^ sw) << 4)) = expand(w.w);
+                const int n_half = wu.n_rows * 2;                            // i = (row, half): 16 packed bytes -> 64 unpacked
+                for (int i0 = rt; i0 < n_half; i0 += 4 * kResThreads) {        // four loads in flight per lane
+                    uint4 w[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        w[k] = i0 + k * kResThreads < n_half ? __ldg(reinterpret_cast<const uint4*>(wu.q_desc) + i0 + k * kResThreads)
+                                                             : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = i0 + k * kResThreads;
+                        if (i >= n_half) break;
+                        const int row = i >> 1, h = i & 1;
+                        uint8_t* const rp = dst + row * ROWB;
+                        const int sw = row & 7;
+                        *reinterpret_cast<uint4*>(rp + (((4 * h + 0) ^ sw) << 4)) = expand(w[k].x);
+                        *reinterpret_cast<uint4*>(rp + (((4 * h + 1) ^ sw) << 4)) = expand(w[k].y);
+                        *reinterpret_cast<uint4*>(rp + (((4 * h + 2) ^ sw) << 4)) = expand(w[k].z);
+                        *reinterpret_cast<uint4*>(rp + (((4 * h + 3) ^ sw) << 4)) = expand(w[k].w);
+                    }
                 }
             } else {
                 for (int i = rt; i < wu.n_rows * kDescWords; i += kResThreads) {

@@ -72,6 +72,31 @@ def test_compact_ragged_vs_oracle(ctx, oracle_mod, rot, sc, chunk_rows):
     assert np.array_equal(full["n_inliers"], res["n_inliers"])
 
 
+@pytest.mark.parametrize("chunk_rows", [3000, 1 << 22])
+def test_compact_index_pair_records(ctx, oracle_mod, chunk_rows):
+    """SFMGMS_OPT_COMPACT_RECORD = 1: `matches` holds 8-byte {queryIdx, trainIdx} rows (what SfMUtil.cpp:25-35 reads of
+    matchesGMS); offsets, counts and coordinates as with cv::DMatch records."""
+    from sfm_gms_b200 import api
+
+    rng = np.random.default_rng(8)
+    off, desc, kp, wh = _ragged_set(rng, SIZES)
+    ctx.set_images(off, desc, kp, wh)
+    exp = _oracle_compact(oracle_mod, off, desc, kp, wh, PAIRS, 0, 0)
+    ctx.set_option(api.OPT_CHUNK_ROWS, chunk_rows)
+    try:
+        r = ctx.match_pairs_compact(PAIRS, index_pairs=True)
+        d = ctx.match_pairs_compact(PAIRS)
+    finally:
+        ctx.set_option(api.OPT_CHUNK_ROWS, 4 << 20)
+    assert r["matches"].dtype == np.int32 and r["matches"].shape == (r["n_total"], 2)
+    assert np.array_equal(r["matches"][:, 0], np.concatenate([e[0] for e in exp]))
+    assert np.array_equal(r["matches"][:, 1], np.concatenate([e[1] for e in exp]))
+    assert np.array_equal(r["offsets"], d["offsets"]) and np.array_equal(r["pts1"], d["pts1"]) and np.array_equal(r["pts2"], d["pts2"])
+    _check_compact(d, exp)                                                # the option does not stick
+    with pytest.raises(api.SfmGmsError):
+        ctx.set_option(api.OPT_COMPACT_RECORD, 2)
+
+
 def test_compact_partial_outputs_and_capacity(ctx, oracle_mod):
     from sfm_gms_b200 import api
 
