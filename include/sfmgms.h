@@ -54,7 +54,7 @@ extern "C" {
 #define SFMGMS_HAMMING_TC 2     /* tcgen05 int8 tensor-core kernel (unpacked +-1 bits, TMEM accumulators) */
 #define SFMGMS_HAMMING_FP4 3    /* tcgen05 block-scaled FP4 (kind::mxf4) kernel: +-1 as E2M1, unit scales */
 #define SFMGMS_OPT_GMS_CHUNK_BYTES 2 /* scratch budget per GMS chunk (bytes), default 64 MiB */
-#define SFMGMS_OPT_TC_OPERAND_CACHE 4 /* 1 (default): keep the unpacked +-1 operands of the image set across
+#define SFMGMS_OPT_TC_OPERAND_CACHE 4 /* 1 (default): keep the unpacked tensor-core operands of the image set across
                                          sfmgms_match_pairs calls; 0: unpack again on every call */
 #define SFMGMS_OPT_L2_KERNEL 5        /* sfmgms_bf_l2: 0 auto, 1 DP4A CUDA-core kernel, 2 tcgen05 kind::i8 kernel (1, 2: integer-valued
                                          data, else the fp32 kernel takes over), 3 always the order-exact fp32 kernel */
@@ -62,8 +62,9 @@ extern "C" {
                                         2: additionally one event after every kernel (sfmgms_kernel_times) */
 #define SFMGMS_OPT_CHUNK_ROWS 6      /* sfmgms_match_pairs[_compact] walk a pair list in chunks of at most this many match
                                         rows (default 4 Mi): per-match device scratch is O(chunk), never O(list) */
-#define SFMGMS_OPT_OVERLAP 8         /* 1 (default): a batch's tensor-core work is split into up to three launches and the small
-                                        tie-resolution kernel of each runs on a second stream beside the next launch; 0: one stream */
+#define SFMGMS_OPT_OVERLAP 8         /* only with the separate tie-resolution kernel (SFMGMS_FP4_FUSED_RESOLVE=0 in the environment; by
+                                        default the fp4 kernel resolves its own ties): 1 (default) splits a batch's tensor-core work
+                                        into up to three launches with the resolution of each on a second stream; 0: one stream */
 #define SFMGMS_OPT_COMPACT_RECORD 9  /* records sfmgms_match_pairs_compact writes to `matches`: 0 (default) cv::DMatch, 16 bytes
                                         {queryIdx, trainIdx, imgIdx = 0, float distance}; 1: index pairs, 8 bytes {int32 queryIdx,
                                         int32 trainIdx} -- all that the reference's consumer of matchesGMS reads (SfMUtil.cpp:25-35
@@ -247,6 +248,7 @@ int sfmgms_match_offsets(sfmgms_ctx* ctx, const int32_t* pairs, int n_pairs, int
  *   n_inliers[n_pairs], best_hyp[n_pairs]      int32 per pair
  *   inlier_offsets[n_pairs + 1]                int64: pair p owns rows [inlier_offsets[p], inlier_offsets[p+1])
  *   matches[capacity]                          16-byte cv::DMatch records {queryIdx, trainIdx, imgIdx = 0, distance (float)}
+ *                                              (SFMGMS_OPT_COMPACT_RECORD = 1: 8-byte {int32 queryIdx, int32 trainIdx} rows)
  *   pts1[capacity * 2], pts2[capacity * 2]     kp1[queryIdx].pt / kp2[trainIdx].pt of the same rows
  * Any output may be NULL.  *n_total = total inliers; if it exceeds `capacity` the first `capacity` rows are valid and
  * the call returns SFMGMS_ERR_CAPACITY.  out_location selects host or device pointers for all outputs.  A pair costs
