@@ -35,11 +35,22 @@ namespace {
 using namespace tcptx;
 
 constexpr int BM = 128;            // UMMA M
+// SFMGMS_FP4_V3: three TMEM accumulator slots of 160 columns, three query sub-tiles per unit, and every epilogue warp OWNS one
+// (lane quadrant, sub-tile = slot): it reads all 160 columns of every third accumulator instead of 80 columns of every
+// accumulator.  The warps of a scheduler are then in different phases (one waits for tensor memory while another runs its max
+// tree) instead of in lockstep on the same accumulator, and a slot has two accumulator times to drain instead of one.
+// MEASURED (bit-exact, 177 parity tests + stress): 1.795 vs 1.760 ms per 256 cfg2 pairs -- 2 % SLOWER than the two-slot layout,
+// so it is not the default.  The lockstep was not the limit: a warp alone in its max tree exposes the FMNMX3 dependency
+// latency that three interleaved warps hide (profiles/r2_notes.md).
+#ifndef SFMGMS_FP4_V3
+#define SFMGMS_FP4_V3 0
+#endif
+constexpr bool kV3 = SFMGMS_FP4_V3 != 0;
 #ifndef SFMGMS_FP4_MSUB
-#define SFMGMS_FP4_MSUB 4
+#define SFMGMS_FP4_MSUB (SFMGMS_FP4_V3 ? 3 : 4)
 #endif
 constexpr int MSUB = SFMGMS_FP4_MSUB;  // query sub-tiles per work unit
-constexpr int BN = 240;            // UMMA N: 2 accumulator slots x 240 columns + 32 scale columns = 512 TMEM columns
+constexpr int BN = kV3 ? 160 : 240;    // UMMA N: accumulator slots x BN columns + 32 scale columns = 512 TMEM columns
 constexpr int ROWB = 128;          // bytes per unpacked row: 256 x e2m1
 constexpr int UMMA_KB = 32;        // bytes of K per mxf4 MMA (64 elements)
 constexpr int NKSTEP = ROWB / UMMA_KB;   // 4
@@ -50,7 +61,8 @@ constexpr int A_BUF_BYTES = MSUB * TILE_BYTES;
 constexpr int STAGES = (222 * 1024 - A_BUFS * A_BUF_BYTES) / BTILE_BYTES;   // 3 (MSUB=4) / 5 (MSUB=2)
 constexpr int SMEM_DATA = A_BUFS * A_BUF_BYTES + STAGES * BTILE_BYTES;
 
-constexpr int ACC_SLOTS = 2;
+constexpr int ACC_SLOTS = kV3 ? 3 : 2;
+static_assert(!kV3 || MSUB == ACC_SLOTS, "V3: sub-tile s lives in slot s");
 constexpr int SF_COL = ACC_SLOTS * BN;   // TMEM columns [480, 512): block scales (all 1.0)
 constexpr int SF_COLS = 32;
 constexpr int kEpiWarp0 = 0;            // epilogue warps first: the scheduler favours HIGH warp ids, which must be the
@@ -58,7 +70,7 @@ constexpr int kEpiWarp0 = 0;            // epilogue warps first: the scheduler f
 #define SFMGMS_FP4_EPIW 12
 #endif
 constexpr int kEpiWarps = SFMGMS_FP4_EPIW;        // 12: 3 per TMEM lane quadrant x 80 columns; 16: 4 x 60 columns
-constexpr int kEpiCols = BN / (kEpiWarps / 4);    // 80 = x64 + x16 tcgen05.ld; 60 = x32 + x16 + x8 + x4
+constexpr int kEpiCols = kV3 ? 80 : BN / (kEpiWarps / 4);    // columns per tcgen05.ld batch: 80 = x64 + x16; 60 = x32 + x16 + x8 + x4
 #ifndef SFMGMS_FP4_PRODW
 #define SFMGMS_FP4_PRODW 0
 #define SFMGMS_FP4_MMAW 1
@@ -70,7 +82,8 @@ constexpr int kAllocWarp = kEpiWarps + SFMGMS_FP4_ALLOCW;
 constexpr int kThreads = 32 * (kEpiWarps + 4);   // 512
 constexpr int kResWarp0 = kAllocWarp;            // fused tie resolution: the allocator warp and the spare one behind it
 constexpr int kResThreads = 64;
-constexpr int kKeyParts = kEpiWarps / 4;         // epilogue warps per TMEM lane quadrant (column parts)
+constexpr int kKeyParts = kV3 ? 1 : kEpiWarps / 4;   // epilogue warps that hold a candidate for the same query row (column parts)
+static_assert(!kV3 || kEpiWarps == 4 * ACC_SLOTS, "V3: one epilogue warp per (lane quadrant, slot)");
 constexpr int SMEM_KEYS = kKeyParts * MSUB * BM * 4;   // one candidate key per (part, row) of a unit
 constexpr int SMEM_LUT = 256 * 4;                      // packed query tiles: descriptor byte -> 8 e2m1 values
 constexpr int SMEM_BYTES = SMEM_DATA + 1024 + 256 + SMEM_KEYS + SMEM_LUT;
@@ -322,7 +335,7 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
         for (int s = 0; s < A_BUFS; ++s) { mbar_init(a_full_bar + 8 * s, 1); mbar_init(a_empty_bar + 8 * s, 1); }
-        for (int s = 0; s < ACC_SLOTS; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, kEpiWarps); }
+        for (int s = 0; s < ACC_SLOTS; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, kV3 ? 4 : kEpiWarps); }
         mbar_init(done_bar, kEpiWarps); mbar_init(free_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -388,7 +401,7 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         }
     } else if (warp == kMmaWarp) {
         // accumulator slot = sub-tile index & 1 (compile-time in the epilogue's unrolled loop); one phase bit per slot
-        uint32_t stage = 0, phase = 0, abuf = 0, a_phase = 0, slot_phase[ACC_SLOTS] = {0, 0};
+        uint32_t stage = 0, phase = 0, abuf = 0, a_phase = 0, slot_phase[ACC_SLOTS] = {};
         int tr_acc = 0;
         const uint32_t a_lo0 = sdesc_lo(a_smem), b_lo0 = sdesc_lo(b_smem);
         const uint32_t sf = tmem_base + SF_COL;
@@ -404,7 +417,7 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 #pragma unroll
                 for (int s = 0; s < MSUB; ++s) {
                     if (s >= nsub) break;
-                    const int slot = s & 1;
+                    const int slot = kV3 ? s : (s & 1);
                     if (dbg == 7) trace_stamp(lm, tr_acc, warp, 0);
                     mbar_wait(tempty_bar + 8 * slot, slot_phase[slot] ^ 1);
                     slot_phase[slot] ^= 1;
@@ -429,7 +442,85 @@ hamming_fp4_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             if (elect_one()) tc_commit(a_empty_bar + 8 * abuf);
             if (++abuf == A_BUFS) { abuf = 0; a_phase ^= 1; }
         }
-    } else if (warp < kEpiWarps) {
+    } else if (kV3 && warp < kEpiWarps) {
+        // ================= epilogue, V3: warp = (lane quadrant, sub-tile = TMEM slot); all BN columns of its accumulators ====
+        const int quad = warp & 3;                        // TMEM lanes [32*quad, 32*quad+32)
+        const int sub = (warp - kEpiWarp0) >> 2;          // query sub-tile of the unit = accumulator slot
+        const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(sub * BN);
+        const uint32_t tfull_e = tmem_ptr_generic[1] + 8 * sub, tempty_e = tmem_ptr_generic[1] + 8 * ACC_SLOTS + 8 * sub;
+        uint32_t ph = 0, free_phase = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const WorkUnit wu = make_unit(lm, pairs, u);
+            const int nsub = (wu.n_rows + BM - 1) / BM;
+            float best_key = -1.0e30f, beat = -1.0e29f;   // see the two-slot epilogue below for the key / tag scheme
+            int best_base = -1;
+            // kEpiCols columns starting at accumulator column col0 of the tile at train row t: group-tagged maximum, one-compare update
+            auto reduce = [&](const int (&r)[kEpiCols], int col0, int t, int valid) {
+                float v[kEpiCols];
+#pragma unroll
+                for (int j = 0; j < kEpiCols; ++j) v[j] = __int_as_float(r[j]);
+                if (col0 + kEpiCols > valid) {                       // tail tile: mask columns outside the image
+#pragma unroll
+                    for (int j = 0; j < kEpiCols; ++j)
+                        if (col0 + j >= valid) v[j] = -1.0e30f;
+                }
+                float gm[kGroups + 1];
+#pragma unroll
+                for (int g = 0; g + 1 < kGroups; ++g) gm[g] = max_tree<kGroup>(v + kGroup * g);
+                gm[kGroups - 1] = max_tree<kLastGroup>(v + kGroup * (kGroups - 1));
+                gm[kGroups] = 0.f;
+#pragma unroll
+                for (int k = 0; k < kGroups / 2; ++k) add2(gm[2 * k], gm[2 * k + 1], c_grouptag[k], gm[2 * k], gm[2 * k + 1]);
+                if constexpr (kGroups & 1) gm[kGroups - 1] += c_grouptag[kGroups / 2].x;
+                const float m = max_tree<kGroups>(gm);
+                if (m > beat) { best_key = m; beat = m + 0.5f; best_base = t + col0; }
+            };
+            if (sub < nsub) {
+                for (int t = wu.t_begin; t < wu.t_end; t += BN) {
+                    const int valid = wu.t_end - t;
+                    mbar_wait(tfull_e, ph);
+                    ph ^= 1;
+                    tc_fence_after();
+                    int r[kEpiCols];
+#pragma unroll
+                    for (int c = 0; c < BN / kEpiCols; ++c) {
+                        ld_part(tbase + c * kEpiCols, r);
+                        tc_wait_ld();
+                        if (c == BN / kEpiCols - 1) {                // everything is in registers: hand the slot back
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(tempty_e);
+                        }
+                        reduce(r, c * kEpiCols, t, valid);
+                    }
+                }
+            }
+            const bool fused = dbg == 0 && lm.fused != 0;
+            if (fused) {
+                mbar_wait(free_bar, free_phase ^ 1);            // the helper warps have taken the previous unit's candidates
+                free_phase ^= 1;
+            }
+            {
+                const int row = sub * BM + quad * 32 + lane;
+                const bool have = sub < nsub && row < wu.n_rows && (best_base >= 0 || dbg != 0);
+                uint32_t packed = kKeyInit;
+                if (have) {
+                    const float fl = floorf(best_key);
+                    const int g = kTagDen - 1 - (int)((best_key - fl) * (float)kTagDen);
+                    constexpr bool kTiming = dbg != 0;
+                    const uint32_t dist = kTiming ? ((uint32_t)(256 - (int)fl) >> 1) & 7u : kTrain01 ? (uint32_t)(256 - (int)fl) : (uint32_t)(256 - (int)fl) >> 1;
+                    const uint32_t idx = kTiming ? (uint32_t)(best_base + kGroup * g) & 7u : (uint32_t)(best_base + kGroup * g);
+                    packed = (dist << kTrainIdxBits) | idx;
+                }
+                if (fused) skeys[row] = packed;
+                else if (have) atomicMin(wu.key + row, packed);
+            }
+            if (fused) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(done_bar);
+            }
+        }
+    } else if (!kV3 && warp < kEpiWarps) {
         // ================= epilogue: 12 warps; warp = (lane quadrant, 80-column part) of every accumulator ==========
         const int quad = warp & 3;                        // TMEM lanes [32*quad, 32*quad+32)
         const int c0 = ((warp - kEpiWarp0) >> 2) * kEpiCols; // accumulator columns [c0, c0+80)
