@@ -81,3 +81,18 @@ def test_host_alloc_fails_loudly_without_gpu():
     assert lib.sfmgms_host_free(None) == 0
     with pytest.raises(sg.SfmGmsError):
         api.host_empty(16, "u1")
+
+
+def test_python_mirror_constants_match_the_header():
+    """api.py restates the header's option keys / kernel ids / error codes by hand: keep them equal."""
+    from sfm_gms_b200 import api
+
+    hdr = open(os.path.join(ROOT, "include", "sfmgms.h")).read()
+    defs = {k: int(v) for k, v in re.findall(r"#define\s+(SFMGMS_[A-Z0-9_]+)\s+(-?\d+)\b", hdr)}
+    keys = [k for k in defs if k.startswith("SFMGMS_OPT_")]
+    assert len(keys) >= 9 and len({defs[k] for k in keys}) == len(keys), "option keys must be distinct"
+    for name in keys:
+        py = name[len("SFMGMS_"):]
+        assert getattr(api, py) == defs[name], name
+    for name in ("SFMGMS_HAMMING_POPC", "SFMGMS_HAMMING_TC", "SFMGMS_HAMMING_FP4", "SFMGMS_HOST", "SFMGMS_DEVICE"):
+        assert getattr(api, name if hasattr(api, name) else name[len("SFMGMS_"):]) == defs[name], name
